@@ -1,0 +1,348 @@
+"""Host-side mirror of the reference's call shapes over the C ABI (ctypes, numpy buffers).
+
+The reference drivers call, per frame pair:
+    cv::BFMatcher(NORM_HAMMING2, true).match(desc0, desc1, matches)      kitti_ba.cpp:602,641
+    cv::findEssentialMat(p0, p1, cam, method, prob, thr, mask)           kitti_E.cpp:98-104
+    cv::recoverPose(E, p0, p1, cam, R, t, mask)                          kitti_E.cpp:120
+    Levenberg_Marquardt(n_zeta, eps, reps, wreps, lambda0, T0s, pr, p_r, lm_res)
+                                                                         jac_Rt_gen_.cpp:287
+The functions here keep those names, argument meanings and error behaviour (empty result /
+None where OpenCV returns an empty Mat) and run on the GPU through libepivo_b200.so.  The
+C++ equivalents (what an unmodified driver links against) are in include/epivo_shims.hpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (EpivoError, LmRes, PairResult, PipelineParams, LMEDS, RANSAC, NORM_HAMMING,  # noqa: F401
+                   NORM_HAMMING2, MATCH_NN, MATCH_CROSSCHECK, MATCH_RATIO)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA stream + workspace on one device (`epivo_ctx`).  Not shared between threads."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.epivo_create(C.byref(h), int(device))
+        if rc != 0 or not h.value:
+            raise EpivoError(rc, f"epivo_create(device={device}) failed: no usable CUDA device "
+                                 "(there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.epivo_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int, allow=()):
+        if rc != 0 and rc not in allow:
+            raise EpivoError(rc, self.lib.epivo_last_error(self.h).decode())
+        return rc
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.epivo_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.epivo_launch_count(self.h))
+
+    def sync(self):
+        self.check(self.lib.epivo_sync(self.h))
+
+    def microbench(self, which: int) -> float:
+        v = C.c_double()
+        self.check(self.lib.epivo_microbench(self.h, which, C.byref(v)))
+        return v.value
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class BFMatcher:
+    """cv::BFMatcher(normType, crossCheck) for binary descriptors (kitti_ba.cpp:602)."""
+
+    def __init__(self, normType: int = NORM_HAMMING2, crossCheck: bool = False, ctx: Context | None = None):
+        self.normType = normType
+        self.crossCheck = bool(crossCheck)
+        self.ctx = ctx or default_context()
+
+    def _descs(self, q, t):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        if q.ndim != 2 or t.ndim != 2:
+            raise ValueError("descriptors must be 2-D uint8 arrays")
+        if q.shape[0] and t.shape[0] and q.shape[1] != t.shape[1]:
+            raise ValueError("descriptor sizes differ")
+        return q, t
+
+    def match(self, queryDescriptors, trainDescriptors):
+        """-> (queryIdx, trainIdx, distance) int32 arrays, sorted by queryIdx (DMatch fields)."""
+        mode = MATCH_CROSSCHECK if self.crossCheck else MATCH_NN
+        return self._run(queryDescriptors, trainDescriptors, mode, 0.0)[:3]
+
+    def ratioMatch(self, queryDescriptors, trainDescriptors, ratio: float = 0.8):
+        """knnMatch(k=2) + Lowe ratio test -> (queryIdx, trainIdx, distance, distance2)."""
+        return self._run(queryDescriptors, trainDescriptors, MATCH_RATIO, ratio)
+
+    def knnMatch2(self, queryDescriptors, trainDescriptors):
+        """knnMatch(k=2) -> (trainIdx (nq,2), distance (nq,2))."""
+        q, t = self._descs(queryDescriptors, trainDescriptors)
+        nq, nt = q.shape[0], t.shape[0]
+        idx = np.full((nq, 2), -1, dtype=np.int32)
+        dist = np.full((nq, 2), -1, dtype=np.int32)
+        db = q.shape[1] if nq else (t.shape[1] if nt else 32)
+        self.ctx.check(self.ctx.lib.epivo_knn2_hamming(self.ctx.h, _p(q), nq, _p(t), nt, db, self.normType,
+                                                       _p(idx), _p(dist)))
+        return idx, dist
+
+    def _run(self, q, t, mode, ratio):
+        q, t = self._descs(q, t)
+        nq, nt = q.shape[0], t.shape[0]
+        qi = np.empty(max(nq, 1), dtype=np.int32)
+        ti = np.empty(max(nq, 1), dtype=np.int32)
+        d = np.empty(max(nq, 1), dtype=np.int32)
+        d2 = np.empty(max(nq, 1), dtype=np.int32)
+        n = C.c_int(0)
+        db = q.shape[1] if nq else (t.shape[1] if nt else 32)
+        self.ctx.check(self.ctx.lib.epivo_match_hamming(self.ctx.h, _p(q), nq, _p(t), nt, db, self.normType,
+                                                        mode, float(ratio), _p(qi), _p(ti), _p(d), _p(d2),
+                                                        C.byref(n)))
+        k = n.value
+        return qi[:k].copy(), ti[:k].copy(), d[:k].copy(), d2[:k].copy()
+
+
+def _pts(p):
+    p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 2)
+    return p
+
+
+def _K(K):
+    return np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(3, 3))
+
+
+def findEssentialMat(points1, points2, cameraMatrix, method: int = RANSAC, prob: float = 0.999,
+                     threshold: float = 1.0, maxIters: int = 1000, samples=None, ctx: Context | None = None,
+                     return_info: bool = False):
+    """cv::findEssentialMat -> (E 3x3 float64 | None, mask (n,) uint8 in {0,1}).
+
+    `samples` (m x 5 int32) injects a fixed hypothesis set; None replays OpenCV's own
+    deterministic sample stream so the whole call reproduces cv2."""
+    ctx = ctx or default_context()
+    p0, p1 = _pts(points1), _pts(points2)
+    if p0.shape != p1.shape:
+        raise ValueError("point sets differ in size")
+    n = p0.shape[0]
+    K = _K(cameraMatrix)
+    E = np.zeros(9, dtype=np.float64)
+    mask = np.zeros(max(n, 1), dtype=np.uint8)
+    ninl, iters = C.c_int(0), C.c_int(0)
+    s = None
+    m = 0
+    if samples is not None:
+        s = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1, 5)
+        m = s.shape[0]
+    rc = ctx.check(ctx.lib.epivo_find_essential(ctx.h, _p(p0), _p(p1), n, _p(K), int(method), float(prob),
+                                                float(threshold), int(maxIters), _p(s), m, _p(E), _p(mask),
+                                                C.byref(ninl), C.byref(iters)), allow=(_lib.ERR_NOMODEL,))
+    Eo = None if rc == _lib.ERR_NOMODEL else E.reshape(3, 3)
+    if return_info:
+        return Eo, mask[:n], {"n_inliers": ninl.value, "iters": iters.value}
+    return Eo, mask[:n]
+
+
+def fivePoint(x1, x2, ctx: Context | None = None):
+    """The minimal solver alone on m samples (m,5,2) of K-normalised points -> list of (k,3,3)."""
+    ctx = ctx or default_context()
+    x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(-1, 5, 2)
+    x2 = np.ascontiguousarray(x2, dtype=np.float64).reshape(-1, 5, 2)
+    m = x1.shape[0]
+    E = np.zeros((m, 10, 9), dtype=np.float64)
+    nm = np.zeros(m, dtype=np.int32)
+    ctx.check(ctx.lib.epivo_five_point(ctx.h, _p(x1), _p(x2), m, _p(E), _p(nm)))
+    return [E[i, :nm[i]].reshape(-1, 3, 3) for i in range(m)]
+
+
+def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None):
+    """K3 alone: (counts (m,), medians (m,) f32, best index, mask of best (n,) {0,1})."""
+    ctx = ctx or default_context()
+    Es = np.ascontiguousarray(Es, dtype=np.float64).reshape(-1, 9)
+    p0, p1 = _pts(points1), _pts(points2)
+    n, m = p0.shape[0], Es.shape[0]
+    K = _K(cameraMatrix)
+    counts = np.zeros(max(m, 1), dtype=np.int32)
+    med = np.zeros(max(m, 1), dtype=np.float32)
+    mask = np.zeros(max(n, 1), dtype=np.uint8)
+    best = C.c_int(-1)
+    ctx.check(ctx.lib.epivo_score_sampson(ctx.h, _p(Es), m, _p(p0), _p(p1), n, _p(K), float(threshold),
+                                          _p(counts), _p(med), C.byref(best), _p(mask)))
+    return counts[:m], med[:m], best.value, mask[:n]
+
+
+def recoverPose(E, points1, points2, cameraMatrix, distanceThresh: float = 50.0, mask=None,
+                ctx: Context | None = None):
+    """cv::recoverPose -> (n_good, R 3x3, t (3,), mask (n,) uint8 in {0,255})."""
+    ctx = ctx or default_context()
+    p0, p1 = _pts(points1), _pts(points2)
+    n = p0.shape[0]
+    K = _K(cameraMatrix)
+    Ein = np.ascontiguousarray(np.asarray(E, dtype=np.float64).reshape(9))
+    R = np.zeros(9)
+    t = np.zeros(3)
+    out = np.zeros(max(n, 1), dtype=np.uint8)
+    im = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+    ng = C.c_int(0)
+    ctx.check(ctx.lib.epivo_recover_pose(ctx.h, _p(Ein), _p(p0), _p(p1), n, _p(K), float(distanceThresh), _p(im),
+                                         _p(R), _p(t), _p(out), C.byref(ng)))
+    return ng.value, R.reshape(3, 3), t, out[:n]
+
+
+def Levenberg_Marquardt(n_zeta: int, epsilon: float, reps, wreps, lambda0: float, T0s, pr, p_r,
+                        huber_delta: float = 1e-5, max_iters: int = 30, ctx: Context | None = None):
+    """jac_Rt_gen_.cpp:287 -- returns (T0s_out (n_zeta,4,4), LM_res dict); T0s is not modified.
+
+    `wreps=None` is the 7-argument form called at kitti_E.cpp:196 (unit weights)."""
+    ctx = ctx or default_context()
+    reps = np.ascontiguousarray(reps, dtype=np.int32).reshape(-1, 2)
+    n_rep = reps.shape[0]
+    w = np.ones(n_rep) if wreps is None else np.ascontiguousarray(wreps, dtype=np.float64).reshape(-1)
+    if w.shape[0] != n_rep:
+        raise ValueError("reps.size() != wreps.size()")            # jac_Rt_gen_.cpp:297
+    T = np.array(T0s, dtype=np.float64).reshape(n_zeta, 16).copy()
+    pr = np.ascontiguousarray(pr, dtype=np.float64)
+    p_r = np.ascontiguousarray(p_r, dtype=np.float64)
+    N = pr.shape[1]
+    res = LmRes()
+    it = C.c_int(0)
+    ctx.check(ctx.lib.epivo_lm_rt(ctx.h, int(n_zeta), float(epsilon), _p(reps), _p(w), n_rep, float(lambda0),
+                                  int(max_iters), float(huber_delta), _p(T), _p(pr), _p(p_r), int(N),
+                                  C.byref(res), C.byref(it)))
+    return T.reshape(n_zeta, 4, 4), {"H_norm": res.H_norm, "r_norm": res.r_norm, "lambda": res.lambda_,
+                                     "iters": it.value}
+
+
+def Levenberg_Marquardt_batch(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r, huber_delta=1e-5,
+                              max_iters=30, ctx: Context | None = None):
+    """B independent windows of identical shape in one launch (kitti_ba windows per GPU)."""
+    ctx = ctx or default_context()
+    reps = np.ascontiguousarray(reps, dtype=np.int32).reshape(-1, 2)
+    n_rep = reps.shape[0]
+    T = np.array(T0s, dtype=np.float64).copy()
+    B = T.shape[0]
+    T = T.reshape(B, n_zeta, 16)
+    w = np.ascontiguousarray(np.broadcast_to(np.asarray(wreps, dtype=np.float64), (B, n_rep)))
+    pr = np.ascontiguousarray(pr, dtype=np.float64)
+    p_r = np.ascontiguousarray(p_r, dtype=np.float64)
+    N = pr.shape[2]
+    res = np.zeros((B, 3), dtype=np.float64)
+    its = np.zeros(B, dtype=np.int32)
+    ctx.check(ctx.lib.epivo_lm_rt_batch(ctx.h, B, int(n_zeta), float(epsilon), _p(reps), _p(w), n_rep,
+                                        float(lambda0), int(max_iters), float(huber_delta), _p(T), _p(pr),
+                                        _p(p_r), int(N), _p(res), _p(its)))
+    return T.reshape(B, n_zeta, 4, 4), res, its
+
+
+def default_params(K=None, **kw) -> PipelineParams:
+    p = PipelineParams()
+    _lib.load().epivo_pipeline_params_default(C.byref(p))
+    if K is not None:
+        Kf = np.asarray(K, dtype=np.float64).reshape(9)
+        for i in range(9):
+            p.K[i] = float(Kf[i])
+    for k, v in kw.items():
+        if k == "fallback_t":
+            for i in range(3):
+                p.fallback_t[i] = float(v[i])
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class SequencePipeline:
+    """Device-resident frame sequence + the fused per-pair pipeline (`epivo_seq`)."""
+
+    def __init__(self, max_frames: int, kp_per_frame: int, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.max_frames, self.kp = int(max_frames), int(kp_per_frame)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.epivo_seq_create(self.ctx.h, C.byref(h), self.max_frames, self.kp))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.ctx.lib.epivo_seq_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, kps: np.ndarray, descs: np.ndarray, first_frame: int = 0):
+        """kps (F, kp, 2) f32 and descs (F, kp, 32) u8 host arrays (ideally pinned) -> device (async)."""
+        assert kps.dtype == np.float32 and descs.dtype == np.uint8
+        assert kps.flags.c_contiguous and descs.flags.c_contiguous
+        F = kps.shape[0]
+        assert kps.shape == (F, self.kp, 2) and descs.shape == (F, self.kp, 32)
+        self.ctx.check(self.ctx.lib.epivo_seq_upload(self.h, int(first_frame), F, _p(kps), _p(descs)))
+
+    def run(self, params: PipelineParams, first_pair: int, n_pairs: int):
+        self.ctx.check(self.ctx.lib.epivo_seq_run(self.h, C.byref(params), int(first_pair), int(n_pairs)))
+
+    def download(self, first_pair: int, n_pairs: int, out=None):
+        if out is None:
+            out = np.zeros(n_pairs, dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and out.shape[0] >= n_pairs
+        self.ctx.check(self.ctx.lib.epivo_seq_download(self.h, _p(out), int(first_pair), int(n_pairs)))
+        return out
+
+    def stage_ms(self):
+        ms = np.zeros(16, dtype=np.float32)
+        self.ctx.check(self.ctx.lib.epivo_seq_stage_ms(self.h, _p(ms), 16))
+        return ms
+
+    def matches(self, pair: int):
+        qi = np.zeros(self.kp, dtype=np.int32)
+        ti = np.zeros(self.kp, dtype=np.int32)
+        d = np.zeros(self.kp, dtype=np.int32)
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.epivo_seq_get_matches(self.h, int(pair), _p(qi), _p(ti), _p(d), C.byref(n)))
+        return qi[:n.value], ti[:n.value], d[:n.value]
+
+    def masks(self, pair: int):
+        em = np.zeros(self.kp, dtype=np.uint8)
+        pm = np.zeros(self.kp, dtype=np.uint8)
+        ne, np_ = C.c_int(0), C.c_int(0)
+        self.ctx.check(self.ctx.lib.epivo_seq_get_masks(self.h, int(pair), _p(em), C.byref(ne), _p(pm),
+                                                        C.byref(np_)))
+        return em[:ne.value], pm[:np_.value]
+
+
+RESULT_DTYPE = np.dtype([("E", "f8", (3, 3)), ("R", "f8", (3, 3)), ("t", "f8", (3,)), ("T0", "f8", (4, 4)),
+                         ("T", "f8", (4, 4)), ("H_norm", "f8"), ("r_norm", "f8"), ("lambda", "f8"),
+                         ("n_matches", "i4"), ("n_inliers", "i4"), ("n_good", "i4"), ("ransac_iters", "i4"),
+                         ("n_models", "i4"), ("lm_iters", "i4"), ("lm_ran", "i4"), ("lm_reverted", "i4")])
+assert RESULT_DTYPE.itemsize == C.sizeof(PairResult), (RESULT_DTYPE.itemsize, C.sizeof(PairResult))

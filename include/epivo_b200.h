@@ -1,0 +1,180 @@
+/*
+ * epivo_b200.h -- C ABI of the B200-native (sm_100a) per-frame-pair geometric core of
+ * Ronnypetson/epivo: descriptor matching -> essential matrix (RANSAC / LMedS, 5-point) ->
+ * cheirality pose recovery -> SE(3)-chain Levenberg-Marquardt refinement.
+ *
+ * The reference has no FFI: the path sits behind ordinary C++ call sites into OpenCV and
+ * its own jac_Rt_gen_.cpp.  Each entry point below names the reference call it replaces
+ * (file:line into the reference tree).  Plain pointers and sizes only; all buffers are
+ * caller-owned HOST memory unless a function says "device"; no pointer is retained after
+ * return.  Every function returns 0 (EPIVO_OK) or a negative error code and never aborts
+ * or throws; epivo_last_error() gives the message.  A context owns one CUDA stream and its
+ * workspaces: one context per host thread; distinct contexts are fully concurrent (the
+ * reference's LM keeps a mutable global T0_mem, jac_Rt_gen_.cpp:20 -- this ABI has no
+ * globals).  There is no CPU fallback: without a CUDA device epivo_create fails.
+ */
+#ifndef EPIVO_B200_H
+#define EPIVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPIVO_OK 0
+#define EPIVO_ERR_INVALID -1      /* bad argument */
+#define EPIVO_ERR_CUDA -2         /* CUDA runtime error (message has the cudaError string) */
+#define EPIVO_ERR_UNSUPPORTED -3  /* size / mode outside what the kernels are built for */
+#define EPIVO_ERR_NOMODEL -4      /* estimator found no model (cv::findEssentialMat returns empty Mat) */
+
+/* cv::NormTypes / cv:: robust method ids, so callers can pass the OpenCV constants through */
+#define EPIVO_NORM_HAMMING 6
+#define EPIVO_NORM_HAMMING2 7
+#define EPIVO_LMEDS 4
+#define EPIVO_RANSAC 8
+
+#define EPIVO_MATCH_NN 0          /* BFMatcher(norm, false).match : 1-NN, first minimum        */
+#define EPIVO_MATCH_CROSSCHECK 1  /* BFMatcher(norm, true).match  : mutual NN (reference mode) */
+#define EPIVO_MATCH_RATIO 2       /* knnMatch(k=2) + Lowe ratio test d1 < ratio*d2             */
+
+typedef struct epivo_ctx epivo_ctx;
+
+int epivo_create(epivo_ctx** out, int device);
+void epivo_destroy(epivo_ctx* ctx);
+const char* epivo_last_error(const epivo_ctx* ctx);
+const char* epivo_version(void);
+/* the context's cudaStream_t (as void*), so callers can record their own CUDA events on it */
+void* epivo_stream(epivo_ctx* ctx);
+/* number of this library's kernels launched on the context so far */
+int64_t epivo_launch_count(const epivo_ctx* ctx);
+int epivo_sync(epivo_ctx* ctx);
+
+/* ---- M1: cv::BFMatcher(normType, crossCheck).match(desc0, desc1, matches) ------------
+ * replaces kitti_ba.cpp:602,641.  q: nq x desc_bytes, t: nt x desc_bytes, row-major u8
+ * (desc_bytes in {16, 32, 64}; ORB = 32).  Outputs (capacity nq each) sorted by query_idx;
+ * dist = integer distance (DMatch::distance is its float); dist2 = second-best distance
+ * (written in EPIVO_MATCH_RATIO mode only, may be NULL otherwise). */
+int epivo_match_hamming(epivo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                        int desc_bytes, int norm, int mode, float ratio,
+                        int32_t* query_idx, int32_t* train_idx, int32_t* dist, int32_t* dist2,
+                        int* n_out);
+/* cv::BFMatcher(normType).knnMatch(q, t, 2): per query the two nearest by (distance, index);
+ * train_idx2/dist2 are nq x 2.  Entries beyond nt are -1. */
+int epivo_knn2_hamming(epivo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                       int desc_bytes, int norm, int32_t* train_idx2, int32_t* dist2);
+
+/* ---- E1/E2: cv::findEssentialMat(p0, p1, cam, method, prob, threshold, mask) ----------
+ * replaces kitti.cpp:98-104, kitti_E.cpp:98-104, euroc_E.cpp:202-208, kitti_ba.cpp:232,308,702.
+ * p0/p1: n x 2 float32 pixels; K: 3x3 row-major float64 (the shim widens the float cv::Mat).
+ * samples: optional fixed hypothesis set, m x 5 int32 indices; NULL => OpenCV's own sample
+ * stream (cv::RNG(-1), ptsetreg.cpp), which makes the whole call reproduce cv2.
+ * E: 3x3 row-major; mask: n bytes in {0,1}.  n < 5 or no model => EPIVO_ERR_NOMODEL.
+ * n == 5 returns only the first solution in E (use epivo_five_point for all of them). */
+int epivo_find_essential(epivo_ctx* ctx, const float* p0, const float* p1, int n, const double K[9],
+                         int method, double prob, double threshold, int max_iters,
+                         const int32_t* samples, int m,
+                         double E[9], uint8_t* mask, int* n_inliers, int* iters_run);
+
+/* K2 alone: the 5-point minimal solver on m samples of 5 K-normalised correspondences
+ * (x1, x2: m x 5 x 2 float64).  E_out: m x 10 x 9, n_models: m. */
+int epivo_five_point(epivo_ctx* ctx, const double* x1, const double* x2, int m,
+                     double* E_out, int32_t* n_models);
+
+/* K3 alone: Sampson scoring of a fixed hypothesis set of m models (m x 9) against n
+ * correspondences with OpenCV's exact inlier rule.  threshold in pixels (RANSAC rule);
+ * counts: m inlier counts; medians: m LMedS medians (float32, may be NULL); best: index of
+ * the first model with the largest count; best_mask: n bytes {0,1} of that model. */
+int epivo_score_sampson(epivo_ctx* ctx, const double* E, int m, const float* p0, const float* p1,
+                        int n, const double K[9], double threshold,
+                        int32_t* counts, float* medians, int* best, uint8_t* best_mask);
+
+/* ---- P1: cv::recoverPose(E, p0, p1, cam, R, t, mask) ----------------------------------
+ * replaces kitti_E.cpp:120, euroc_E.cpp:251, kitti_ba.cpp:245,322,715.  mask: {0,255}. */
+int epivo_recover_pose(epivo_ctx* ctx, const double E[9], const float* p0, const float* p1, int n,
+                       const double K[9], double dist_thresh, const uint8_t* in_mask,
+                       double R[9], double t[3], uint8_t* mask, int* n_good);
+
+/* ---- L4: Levenberg_Marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r, lm_res)
+ * replaces jac_Rt_gen_.cpp:287-478 (called at kitti_E.cpp:196, kitti_ba.cpp:881,1044).
+ * reps: n_rep x 2 int32 (first zeta, last zeta); wreps: n_rep; T0s: n_zeta x 16 row-major,
+ * updated in place; pr / p_r: n_rep x N x 3.  epivo_lm_res is the reference's LM_res
+ * (used at jac_Rt_gen_.cpp:473-475 but defined nowhere in the reference). */
+typedef struct { double H_norm, r_norm, lambda; } epivo_lm_res;
+int epivo_lm_rt(epivo_ctx* ctx, int n_zeta, double epsilon, const int32_t* reps, const double* wreps,
+                int n_rep, double lambda0, int max_iters, double huber_delta,
+                double* T0s, const double* pr, const double* p_r, int N,
+                epivo_lm_res* out, int* iters_run);
+/* B independent problems of identical shape in one launch (kitti_ba windows sharded per GPU):
+ * T0s: B x n_zeta x 16, pr/p_r: B x n_rep x N x 3, wreps: B x n_rep, out: B, iters_run: B. */
+int epivo_lm_rt_batch(epivo_ctx* ctx, int B, int n_zeta, double epsilon, const int32_t* reps,
+                      const double* wreps, int n_rep, double lambda0, int max_iters,
+                      double huber_delta, double* T0s, const double* pr, const double* p_r, int N,
+                      epivo_lm_res* out, int32_t* iters_run);
+
+/* ---- fused per-pair pipeline over a frame sequence (the benchmark's hot path) --------
+ * frame f = kp_per_frame keypoints (float32 x,y) + descriptors (32 B); pair i = (f_i, f_i+1):
+ * match -> gather -> findEssentialMat -> compact -> recoverPose -> fallbacks -> LM -> revert,
+ * i.e. the body of the loop kitti_E.cpp:54-201 with the BFMatcher association of
+ * kitti_ba.cpp:641-693 in place of the optical-flow front end. */
+typedef struct {
+    int norm;               /* EPIVO_NORM_HAMMING2            kitti_ba.cpp:602 */
+    int match_mode;         /* EPIVO_MATCH_CROSSCHECK         kitti_ba.cpp:602 */
+    float ratio;            /* 0.8 (ratio mode only) */
+    double K[9];            /* kitti_E.cpp:38-40 */
+    int method;             /* EPIVO_RANSAC (kitti.cpp:101) or EPIVO_LMEDS (kitti_E.cpp:101) */
+    double prob;            /* 0.99 */
+    double threshold;       /* 1.0  (kitti.cpp:103) */
+    int max_iters;          /* 1000 (OpenCV default) */
+    double dist_thresh;     /* 50   (recoverPose default) */
+    double min_trace;       /* 2.7: trace(R) < 3*0.9 -> R = I, t = fallback_t   kitti_E.cpp:128-131 */
+    double fallback_t[3];   /* (0.1, 0.1, -0.9)                                  kitti_E.cpp:130 */
+    double min_t_norm;      /* 1e-5                                              kitti_E.cpp:133 */
+    int lm_points;          /* 48                                                kitti_E.cpp:170 */
+    double lm_lambda0;      /* 1e-2                                              kitti_E.cpp:196 */
+    double lm_epsilon;      /* 1e-8 */
+    int lm_max_iters;       /* 30                                                jac_Rt_gen_.cpp:323 */
+    double huber_delta;     /* 1e-5                                              jac_Rt_gen_.cpp:17 */
+    double lm_revert;       /* revert T to the recoverPose init if r_norm > this (1e-9, kitti_E.cpp:198) */
+} epivo_pipeline_params;
+void epivo_pipeline_params_default(epivo_pipeline_params* p);   /* the KITTI values above */
+
+typedef struct {
+    double E[9];
+    double R[9];            /* recoverPose */
+    double t[3];
+    double T0[16];          /* LM initial pose after the kitti_E.cpp:128-135 fallbacks */
+    double T[16];           /* final pose (LM result, or T0 if reverted / LM not run) */
+    epivo_lm_res lm;
+    int32_t n_matches, n_inliers, n_good, ransac_iters, n_models, lm_iters;
+    int32_t lm_ran;         /* 1 if >= lm_points cheirality-good points existed (kitti_E.cpp:194) */
+    int32_t lm_reverted;
+} epivo_pair_result;
+
+typedef struct epivo_seq epivo_seq;
+int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per_frame);
+void epivo_seq_destroy(epivo_seq* seq);
+/* host -> device copy of n_frames frames starting at frame slot first_frame (async on the
+ * context stream; kps n_frames x kp x 2 f32, descs n_frames x kp x 32 u8) */
+int epivo_seq_upload(epivo_seq* seq, int first_frame, int n_frames, const float* kps, const uint8_t* descs);
+/* enqueue the pipeline for pairs [first_pair, first_pair + n_pairs) (async) */
+int epivo_seq_run(epivo_seq* seq, const epivo_pipeline_params* p, int first_pair, int n_pairs);
+/* device -> host copy of the results of the last run and stream sync */
+int epivo_seq_download(epivo_seq* seq, epivo_pair_result* out, int first_pair, int n_pairs);
+/* per-stage device time of the last run (CUDA events on the context stream), ms:
+ * [0] prep [1] match [2] finalize/gather [3] essential [4] pose [5] lm [6] total.
+ * n_match_launches/ms_match_kernel give the matcher kernel's launches and summed time. */
+int epivo_seq_stage_ms(epivo_seq* seq, float* ms, int n);
+/* debug/parity views of the last run, host copies: matches of one pair */
+int epivo_seq_get_matches(epivo_seq* seq, int pair, int32_t* query_idx, int32_t* train_idx,
+                          int32_t* dist, int* n_out);
+int epivo_seq_get_masks(epivo_seq* seq, int pair, uint8_t* e_mask, int* n_e, uint8_t* pose_mask, int* n_pose);
+
+/* ---- pipe micro-benchmarks (roofline denominators MEASURED_PEAKS.json lacks) ----------
+ * which: 0 POPC.32, 1 LOP3, 2 FP64 FMA, 3 FP32 FMA, 4 IADD3; result = thread-ops / s on the whole GPU */
+int epivo_microbench(epivo_ctx* ctx, int which, double* ops_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPIVO_B200_H */
