@@ -13,6 +13,7 @@ C++ equivalents (what an unmodified driver links against) are in include/epivo_s
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -37,9 +38,12 @@ class Context:
                                  "(there is no CPU fallback)")
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()       # SequencePipelines: destroyed before the context
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
+            for child in list(self._children):
+                child.close()
             self.lib.epivo_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -289,10 +293,12 @@ class SequencePipeline:
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.epivo_seq_create(self.ctx.h, C.byref(h), self.max_frames, self.kp))
         self.h = h
+        self.ctx._children.add(self)
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
-            self.ctx.lib.epivo_seq_destroy(self.h)
+            if self.ctx.h.value:                 # a closed context has already destroyed us
+                self.ctx.lib.epivo_seq_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

@@ -198,3 +198,263 @@ int epivo_knn2_hamming(epivo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* 
 }
 
 }  // extern "C"
+
+// ---- E1/E2, K2, K3 ---------------------------------------------------------------------
+extern "C" {
+
+int epivo_find_essential(epivo_ctx* ctx, const float* p0, const float* p1, int n, const double K[9], int method,
+                         double prob, double threshold, int max_iters, const int32_t* samples, int m, double E[9],
+                         uint8_t* mask, int* n_inliers, int* iters_run) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!p0 || !p1)) || !K || !E) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (method != EPIVO_RANSAC && method != EPIVO_LMEDS)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "method %d is not RANSAC(8) / LMEDS(4)", method);
+    if (!(prob > 0 && prob < 1)) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "prob must be in (0,1)");   // CV_Assert in ptsetreg.cpp
+    if (samples && m <= 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "empty sample set");
+    if (samples)
+        for (int i = 0; i < m * 5; ++i)
+            if (samples[i] < 0 || samples[i] >= n) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "sample index out of range");
+    if (n_inliers) *n_inliers = 0;
+    if (iters_run) *iters_run = 0;
+    for (int i = 0; i < 9; ++i) E[i] = 0.0;
+    if (n < 5) {
+        if (mask) memset(mask, 0, (size_t)std::max(n, 0));
+        EPV_FAIL(ctx, EPIVO_ERR_NOMODEL, "fewer than 5 correspondences");
+    }
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int stride = n;
+    const size_t nerr = epv_essential_errbuf_floats(1, stride);
+    size_t need = epv_align((size_t)n * 8) * 2 + epv_align((size_t)stride * 32) + epv_align(nerr * 4) +
+                  epv_align((size_t)n) + epv_align((size_t)std::max(m, 1) * 20) + 8 * 256 + 4096;
+    int rc = epv_ws_reserve(ctx, need);
+    if (rc) return rc;
+    float* d_p0 = epv_ws_take<float>(ctx, (size_t)n * 2);
+    float* d_p1 = epv_ws_take<float>(ctx, (size_t)n * 2);
+    double* d_xn = epv_ws_take<double>(ctx, (size_t)stride * 4);
+    float* d_err = epv_ws_take<float>(ctx, nerr);
+    uint8_t* d_mask = epv_ws_take<uint8_t>(ctx, n);
+    int32_t* d_samples = samples ? epv_ws_take<int32_t>(ctx, (size_t)m * 5) : nullptr;
+    double* d_E = epv_ws_take<double>(ctx, 9);
+    int32_t* d_n = epv_ws_take<int32_t>(ctx, 1);
+    int32_t* d_out = epv_ws_take<int32_t>(ctx, 4);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_p0, p0, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_p1, p1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_n, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (samples)
+        EPV_CUDA(ctx, cudaMemcpyAsync(d_samples, samples, (size_t)m * 20, cudaMemcpyHostToDevice, ctx->stream));
+    rc = epv_normalize_launch(ctx, d_p0, d_p1, n, stride, K, d_xn);
+    if (rc) return rc;
+    EssentialPlan ep{};
+    ep.n_pairs = 1;
+    ep.stride = stride;
+    ep.xn = d_xn;
+    ep.n = d_n;
+    ep.method = method;
+    ep.prob = prob;
+    ep.thresh = threshold / ((K[0] + K[4]) / 2.0);
+    ep.max_iters = max_iters;
+    ep.samples = d_samples;
+    ep.m = m;
+    ep.errbuf = d_err;
+    ep.E = d_E;
+    ep.mask = d_mask;
+    ep.n_inliers = d_out;
+    ep.iters = d_out + 1;
+    ep.n_models = d_out + 2;
+    ep.status = d_out + 3;
+    rc = epv_essential_launch(ctx, ep);
+    if (rc) return rc;
+    int32_t h_out[4];
+    EPV_CUDA(ctx, cudaMemcpyAsync(E, d_E, 72, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask) EPV_CUDA(ctx, cudaMemcpyAsync(mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_inliers) *n_inliers = h_out[0];
+    if (iters_run) *iters_run = h_out[1];
+    if (h_out[3] != 0) EPV_FAIL(ctx, EPIVO_ERR_NOMODEL, "no essential matrix found");
+    return EPIVO_OK;
+}
+
+int epivo_five_point(epivo_ctx* ctx, const double* x1, const double* x2, int m, double* E_out, int32_t* n_models) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (m < 0 || (m > 0 && (!x1 || !x2 || !E_out || !n_models))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (m == 0) return EPIVO_OK;
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = epv_ws_reserve(ctx, (size_t)m * (80 * 2 + 720 + 4) + 4096);
+    if (rc) return rc;
+    double* d_x1 = epv_ws_take<double>(ctx, (size_t)m * 10);
+    double* d_x2 = epv_ws_take<double>(ctx, (size_t)m * 10);
+    double* d_E = epv_ws_take<double>(ctx, (size_t)m * 90);
+    int32_t* d_nm = epv_ws_take<int32_t>(ctx, m);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_x1, x1, (size_t)m * 80, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_x2, x2, (size_t)m * 80, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemsetAsync(d_E, 0, (size_t)m * 720, ctx->stream));
+    rc = epv_five_point_launch(ctx, d_x1, d_x2, m, d_E, d_nm);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaMemcpyAsync(E_out, d_E, (size_t)m * 720, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(n_models, d_nm, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPIVO_OK;
+}
+
+int epivo_score_sampson(epivo_ctx* ctx, const double* E, int m, const float* p0, const float* p1, int n,
+                        const double K[9], double threshold, int32_t* counts, float* medians, int* best,
+                        uint8_t* best_mask) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (m < 0 || n < 0 || (m > 0 && !E) || (n > 0 && (!p0 || !p1)) || !K || !counts)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (best) *best = -1;
+    if (m == 0) return EPIVO_OK;
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int stride = std::max(n, 1);
+    size_t need = epv_align((size_t)m * 72) + epv_align((size_t)stride * 8) * 2 + epv_align((size_t)stride * 32) +
+                  epv_align((size_t)m * 4) * 2 + epv_align(stride) + 4096 +
+                  (medians ? epv_align((size_t)m * stride * 4) : 0);
+    int rc = epv_ws_reserve(ctx, need);
+    if (rc) return rc;
+    double* d_E = epv_ws_take<double>(ctx, (size_t)m * 9);
+    float* d_p0 = epv_ws_take<float>(ctx, (size_t)stride * 2);
+    float* d_p1 = epv_ws_take<float>(ctx, (size_t)stride * 2);
+    double* d_xn = epv_ws_take<double>(ctx, (size_t)stride * 4);
+    int32_t* d_counts = epv_ws_take<int32_t>(ctx, m);
+    float* d_med = epv_ws_take<float>(ctx, m);
+    uint8_t* d_mask = epv_ws_take<uint8_t>(ctx, stride);
+    int* d_best = epv_ws_take<int>(ctx, 1);
+    float* d_err = medians ? epv_ws_take<float>(ctx, (size_t)m * stride) : nullptr;
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_E, E, (size_t)m * 72, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+        EPV_CUDA(ctx, cudaMemcpyAsync(d_p0, p0, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        EPV_CUDA(ctx, cudaMemcpyAsync(d_p1, p1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = epv_normalize_launch(ctx, d_p0, d_p1, n, stride, K, d_xn);
+    if (rc) return rc;
+    rc = epv_score_launch(ctx, d_E, m, d_xn, stride, n, threshold / ((K[0] + K[4]) / 2.0), d_counts,
+                          medians ? d_med : nullptr, d_err, d_best, d_mask);
+    if (rc) return rc;
+    int h_best = -1;
+    EPV_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (medians) EPV_CUDA(ctx, cudaMemcpyAsync(medians, d_med, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(&h_best, d_best, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (best_mask && n > 0)
+        EPV_CUDA(ctx, cudaMemcpyAsync(best_mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (best) *best = h_best;
+    return EPIVO_OK;
+}
+
+// ---- P1 ------------------------------------------------------------------------------
+int epivo_recover_pose(epivo_ctx* ctx, const double E[9], const float* p0, const float* p1, int n, const double K[9],
+                       double dist_thresh, const uint8_t* in_mask, double R[9], double t[3], uint8_t* mask,
+                       int* n_good) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (!E || !K || !R || !t || n < 0 || (n > 0 && (!p0 || !p1))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int stride = std::max(n, 1);
+    int rc = epv_ws_reserve(ctx, (size_t)stride * (16 + 32 + 2) + 16 * 256 + 4096);
+    if (rc) return rc;
+    float* d_p0 = epv_ws_take<float>(ctx, (size_t)stride * 2);
+    float* d_p1 = epv_ws_take<float>(ctx, (size_t)stride * 2);
+    double* d_xn = epv_ws_take<double>(ctx, (size_t)stride * 4);
+    uint8_t* d_mask = epv_ws_take<uint8_t>(ctx, stride);
+    uint8_t* d_in = in_mask ? epv_ws_take<uint8_t>(ctx, stride) : nullptr;
+    double* d_E = epv_ws_take<double>(ctx, 9);
+    double* d_R = epv_ws_take<double>(ctx, 9);
+    double* d_t = epv_ws_take<double>(ctx, 3);
+    int32_t* d_n = epv_ws_take<int32_t>(ctx, 2);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_E, E, 72, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_n, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+        EPV_CUDA(ctx, cudaMemcpyAsync(d_p0, p0, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        EPV_CUDA(ctx, cudaMemcpyAsync(d_p1, p1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (in_mask) EPV_CUDA(ctx, cudaMemcpyAsync(d_in, in_mask, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = epv_normalize_launch(ctx, d_p0, d_p1, n, stride, K, d_xn);
+    if (rc) return rc;
+    PosePlan pp{};
+    pp.n_pairs = 1;
+    pp.stride = stride;
+    pp.E = d_E;
+    pp.xn = d_xn;
+    pp.n = d_n;
+    pp.in_mask = d_in;
+    pp.dist_thresh = dist_thresh;
+    pp.R = d_R;
+    pp.t = d_t;
+    pp.mask = d_mask;
+    pp.n_good = d_n + 1;
+    rc = epv_pose_launch(ctx, pp);
+    if (rc) return rc;
+    int ng = 0;
+    EPV_CUDA(ctx, cudaMemcpyAsync(R, d_R, 72, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(t, d_t, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(&ng, d_n + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask && n > 0) EPV_CUDA(ctx, cudaMemcpyAsync(mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_good) *n_good = ng;
+    return EPIVO_OK;
+}
+
+// ---- L4 ------------------------------------------------------------------------------
+int epivo_lm_rt_batch(epivo_ctx* ctx, int B, int n_zeta, double epsilon, const int32_t* reps, const double* wreps,
+                      int n_rep, double lambda0, int max_iters, double huber_delta, double* T0s, const double* pr,
+                      const double* p_r, int N, epivo_lm_res* out, int32_t* iters_run) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (B < 0 || !reps || !wreps || !T0s || !pr || !p_r || !out) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (n_zeta < 1 || n_rep < 1 || N < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_zeta, n_rep and N must be >= 1");
+    for (int j = 0; j < n_rep; ++j)                                  // sequence.hpp:118-122 asserts
+        if (reps[2 * j] < 0 || reps[2 * j] >= n_zeta || reps[2 * j + 1] < 0 || reps[2 * j + 1] >= n_zeta)
+            EPV_FAIL(ctx, EPIVO_ERR_INVALID, "rep %d = (%d,%d) outside [0,%d)", j, reps[2 * j], reps[2 * j + 1], n_zeta);
+    if (B == 0) return EPIVO_OK;
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nT = (size_t)B * n_zeta * 16, nP = (size_t)B * n_rep * N * 3, nW = (size_t)B * n_rep;
+    int rc = epv_ws_reserve(ctx, (nT + 2 * nP + nW) * 8 + (size_t)n_rep * 8 + (size_t)B * (24 + 4) + 8 * 256);
+    if (rc) return rc;
+    double* d_T = epv_ws_take<double>(ctx, nT);
+    double* d_pr = epv_ws_take<double>(ctx, nP);
+    double* d_p_r = epv_ws_take<double>(ctx, nP);
+    double* d_w = epv_ws_take<double>(ctx, nW);
+    int32_t* d_reps = epv_ws_take<int32_t>(ctx, (size_t)n_rep * 2);
+    epivo_lm_res* d_out = epv_ws_take<epivo_lm_res>(ctx, B);
+    int32_t* d_it = epv_ws_take<int32_t>(ctx, B);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_T, T0s, nT * 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_pr, pr, nP * 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_p_r, p_r, nP * 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_w, wreps, nW * 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_reps, reps, (size_t)n_rep * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LmPlan lp{};
+    lp.B = B;
+    lp.n_zeta = n_zeta;
+    lp.n_rep = n_rep;
+    lp.N = N;
+    lp.reps = d_reps;
+    lp.wreps = d_w;
+    lp.epsilon = epsilon;
+    lp.lambda0 = lambda0;
+    lp.huber_delta = huber_delta;
+    lp.max_iters = max_iters;
+    lp.T0s = d_T;
+    lp.pr = d_pr;
+    lp.p_r = d_p_r;
+    lp.out = d_out;
+    lp.iters = d_it;
+    lp.active = nullptr;
+    rc = epv_lm_launch(ctx, lp);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaMemcpyAsync(T0s, d_T, nT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)B * sizeof(epivo_lm_res), cudaMemcpyDeviceToHost, ctx->stream));
+    if (iters_run) EPV_CUDA(ctx, cudaMemcpyAsync(iters_run, d_it, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPIVO_OK;
+}
+
+int epivo_lm_rt(epivo_ctx* ctx, int n_zeta, double epsilon, const int32_t* reps, const double* wreps, int n_rep,
+                double lambda0, int max_iters, double huber_delta, double* T0s, const double* pr, const double* p_r,
+                int N, epivo_lm_res* out, int* iters_run) {
+    int32_t it = 0;
+    int rc = epivo_lm_rt_batch(ctx, 1, n_zeta, epsilon, reps, wreps, n_rep, lambda0, max_iters, huber_delta, T0s, pr,
+                               p_r, N, out, &it);
+    if (iters_run) *iters_run = it;
+    return rc;
+}
+
+}  // extern "C"

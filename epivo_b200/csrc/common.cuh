@@ -86,6 +86,7 @@ struct MatchPlan {
     uint32_t* rowkey2;         // [tsplits][n_pairs][stride] or nullptr
     uint32_t* colkey;          // [n_pairs][stride]
     int stride;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // optional: recorded right around the tile kernel
 };
 int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass);
 int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt);   // train splits that fill the GPU

@@ -1,0 +1,470 @@
+// K5: the reference's SE(3)-chain Levenberg-Marquardt (jac_Rt_gen_.cpp:287-478), one CTA per
+// problem, every iteration on the device (no host round trips).
+//
+// Per iteration (reference line numbers in brackets):
+//   chain memo  mem[a][b] = T[b] ... T[a]  and its inverses                     [:328-335]
+//   weighted residuals r = w * res(T_rep, p, p')                                 [:338-360, :212-259]
+//   Jacobian rows wrt every zeta in each rep's span, Dr_Deps as written          [:363-399, :23-209]
+//     (closed form: the 6 generator columns are constant; only non-zero blocks are formed)
+//   H = J'J, b = J'r accumulated tile by tile in shared memory                   [:401-402]
+//   H += lambda diag(H);  delta = -H^-1 b  by LU with partial pivoting           [:403-405]
+//   stop on NaN or |delta| < eps                                                 [:407-414]
+//   T'_k = T_k exp(delta_k)  (Sophus SE3::exp, right-multiplied)                 [:416-422]
+//   candidate chains by explicit products, UNWEIGHTED candidate residual norm    [:425-456]
+//   accept if smaller: lambda /= 2, else lambda *= 5                             [:457-467]
+// Reference quirks kept on purpose: the Jacobian's Huber branch switches on e'e <= delta
+// while res switches on e'e/2 > delta (sqrt(2) mismatch at delta = 1e-5); reverse reps
+// differentiate a LEFT perturbation of the zeta although the update is right-multiplied.
+#include "common.cuh"
+#include "stages.cuh"
+
+namespace {
+
+constexpr int LM_THREADS = 128;
+constexpr int LM_TP = 64;          // points per Jacobian tile
+constexpr int LM_MAX_ZETA = 16;
+
+struct Rt { double R[9]; double t[3]; };
+
+__device__ __forceinline__ void rt_identity(Rt& o) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    o.t[0] = o.t[1] = o.t[2] = 0.0;
+}
+// o = a * b   (4x4 with last row 0 0 0 1)
+__device__ __forceinline__ void rt_mul(const Rt& a, const Rt& b, Rt& o) {
+    Rt r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r.R[i * 3 + j] = a.R[i * 3] * b.R[j] + a.R[i * 3 + 1] * b.R[3 + j] + a.R[i * 3 + 2] * b.R[6 + j];
+        r.t[i] = a.R[i * 3] * b.t[0] + a.R[i * 3 + 1] * b.t[1] + a.R[i * 3 + 2] * b.t[2] + a.t[i];
+    }
+    o = r;
+}
+// general inverse of [A t; 0 1] (the reference calls MatrixXd::inverse(), not a rigid inverse)
+__device__ __forceinline__ void rt_inv(const Rt& a, Rt& o) {
+    const double* m = a.R;
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const double id = 1.0 / det;
+    Rt r;
+    r.R[0] = c00 * id; r.R[1] = (m[2] * m[7] - m[1] * m[8]) * id; r.R[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    r.R[3] = c01 * id; r.R[4] = (m[0] * m[8] - m[2] * m[6]) * id; r.R[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    r.R[6] = c02 * id; r.R[7] = (m[1] * m[6] - m[0] * m[7]) * id; r.R[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.t[i] = -(r.R[i * 3] * a.t[0] + r.R[i * 3 + 1] * a.t[1] + r.R[i * 3 + 2] * a.t[2]);
+    o = r;
+}
+
+// Sophus::SE3<double>::exp(delta), delta = (upsilon, omega)                         [:419]
+__device__ void se3_exp(const double* d, Rt& o) {
+    const double wx = d[3], wy = d[4], wz = d[5];
+    const double th2 = wx * wx + wy * wy + wz * wz;
+    const double th = sqrt(th2);
+    double a, b, c;   // R = I + a Om + b Om^2 ; V = I + b Om + c Om^2
+    if (th < 1e-10) {
+        a = 1.0; b = 0.5; c = 1.0 / 6.0;
+    } else {
+        a = sin(th) / th;
+        b = (1.0 - cos(th)) / th2;
+        c = (th - sin(th)) / (th2 * th);
+    }
+    const double Om[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double Om2[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Om2[i * 3 + j] = Om[i * 3] * Om[j] + Om[i * 3 + 1] * Om[3 + j] + Om[i * 3 + 2] * Om[6 + j];
+    double V[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1.0 : 0.0;
+        o.R[i] = I + a * Om[i] + b * Om2[i];
+        V[i] = I + b * Om[i] + c * Om2[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o.t[i] = V[i * 3] * d[0] + V[i * 3 + 1] * d[1] + V[i * 3 + 2] * d[2];
+}
+
+// res() for one correspondence                                                     [:230-258]
+__device__ __forceinline__ double res_one(const Rt& T, const double* p, const double* p_, double hd) {
+    const double px = -p_[0], py = -p_[1];
+    const double A0 = T.t[0] + px * T.t[2], A1 = T.t[1] + py * T.t[2];
+    const double q0 = T.R[0] * p[0] + T.R[1] * p[1] + T.R[2] * p[2];
+    const double q1 = T.R[3] * p[0] + T.R[4] * p[1] + T.R[5] * p[2];
+    const double q2 = T.R[6] * p[0] + T.R[7] * p[1] + T.R[8] * p[2];
+    const double B0 = q0 + px * q2, B1 = q1 + py * q2;
+    const double nb = sqrt(B0 * B0 + B1 * B1);
+    double d = 0.0;
+    if (nb > 0) d = sqrt(A0 * A0 + A1 * A1) / nb;
+    const double X0 = q0 * d + T.t[0], X1 = q1 * d + T.t[1], X2 = q2 * d + T.t[2];
+    const double e0 = p_[0] - X0 / X2, e1 = p_[1] - X1 / X2, e2 = p_[2] - X2 / X2;
+    double r = (e0 * e0 + e1 * e1 + e2 * e2) / 2.0;
+    if (r > hd) r = hd * (sqrt(r) - hd / 2.0);
+    return r;
+}
+
+// One row of Dr_Deps: d r / d eps for T = Tl exp(eps) Tr (sign s for reverse reps)   [:109-208]
+__device__ __forceinline__ void jac_row(const Rt& Tl, const Rt& Tr, const Rt& T0, double s, const double* p,
+                                        const double* p_, double hd, double* row) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) row[j] = 0.0;
+    const double px = -p_[0], py = -p_[1];
+    const double A0 = T0.t[0] + px * T0.t[2], A1 = T0.t[1] + py * T0.t[2];
+    const double q0 = T0.R[0] * p[0] + T0.R[1] * p[1] + T0.R[2] * p[2];
+    const double q1 = T0.R[3] * p[0] + T0.R[4] * p[1] + T0.R[5] * p[2];
+    const double q2 = T0.R[6] * p[0] + T0.R[7] * p[1] + T0.R[8] * p[2];
+    const double B0 = q0 + px * q2, B1 = q1 + py * q2;
+    const double ATA = A0 * A0 + A1 * A1, BTB = B0 * B0 + B1 * B1;
+    if (ATA == 0 || BTB == 0) return;                                              // [:152-154]
+    const double sa = sqrt(ATA), sb = sqrt(BTB);
+    const double ka = (1.0 / sa) * sb, kb = (1.0 / sb) * sa;
+    const double d0 = sa / sb;
+    const double X0 = q0 * d0 + T0.t[0], X1 = q1 * d0 + T0.t[1], X2 = q2 * d0 + T0.t[2];
+    // u = Rr p, ut = tr  (the generator acts on Tr [p d0; 1] = Rr p d0 + tr)
+    const double u0 = Tr.R[0] * p[0] + Tr.R[1] * p[1] + Tr.R[2] * p[2];
+    const double u1 = Tr.R[3] * p[0] + Tr.R[4] * p[1] + Tr.R[5] * p[2];
+    const double u2 = Tr.R[6] * p[0] + Tr.R[7] * p[1] + Tr.R[8] * p[2];
+    double e0, e1, e2, j00 = 0, j02 = 0, j12 = 0;   // J_pi rows: (j00, 0, j02), (0, j00, j12), 0
+    if (X2 != 0) {
+        j00 = 1.0 / X2;
+        j02 = -X0 / (X2 * X2);
+        j12 = -X1 / (X2 * X2);
+    }
+    e0 = X0 / X2 - p_[0];
+    e1 = X1 / X2 - p_[1];
+    e2 = 1.0 - p_[2];
+    const double ee = e0 * e0 + e1 * e1 + e2 * e2;
+    double g0 = e0, g1 = e1;                                                        // [:203-207]
+    if (!(ee <= hd)) {
+        const double k = hd / sqrt(ee);
+        g0 = k * e0;
+        g1 = k * e1;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double mt0, mt1, mt2;          // M_j[:3,3]
+        double mp0 = 0, mp1 = 0, mp2 = 0;   // M_j[:3,:3] p
+        if (j < 3) {
+            mt0 = s * Tl.R[j]; mt1 = s * Tl.R[3 + j]; mt2 = s * Tl.R[6 + j];
+        } else {
+            // hat(e_k) v = e_k x v
+            const int k = j - 3;
+            double c0, c1, c2, h0, h1, h2;
+            if (k == 0) { c0 = 0; c1 = -u2; c2 = u1; h0 = 0; h1 = -Tr.t[2]; h2 = Tr.t[1]; }
+            else if (k == 1) { c0 = u2; c1 = 0; c2 = -u0; h0 = Tr.t[2]; h1 = 0; h2 = -Tr.t[0]; }
+            else { c0 = -u1; c1 = u0; c2 = 0; h0 = -Tr.t[1]; h1 = Tr.t[0]; h2 = 0; }
+            mp0 = s * (Tl.R[0] * c0 + Tl.R[1] * c1 + Tl.R[2] * c2);
+            mp1 = s * (Tl.R[3] * c0 + Tl.R[4] * c1 + Tl.R[5] * c2);
+            mp2 = s * (Tl.R[6] * c0 + Tl.R[7] * c1 + Tl.R[8] * c2);
+            mt0 = s * (Tl.R[0] * h0 + Tl.R[1] * h1 + Tl.R[2] * h2);
+            mt1 = s * (Tl.R[3] * h0 + Tl.R[4] * h1 + Tl.R[5] * h2);
+            mt2 = s * (Tl.R[6] * h0 + Tl.R[7] * h1 + Tl.R[8] * h2);
+        }
+        const double dA0 = mt0 + px * mt2, dA1 = mt1 + py * mt2;
+        const double dB0 = mp0 + px * mp2, dB1 = mp1 + py * mp2;
+        const double jd = (ka * (A0 * dA0 + A1 * dA1) - kb * (B0 * dB0 + B1 * dB1)) / BTB;   // [:162]
+        const double dX0 = mp0 * d0 + mt0 + q0 * jd;                                        // [:171,175]
+        const double dX1 = mp1 * d0 + mt1 + q1 * jd;
+        const double dX2 = mp2 * d0 + mt2 + q2 * jd;
+        row[j] = g0 * (j00 * dX0 + j02 * dX2) + g1 * (j00 * dX1 + j12 * dX2);
+    }
+}
+
+struct LmArgs {
+    LmPlan p;
+    int D;
+    size_t smem_doubles;
+};
+
+__global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const LmPlan& p = a.p;
+    const int nz = p.n_zeta, nr = p.n_rep, N = p.N, D = a.D;
+    const int tid = threadIdx.x, prob = blockIdx.x;
+    if (p.active && !p.active[prob]) return;
+    // shared layout
+    Rt* sT = reinterpret_cast<Rt*>(sm);            // [nz] current
+    Rt* sTn = sT + nz;                             // [nz] candidate
+    Rt* sMem = sTn + nz;                           // [nz*nz] chain memo
+    Rt* sInv = sMem + nz * nz;                     // [nz*nz] inverses
+    Rt* sRep = sInv + nz * nz;                     // [nr] per-rep transform
+    double* sH = reinterpret_cast<double*>(sRep + nr);   // [D][D+1] augmented
+    double* sJ = sH + (size_t)D * (D + 1);         // [LM_TP][D+1] tile: J columns of the span + residual
+    double* sDelta = sJ + (size_t)LM_TP * (D + 1);  // [D]
+    double* sRed = sDelta + D;                     // [LM_THREADS]
+    __shared__ double s_lambda, s_prevE, s_Hnorm, s_rnorm;
+    __shared__ int s_stop, s_iters, s_piv;
+
+    double* gT = p.T0s + (size_t)prob * nz * 16;
+    const double* gpr = p.pr + (size_t)prob * nr * N * 3;
+    const double* gp_r = p.p_r + (size_t)prob * nr * N * 3;
+    const double* w = p.wreps + (size_t)prob * nr;
+    const double hd = p.huber_delta;
+
+    for (int k = tid; k < nz; k += LM_THREADS) {
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) sT[k].R[i * 3 + j] = gT[k * 16 + i * 4 + j];
+            sT[k].t[i] = gT[k * 16 + i * 4 + 3];
+        }
+    }
+    if (tid == 0) {
+        s_lambda = p.lambda0;
+        s_prevE = 1e10;                                                            // [:322]
+        s_stop = 0;
+        s_iters = 0;
+        s_Hnorm = 0.0;
+        s_rnorm = 0.0;
+    }
+    __syncthreads();
+
+    for (int iter = 0; iter < p.max_iters; ++iter) {
+        if (tid == 0) s_iters = iter + 1;
+        // ---- chain memo + inverses                                              [:328-335]
+        for (int j = tid; j < nz; j += LM_THREADS) {
+            Rt acc = sT[j];
+            sMem[j * nz + j] = acc;
+            rt_inv(acc, sInv[j * nz + j]);
+            for (int k = j + 1; k < nz; ++k) {
+                rt_mul(sT[k], acc, acc);
+                sMem[j * nz + k] = acc;
+                rt_inv(acc, sInv[j * nz + k]);
+            }
+        }
+        for (int i = tid; i < D * (D + 1); i += LM_THREADS) sH[i] = 0.0;
+        __syncthreads();
+        for (int j = tid; j < nr; j += LM_THREADS) {                                // [:338-348]
+            const int z0 = p.reps[2 * j], z1 = p.reps[2 * j + 1];
+            sRep[j] = (z0 <= z1) ? sMem[z0 * nz + z1] : sInv[z1 * nz + z0];
+        }
+        __syncthreads();
+        // ---- residuals, Jacobian tiles, H = J'J, b = J'r
+        double rsq = 0.0;
+        for (int j = 0; j < nr; ++j) {
+            const int z0 = p.reps[2 * j], z1 = p.reps[2 * j + 1];
+            const int lo = min(z0, z1), hi = max(z0, z1);
+            const int span = hi - lo + 1, W = 6 * span;
+            const bool fwd = z0 <= z1;
+            const double wj = w[j];
+            for (int base = 0; base < N; base += LM_TP) {
+                const int np = min(LM_TP, N - base);
+                // work item = (point, zeta in span)
+                for (int it = tid; it < np * (span + 1); it += LM_THREADS) {
+                    const int pt = it / (span + 1), zi = it % (span + 1);
+                    const double* pp = gpr + ((size_t)j * N + base + pt) * 3;
+                    const double* pq = gp_r + ((size_t)j * N + base + pt) * 3;
+                    double* dst = sJ + (size_t)pt * (D + 1);
+                    if (zi == span) {
+                        dst[W] = wj * res_one(sRep[j], pp, pq, hd);                  // [:356-359]
+                    } else {
+                        const int k = lo + zi;
+                        Rt Tl, Tr;
+                        rt_identity(Tr);
+                        if (fwd) {                                                  // [:271-275]
+                            if (z0 < k) Tr = sMem[z0 * nz + (k - 1)];
+                            Tl = sMem[k * nz + z1];
+                        } else {                                                    // [:276-281]
+                            if (z0 > k) Tr = sInv[(k + 1) * nz + z0];
+                            Tl = sInv[z1 * nz + k];
+                        }
+                        Rt T0;
+                        rt_mul(Tl, Tr, T0);                                         // [:96]
+                        double row[6];
+                        jac_row(Tl, Tr, T0, fwd ? 1.0 : -1.0, pp, pq, hd, row);
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) dst[6 * zi + c] = wj * row[c];  // [:381,397]
+                    }
+                }
+                __syncthreads();
+                // accumulate the (W+1) x (W+1) upper block: columns 0..W-1 -> H, column W -> b
+                const int ncol = W + 1;
+                for (int e = tid; e < W * ncol; e += LM_THREADS) {
+                    const int r = e / ncol, c = e % ncol;
+                    if (c < r) continue;
+                    double acc = 0.0;
+                    for (int pt = 0; pt < np; ++pt) acc += sJ[(size_t)pt * (D + 1) + r] * sJ[(size_t)pt * (D + 1) + c];
+                    const int gr = 6 * lo + r;
+                    if (c == W) sH[(size_t)gr * (D + 1) + D] += acc;
+                    else sH[(size_t)gr * (D + 1) + 6 * lo + c] += acc;
+                }
+                for (int pt = tid; pt < np; pt += LM_THREADS) {
+                    const double r = sJ[(size_t)pt * (D + 1) + W];
+                    rsq += r * r;
+                }
+                __syncthreads();
+            }
+        }
+        // symmetrise, damp, Frobenius norm, negate b                                [:403,473]
+        for (int e = tid; e < D * D; e += LM_THREADS) {
+            const int r = e / D, c = e % D;
+            if (c < r) sH[(size_t)r * (D + 1) + c] = sH[(size_t)c * (D + 1) + r];
+        }
+        sRed[tid] = rsq;
+        __syncthreads();
+        const double lam = s_lambda;
+        for (int r = tid; r < D; r += LM_THREADS) {
+            sH[(size_t)r * (D + 1) + r] += lam * sH[(size_t)r * (D + 1) + r];
+            sH[(size_t)r * (D + 1) + D] = -sH[(size_t)r * (D + 1) + D];
+        }
+        if (tid == 0) {
+            double s = 0.0;
+            for (int i = 0; i < LM_THREADS; ++i) s += sRed[i];
+            s_rnorm = sqrt(s);
+        }
+        __syncthreads();
+        {
+            double hs = 0.0;
+            for (int e = tid; e < D * D; e += LM_THREADS) {
+                const double v = sH[(size_t)(e / D) * (D + 1) + e % D];
+                hs += v * v;
+            }
+            __syncthreads();
+            sRed[tid] = hs;
+            __syncthreads();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int i = 0; i < LM_THREADS; ++i) s += sRed[i];
+                s_Hnorm = sqrt(s);
+            }
+        }
+        // ---- solve H delta = -b: LU with partial pivoting on the augmented matrix  [:405]
+        for (int k = 0; k < D; ++k) {
+            __syncthreads();
+            if (tid == 0) {
+                int pv = k;
+                double best = fabs(sH[(size_t)k * (D + 1) + k]);
+                for (int r = k + 1; r < D; ++r) {
+                    const double v = fabs(sH[(size_t)r * (D + 1) + k]);
+                    if (v > best) { best = v; pv = r; }
+                }
+                s_piv = pv;
+            }
+            __syncthreads();
+            const int pv = s_piv;
+            if (pv != k) {
+                for (int c = k + tid; c <= D; c += LM_THREADS) {
+                    const double t = sH[(size_t)k * (D + 1) + c];
+                    sH[(size_t)k * (D + 1) + c] = sH[(size_t)pv * (D + 1) + c];
+                    sH[(size_t)pv * (D + 1) + c] = t;
+                }
+                __syncthreads();
+            }
+            const double piv = sH[(size_t)k * (D + 1) + k];
+            // eliminate below: element (r, c) for r > k, c > k
+            const int rows = D - k - 1, cols = D - k;     // cols k+1..D
+            for (int e = tid; e < rows * cols; e += LM_THREADS) {
+                const int r = k + 1 + e / cols, c = k + 1 + e % cols;
+                const double f = sH[(size_t)r * (D + 1) + k] / piv;
+                sH[(size_t)r * (D + 1) + c] -= f * sH[(size_t)k * (D + 1) + c];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            bool nan = false;
+            double nrm = 0.0;
+            for (int r = D - 1; r >= 0; --r) {
+                double s = sH[(size_t)r * (D + 1) + D];
+                for (int c = r + 1; c < D; ++c) s -= sH[(size_t)r * (D + 1) + c] * sDelta[c];
+                const double v = s / sH[(size_t)r * (D + 1) + r];
+                sDelta[r] = v;
+                nan |= !(v == v) || isinf(v);
+                nrm += v * v;
+            }
+            if (nan || sqrt(nrm) < p.epsilon) s_stop = 1;                            // [:407-414]
+        }
+        __syncthreads();
+        if (s_stop) break;
+        // ---- candidate update T' = T exp(delta_k)                                  [:416-422]
+        for (int k = tid; k < nz; k += LM_THREADS) {
+            Rt ex;
+            se3_exp(sDelta + 6 * k, ex);
+            rt_mul(sT[k], ex, sTn[k]);
+        }
+        __syncthreads();
+        for (int j = tid; j < nr; j += LM_THREADS) {                                 // [:425-442]
+            const int z0 = p.reps[2 * j], z1 = p.reps[2 * j + 1];
+            Rt acc;
+            rt_identity(acc);
+            if (z0 <= z1) {
+                for (int k = z0; k <= z1; ++k) rt_mul(sTn[k], acc, acc);
+            } else {
+                for (int k = z0; k >= z1; --k) {
+                    Rt inv;
+                    rt_inv(sTn[k], inv);
+                    rt_mul(inv, acc, acc);
+                }
+            }
+            sRep[j] = acc;
+        }
+        __syncthreads();
+        double csq = 0.0;                                                            // [:445-456]
+        for (int it = tid; it < nr * N; it += LM_THREADS) {
+            const int j = it / N;
+            const double r = res_one(sRep[j], gpr + (size_t)it * 3, gp_r + (size_t)it * 3, hd);
+            csq += r * r;
+        }
+        sRed[tid] = csq;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int i = 0; i < LM_THREADS; ++i) s += sRed[i];
+            const double currE = sqrt(s);
+            s_rnorm = currE;                                                         // r0 now holds the candidate residuals
+            if (currE < s_prevE) {                                                   // [:457-467]
+                s_prevE = currE;
+                s_piv = 1;
+                s_lambda /= 2.0;
+            } else {
+                s_piv = 0;
+                s_lambda *= 5.0;
+            }
+        }
+        __syncthreads();
+        if (s_piv) {
+            for (int k = tid; k < nz; k += LM_THREADS) sT[k] = sTn[k];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int k = tid; k < nz; k += LM_THREADS) {
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) gT[k * 16 + i * 4 + j] = sT[k].R[i * 3 + j];
+            gT[k * 16 + i * 4 + 3] = sT[k].t[i];
+        }
+        gT[k * 16 + 12] = 0.0; gT[k * 16 + 13] = 0.0; gT[k * 16 + 14] = 0.0; gT[k * 16 + 15] = 1.0;
+    }
+    if (tid == 0) {
+        p.out[prob].H_norm = s_Hnorm;                                                // [:473-475]
+        p.out[prob].r_norm = s_rnorm;
+        p.out[prob].lambda = s_lambda;
+        if (p.iters) p.iters[prob] = s_iters;
+    }
+}
+
+size_t lm_smem_doubles(int nz, int nr, int D) {
+    size_t rt = sizeof(Rt) / sizeof(double);
+    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)LM_TP * (D + 1) + D +
+           LM_THREADS;
+}
+
+}  // namespace
+
+int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
+    if (p.B <= 0) return EPIVO_OK;
+    if (p.n_zeta < 1 || p.n_zeta > LM_MAX_ZETA)
+        EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "n_zeta = %d outside [1, %d]", p.n_zeta, LM_MAX_ZETA);
+    if (p.n_rep < 1 || p.N < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_rep = %d, N = %d", p.n_rep, p.N);
+    LmArgs a;
+    a.p = p;
+    a.D = 6 * p.n_zeta;
+    a.smem_doubles = lm_smem_doubles(p.n_zeta, p.n_rep, a.D);
+    const size_t bytes = a.smem_doubles * sizeof(double);
+    if (bytes > 220 * 1024)
+        EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "LM problem needs %zu bytes of shared memory (n_zeta=%d, n_rep=%d)",
+                 bytes, p.n_zeta, p.n_rep);
+    EPV_CUDA(ctx, cudaFuncSetAttribute(lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    lm_kernel<<<p.B, LM_THREADS, bytes, ctx->stream>>>(a);
+    EPV_LAUNCHED(ctx);
+    return EPIVO_OK;
+}

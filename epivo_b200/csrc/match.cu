@@ -312,7 +312,9 @@ int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt) {
     const int64_t ctas = std::max<int64_t>(1, qblocks * n_pairs);
     const int64_t want = 4LL * ctx->sm_count;             // ~4 CTAs per SM
     int64_t s = (want + ctas - 1) / ctas;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(s, std::max(1, n_tiles / 2)));
+    s = std::max<int64_t>(1, std::min<int64_t>(s, std::max(1, n_tiles / 2)));
+    const int64_t tps = (n_tiles + s - 1) / s;            // tiles per split
+    return (int)std::max<int64_t>(1, (n_tiles + tps - 1) / tps);   // splits actually launched (no empty part)
 }
 
 int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass) {
@@ -338,11 +340,16 @@ int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass) {
     fill_u32_kernel<<<(unsigned)((nkeys + 255) / 256), 256, 0, ctx->stream>>>(mp.colkey, nkeys, 0xFFFFFFFFu);
     EPV_LAUNCHED(ctx);
     if (mp.nt <= 0) return EPIVO_OK;
+    if (mp.ev0) EPV_CUDA(ctx, cudaEventRecord(mp.ev0, ctx->stream));
+    int rc;
     switch (mp.words) {
-        case 4: return launch_words<4>(ctx, mp, src);
-        case 8: return launch_words<8>(ctx, mp, src);
-        default: return launch_words<16>(ctx, mp, src);
+        case 4: rc = launch_words<4>(ctx, mp, src); break;
+        case 8: rc = launch_words<8>(ctx, mp, src); break;
+        default: rc = launch_words<16>(ctx, mp, src); break;
     }
+    if (rc) return rc;
+    if (mp.ev1) EPV_CUDA(ctx, cudaEventRecord(mp.ev1, ctx->stream));
+    return EPIVO_OK;
 }
 
 int epv_finalize_launch(epivo_ctx* ctx, const FinalizePlan& fp) {

@@ -1,0 +1,235 @@
+// K4: fused cv::recoverPose -- decomposeEssentialMat + 4x DLT triangulation of every
+// correspondence + cheirality/distance tests + candidate selection, one CTA per pair.
+//
+// Replaces kitti_E.cpp:120, euroc_E.cpp:251, kitti_ba.cpp:245,322,715.  OpenCV
+// (modules/calib3d/src/five-point.cpp recoverPose, triangulate.cpp) runs four passes of a
+// per-point 4x4 SVD; here each thread triangulates its correspondences against the four
+// (R, t) candidates in registers and only a 4-bit flag per point leaves the thread.
+//   E = U diag(s) V'  (V from the Jacobi eigen-decomposition of E'E, U = E V / s,
+//                      third columns by cross product so det U = det V = +1)
+//   R1 = U W V', R2 = U W' V', t = U[:,2];  candidates (R1,t) (R2,t) (R1,-t) (R2,-t)
+//   Q = smallest right singular vector of the DLT matrix (Jacobi on A'A)
+//   good = Qz*Qw > 0 && Qz/Qw < d && 0 < ([R|t] Q/Qw)_z < d   [&& input mask]
+//   winner = first candidate whose count is >= all the others; mask values {0,255}.
+#include "common.cuh"
+#include "stages.cuh"
+
+namespace {
+
+constexpr int PS_THREADS = 256;
+
+// Cyclic Jacobi eigen-decomposition of a symmetric NxN matrix (N = 3, 4): A -> diag, V = eigenvectors (columns)
+template <int N>
+__device__ __forceinline__ void jacobi_eig(double (&A)[N][N], double (&V)[N][N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            diag += A[i][i] * A[i][i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-34 * diag || off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {                 // A <- A J
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {                 // A <- J' A
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+        }
+    }
+}
+
+__device__ void decompose_essential(const double* E, double (&R1)[9], double (&R2)[9], double (&t)[3]) {
+    double M[3][3], V[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) M[i][j] = E[0 * 3 + i] * E[0 * 3 + j] + E[1 * 3 + i] * E[1 * 3 + j] + E[2 * 3 + i] * E[2 * 3 + j];
+    jacobi_eig<3>(M, V);
+    // order eigenvalues descending
+    int o[3] = {0, 1, 2};
+    double ev[3] = {M[0][0], M[1][1], M[2][2]};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2 - i; ++j)
+            if (ev[o[j]] < ev[o[j + 1]]) { int tmp = o[j]; o[j] = o[j + 1]; o[j + 1] = tmp; }
+    double v[3][3], u[3][3];   // v[k] = k-th right singular vector, u[k] = k-th left
+    for (int k = 0; k < 2; ++k) {
+        for (int i = 0; i < 3; ++i) v[k][i] = V[i][o[k]];
+    }
+    v[2][0] = v[0][1] * v[1][2] - v[0][2] * v[1][1];
+    v[2][1] = v[0][2] * v[1][0] - v[0][0] * v[1][2];
+    v[2][2] = v[0][0] * v[1][1] - v[0][1] * v[1][0];
+    for (int k = 0; k < 2; ++k) {
+        double w[3], nn = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            w[i] = E[i * 3 + 0] * v[k][0] + E[i * 3 + 1] * v[k][1] + E[i * 3 + 2] * v[k][2];
+            nn += w[i] * w[i];
+        }
+        const double inv = nn > 0 ? 1.0 / sqrt(nn) : 0.0;
+        for (int i = 0; i < 3; ++i) u[k][i] = w[i] * inv;
+    }
+    {   // re-orthogonalise u1 against u0 (exact for a true essential matrix, a guard otherwise)
+        const double d = u[0][0] * u[1][0] + u[0][1] * u[1][1] + u[0][2] * u[1][2];
+        double nn = 0.0;
+        for (int i = 0; i < 3; ++i) { u[1][i] -= d * u[0][i]; nn += u[1][i] * u[1][i]; }
+        const double inv = nn > 0 ? 1.0 / sqrt(nn) : 0.0;
+        for (int i = 0; i < 3; ++i) u[1][i] *= inv;
+    }
+    u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];
+    u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
+    u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+    // U W = [-u1, u0, u2], U W' = [u1, -u0, u2]
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const double a = u[0][i] * v[1][j] - u[1][i] * v[0][j];
+            const double b = u[2][i] * v[2][j];
+            R1[i * 3 + j] = a + b;
+            R2[i * 3 + j] = -a + b;
+        }
+    for (int i = 0; i < 3; ++i) t[i] = u[2][i];
+}
+
+// cheirality / distance test of one correspondence against one candidate [R | t]
+__device__ __forceinline__ bool triangulate_good(const double* R, const double* t, double a1, double b1, double a2,
+                                                 double b2, double dist) {
+    // DLT rows (triangulate.cpp): x*P[2] - P[0], y*P[2] - P[1] for P0 = [I|0], P1 = [R|t]
+    double A[4][4] = {{-1.0, 0.0, a1, 0.0},
+                      {0.0, -1.0, b1, 0.0},
+                      {a2 * R[6] - R[0], a2 * R[7] - R[1], a2 * R[8] - R[2], a2 * t[2] - t[0]},
+                      {b2 * R[6] - R[3], b2 * R[7] - R[4], b2 * R[8] - R[5], b2 * t[2] - t[1]}};
+    double M[4][4], V[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) {
+            const double s = A[0][i] * A[0][j] + A[1][i] * A[1][j] + A[2][i] * A[2][j] + A[3][i] * A[3][j];
+            M[i][j] = s;
+            M[j][i] = s;
+        }
+    jacobi_eig<4>(M, V);
+    int k = 0;
+    double best = M[0][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (M[i][i] < best) { best = M[i][i]; k = i; }
+    double Q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double v = V[i][0];
+        if (k == 1) v = V[i][1];
+        if (k == 2) v = V[i][2];
+        if (k == 3) v = V[i][3];
+        Q[i] = v;
+    }
+    bool good = (Q[2] * Q[3]) > 0;
+    const double X = Q[0] / Q[3], Y = Q[1] / Q[3], Z = Q[2] / Q[3];
+    good = good && (Z < dist);
+    const double z2 = ((R[6] * X + R[7] * Y) + R[8] * Z) + t[2];
+    good = good && (z2 > 0) && (z2 < dist);
+    return good;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) pose_kernel(PosePlan p) {
+    __shared__ double s_R[2][9];
+    __shared__ double s_t[3];
+    __shared__ int s_cnt[4];
+    __shared__ int s_choice;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int n = p.n[pair];
+    const bool skip = p.skip && p.skip[pair] != 0;
+    uint8_t* mask = p.mask + (int64_t)pair * p.stride;
+    if (skip) {
+        if (tid < 9) p.R[(int64_t)pair * 9 + tid] = 0.0;
+        if (tid < 3) p.t[(int64_t)pair * 3 + tid] = 0.0;
+        if (tid == 0) p.n_good[pair] = 0;
+        for (int i = tid; i < n; i += PS_THREADS) mask[i] = 0;
+        return;
+    }
+    if (tid == 0) {
+        double R1[9], R2[9], t[3];
+        decompose_essential(p.E + (int64_t)pair * 9, R1, R2, t);
+        for (int i = 0; i < 9; ++i) { s_R[0][i] = R1[i]; s_R[1][i] = R2[i]; }
+        for (int i = 0; i < 3; ++i) s_t[i] = t[i];
+    }
+    if (tid < 4) s_cnt[tid] = 0;
+    __syncthreads();
+    const double* X1 = p.xn + (int64_t)pair * 4 * p.stride;
+    const double* Y1 = X1 + p.stride;
+    const double* X2 = Y1 + p.stride;
+    const double* Y2 = X2 + p.stride;
+    const uint8_t* im = p.in_mask ? p.in_mask + (int64_t)pair * p.stride : nullptr;
+    const double tp[3] = {s_t[0], s_t[1], s_t[2]};
+    const double tn[3] = {-s_t[0], -s_t[1], -s_t[2]};
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int i = tid; i < n; i += PS_THREADS) {
+        const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
+        unsigned f = 0;
+        if (!im || im[i]) {
+            f |= triangulate_good(s_R[0], tp, a1, b1, a2, b2, p.dist_thresh) ? 1u : 0u;
+            f |= triangulate_good(s_R[1], tp, a1, b1, a2, b2, p.dist_thresh) ? 2u : 0u;
+            f |= triangulate_good(s_R[0], tn, a1, b1, a2, b2, p.dist_thresh) ? 4u : 0u;
+            f |= triangulate_good(s_R[1], tn, a1, b1, a2, b2, p.dist_thresh) ? 8u : 0u;
+        }
+        mask[i] = (uint8_t)f;
+        c0 += f & 1; c1 += (f >> 1) & 1; c2 += (f >> 2) & 1; c3 += (f >> 3) & 1;
+    }
+    c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
+    c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+    c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
+    c3 = __reduce_add_sync(0xFFFFFFFFu, c3);
+    if (lane == 0) {
+        atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); atomicAdd(&s_cnt[2], c2); atomicAdd(&s_cnt[3], c3);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int g1 = s_cnt[0], g2 = s_cnt[1], g3 = s_cnt[2], g4 = s_cnt[3];
+        int k;
+        if (g1 >= g2 && g1 >= g3 && g1 >= g4) k = 0;
+        else if (g2 >= g1 && g2 >= g3 && g2 >= g4) k = 1;
+        else if (g3 >= g1 && g3 >= g2 && g3 >= g4) k = 2;
+        else k = 3;
+        s_choice = k;
+        p.n_good[pair] = s_cnt[k];
+    }
+    __syncthreads();
+    const int k = s_choice;
+    if (tid < 9) p.R[(int64_t)pair * 9 + tid] = s_R[k & 1][tid];
+    if (tid < 3) p.t[(int64_t)pair * 3 + tid] = (k & 2) ? -s_t[tid] : s_t[tid];
+    for (int i = tid; i < n; i += PS_THREADS) mask[i] = ((mask[i] >> k) & 1) ? 255 : 0;   // own writes only
+}
+
+}  // namespace
+
+int epv_pose_launch(epivo_ctx* ctx, const PosePlan& p) {
+    if (p.n_pairs <= 0) return EPIVO_OK;
+    pose_kernel<<<p.n_pairs, PS_THREADS, 0, ctx->stream>>>(p);
+    EPV_LAUNCHED(ctx);
+    return EPIVO_OK;
+}

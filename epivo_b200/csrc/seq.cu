@@ -1,0 +1,488 @@
+// Fused per-pair pipeline over a device-resident frame sequence (the benchmark's hot path):
+//   match (K1) -> gather + K-normalise -> findEssentialMat (K2+K3) -> inlier compaction ->
+//   recoverPose (K4) -> kitti_E.cpp:128-135 fallbacks -> Levenberg_Marquardt (K5) -> revert rule.
+// This is the body of the reference loop kitti_E.cpp:54-201 with the BFMatcher association
+// of kitti_ba.cpp:641-693 as the correspondence source.  Pairs are processed in chunks so
+// that a chunk's intermediates (keys, matches, normalised points, masks) stay L2-resident;
+// everything is enqueued on the context stream with no host synchronisation in between.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "stages.cuh"
+
+namespace {
+constexpr int SEQ_CHUNK = 512;
+constexpr int SEQ_STAGES = 7;      // prep, match, finalize, essential, pose, lm, (total)
+constexpr int SEQ_MAX_CHUNKS = 128;
+}  // namespace
+
+struct epivo_seq {
+    epivo_ctx* ctx = nullptr;
+    int max_frames = 0, kp = 0, stride = 0, chunk = SEQ_CHUNK;
+    // frames
+    float* d_kps = nullptr;
+    uint32_t* d_desc = nullptr;
+    uint32_t* d_planes = nullptr;
+    // per pair, whole sequence
+    int32_t *d_mq = nullptr, *d_mt = nullptr, *d_md = nullptr, *d_nmatch = nullptr;
+    uint8_t *d_emask = nullptr, *d_pmask = nullptr;
+    double *d_E = nullptr, *d_R = nullptr, *d_t = nullptr, *d_T = nullptr, *d_T0 = nullptr;
+    int32_t *d_ninl = nullptr, *d_iters = nullptr, *d_nmodels = nullptr, *d_status = nullptr, *d_ngood = nullptr;
+    int32_t *d_lmactive = nullptr, *d_lmiters = nullptr;
+    epivo_lm_res* d_lmres = nullptr;
+    epivo_pair_result* d_results = nullptr;
+    // per chunk
+    uint32_t *d_rowkey = nullptr, *d_rowkey2 = nullptr, *d_colkey = nullptr;
+    double *d_xn = nullptr, *d_xin = nullptr, *d_lmp = nullptr, *d_lmq = nullptr, *d_w = nullptr;
+    float* d_err = nullptr;
+    int32_t* d_reps = nullptr;
+    // host staging for results
+    epivo_pair_result* h_results = nullptr;
+    // timing
+    cudaEvent_t ev[SEQ_MAX_CHUNKS][SEQ_STAGES] = {};
+    cudaEvent_t evk[SEQ_MAX_CHUNKS][2] = {};     // around the matcher tile kernel alone
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    int last_chunks = 0;
+    int last_n_pairs = 0, last_first = 0;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int seq_alloc(epivo_seq* s, T** p, size_t count) {
+    epivo_ctx* ctx = s->ctx;
+    void* q = nullptr;
+    EPV_CUDA(ctx, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    s->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return EPIVO_OK;
+}
+
+// After recoverPose: the reference's sanity fallbacks, LM input assembly (first lm_points
+// compacted E-inliers, gated on >= lm_points cheirality-good points; kitti_E.cpp:170-194).
+__global__ void lm_prep_kernel(int n_pairs, int stride, epivo_pipeline_params prm, const double* __restrict__ R,
+                               const double* __restrict__ t, const int32_t* __restrict__ status,
+                               const int32_t* __restrict__ n_inl, const int32_t* __restrict__ n_good,
+                               const double* __restrict__ xin, double* __restrict__ T0, double* __restrict__ T,
+                               double* __restrict__ lmp, double* __restrict__ lmq, double* __restrict__ w,
+                               int32_t* __restrict__ active) {
+    const int pair = blockIdx.x;
+    if (pair >= n_pairs) return;
+    const int tid = threadIdx.x;
+    const int N = prm.lm_points;
+    __shared__ double sT[16];
+    if (tid == 0) {
+        double Rm[9], tv[3];
+        for (int i = 0; i < 9; ++i) Rm[i] = R[(int64_t)pair * 9 + i];
+        for (int i = 0; i < 3; ++i) tv[i] = t[(int64_t)pair * 3 + i];
+        const bool ok = status[pair] == 0;
+        if (!ok || (Rm[0] + Rm[4] + Rm[8]) < prm.min_trace) {            // kitti_E.cpp:128-131
+            for (int i = 0; i < 9; ++i) Rm[i] = (i % 4 == 0) ? 1.0 : 0.0;
+            for (int i = 0; i < 3; ++i) tv[i] = prm.fallback_t[i];
+        }
+        if (sqrt(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]) < prm.min_t_norm)   // kitti_E.cpp:133-135
+            for (int i = 0; i < 3; ++i) tv[i] = prm.fallback_t[i];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) sT[i * 4 + j] = Rm[i * 3 + j];
+            sT[i * 4 + 3] = tv[i];
+        }
+        sT[12] = sT[13] = sT[14] = 0.0;
+        sT[15] = 1.0;
+        // kitti_E.cpp:170-194: N = min(48, #E-inliers) (asserted >= 48), LM runs iff 48 of the
+        // recoverPose mask entries are 255
+        active[pair] = (ok && n_inl[pair] >= N && n_good[pair] >= N) ? 1 : 0;
+        w[pair] = 1.0;
+    }
+    __syncthreads();
+    if (tid < 16) {
+        T0[(int64_t)pair * 16 + tid] = sT[tid];
+        T[(int64_t)pair * 16 + tid] = sT[tid];
+    }
+    // rows j_ = 0..N-1 of the compacted inlier list (kitti_E.cpp:176-182 indexes cpt0[N_mask])
+    const double* x = xin + (int64_t)pair * 4 * stride;
+    for (int i = tid; i < N; i += blockDim.x) {
+        const bool have = i < n_inl[pair];
+        double* p = lmp + ((int64_t)pair * N + i) * 3;
+        double* q = lmq + ((int64_t)pair * N + i) * 3;
+        p[0] = have ? x[i] : 1.0;
+        p[1] = have ? x[stride + i] : 1.0;
+        p[2] = 1.0;
+        q[0] = have ? x[2 * stride + i] : 1.0;
+        q[1] = have ? x[3 * stride + i] : 1.0;
+        q[2] = 1.0;
+    }
+}
+
+__global__ void finish_kernel(int n_pairs, epivo_pipeline_params prm, const double* __restrict__ E,
+                              const double* __restrict__ R, const double* __restrict__ t,
+                              const double* __restrict__ T0, double* __restrict__ T,
+                              const epivo_lm_res* __restrict__ lmres, const int32_t* __restrict__ lmiters,
+                              const int32_t* __restrict__ active, const int32_t* __restrict__ nmatch,
+                              const int32_t* __restrict__ ninl, const int32_t* __restrict__ ngood,
+                              const int32_t* __restrict__ iters, const int32_t* __restrict__ nmodels,
+                              epivo_pair_result* __restrict__ out) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    epivo_pair_result r;
+    for (int i = 0; i < 9; ++i) { r.E[i] = E[(int64_t)pair * 9 + i]; r.R[i] = R[(int64_t)pair * 9 + i]; }
+    for (int i = 0; i < 3; ++i) r.t[i] = t[(int64_t)pair * 3 + i];
+    const bool ran = active[pair] != 0;
+    r.lm.H_norm = ran ? lmres[pair].H_norm : 0.0;
+    r.lm.r_norm = ran ? lmres[pair].r_norm : 0.0;
+    r.lm.lambda = ran ? lmres[pair].lambda : prm.lm_lambda0;
+    const bool revert = ran && !(r.lm.r_norm <= prm.lm_revert);        // kitti_E.cpp:198-200 (NaN reverts too)
+    for (int i = 0; i < 16; ++i) {
+        r.T0[i] = T0[(int64_t)pair * 16 + i];
+        r.T[i] = (ran && !revert) ? T[(int64_t)pair * 16 + i] : r.T0[i];
+    }
+    r.n_matches = nmatch[pair];
+    r.n_inliers = ninl[pair];
+    r.n_good = ngood[pair];
+    r.ransac_iters = iters[pair];
+    r.n_models = nmodels[pair];
+    r.lm_iters = ran ? lmiters[pair] : 0;
+    r.lm_ran = ran ? 1 : 0;
+    r.lm_reverted = revert ? 1 : 0;
+    out[pair] = r;
+}
+
+}  // namespace
+
+extern "C" {
+
+void epivo_pipeline_params_default(epivo_pipeline_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->norm = EPIVO_NORM_HAMMING2;
+    p->match_mode = EPIVO_MATCH_CROSSCHECK;
+    p->ratio = 0.8f;
+    const double K[9] = {718.8560, 0.0, 607.1928, 0.0, 718.8560, 185.2157, 0.0, 0.0, 1.0};   // kitti_E.cpp:38-40
+    memcpy(p->K, K, sizeof(K));
+    p->method = EPIVO_RANSAC;
+    p->prob = 0.99;
+    p->threshold = 1.0;
+    p->max_iters = 1000;
+    p->dist_thresh = 50.0;
+    p->min_trace = 3.0 * 0.9;
+    p->fallback_t[0] = 0.1;
+    p->fallback_t[1] = 0.1;
+    p->fallback_t[2] = -0.9;
+    p->min_t_norm = 1e-5;
+    p->lm_points = 48;
+    p->lm_lambda0 = 1e-2;
+    p->lm_epsilon = 1e-8;
+    p->lm_max_iters = 30;
+    p->huber_delta = 1e-5;
+    p->lm_revert = 1e-9;
+}
+
+int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per_frame) {
+    if (!ctx || !out) return EPIVO_ERR_INVALID;
+    *out = nullptr;
+    if (max_frames < 2 || kp_per_frame < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "need >= 2 frames and >= 1 keypoint");
+    if (kp_per_frame > (int)EPV_IDX_MASK) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "too many keypoints per frame");
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    epivo_seq* s = new epivo_seq();
+    s->ctx = ctx;
+    s->max_frames = max_frames;
+    s->kp = kp_per_frame;
+    s->stride = (kp_per_frame + 31) / 32 * 32;
+    const size_t F = max_frames, P = max_frames - 1, st = s->stride, kp = kp_per_frame;
+    s->chunk = (int)std::min<size_t>(SEQ_CHUNK, P);
+    const size_t C = s->chunk;
+    int rc = 0;
+#define A(ptr, count) if (!rc) rc = seq_alloc(s, &s->ptr, (count))
+    A(d_kps, F * kp * 2);
+    A(d_desc, F * kp * 8);
+    A(d_planes, F * kp * 8);
+    A(d_mq, P * st); A(d_mt, P * st); A(d_md, P * st); A(d_nmatch, P);
+    A(d_emask, P * st); A(d_pmask, P * st);
+    A(d_E, P * 9); A(d_R, P * 9); A(d_t, P * 3); A(d_T, P * 16); A(d_T0, P * 16);
+    A(d_ninl, P); A(d_iters, P); A(d_nmodels, P); A(d_status, P); A(d_ngood, P);
+    A(d_lmactive, P); A(d_lmiters, P); A(d_lmres, P); A(d_results, P);
+    A(d_rowkey, C * st); A(d_rowkey2, C * st); A(d_colkey, C * st);
+    A(d_xn, C * 4 * st); A(d_xin, C * 4 * st);
+    A(d_lmp, C * 64 * 3); A(d_lmq, C * 64 * 3); A(d_w, C);
+    A(d_err, epv_essential_errbuf_floats((int)C, (int)st));
+    A(d_reps, 2);
+#undef A
+    if (!rc && cudaMallocHost(&s->h_results, P * sizeof(epivo_pair_result)) != cudaSuccess) rc = EPIVO_ERR_CUDA;
+    bool ev_ok = true;
+    for (int c = 0; c < SEQ_MAX_CHUNKS && ev_ok; ++c)
+    {
+        for (int k = 0; k < SEQ_STAGES; ++k) ev_ok &= cudaEventCreate(&s->ev[c][k]) == cudaSuccess;
+        for (int k = 0; k < 2; ++k) ev_ok &= cudaEventCreate(&s->evk[c][k]) == cudaSuccess;
+    }
+    ev_ok = ev_ok && cudaEventCreate(&s->ev_begin) == cudaSuccess && cudaEventCreate(&s->ev_end) == cudaSuccess;
+    if (rc || !ev_ok) {
+        epivo_seq_destroy(s);
+        if (!rc) EPV_FAIL(ctx, EPIVO_ERR_CUDA, "event creation failed");
+        return rc;
+    }
+    const int32_t reps[2] = {0, 0};
+    EPV_CUDA(ctx, cudaMemcpyAsync(s->d_reps, reps, 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return EPIVO_OK;
+}
+
+void epivo_seq_destroy(epivo_seq* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->h_results) cudaFreeHost(s->h_results);
+    for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
+        for (int k = 0; k < SEQ_STAGES; ++k)
+            if (s->ev[c][k]) cudaEventDestroy(s->ev[c][k]);
+    for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
+        for (int k = 0; k < 2; ++k)
+            if (s->evk[c][k]) cudaEventDestroy(s->evk[c][k]);
+    if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+    if (s->ev_end) cudaEventDestroy(s->ev_end);
+    delete s;
+}
+
+int epivo_seq_upload(epivo_seq* s, int first_frame, int n_frames, const float* kps, const uint8_t* descs) {
+    if (!s) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (first_frame < 0 || n_frames < 0 || first_frame + n_frames > s->max_frames || !kps || !descs)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "frame range [%d,+%d) outside [0,%d)", first_frame, n_frames, s->max_frames);
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t kp = s->kp;
+    EPV_CUDA(ctx, cudaMemcpyAsync(s->d_kps + (size_t)first_frame * kp * 2, kps, (size_t)n_frames * kp * 8,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(s->d_desc + (size_t)first_frame * kp * 8, descs, (size_t)n_frames * kp * 32,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    return EPIVO_OK;
+}
+
+int epivo_seq_run(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair, int n_pairs) {
+    if (!s || !prm) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range [%d,+%d) outside [0,%d)", first_pair, n_pairs, s->max_frames - 1);
+    if (prm->lm_points < 1 || prm->lm_points > 64) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "lm_points must be in [1,64]");
+    if (prm->method != EPIVO_RANSAC && prm->method != EPIVO_LMEDS) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "method");
+    if (prm->match_mode < 0 || prm->match_mode > 2) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "match_mode");
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int kp = s->kp, st = s->stride;
+    const int n_chunks = (n_pairs + s->chunk - 1) / s->chunk;
+    if (n_chunks > SEQ_MAX_CHUNKS) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "too many chunks");
+    s->last_chunks = n_chunks;
+    s->last_n_pairs = n_pairs;
+    s->last_first = first_pair;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, ctx->stream));
+    const double ax = 1.0 / prm->K[0], ay = 1.0 / prm->K[4];
+    for (int c = 0; c < n_chunks; ++c) {
+        const int p0 = first_pair + c * s->chunk;
+        const int np = std::min(s->chunk, first_pair + n_pairs - p0);
+        int rc;
+        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][0], ctx->stream));
+        MatchPlan mp{};
+        mp.desc = s->d_desc + (size_t)p0 * kp * 8;          // chunk-local view: frames p0 .. p0+np
+        mp.planes = s->d_planes + (size_t)p0 * kp * 8;
+        // bit planes of the chunk's frames; the first frame of a later chunk was already
+        // converted as the last frame of the previous one, converting it again is idempotent
+        mp.total_rows = (int64_t)(np + 1) * kp;
+        mp.words = 8;
+        mp.norm = prm->norm;
+        mp.top2 = prm->match_mode == EPIVO_MATCH_RATIO;
+        mp.n_pairs = np;
+        mp.q0 = 0;
+        mp.qs = kp;
+        mp.t0 = kp;
+        mp.ts = kp;
+        mp.nq = kp;
+        mp.nt = kp;
+        mp.tsplits = 1;
+        mp.rowkey = s->d_rowkey;
+        mp.rowkey2 = s->d_rowkey2;
+        mp.colkey = s->d_colkey;
+        mp.stride = st;
+        mp.ev0 = s->evk[c][0];
+        mp.ev1 = s->evk[c][1];
+        rc = epv_match_launch(ctx, mp, true);
+        if (rc) return rc;
+        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][1], ctx->stream));
+        FinalizePlan fp{};
+        fp.n_pairs = np;
+        fp.nq = kp;
+        fp.nt = kp;
+        fp.stride = st;
+        fp.mode = prm->match_mode;
+        fp.tsplits = 1;
+        fp.ratio = prm->ratio;
+        fp.rowkey = s->d_rowkey;
+        fp.rowkey2 = s->d_rowkey2;
+        fp.colkey = s->d_colkey;
+        fp.mq = s->d_mq + (size_t)p0 * st;
+        fp.mt = s->d_mt + (size_t)p0 * st;
+        fp.md = s->d_md + (size_t)p0 * st;
+        fp.md2 = nullptr;
+        fp.n_matches = s->d_nmatch + p0;
+        fp.kps = s->d_kps + (size_t)p0 * kp * 2;
+        fp.q0 = 0;
+        fp.qs = kp;
+        fp.t0 = kp;
+        fp.ts = kp;
+        fp.p0 = nullptr;
+        fp.p1 = nullptr;
+        fp.xn = s->d_xn;
+        fp.ax = ax;
+        fp.bx = -prm->K[2] * ax;
+        fp.ay = ay;
+        fp.by = -prm->K[5] * ay;
+        rc = epv_finalize_launch(ctx, fp);
+        if (rc) return rc;
+        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][2], ctx->stream));
+        EssentialPlan ep{};
+        ep.n_pairs = np;
+        ep.stride = st;
+        ep.xn = s->d_xn;
+        ep.n = s->d_nmatch + p0;
+        ep.method = prm->method;
+        ep.prob = prm->prob;
+        ep.thresh = prm->threshold / ((prm->K[0] + prm->K[4]) / 2.0);
+        ep.max_iters = prm->max_iters;
+        ep.samples = nullptr;
+        ep.m = 0;
+        ep.errbuf = s->d_err;
+        ep.E = s->d_E + (size_t)p0 * 9;
+        ep.mask = s->d_emask + (size_t)p0 * st;
+        ep.n_inliers = s->d_ninl + p0;
+        ep.iters = s->d_iters + p0;
+        ep.n_models = s->d_nmodels + p0;
+        ep.status = s->d_status + p0;
+        ep.xin = s->d_xin;
+        rc = epv_essential_launch(ctx, ep);
+        if (rc) return rc;
+        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][3], ctx->stream));
+        PosePlan pp{};
+        pp.n_pairs = np;
+        pp.stride = st;
+        pp.E = s->d_E + (size_t)p0 * 9;
+        pp.xn = s->d_xin;
+        pp.n = s->d_ninl + p0;
+        pp.in_mask = nullptr;
+        pp.dist_thresh = prm->dist_thresh;
+        pp.R = s->d_R + (size_t)p0 * 9;
+        pp.t = s->d_t + (size_t)p0 * 3;
+        pp.mask = s->d_pmask + (size_t)p0 * st;
+        pp.n_good = s->d_ngood + p0;
+        pp.skip = s->d_status + p0;
+        rc = epv_pose_launch(ctx, pp);
+        if (rc) return rc;
+        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][4], ctx->stream));
+        lm_prep_kernel<<<np, 64, 0, ctx->stream>>>(np, st, *prm, s->d_R + (size_t)p0 * 9, s->d_t + (size_t)p0 * 3,
+                                                   s->d_status + p0, s->d_ninl + p0, s->d_ngood + p0, s->d_xin,
+                                                   s->d_T0 + (size_t)p0 * 16, s->d_T + (size_t)p0 * 16, s->d_lmp,
+                                                   s->d_lmq, s->d_w, s->d_lmactive + p0);
+        EPV_LAUNCHED(ctx);
+        LmPlan lp{};
+        lp.B = np;
+        lp.n_zeta = 1;
+        lp.n_rep = 1;
+        lp.N = prm->lm_points;
+        lp.reps = s->d_reps;
+        lp.wreps = s->d_w;
+        lp.epsilon = prm->lm_epsilon;
+        lp.lambda0 = prm->lm_lambda0;
+        lp.huber_delta = prm->huber_delta;
+        lp.max_iters = prm->lm_max_iters;
+        lp.T0s = s->d_T + (size_t)p0 * 16;
+        lp.pr = s->d_lmp;
+        lp.p_r = s->d_lmq;
+        lp.out = s->d_lmres + p0;
+        lp.iters = s->d_lmiters + p0;
+        lp.active = s->d_lmactive + p0;
+        rc = epv_lm_launch(ctx, lp);
+        if (rc) return rc;
+        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][5], ctx->stream));
+        finish_kernel<<<(np + 127) / 128, 128, 0, ctx->stream>>>(
+            np, *prm, s->d_E + (size_t)p0 * 9, s->d_R + (size_t)p0 * 9, s->d_t + (size_t)p0 * 3,
+            s->d_T0 + (size_t)p0 * 16, s->d_T + (size_t)p0 * 16, s->d_lmres + p0, s->d_lmiters + p0,
+            s->d_lmactive + p0, s->d_nmatch + p0, s->d_ninl + p0, s->d_ngood + p0, s->d_iters + p0,
+            s->d_nmodels + p0, s->d_results + p0);
+        EPV_LAUNCHED(ctx);
+        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][6], ctx->stream));
+    }
+    EPV_CUDA(ctx, cudaEventRecord(s->ev_end, ctx->stream));
+    return EPIVO_OK;
+}
+
+int epivo_seq_download(epivo_seq* s, epivo_pair_result* out, int first_pair, int n_pairs) {
+    if (!s || !out) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range");
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    EPV_CUDA(ctx, cudaMemcpyAsync(s->h_results, s->d_results + first_pair, (size_t)n_pairs * sizeof(epivo_pair_result),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out, s->h_results, (size_t)n_pairs * sizeof(epivo_pair_result));
+    return EPIVO_OK;
+}
+
+int epivo_seq_stage_ms(epivo_seq* s, float* ms, int n) {
+    if (!s || !ms) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < s->last_chunks; ++c) {
+        for (int k = 0; k < SEQ_STAGES - 1; ++k) {
+            float t = 0;
+            EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->ev[c][k], s->ev[c][k + 1]));
+            acc[k + 1] += t;       // [1] match (incl. plane pre-pass + key init) [2] finalize [3] essential [4] pose [5] lm [6] finish
+        }
+    }
+    for (int c = 0; c < s->last_chunks; ++c) {
+        float t = 0;
+        EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->evk[c][0], s->evk[c][1]));
+        acc[7] += t;                // [7] matcher tile kernel alone, summed over the chunk launches
+    }
+    float tot = 0;
+    if (s->last_chunks > 0) EPV_CUDA(ctx, cudaEventElapsedTime(&tot, s->ev_begin, s->ev_end));
+    acc[0] = tot;
+    for (int i = 0; i < n; ++i) ms[i] = i < 8 ? acc[i] : (i == 8 ? (float)s->last_chunks : 0.f);
+    return EPIVO_OK;
+}
+
+int epivo_seq_get_matches(epivo_seq* s, int pair, int32_t* query_idx, int32_t* train_idx, int32_t* dist, int* n_out) {
+    if (!s || !n_out) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (pair < 0 || pair >= s->max_frames - 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair index");
+    int32_t n = 0;
+    const size_t o = (size_t)pair * s->stride;
+    EPV_CUDA(ctx, cudaMemcpyAsync(&n, s->d_nmatch + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (query_idx) EPV_CUDA(ctx, cudaMemcpyAsync(query_idx, s->d_mq + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (train_idx) EPV_CUDA(ctx, cudaMemcpyAsync(train_idx, s->d_mt + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist) EPV_CUDA(ctx, cudaMemcpyAsync(dist, s->d_md + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return EPIVO_OK;
+}
+
+int epivo_seq_get_masks(epivo_seq* s, int pair, uint8_t* e_mask, int* n_e, uint8_t* pose_mask, int* n_pose) {
+    if (!s) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (pair < 0 || pair >= s->max_frames - 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair index");
+    int32_t nm = 0, ni = 0;
+    const size_t o = (size_t)pair * s->stride;
+    EPV_CUDA(ctx, cudaMemcpyAsync(&nm, s->d_nmatch + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(&ni, s->d_ninl + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e_mask) EPV_CUDA(ctx, cudaMemcpyAsync(e_mask, s->d_emask + o, (size_t)nm, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pose_mask) EPV_CUDA(ctx, cudaMemcpyAsync(pose_mask, s->d_pmask + o, (size_t)ni, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_e) *n_e = nm;
+    if (n_pose) *n_pose = ni;
+    return EPIVO_OK;
+}
+
+}  // extern "C"

@@ -1,3 +1,61 @@
-// Declarations of the per-stage launchers shared by api.cu and seq.cu.
+// Declarations of the per-stage launchers shared by api.cu and seq.cu.  All pointers are
+// DEVICE pointers; launches go to ctx->stream.
 #pragma once
 #include "common.cuh"
+
+// ---- essential.cu --------------------------------------------------------------------
+struct EssentialPlan {
+    int n_pairs, stride;
+    const double* xn;        // [pair][4][stride]
+    const int32_t* n;        // [pair]
+    int method;
+    double prob, thresh;     // thresh = pixel threshold / ((fx+fy)/2)
+    int max_iters;
+    const int32_t* samples;  // optional [m][5]
+    int m;
+    float* errbuf;           // epv_essential_errbuf_floats() floats (LMedS scratch)
+    double* E;               // [pair][9]
+    uint8_t* mask;           // [pair][stride]
+    int32_t *n_inliers, *iters, *n_models, *status;   // [pair]
+    double* xin;             // optional [pair][4][stride]
+};
+int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p);
+size_t epv_essential_errbuf_floats(int n_pairs, int stride);
+int epv_normalize_launch(epivo_ctx* ctx, const float* d_p0, const float* d_p1, int n, int stride, const double K[9],
+                         double* d_xn);
+int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_E, int32_t* d_nm);
+int epv_score_launch(epivo_ctx* ctx, const double* d_E, int m, const double* d_xn, int stride, int n, double thresh,
+                     int32_t* d_counts, float* d_medians, float* d_errbuf, int* d_best, uint8_t* d_mask);
+
+// ---- pose.cu -------------------------------------------------------------------------
+struct PosePlan {
+    int n_pairs, stride;
+    const double* E;         // [pair][9]
+    const double* xn;        // [pair][4][stride] K-normalised points (the E inliers)
+    const int32_t* n;        // [pair]
+    const uint8_t* in_mask;  // optional [pair][stride]
+    double dist_thresh;
+    double* R;               // [pair][9]
+    double* t;               // [pair][3]
+    uint8_t* mask;           // [pair][stride] {0,255}
+    int32_t* n_good;         // [pair]
+    const int32_t* skip;     // optional [pair]: nonzero status => pair skipped (outputs zeroed)
+};
+int epv_pose_launch(epivo_ctx* ctx, const PosePlan& p);
+
+// ---- lm.cu ---------------------------------------------------------------------------
+struct LmPlan {
+    int B;                   // independent problems
+    int n_zeta, n_rep, N;
+    const int32_t* reps;     // [n_rep][2] (shared by all problems)
+    const double* wreps;     // [B][n_rep]
+    double epsilon, lambda0, huber_delta;
+    int max_iters;
+    double* T0s;             // [B][n_zeta][16] in/out
+    const double* pr;        // [B][n_rep][N][3]
+    const double* p_r;       // [B][n_rep][N][3]
+    epivo_lm_res* out;       // [B]
+    int32_t* iters;          // [B]
+    const int32_t* active;   // optional [B]: 0 => problem skipped, T0s untouched
+};
+int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p);

@@ -262,14 +262,79 @@ def five_point_constraints(EE: np.ndarray) -> np.ndarray:
     return A
 
 
-def five_point(x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
+
+def _eval_B(B, z):
+    """B(z) and dB/dz (3x3 each) from the 3x13 coefficient rows (descending powers)."""
+    Bz = np.array([[np.polyval(B[j, 0:4], z), np.polyval(B[j, 4:8], z), np.polyval(B[j, 8:13], z)]
+                   for j in range(3)])
+    dB = np.array([[np.polyval(np.polyder(B[j, 0:4]), z), np.polyval(np.polyder(B[j, 4:8]), z),
+                    np.polyval(np.polyder(B[j, 8:13]), z)] for j in range(3)])
+    return Bz, dB
+
+
+def _det3(M):
+    return (M[0, 0] * (M[1, 1] * M[2, 2] - M[1, 2] * M[2, 1]) - M[0, 1] * (M[1, 0] * M[2, 2] - M[1, 2] * M[2, 0])
+            + M[0, 2] * (M[1, 0] * M[2, 1] - M[1, 1] * M[2, 0]))
+
+
+def _essential_constraints(E):
+    """the ten cubic constraints: 2 E E'E - tr(E E')E (9) and det E (1)"""
+    return np.append((2.0 * E @ E.T @ E - np.trace(E @ E.T) * E).ravel(), _det3(E))
+
+
+def _essential_constraints_dir(E, D):
+    """directional derivative of the ten constraints along D"""
+    cof = np.array([[E[(i + 1) % 3, (j + 1) % 3] * E[(i + 2) % 3, (j + 2) % 3]
+                     - E[(i + 1) % 3, (j + 2) % 3] * E[(i + 2) % 3, (j + 1) % 3] for j in range(3)] for i in range(3)])
+    d = 2.0 * (D @ E.T @ E + E @ D.T @ E + E @ E.T @ D) - 2.0 * np.trace(E @ D.T) * E - np.trace(E @ E.T) * D
+    return np.append(d.ravel(), float((cof * D).sum()))
+
+
+def refine_essential(E, EE, iters=6):
+    """Gauss-Newton refinement of one 5-point solution inside the 4-D null space.
+
+    NOT part of OpenCV's runKernel.  Nister's elimination works in the chart "coefficient of
+    EE[3] = 1" of an ARBITRARY null-space basis (OpenCV's comes from LAPACK's SVD, this
+    restatement's from numpy's, the CUDA solver's from Householder QR); when a solution has a
+    small EE[3] component, or the sample is close to degenerate (low parallax), the expanded
+    degree-10 polynomial loses many digits, by an amount that differs from basis to basis.
+    A few Newton steps on the constraints themselves, on the unit sphere of coefficients,
+    make every implementation converge to the same exact solutions (quadratically: 2-5 steps).
+    A step is kept only if it lowers the constraint residual."""
+    B = EE.reshape(4, 3, 3)
+    c = np.array([float((E * B[k]).sum()) for k in range(4)])
+    c /= np.linalg.norm(c)
+    Ecur = np.tensordot(c, B, 1)
+    f = _essential_constraints(Ecur)
+    for _ in range(iters):
+        J = np.stack([_essential_constraints_dir(Ecur, B[k]) for k in range(4)], axis=1)
+        N = J.T @ J
+        N = N + 1e3 * np.trace(N) * np.outer(c, c)            # pins the radial (scale) direction
+        try:
+            d = np.linalg.solve(N, -J.T @ f)
+        except np.linalg.LinAlgError:
+            break
+        c2 = c + d
+        c2 /= np.linalg.norm(c2)
+        E2 = np.tensordot(c2, B, 1)
+        f2 = _essential_constraints(E2)
+        if not np.isfinite(f2).all() or np.abs(f2).max() >= np.abs(f).max():
+            break
+        c, Ecur, f = c2, E2, f2
+        if np.linalg.norm(d) < 1e-14:
+            break
+    return Ecur
+
+
+def five_point(x1: np.ndarray, x2: np.ndarray, refine: bool = True) -> np.ndarray:
     """EMEstimatorCallback::runKernel on 5 K-normalised correspondences -> (k, 3, 3), k<=10.
 
     Follows OpenCV's steps: 5x9 epipolar system (row-major E, x2' E x1 = 0), its 4-D null
     space, Nister's 10x20 system reduced by the inverse of its left block, the 3x3
     polynomial matrix B(z) = {rows 4,6,8} - z*{rows 5,7,9}, det B(z) = degree-10 polynomial,
     real roots (|imag| <= 1e-10), (x, y) from the null vector of B(z), skip if its last
-    entry is < 1e-10 in magnitude, E normalised to unit Frobenius norm.  The null-space
+    entry is < 1e-10 in magnitude, E normalised to unit Frobenius norm; then, beyond OpenCV,
+    each solution is refined on the constraints (refine_essential) unless refine=False.  The null-space
     basis, and therefore the order of the solutions, depends on the SVD implementation;
     OpenCV's comes from LAPACK and is not reproducible bit-for-bit, so solutions are compared
     as a set.
@@ -310,14 +375,14 @@ def five_point(x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
         if abs(r.imag) > 1e-10:
             continue
         z = r.real
-        Bz = np.array([[np.polyval(B[j, 0:4], z), np.polyval(B[j, 4:8], z), np.polyval(B[j, 8:13], z)]
-                       for j in range(3)])
+        Bz = _eval_B(B, z)[0]
         xy1 = np.linalg.svd(Bz)[2][2]
         if abs(xy1[2]) < 1e-10:
             continue
         x, y = xy1[0] / xy1[2], xy1[1] / xy1[2]
         Ev = EE[0] * x + EE[1] * y + EE[2] * z + EE[3]
-        sols.append((Ev / np.linalg.norm(Ev)).reshape(3, 3))
+        Ev = (Ev / np.linalg.norm(Ev)).reshape(3, 3)
+        sols.append(refine_essential(Ev, EE) if refine else Ev)
     return np.array(sols).reshape(-1, 3, 3)
 
 

@@ -1,0 +1,176 @@
+"""E1/E2/K2/K3 parity through the C ABI: cv2 golden vectors, the oracle, fixed hypothesis sets."""
+import numpy as np
+import pytest
+
+from conftest import esame
+from epivo_b200 import api, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+CASES = ["kitti", "kitti_b", "euroc"]
+E_TOL = 1e-6      # max |dE| up to sign, unit-norm E: tolerance against cv2 (cv2's solver is not refined)
+CALLS = [("ransac10", api.RANSAC, 1.0), ("ransac03", api.RANSAC, 0.3), ("ransac005", api.RANSAC, 0.05),
+         ("lmeds", api.LMEDS, 0.01)]
+
+
+def _set_dist(Ea, Eb):
+    """max over a of min over b of the sign/scale-free distance"""
+    if len(Ea) == 0 or len(Eb) == 0:
+        return 0.0 if len(Ea) == len(Eb) else np.inf
+    return max(min(esame(a, b) for b in Eb) for a in Ea)
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_five_point_vs_cv2_minimal(ctx, golden_ess, trial):
+    """N == 5: cv2 returns every solution of its solver; compare as a set (E_TOL vs cv2, whose own
+    roots carry the un-refined error of the expanded polynomial; 1e-9 vs the oracle)."""
+    p0, p1, K = golden_ess[f"min{trial}_p0"], golden_ess[f"min{trial}_p1"], golden_ess[f"min{trial}_K"]
+    Ecv = golden_ess[f"min{trial}_E"].reshape(-1, 3, 3)
+    x1, x2 = O.normalize_points(p0, K), O.normalize_points(p1, K)
+    Eg = api.fivePoint(x1[None], x2[None], ctx=ctx)[0]
+    Eo = O.five_point(x1, x2)
+    assert len(Eg) == len(Ecv) == len(Eo)
+    assert _set_dist(Ecv, Eg) < E_TOL and _set_dist(Eg, Ecv) < E_TOL
+    assert _set_dist(Eo, Eg) < 1e-9 and _set_dist(Eg, Eo) < 1e-9
+    for E in Eg:                                   # solutions satisfy the epipolar + essential constraints
+        assert abs(np.linalg.norm(E) - 1) < 1e-12
+        r = np.einsum("ni,ij,nj->n", np.c_[x2, np.ones(5)], E, np.c_[x1, np.ones(5)])
+        assert np.abs(r).max() < 1e-9
+        assert np.abs(2 * E @ E.T @ E - np.trace(E @ E.T) * E).max() < 1e-8
+
+
+def test_five_point_batch_vs_oracle(ctx):
+    pr = synth.make_kitti_pair(4, n=400)
+    qi, ti, _ = O.bf_match(pr.desc0, pr.desc1)
+    x1, x2 = O.normalize_points(pr.kp0[qi], pr.K), O.normalize_points(pr.kp1[ti], pr.K)
+    S = O.generate_samples(len(qi), 64)
+    Eg = api.fivePoint(x1[S], x2[S], ctx=ctx)
+    for s in range(64):
+        Eo = O.five_point(x1[S[s]], x2[S[s]])
+        assert len(Eg[s]) == len(Eo)
+        assert _set_dist(Eo, Eg[s]) < 1e-9 and _set_dist(Eg[s], Eo) < 1e-9
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("call", CALLS)
+def test_score_fixed_hypothesis_mask_bit_exact(ctx, golden_ess, case, call):
+    """K3 known-answer: (E_cv2, points, thr) -> mask_cv2, bit-exact."""
+    cname, method, thr = call
+    p0, p1, K = golden_ess[f"{case}_p0"], golden_ess[f"{case}_p1"], golden_ess[f"{case}_K"]
+    E, mask = golden_ess[f"{case}_{cname}_E"], golden_ess[f"{case}_{cname}_mask"]
+    if method == api.RANSAC:
+        counts, med, best, bm = api.scoreSampson(E[None], p0, p1, K, thr, ctx=ctx)
+        assert best == 0 and counts[0] == int(mask.sum())
+        assert np.array_equal(bm, mask)
+    else:
+        # LMedS: the inlier rule is driven by the median of the best model
+        counts, med, best, bm = api.scoreSampson(E[None], p0, p1, K, 1.0, ctx=ctx)
+        x1, x2 = O.normalize_points(p0, K), O.normalize_points(p1, K)
+        err = O.sampson_err_f32(E, x1, x2)
+        assert med[0] == np.float32(O.lmeds_median(err))
+        sigma = O.lmeds_sigma(float(med[0]), len(p0))
+        assert np.array_equal(O.find_inliers(err, sigma), mask)
+
+
+def test_score_many_models_vs_oracle(ctx):
+    pr = synth.make_kitti_pair(5, n=900)
+    qi, ti, _ = O.bf_match(pr.desc0, pr.desc1)
+    p0, p1 = pr.kp0[qi], pr.kp1[ti]
+    x1, x2 = O.normalize_points(p0, pr.K), O.normalize_points(p1, pr.K)
+    S = O.generate_samples(len(qi), 40)
+    Es = np.concatenate([O.five_point(x1[s], x2[s]) for s in S])
+    thr = 0.7
+    counts, med, best, bm = api.scoreSampson(Es, p0, p1, pr.K, thr, ctx=ctx)
+    oc, om = O.score_models(Es, x1, x2, O.ransac_threshold(thr, pr.K))
+    assert np.array_equal(counts, oc)
+    assert np.array_equal(med, om)
+    assert best == int(np.argmax(oc))              # first maximum
+    assert np.array_equal(bm, O.find_inliers(O.sampson_err_f32(Es[best], x1, x2), O.ransac_threshold(thr, pr.K)))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("call", CALLS)
+def test_find_essential_whole_call_vs_cv2(ctx, golden_ess, case, call):
+    """Whole-call parity: same RNG stream, same sequential best-model rule as OpenCV.
+    E agrees up to sign within 1e-8; the inlier mask is identical."""
+    cname, method, thr = call
+    p0, p1, K = golden_ess[f"{case}_p0"], golden_ess[f"{case}_p1"], golden_ess[f"{case}_K"]
+    Ecv, mask = golden_ess[f"{case}_{cname}_E"], golden_ess[f"{case}_{cname}_mask"]
+    E, m, info = api.findEssentialMat(p0, p1, K, method, 0.99, thr, ctx=ctx, return_info=True)
+    assert E is not None
+    assert esame(E, Ecv) < E_TOL
+    assert np.array_equal(m, mask)
+    assert info["n_inliers"] == int(mask.sum())
+    Eo, mo, oinfo = O.find_essential_mat(p0, p1, K, method, 0.99, thr)
+    assert info["iters"] == oinfo["iters"]
+
+
+@pytest.mark.parametrize("trial", range(8))
+def test_lmeds_small_even_n(ctx, golden_ess, trial):
+    key = f"small{trial}_E"
+    if key not in golden_ess.files:
+        pytest.skip("cv2 returned no single model for this draw")
+    p0, p1, K = golden_ess[f"small{trial}_p0"], golden_ess[f"small{trial}_p1"], golden_ess[f"small{trial}_K"]
+    E, m = api.findEssentialMat(p0, p1, K, api.LMEDS, 0.99, 0.01, ctx=ctx)
+    assert esame(E, golden_ess[key]) < E_TOL
+    assert np.array_equal(m, golden_ess[f"small{trial}_mask"])
+
+
+def test_fixed_sample_set_vs_oracle(ctx):
+    """north_star: bit-exact inlier mask for a fixed hypothesis set and seed."""
+    pr = synth.make_euroc_pair(3, n=800)
+    qi, ti, _ = O.bf_match(pr.desc0, pr.desc1)
+    p0, p1 = pr.kp0[qi], pr.kp1[ti]
+    rng = np.random.default_rng(99)
+    S = np.stack([rng.choice(len(qi), 5, replace=False) for _ in range(200)]).astype(np.int32)
+    for method, thr in ((api.RANSAC, 0.3), (api.LMEDS, 0.0)):
+        E, m, info = api.findEssentialMat(p0, p1, pr.K, method, 0.99, thr, samples=S, ctx=ctx, return_info=True)
+        Eo, mo, oinfo = O.find_essential_mat(p0, p1, pr.K, method, 0.99, thr, samples=S)
+        assert esame(E, Eo) < 1e-9
+        assert np.array_equal(m, mo)
+        assert info["iters"] == oinfo["iters"]
+
+
+def test_edge_cases(ctx):
+    K = synth.KITTI_K
+    p = np.random.default_rng(0).uniform(0, 300, (4, 2)).astype(np.float32)
+    E, m = api.findEssentialMat(p, p + 1, K, api.RANSAC, 0.99, 1.0, ctx=ctx)
+    assert E is None and not m.any()               # N < 5 -> cv2 returns None
+    with pytest.raises(api.EpivoError):
+        api.findEssentialMat(p, p, K, 16, 0.99, 1.0, ctx=ctx)       # not RANSAC / LMEDS
+    with pytest.raises(api.EpivoError):
+        api.findEssentialMat(np.zeros((6, 2), np.float32), np.zeros((6, 2), np.float32), K, api.RANSAC, 1.5, 1.0, ctx=ctx)
+    # N == 5: all-ones mask, E is one of the minimal solutions
+    pr = synth.make_kitti_pair(6, n=200)
+    qi, ti, _ = O.bf_match(pr.desc0, pr.desc1)
+    good = pr.gt_match[qi] == ti
+    p0, p1 = pr.kp0[qi][good][:5], pr.kp1[ti][good][:5]
+    E, m = api.findEssentialMat(p0, p1, K, api.RANSAC, 0.99, 1.0, ctx=ctx)
+    assert m.tolist() == [1] * 5
+    sols = O.five_point(O.normalize_points(p0, K), O.normalize_points(p1, K))
+    assert min(esame(E, s) for s in sols) < 1e-7
+
+
+def test_stress_sweep_properties(ctx):
+    """cfg4-sized scoring (16384 models x 8000 correspondences) through size-independent
+    properties: the count of a model equals the sum of its mask; planting the true E among random
+    models makes it the argmax; scoring is invariant to the sign/scale of E."""
+    rng = np.random.default_rng(7)
+    pr = synth.make_pair(seed=40_001, n=8000, outlier_frac=0.5)
+    gt = pr.gt_match
+    keep = gt >= 0
+    p0 = np.concatenate([pr.kp0[keep], rng.uniform(0, 1241, (int((~keep).sum()), 2)).astype(np.float32)])
+    p1 = np.concatenate([pr.kp1[gt[keep]], rng.uniform(0, 376, (int((~keep).sum()), 2)).astype(np.float32)])
+    tx = np.array([[0, -pr.t[2], pr.t[1]], [pr.t[2], 0, -pr.t[0]], [-pr.t[1], pr.t[0], 0]])
+    Etrue = tx @ pr.R
+    M = 16384
+    Es = rng.normal(size=(M, 9))
+    Es[1234] = Etrue.ravel()
+    Es[77] = -3.0 * Etrue.ravel()
+    counts, _, best, bm = api.scoreSampson(Es, p0, p1, pr.K, 2.0, ctx=ctx)
+    assert best == 77 and counts[77] == counts[1234]
+    assert counts[best] == int(bm.sum()) and counts[best] > 0.45 * len(p0)
+    x1, x2 = O.normalize_points(p0, pr.K), O.normalize_points(p1, pr.K)
+    sel = rng.choice(M, 32, replace=False)
+    oc, _ = O.score_models(Es[sel], x1, x2, O.ransac_threshold(2.0, pr.K))
+    assert np.array_equal(counts[sel], oc)

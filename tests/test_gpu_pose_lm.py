@@ -1,0 +1,129 @@
+"""P1 (recoverPose) and L4 (Levenberg_Marquardt) parity through the C ABI."""
+import numpy as np
+import pytest
+
+from epivo_b200 import api, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+CASES = ["kitti", "kitti_b", "euroc"]
+CALLS = ["ransac10", "ransac03", "ransac005", "lmeds"]
+ROT_TOL, T_TOL = 1e-4, 1e-3          # north_star: rotation <= 1e-4 rad, unit-t angle <= 1e-3 rad
+
+
+def rot_angle(Ra, Rb):
+    return float(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
+def vec_angle(a, b):
+    a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+    return float(np.arccos(np.clip(a @ b, -1, 1)))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("cname", CALLS)
+def test_recover_pose_vs_cv2(ctx, golden_ess, case, cname):
+    p0, p1, K = golden_ess[f"{case}_p0"], golden_ess[f"{case}_p1"], golden_ess[f"{case}_K"]
+    E, m = golden_ess[f"{case}_{cname}_E"], golden_ess[f"{case}_{cname}_mask"] == 1
+    n, R, t, mask = api.recoverPose(E, p0[m], p1[m], K, ctx=ctx)
+    assert rot_angle(R, golden_ess[f"{case}_{cname}_R"]) < ROT_TOL
+    assert vec_angle(t, golden_ess[f"{case}_{cname}_t"]) < T_TOL
+    assert np.array_equal(mask, golden_ess[f"{case}_{cname}_pose_mask"])     # {0,255}, identical
+    assert n == int(golden_ess[f"{case}_{cname}_pose_n"])
+    assert abs(np.linalg.det(R) - 1) < 1e-12 and abs(np.linalg.norm(t) - 1) < 1e-12
+
+
+def test_recover_pose_input_mask_and_sign(ctx, golden_ess):
+    p0, p1, K = golden_ess["kitti_p0"], golden_ess["kitti_p1"], golden_ess["kitti_K"]
+    E, m = golden_ess["kitti_ransac10_E"], golden_ess["kitti_ransac10_mask"] == 1
+    c0, c1 = p0[m], p1[m]
+    im = (np.arange(len(c0)) % 3 != 0).astype(np.uint8)
+    n, R, t, mask = api.recoverPose(E, c0, c1, K, mask=im, ctx=ctx)
+    no, Ro, to, mo = O.recover_pose(E, c0, c1, K, in_mask=im)
+    assert n == no and np.array_equal(mask, mo) and not mask[im == 0].any()
+    # -E decomposes into the same four candidates: same winner
+    n2, R2, t2, mask2 = api.recoverPose(-E, c0, c1, K, ctx=ctx)
+    n1, R1, t1, mask1 = api.recoverPose(E, c0, c1, K, ctx=ctx)
+    assert n1 == n2 and np.abs(R1 - R2).max() < 1e-9 and np.abs(t1 - t2).max() < 1e-9 and np.array_equal(mask1, mask2)
+    # empty input
+    n0, R0, t0, m0 = api.recoverPose(E, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), K, ctx=ctx)
+    assert n0 == 0 and len(m0) == 0
+
+
+REPS10 = [(i, i) for i in range(10)] + [(0, i) for i in range(10)]    # test_jac_Rt_gen.cpp:294-297
+
+
+def _check_lm(ctx, n_zeta, reps, N, seed, delta, iters, w=None, tol=1e-5):
+    Ts, T0s, pr, p_r = synth.gen_scene_sequence(seed, N, n_zeta, reps)
+    w = [1.0] * len(reps) if w is None else w
+    To, lo = O.levenberg_marquardt(n_zeta, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=delta, max_iters=iters)
+    Tg, lg = api.Levenberg_Marquardt(n_zeta, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=delta,
+                                     max_iters=iters, ctx=ctx)
+    assert lg["iters"] == lo["iters"]
+    for k in range(n_zeta):
+        assert rot_angle(Tg[k][:3, :3], To[k][:3, :3]) < ROT_TOL
+        assert np.abs(Tg[k][:3, 3] - To[k][:3, 3]).max() < 1e-6 * max(1.0, np.abs(To[k][:3, 3]).max())
+    assert abs(lg["r_norm"] - lo["r_norm"]) <= tol * max(lo["r_norm"], 1e-12) + 1e-15   # relative residual <= 1e-5
+    assert abs(lg["lambda"] - lo["lambda"]) <= 1e-9 * lo["lambda"]
+    assert abs(lg["H_norm"] - lo["H_norm"]) <= 1e-5 * max(lo["H_norm"], 1e-12) + 1e-15
+    return Ts, Tg, lg
+
+
+def test_lm_single_pair_shipped_delta(ctx):
+    """kitti_E.cpp:196 shape: n_zeta = 1, reps = {(0,0)}, N = 48, delta = 1e-5 (as shipped)."""
+    for seed in (1, 2, 3):
+        _check_lm(ctx, 1, [(0, 0)], 48, seed, 1e-5, 30)
+
+
+def test_lm_single_pair_converges(ctx):
+    Ts, Tg, lg = _check_lm(ctx, 1, [(0, 0)], 48, 11, 1.0, 60)
+    assert lg["r_norm"] < 1e-12
+    assert np.linalg.norm(Tg[0][:3, :3] - Ts[0][:3, :3]) < 1e-6
+    ratio = Ts[0][:3, 3] / Tg[0][:3, 3]                       # scale is unobservable: constant ratio
+    assert np.ptp(ratio) < 1e-5 * abs(ratio.mean())
+
+
+def test_lm_window_demo_shape(ctx):
+    """test_jac_Rt_gen.cpp:280-513: n_zeta = 10, 20 reps, N = 15, delta = 1.0, 60 iterations."""
+    Ts, Tg, lg = _check_lm(ctx, 10, REPS10, 15, 21, 1.0, 60)
+    for k in range(10):
+        assert np.linalg.norm(Tg[k][:3, :3] - Ts[k][:3, :3]) < 1e-5
+
+
+def test_lm_reverse_reps_and_weights(ctx):
+    reps = [(0, 0), (1, 1), (2, 2), (0, 2), (2, 0), (1, 0), (2, 1)]
+    _check_lm(ctx, 3, reps, 32, 31, 1.0, 30, w=[1.0, 1.0, 1.0, 0.5, 1.0, 2.0, 1.0])
+    _check_lm(ctx, 3, reps, 32, 32, 1e-5, 30)
+
+
+def test_lm_zero_weight_rep_gives_nan_stop(ctx):
+    """kitti_ba.cpp:821-826: a '<32 points' rep gets weight 0 and all-ones dummy points; if a zeta
+    is covered by nothing else H is singular, delta has NaN and the loop stops (jac_Rt_gen_.cpp:407)."""
+    reps = [(0, 0), (1, 1)]
+    Ts, T0s, pr, p_r = synth.gen_scene_sequence(5, 32, 2, reps)
+    pr[1][:] = 1.0
+    p_r[1][:] = 1.0
+    To, lo = O.levenberg_marquardt(2, 1e-8, reps, [1.0, 0.0], 1e-2, T0s, pr, p_r)
+    Tg, lg = api.Levenberg_Marquardt(2, 1e-8, reps, [1.0, 0.0], 1e-2, T0s, pr, p_r, ctx=ctx)
+    assert lo["iters"] == lg["iters"] == 1
+    assert np.allclose(Tg, T0s) and np.allclose(To, T0s)
+
+
+def test_lm_batch_and_errors(ctx):
+    reps = [(0, 0), (0, 1), (1, 1)]
+    B = 6
+    T0b, prb, p_rb = [], [], []
+    for b in range(B):
+        _, T0s, pr, p_r = synth.gen_scene_sequence(100 + b, 32, 2, reps)
+        T0b.append(T0s); prb.append(pr); p_rb.append(p_r)
+    Tb, res, its = api.Levenberg_Marquardt_batch(2, 1e-8, reps, [1.0, 1.0, 1.0], 1e-2, np.stack(T0b), np.stack(prb),
+                                                 np.stack(p_rb), huber_delta=1.0, ctx=ctx)
+    for b in range(B):
+        To, lo = O.levenberg_marquardt(2, 1e-8, reps, [1.0] * 3, 1e-2, T0b[b], prb[b], p_rb[b], huber_delta=1.0)
+        assert its[b] == lo["iters"]
+        assert np.abs(Tb[b] - To).max() < 1e-6
+        assert abs(res[b][1] - lo["r_norm"]) <= 1e-5 * lo["r_norm"] + 1e-15
+    with pytest.raises(api.EpivoError):
+        api.Levenberg_Marquardt(2, 1e-8, [(0, 2)], [1.0], 1e-2, T0b[0], prb[0][:1], p_rb[0][:1], ctx=ctx)
+    with pytest.raises(ValueError):
+        api.Levenberg_Marquardt(2, 1e-8, reps, [1.0], 1e-2, T0b[0], prb[0], p_rb[0], ctx=ctx)
