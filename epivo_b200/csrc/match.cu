@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(FinalizePlan fp) {
 
 template <int WORDS>
 int launch_words(epivo_ctx* ctx, const MatchPlan& mp, const uint32_t* src) {
-    const int n_tiles = (mp.nt + MT_TILE - 1) / MT_TILE;
+    const int n_tiles = std::max(1, (mp.nt + MT_TILE - 1) / MT_TILE);
     const int tps = (n_tiles + mp.tsplits - 1) / mp.tsplits;
     dim3 grid((mp.nq + MT_THREADS * MT_RQ - 1) / (MT_THREADS * MT_RQ), mp.n_pairs, (n_tiles + tps - 1) / tps);
     const int64_t part = (int64_t)mp.n_pairs * mp.stride;
@@ -309,6 +309,7 @@ int launch_words(epivo_ctx* ctx, const MatchPlan& mp, const uint32_t* src) {
 int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt) {
     const int64_t qblocks = (nq + MT_THREADS * MT_RQ - 1) / (MT_THREADS * MT_RQ);
     const int n_tiles = (nt + MT_TILE - 1) / MT_TILE;
+    if (n_tiles <= 1) return 1;
     const int64_t ctas = std::max<int64_t>(1, qblocks * n_pairs);
     const int64_t want = 4LL * ctx->sm_count;             // ~4 CTAs per SM
     int64_t s = (want + ctas - 1) / ctas;

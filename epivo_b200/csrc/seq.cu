@@ -160,7 +160,9 @@ void epivo_pipeline_params_default(epivo_pipeline_params* p) {
     p->norm = EPIVO_NORM_HAMMING2;
     p->match_mode = EPIVO_MATCH_CROSSCHECK;
     p->ratio = 0.8f;
-    const double K[9] = {718.8560, 0.0, 607.1928, 0.0, 718.8560, 185.2157, 0.0, 0.0, 1.0};   // kitti_E.cpp:38-40
+    // kitti_E.cpp:38-40: cam is a float Mat, which findEssentialMat widens to double
+    const double K[9] = {(double)718.8560f, 0.0, (double)607.1928f, 0.0, (double)718.8560f, (double)185.2157f,
+                         0.0, 0.0, 1.0};
     memcpy(p->K, K, sizeof(K));
     p->method = EPIVO_RANSAC;
     p->prob = 0.99;

@@ -1,0 +1,48 @@
+"""CPU ORACLE -- TEST / BASELINE INFRASTRUCTURE ONLY.  ctypes wrapper of oracle/lm_c.c."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "liboracle_lm.so")
+
+
+class _LmRes(C.Structure):
+    _fields_ = [("H_norm", C.c_double), ("r_norm", C.c_double), ("lambda_", C.c_double)]
+
+
+def build() -> str:
+    src = os.path.join(HERE, "lm_c.c")
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "-s"], check=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_lm.restype = C.c_int
+        _lib.oracle_lm.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                   C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_LmRes)]
+    return _lib
+
+
+def levenberg_marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r, huber_delta=1e-5, max_iters=30):
+    reps = np.ascontiguousarray(reps, dtype=np.int32).reshape(-1, 2)
+    w = np.ascontiguousarray(wreps, dtype=np.float64)
+    T = np.array(T0s, dtype=np.float64).reshape(n_zeta, 16).copy()
+    pr = np.ascontiguousarray(pr, dtype=np.float64)
+    p_r = np.ascontiguousarray(p_r, dtype=np.float64)
+    res = _LmRes()
+    it = lib().oracle_lm(int(n_zeta), float(epsilon), reps.ctypes.data, w.ctypes.data, reps.shape[0], float(lambda0),
+                         int(max_iters), float(huber_delta), T.ctypes.data, pr.ctypes.data, p_r.ctypes.data,
+                         int(pr.shape[1]), C.byref(res))
+    return T.reshape(n_zeta, 4, 4), {"H_norm": res.H_norm, "r_norm": res.r_norm, "lambda": res.lambda_, "iters": it}

@@ -1,0 +1,106 @@
+"""CPU BASELINE -- used only by bench.py (`cpu_baseline`, `--impl reference`) and tests.
+
+The reference's per-pair path on host cores: the OpenCV calls the reference itself makes
+(through the cv2 wheel: BFMatcher.match, findEssentialMat, recoverPose -- kitti_ba.cpp:641,
+kitti_E.cpp:98-120) followed by the plain-C restatement of its Levenberg-Marquardt
+(oracle/lm_c.c; the Eigen/Sophus original cannot be built in this image).  If cv2 cannot be
+imported the numpy restatement (oracle.oracle) is timed instead and the JSON says so.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+try:
+    import cv2
+    HAVE_CV2 = True
+except Exception:                                       # pragma: no cover
+    cv2 = None
+    HAVE_CV2 = False
+
+from . import clib
+from . import oracle as O
+
+_SEQ = {}
+
+
+def pair_cv2(kp0, d0, kp1, d1, Kf, method=8, prob=0.99, thr=1.0, lm_points=48, huber_delta=1e-5):
+    """One frame pair through the reference's CPU path.  Returns (T 4x4, n_matches, n_inliers, n_good)."""
+    ms = cv2.BFMatcher(cv2.NORM_HAMMING2, True).match(d0, d1)             # kitti_ba.cpp:602,641
+    qi = np.fromiter((m.queryIdx for m in ms), dtype=np.int64, count=len(ms))
+    ti = np.fromiter((m.trainIdx for m in ms), dtype=np.int64, count=len(ms))
+    p0, p1 = kp0[qi], kp1[ti]                                             # kitti_ba.cpp:684-693
+    T = np.eye(4)
+    if len(p0) < 5:
+        T[:3, 3] = (0.1, 0.1, -0.9)
+        return T, len(p0), 0, 0
+    E, mask = cv2.findEssentialMat(p0, p1, Kf, method, prob, thr)         # kitti_E.cpp:98-104
+    if E is None or E.shape != (3, 3):
+        T[:3, 3] = (0.1, 0.1, -0.9)
+        return T, len(p0), 0, 0
+    m = mask.ravel() == 1
+    c0, c1 = p0[m], p1[m]                                                 # kitti_E.cpp:106-112
+    n_good, R, t, rm = cv2.recoverPose(E, c0, c1, Kf)                     # kitti_E.cpp:120
+    t = t.ravel()
+    if np.trace(R) < 2.7:                                                 # kitti_E.cpp:128-135
+        R, t = np.eye(3), np.array([0.1, 0.1, -0.9])
+    if np.linalg.norm(t) < 1e-5:
+        t = np.array([0.1, 0.1, -0.9])
+    T[:3, :3], T[:3, 3] = R, t
+    N = lm_points
+    if len(c0) >= N and int((rm.ravel() == 255).sum()) >= N:              # kitti_E.cpp:170-201
+        x0 = O.normalize_points(c0[:N], Kf)
+        x1 = O.normalize_points(c1[:N], Kf)
+        pr = np.concatenate([x0, np.ones((N, 1))], axis=1)[None]
+        p_r = np.concatenate([x1, np.ones((N, 1))], axis=1)[None]
+        Tl, lm = clib.levenberg_marquardt(1, 1e-8, [(0, 0)], [1.0], 1e-2, T[None], pr, p_r, huber_delta, 30)
+        if lm["r_norm"] <= 1e-9:
+            T = Tl[0]
+    return T, len(p0), int(m.sum()), int(n_good)
+
+
+def pair_numpy(kp0, d0, kp1, d1, Kf, method=8, prob=0.99, thr=1.0, **kw):
+    from . import pipeline
+    o = pipeline.pair_pipeline(kp0, d0, kp1, d1, Kf, method, prob, thr)
+    return o["T"], len(o["matches"][0]), int(o["e_mask"].sum()), int(o["n_good"])
+
+
+def _init(kps, descs, Kf, method, prob, thr):
+    _SEQ["kps"], _SEQ["descs"], _SEQ["K"], _SEQ["args"] = kps, descs, Kf, (method, prob, thr)
+    if HAVE_CV2:
+        cv2.setNumThreads(1)                                # pair-parallel: one core per pair
+    clib.lib()
+
+
+def _work(i):
+    kps, descs, Kf = _SEQ["kps"], _SEQ["descs"], _SEQ["K"]
+    method, prob, thr = _SEQ["args"]
+    fn = pair_cv2 if HAVE_CV2 else pair_numpy
+    T, nm, ni, ng = fn(kps[i], descs[i], kps[i + 1], descs[i + 1], Kf, method, prob, thr)
+    return i, T, nm, ni, ng
+
+
+class CpuPool:
+    """Pair-parallel CPU workers (how a CPU user would saturate the box): `cores` processes,
+    cv2.setNumThreads(1) each.  The sequence is inherited by fork, not pickled per task."""
+
+    def __init__(self, kps, descs, K, method=8, prob=0.99, thr=1.0, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or (os.cpu_count() or 1)
+        clib.build()
+        Kf = np.asarray(K, dtype=np.float32)
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_init,
+                                                initargs=(kps, descs, Kf, method, prob, thr))
+
+    def run(self, pair_indices):
+        """-> (pairs/s, results)"""
+        t0 = time.perf_counter()
+        res = self.pool.map(_work, list(pair_indices), chunksize=1)
+        dt = time.perf_counter() - t0
+        return len(res) / dt, res
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()

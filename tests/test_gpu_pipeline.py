@@ -24,7 +24,7 @@ def test_sequence_vs_oracle(ctx, seq, method, thr):
     P = seq.n_pairs
     pipe = api.SequencePipeline(seq.n_frames, 2000, ctx=ctx)
     pipe.upload(seq.kps, seq.descs)
-    prm = api.default_params(seq.K, method=method, threshold=thr)
+    prm = api.default_params(seq.K.astype(np.float32), method=method, threshold=thr)   # cam is a float Mat (kitti_E.cpp:38)
     pipe.run(prm, 0, P)
     res = pipe.download(0, P)
     for i in range(P):
@@ -59,7 +59,7 @@ def test_sequence_chunking_and_subranges(ctx, seq):
     """Running a sub-range, or the same range twice, gives identical results (idempotence)."""
     pipe = api.SequencePipeline(seq.n_frames, 2000, ctx=ctx)
     pipe.upload(seq.kps, seq.descs)
-    prm = api.default_params(seq.K)
+    prm = api.default_params(seq.K.astype(np.float32))
     pipe.run(prm, 0, seq.n_pairs)
     a = pipe.download(0, seq.n_pairs).copy()
     pipe.run(prm, 2, 3)
@@ -74,7 +74,7 @@ def test_sequence_chunking_and_subranges(ctx, seq):
 def test_ratio_mode_pipeline(ctx, seq):
     pipe = api.SequencePipeline(seq.n_frames, 2000, ctx=ctx)
     pipe.upload(seq.kps, seq.descs)
-    prm = api.default_params(seq.K, norm=api.NORM_HAMMING, match_mode=api.MATCH_RATIO)
+    prm = api.default_params(seq.K.astype(np.float32), norm=api.NORM_HAMMING, match_mode=api.MATCH_RATIO)
     pipe.run(prm, 0, 2)
     res = pipe.download(0, 2)
     for i in range(2):

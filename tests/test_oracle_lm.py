@@ -106,3 +106,19 @@ def test_se3_exp_small_angle_and_group_property():
     assert np.abs(O.se3_exp(d) @ O.se3_exp(-d) - np.eye(4)).max() < 1e-14
     z = O.se3_exp(np.array([1.0, 2.0, 3.0, 0, 0, 0]))
     assert np.allclose(z[:3, 3], [1, 2, 3]) and np.allclose(z[:3, :3], np.eye(3))
+
+
+def test_c_restatement_matches_numpy_restatement():
+    from oracle import clib
+    cases = [(1, [(0, 0)], 48, 1e-5, 30), (1, [(0, 0)], 48, 1.0, 30),
+             (3, [(0, 0), (1, 1), (2, 2), (0, 2), (2, 0), (1, 0)], 20, 1.0, 20),
+             (3, [(0, 0), (1, 1), (2, 2), (0, 2), (2, 0), (1, 0)], 20, 1e-5, 20)]
+    for n_zeta, reps, N, delta, iters in cases:
+        Ts, T0s, pr, p_r = synth.gen_scene_sequence(40 + n_zeta, N, n_zeta, reps)
+        w = [1.0] * len(reps)
+        Ta, a = O.levenberg_marquardt(n_zeta, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=delta, max_iters=iters)
+        Tb, b = clib.levenberg_marquardt(n_zeta, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=delta, max_iters=iters)
+        assert a["iters"] == b["iters"]
+        assert np.abs(Ta - Tb).max() < 1e-7
+        assert abs(a["r_norm"] - b["r_norm"]) <= 1e-6 * a["r_norm"] + 1e-18
+        assert abs(a["lambda"] - b["lambda"]) <= 1e-12 * a["lambda"]
