@@ -11,6 +11,9 @@
 // chunk in sample order, stopping where the sequential loop would have stopped.  The result
 // is the model the sequential loop would return; at most CHUNK-1 samples are wasted.
 #include <float.h>
+#include <math.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "fivept.cuh"
@@ -30,6 +33,20 @@ struct CvRng {   // cv::RNG: multiply-with-carry
     }
     __device__ int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a)) + a; }
 };
+
+// ptsetreg.cpp getSubset: 5 distinct indices, redraw on duplicates
+__device__ __forceinline__ void draw_subset(CvRng& rng, int n, int* idx) {
+    for (int i = 0; i < 5; ++i) {
+        int v;
+        bool dup;
+        do {
+            v = rng.uniform(0, n);
+            dup = false;
+            for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
+        } while (dup);
+        idx[i] = v;
+    }
+}
 
 // ptsetreg.cpp RANSACUpdateNumIters
 __device__ int update_num_iters(double p, double ep, int model_points, int max_iters) {
@@ -87,6 +104,11 @@ struct EssArgs {
     const int32_t* samples;     // optional injected samples [m][5] (shared by all pairs) or nullptr
     int m;
     float* errbuf;              // LMedS scratch [pair][ES_WARPS][stride]
+    // pre-solved first samples (presolve_kernel): models of samples [0, pre_count) of every pair
+    int pre_count;              // multiple of ES_CHUNK (0 = none)
+    const double* pre_models;   // [pair][pre_count][10][9]
+    const int32_t* pre_nmodels; // [pair][pre_count]
+    const unsigned long long* pre_rng;   // [pair] RNG state after pre_count samples
     // outputs
     double* E;                  // [pair][9]
     uint8_t* mask;              // [pair][stride] {0,1}
@@ -119,7 +141,7 @@ __global__ void __launch_bounds__(ES_THREADS) essential_kernel(EssArgs a) {
     const float thr32 = (float)(a.thresh * a.thresh);
 
     if (tid == 0) {
-        s_rng = 0xFFFFFFFFFFFFFFFFULL;                       // RNG rng((uint64)-1)
+        s_rng = a.pre_count > 0 && !a.samples ? a.pre_rng[pair] : 0xFFFFFFFFFFFFFFFFULL;   // RNG rng((uint64)-1)
         s_iter = 0;
         s_have = 0;
         s_total_models = 0;
@@ -137,7 +159,14 @@ __global__ void __launch_bounds__(ES_THREADS) essential_kernel(EssArgs a) {
         const int iter0 = s_iter, niters = s_niters;
         if (iter0 >= niters) break;
         const int ch = min(ES_CHUNK, niters - iter0);
-        if (tid == 0) {
+        const bool presolved = iter0 + ES_CHUNK <= a.pre_count;
+        if (presolved) {
+            // models of this chunk were solved by presolve_kernel at full occupancy
+            const double* gm = a.pre_models + ((int64_t)pair * a.pre_count + iter0) * 90;
+            const int32_t* gn = a.pre_nmodels + (int64_t)pair * a.pre_count + iter0;
+            for (int i = tid; i < ch * 90; i += ES_THREADS) (&s_models[0][0][0])[i] = gm[i];
+            for (int i = tid; i < ch; i += ES_THREADS) s_nmodels[i] = gn[i];
+        } else if (tid == 0) {
             if (n == 5) {
                 for (int k = 0; k < 5; ++k) s_idx[0][k] = k;
             } else if (a.samples) {
@@ -145,87 +174,90 @@ __global__ void __launch_bounds__(ES_THREADS) essential_kernel(EssArgs a) {
                     for (int k = 0; k < 5; ++k) s_idx[s][k] = a.samples[(int64_t)(iter0 + s) * 5 + k];
             } else {
                 CvRng rng{s_rng};
-                for (int s = 0; s < ch; ++s) {                // ptsetreg.cpp getSubset
-                    for (int i = 0; i < 5; ++i) {
-                        int v;
-                        bool dup;
-                        do {
-                            v = rng.uniform(0, n);
-                            dup = false;
-                            for (int k = 0; k < i; ++k) dup |= (s_idx[s][k] == v);
-                        } while (dup);
-                        s_idx[s][i] = v;
-                    }
-                }
+                for (int s = 0; s < ch; ++s) draw_subset(rng, n, s_idx[s]);
                 s_rng = rng.state;
             }
         }
         __syncthreads();
-        if (tid < ch) {
-            double x1[5][2], x2[5][2];
-            for (int k = 0; k < 5; ++k) {
-                const int i = s_idx[tid][k];
-                x1[k][0] = X1[i]; x1[k][1] = Y1[i];
-                x2[k][0] = X2[i]; x2[k][1] = Y2[i];
+        if (!presolved) {
+            if (tid < ch) {
+                double x1[5][2], x2[5][2];
+                for (int k = 0; k < 5; ++k) {
+                    const int i = s_idx[tid][k];
+                    x1[k][0] = X1[i]; x1[k][1] = Y1[i];
+                    x2[k][0] = X2[i]; x2[k][1] = Y2[i];
+                }
+                s_nmodels[tid] = fivept::solve(x1, x2, s_models[tid]);
             }
-            s_nmodels[tid] = fivept::solve(x1, x2, s_models[tid]);
+            __syncthreads();
         }
-        __syncthreads();
-        // score: warp w takes flattened (sample, model) slots w, w + ES_WARPS, ...
-        for (int slot = warp; slot < ch * 10; slot += ES_WARPS) {
-            const int s = slot / 10, k = slot % 10;
-            if (k >= s_nmodels[s]) continue;
-            const double* E = s_models[s][k];
-            if (!lmeds) {
-                int cnt = 0;
-                for (int i = lane; i < n; i += 32) cnt += (sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]) <= thr32);
-                cnt = warp_sum(cnt);
-                if (lane == 0) s_score[s][k] = (float)cnt;
-            } else {
-                float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
-                for (int i = lane; i < n; i += 32) buf[i] = sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]);
-                __syncwarp();
-                const float med = warp_select(buf, n, n / 2, lane);
-                __syncwarp();
-                if (lane == 0) s_score[s][k] = med;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {                                      // sequential bookkeeping of ptsetreg.cpp run()
-            int ni = niters, s = 0;
-            for (; s < ch; ++s) {
-                if (iter0 + s >= ni) break;
+        // score + replay in sub-chunks of ES_WARPS samples (warp w owns sample sub*ES_WARPS + w):
+        // RANSAC usually shrinks niters after the first few samples, so later ones are never scored
+        int done = 0;                                        // samples of this chunk consumed by the replay
+        for (int sub = 0; sub * ES_WARPS < ch; ++sub) {
+            const int s = sub * ES_WARPS + warp;
+            if (s < ch) {
                 for (int k = 0; k < s_nmodels[s]; ++k) {
-                    s_total_models++;
-                    if (n == 5) {                            // minimal case: first solution, all inliers
-                        if (!s_have) {
-                            s_have = 1;
-                            for (int q = 0; q < 9; ++q) s_bestE[q] = s_models[s][k][q];
-                        }
-                        continue;
-                    }
+                    const double* E = s_models[s][k];
+                    if (n == 5) continue;
                     if (!lmeds) {
-                        const int good = (int)s_score[s][k];
-                        if (good > max((int)best_score, 4)) {
-                            best_score = good;
-                            s_have = 1;
-                            for (int q = 0; q < 9; ++q) s_bestE[q] = s_models[s][k][q];
-                            ni = update_num_iters(a.prob, (double)(n - good) / n, 5, ni);
-                        }
+                        int cnt = 0;
+                        for (int i = lane; i < n; i += 32)
+                            cnt += (sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]) <= thr32);
+                        cnt = warp_sum(cnt);
+                        if (lane == 0) s_score[s][k] = (float)cnt;
                     } else {
-                        const double med = (double)s_score[s][k];
-                        if (med < best_score) {
-                            best_score = med;
-                            s_have = 1;
-                            for (int q = 0; q < 9; ++q) s_bestE[q] = s_models[s][k][q];
-                        }
+                        float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
+                        for (int i = lane; i < n; i += 32) buf[i] = sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]);
+                        __syncwarp();
+                        const float med = warp_select(buf, n, n / 2, lane);
+                        __syncwarp();
+                        if (lane == 0) s_score[s][k] = med;
                     }
                 }
             }
-            s_iter = iter0 + s;
-            s_niters = ni;
-            if (lmeds && s_iter >= ni && s_have) best_score = best_score;   // (sigma computed below)
+            __syncthreads();
+            if (tid == 0) {                                  // sequential bookkeeping of ptsetreg.cpp run()
+                int ni = s_niters;
+                int q = sub * ES_WARPS;
+                const int qend = min(ch, q + ES_WARPS);
+                for (; q < qend; ++q) {
+                    if (iter0 + q >= ni) break;
+                    for (int k = 0; k < s_nmodels[q]; ++k) {
+                        s_total_models++;
+                        if (n == 5) {                        // minimal case: first solution, all inliers
+                            if (!s_have) {
+                                s_have = 1;
+                                for (int c = 0; c < 9; ++c) s_bestE[c] = s_models[q][k][c];
+                            }
+                            continue;
+                        }
+                        if (!lmeds) {
+                            const int good = (int)s_score[q][k];
+                            if (good > max((int)best_score, 4)) {
+                                best_score = good;
+                                s_have = 1;
+                                for (int c = 0; c < 9; ++c) s_bestE[c] = s_models[q][k][c];
+                                ni = update_num_iters(a.prob, (double)(n - good) / n, 5, ni);
+                            }
+                        } else {
+                            const double med = (double)s_score[q][k];
+                            if (med < best_score) {
+                                best_score = med;
+                                s_have = 1;
+                                for (int c = 0; c < 9; ++c) s_bestE[c] = s_models[q][k][c];
+                            }
+                        }
+                    }
+                }
+                s_iter = iter0 + q;
+                s_niters = ni;
+            }
+            __syncthreads();
+            done = s_iter - iter0;
+            if (s_iter >= s_niters) break;                   // the sequential loop would have stopped here
         }
+        (void)done;
         __syncthreads();
     }
 
@@ -282,6 +314,55 @@ __global__ void __launch_bounds__(ES_THREADS) essential_kernel(EssArgs a) {
         a.status[pair] = have ? 0 : EPIVO_ERR_NOMODEL;
     }
     if (tid < 9) a.E[(int64_t)pair * 9 + tid] = have ? s_bestE[tid] : 0.0;
+}
+
+// ---- first samples of every pair, solved at full occupancy --------------------------------
+// sample_kernel: one thread per pair draws the first `count` samples of OpenCV's stream;
+// presolve_kernel: one thread per (pair, sample) runs the 5-point solver.
+__global__ void sample_kernel(int n_pairs, const int32_t* __restrict__ n_arr, int count, int32_t* __restrict__ idx,
+                              unsigned long long* __restrict__ rng_out) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const int n = n_arr[pair];
+    CvRng rng{0xFFFFFFFFFFFFFFFFULL};
+    int32_t* out = idx + (int64_t)pair * count * 5;
+    if (n > 5) {
+        for (int s = 0; s < count; ++s) {
+            int v[5];
+            draw_subset(rng, n, v);
+            for (int k = 0; k < 5; ++k) out[s * 5 + k] = v[k];
+        }
+    } else {
+        for (int s = 0; s < count; ++s)
+            for (int k = 0; k < 5; ++k) out[s * 5 + k] = (n == 5) ? k : -1;
+    }
+    rng_out[pair] = rng.state;
+}
+
+__global__ void __launch_bounds__(64)
+presolve_kernel(int n_pairs, int stride, const double* __restrict__ xn, const int32_t* __restrict__ n_arr, int count,
+                int used, const int32_t* __restrict__ idx, const int32_t* __restrict__ shared_samples,
+                double* __restrict__ models, int32_t* __restrict__ nmodels) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (int64_t)n_pairs * count) return;
+    const int pair = (int)(g / count), s = (int)(g % count);
+    const int n = n_arr[pair];
+    int32_t* nm = nmodels + g;
+    if (n < 5 || s >= used || (n == 5 && s > 0)) { *nm = 0; return; }
+    const int32_t* id = shared_samples ? shared_samples + (int64_t)s * 5 : idx + g * 5;
+    const double* X1 = xn + (int64_t)pair * 4 * stride;
+    double x1[5][2], x2[5][2];
+    for (int k = 0; k < 5; ++k) {
+        const int i = (n == 5) ? k : id[k];
+        x1[k][0] = X1[i]; x1[k][1] = X1[stride + i];
+        x2[k][0] = X1[2 * stride + i]; x2[k][1] = X1[3 * stride + i];
+    }
+    double E[10][9];
+    const int c = fivept::solve(x1, x2, E);
+    *nm = c;
+    double* out = models + g * 90;
+    for (int k = 0; k < c; ++k)
+        for (int q = 0; q < 9; ++q) out[k * 9 + q] = E[k][q];
 }
 
 // ---- K2 alone: one thread per sample ------------------------------------------------
@@ -407,6 +488,22 @@ int epv_normalize_launch(epivo_ctx* ctx, const float* d_p0, const float* d_p1, i
     return EPIVO_OK;
 }
 
+int epv_essential_pre_count(int method, double prob, int max_iters, int m_samples) {
+    // how many leading samples are solved ahead of the per-pair kernel: one chunk for RANSAC (it
+    // nearly always stops within it), every sample for LMedS (its iteration count is fixed)
+    int want = ES_CHUNK;
+    if (method == EPIVO_LMEDS) {
+        double num = log(fmax(1.0 - prob, DBL_MIN)), den = log(1.0 - pow(1.0 - 0.45, 5.0));
+        int ni = (int)rint(num / den);
+        ni = std::max(std::min(ni, max_iters), 3);
+        want = ni;
+    }
+    if (m_samples > 0) want = std::min(want, m_samples);
+    want = std::min(want, std::max(max_iters, 1));
+    int c = (want + ES_CHUNK - 1) / ES_CHUNK * ES_CHUNK;
+    return std::min(c, 4 * ES_CHUNK);
+}
+
 int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
     if (p.n_pairs <= 0) return EPIVO_OK;
     EssArgs a{};
@@ -428,6 +525,24 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
     a.n_models = p.n_models;
     a.status = p.status;
     a.xin = p.xin;
+    a.pre_count = 0;
+    if (p.pre_count > 0 && p.pre_models && p.pre_nmodels && p.pre_idx && p.pre_rng) {
+        const int count = p.pre_count;
+        int used = count;
+        if (p.samples) used = std::min(count, p.m);
+        if (!p.samples) {
+            sample_kernel<<<(p.n_pairs + 127) / 128, 128, 0, ctx->stream>>>(p.n_pairs, p.n, count, p.pre_idx, p.pre_rng);
+            EPV_LAUNCHED(ctx);
+        }
+        const int64_t total = (int64_t)p.n_pairs * count;
+        presolve_kernel<<<(unsigned)((total + 63) / 64), 64, 0, ctx->stream>>>(
+            p.n_pairs, p.stride, p.xn, p.n, count, used, p.pre_idx, p.samples, p.pre_models, p.pre_nmodels);
+        EPV_LAUNCHED(ctx);
+        a.pre_count = count;
+        a.pre_models = p.pre_models;
+        a.pre_nmodels = p.pre_nmodels;
+        a.pre_rng = p.pre_rng;
+    }
     essential_kernel<<<p.n_pairs, ES_THREADS, 0, ctx->stream>>>(a);
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;

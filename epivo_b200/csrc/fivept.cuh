@@ -10,8 +10,8 @@
 //   3. Gauss-Jordan with partial pivoting on the left 10x10 block (OpenCV: inv() * right),
 //   4. B(z) = {rows 4,6,8} - z {rows 5,7,9}, det B(z) = degree-10 polynomial,
 //   5. all complex roots by the Durand-Kerner iteration of cv::solvePoly (same start
-//      values (1+i)^k, same Gauss-Seidel sweep, 300 sweeps at most; stops early once a
-//      whole sweep leaves every root bit-identical, after which further sweeps are no-ops),
+//      values (1+i)^k, same Gauss-Seidel sweep, 300 sweeps at most; stops early once every
+//      update of a sweep is below 1e-13 of its root -- OpenCV keeps sweeping at round-off level),
 //   6. per root with |imag| <= 1e-10: (x, y) from the null vector of B(z) (skipped if its
 //      third component is < 1e-10 in magnitude), E = x E0 + y E1 + z E2 + E3, normalised,
 //   7. (not in OpenCV) each solution is refined by Gauss-Newton on the ten constraints inside the
@@ -125,7 +125,7 @@ __device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)
         pi = pr + pi; pr = t;
     }
     for (int iter = 0; iter < 300; ++iter) {
-        bool changed = false;
+        double maxrel2 = 0.0;                                // max |update|^2 / max(1, |root|^2) of the sweep
         for (int i = 0; i < n; ++i) {
             const double xr = re[i], xi = im[i];
             double nr = c[n], ni = 0.0, dr = c[n], di = 0.0;
@@ -146,11 +146,14 @@ __device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)
             const double s = 1.0 / (dr * dr + di * di);
             const double qr = (nr * dr + ni * di) * s;
             const double qi = (ni * dr - nr * di) * s;
-            const double zr = xr - qr, zi = xi - qi;
-            changed |= (zr != xr) | (zi != xi);
-            re[i] = zr; im[i] = zi;
+            re[i] = xr - qr; im[i] = xi - qi;
+            maxrel2 = fmax(maxrel2, (qr * qr + qi * qi) / fmax(1.0, xr * xr + xi * xi));
         }
-        if (!changed) break;
+        // cv::solvePoly only stops when a sweep's update is exactly zero, which practically never
+        // happens: it runs all 300 sweeps while the roots jitter at round-off level.  Stopping
+        // once every update is below 1e-13 of the root leaves the roots equal to OpenCV's up to
+        // that jitter (the solutions are refined on the constraints afterwards anyway).
+        if (!(maxrel2 > 1e-26)) break;
     }
     return n;
 }

@@ -14,7 +14,8 @@
 #include "stages.cuh"
 
 namespace {
-constexpr int SEQ_CHUNK = 512;
+constexpr int SEQ_CHUNK = 8192;    // pairs per launch group (intermediates are streamed once; no L2 reuse to protect)
+constexpr int SEQ_PRE_MAX = 128;   // max pre-solved samples per pair (4 chunks of 32)
 constexpr int SEQ_STAGES = 7;      // prep, match, finalize, essential, pose, lm, (total)
 constexpr int SEQ_MAX_CHUNKS = 128;
 }  // namespace
@@ -39,6 +40,9 @@ struct epivo_seq {
     double *d_xn = nullptr, *d_xin = nullptr, *d_lmp = nullptr, *d_lmq = nullptr, *d_w = nullptr;
     float* d_err = nullptr;
     int32_t* d_reps = nullptr;
+    double* d_pm = nullptr;
+    int32_t *d_pn = nullptr, *d_pi = nullptr;
+    unsigned long long* d_prng = nullptr;
     // host staging for results
     epivo_pair_result* h_results = nullptr;
     // timing
@@ -211,6 +215,7 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     A(d_lmp, C * 64 * 3); A(d_lmq, C * 64 * 3); A(d_w, C);
     A(d_err, epv_essential_errbuf_floats((int)C, (int)st));
     A(d_reps, 2);
+    A(d_pm, C * SEQ_PRE_MAX * 90); A(d_pn, C * SEQ_PRE_MAX); A(d_pi, C * SEQ_PRE_MAX * 5); A(d_prng, C);
 #undef A
     if (!rc && cudaMallocHost(&s->h_results, P * sizeof(epivo_pair_result)) != cudaSuccess) rc = EPIVO_ERR_CUDA;
     bool ev_ok = true;
@@ -361,6 +366,11 @@ int epivo_seq_run(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair
         ep.n_models = s->d_nmodels + p0;
         ep.status = s->d_status + p0;
         ep.xin = s->d_xin;
+        ep.pre_count = std::min(SEQ_PRE_MAX, epv_essential_pre_count(prm->method, prm->prob, prm->max_iters, 0));
+        ep.pre_models = s->d_pm;
+        ep.pre_nmodels = s->d_pn;
+        ep.pre_idx = s->d_pi;
+        ep.pre_rng = s->d_prng;
         rc = epv_essential_launch(ctx, ep);
         if (rc) return rc;
         EPV_CUDA(ctx, cudaEventRecord(s->ev[c][3], ctx->stream));

@@ -18,7 +18,15 @@ struct EssentialPlan {
     uint8_t* mask;           // [pair][stride]
     int32_t *n_inliers, *iters, *n_models, *status;   // [pair]
     double* xin;             // optional [pair][4][stride]
+    // optional buffers for solving the first pre_count samples of every pair ahead of the per-pair
+    // kernel (pre_count from epv_essential_pre_count; all four must be given)
+    int pre_count;
+    double* pre_models;               // [pair][pre_count][10][9]
+    int32_t* pre_nmodels;             // [pair][pre_count]
+    int32_t* pre_idx;                 // [pair][pre_count][5]
+    unsigned long long* pre_rng;      // [pair]
 };
+int epv_essential_pre_count(int method, double prob, int max_iters, int m_samples);
 int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p);
 size_t epv_essential_errbuf_floats(int n_pairs, int stride);
 int epv_normalize_launch(epivo_ctx* ctx, const float* d_p0, const float* d_p1, int n, int stride, const double K[9],
