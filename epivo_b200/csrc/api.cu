@@ -449,6 +449,7 @@ int epivo_lm_rt_batch(epivo_ctx* ctx, int B, int n_zeta, double epsilon, const i
     lp.out = d_out;
     lp.iters = d_it;
     lp.active = nullptr;
+    lp.single_pair = (n_zeta == 1 && n_rep == 1 && reps[0] == 0 && reps[1] == 0) ? 1 : 0;
     rc = epv_lm_launch(ctx, lp);
     if (rc) return rc;
     EPV_CUDA(ctx, cudaMemcpyAsync(T0s, d_T, nT * 8, cudaMemcpyDeviceToHost, ctx->stream));

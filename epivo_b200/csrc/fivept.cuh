@@ -124,6 +124,7 @@ __device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)
         const double t = pr - pi;
         pi = pr + pi; pr = t;
     }
+    double prev2 = 1e300;
     for (int iter = 0; iter < 300; ++iter) {
         double maxrel2 = 0.0;                                // max |update|^2 / max(1, |root|^2) of the sweep
         for (int i = 0; i < n; ++i) {
@@ -153,7 +154,12 @@ __device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)
         // happens: it runs all 300 sweeps while the roots jitter at round-off level.  Stopping
         // once every update is below 1e-13 of the root leaves the roots equal to OpenCV's up to
         // that jitter (the solutions are refined on the constraints afterwards anyway).
+        // Clustered roots never get below their own noise floor (1e-12 .. 1e-9): once the
+        // update is small and no longer shrinking by 10x per sweep (the quadratic phase is
+        // over), more sweeps only re-draw the noise -- and would stall the whole warp.
         if (!(maxrel2 > 1e-26)) break;
+        if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) break;
+        prev2 = maxrel2;
     }
     return n;
 }

@@ -442,6 +442,170 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     }
 }
 
+// ---- single-pair specialisation: n_zeta = 1, reps = {(0,0)} (the kitti_E.cpp:196 call) --------
+// One WARP per problem, everything in registers: each lane owns up to two correspondences,
+// the 6x6 normal equations are reduced with warp shuffles and solved redundantly by every lane,
+// so the 30 dependent iterations need no shared memory and no block barrier.
+constexpr int LMP_WARPS = 4;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
+    const int lane = threadIdx.x & 31;
+    const int prob = blockIdx.x * LMP_WARPS + (threadIdx.x >> 5);
+    if (prob >= p.B) return;
+    if (p.active && !p.active[prob]) return;
+    const int N = p.N;
+    double* gT = p.T0s + (size_t)prob * 16;
+    const double* gpr = p.pr + (size_t)prob * N * 3;
+    const double* gp_r = p.p_r + (size_t)prob * N * 3;
+    const double w = p.wreps[prob];
+    const double hd = p.huber_delta;
+    Rt T, I;
+    rt_identity(I);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T.R[i * 3 + j] = gT[i * 4 + j];
+        T.t[i] = gT[i * 4 + 3];
+    }
+    // this lane's correspondences
+    double pa[2][3], pb[2][3];
+    bool have[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = lane + 32 * k;
+        have[k] = i < N;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            pa[k][c] = have[k] ? gpr[i * 3 + c] : 1.0;
+            pb[k][c] = have[k] ? gp_r[i * 3 + c] : 1.0;
+        }
+    }
+    double lambda = p.lambda0, prevE = 1e10, Hnorm = 0.0, rnorm = 0.0;
+    int iters = 0;
+    for (int iter = 0; iter < p.max_iters; ++iter) {
+        iters = iter + 1;
+        double H[21], b[6], rsq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 21; ++i) H[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) b[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!have[k]) continue;
+            const double r = w * res_one(T, pa[k], pb[k], hd);                      // [:356-359]
+            double row[6];
+            jac_row(T, I, T, 1.0, pa[k], pb[k], hd, row);                           // [:372-381]
+#pragma unroll
+            for (int c = 0; c < 6; ++c) row[c] *= w;
+            int e = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                for (int c = a; c < 6; ++c) H[e++] += row[a] * row[c];
+                b[a] += row[a] * r;
+            }
+            rsq += r * r;
+        }
+#pragma unroll
+        for (int i = 0; i < 21; ++i) H[i] = warp_sum_d(H[i]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) b[i] = warp_sum_d(b[i]);
+        rsq = warp_sum_d(rsq);
+        rnorm = sqrt(rsq);
+        // augmented, damped system  [H + lambda diag(H) | -b]                      [:403-405]
+        double A[6][7];
+        {
+            int e = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = a; c < 6; ++c) { A[a][c] = H[e]; A[c][a] = H[e]; ++e; }
+        }
+        double hs = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            A[a][a] += lambda * A[a][a];
+            A[a][6] = -b[a];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) hs += A[a][c] * A[a][c];
+        Hnorm = sqrt(hs);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {                       // LU, partial pivoting (uniform across lanes)
+            int pv = k;
+            double best = fabs(A[k][k]);
+#pragma unroll
+            for (int r = k + 1; r < 6; ++r)
+                if (fabs(A[r][k]) > best) { best = fabs(A[r][k]); pv = r; }
+#pragma unroll
+            for (int r = k + 1; r < 6; ++r)
+                if (r == pv) {
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) { const double t = A[k][c]; A[k][c] = A[r][c]; A[r][c] = t; }
+                }
+#pragma unroll
+            for (int r = k + 1; r < 6; ++r) {
+                const double f = A[r][k] / A[k][k];
+#pragma unroll
+                for (int c = k + 1; c < 7; ++c) A[r][c] -= f * A[k][c];
+            }
+        }
+        double d[6], dn = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int r = 5; r >= 0; --r) {
+            double s = A[r][6];
+#pragma unroll
+            for (int c = r + 1; c < 6; ++c) s -= A[r][c] * d[c];
+            d[r] = s / A[r][r];
+            bad |= !(d[r] == d[r]) || isinf(d[r]);
+            dn += d[r] * d[r];
+        }
+        if (bad || sqrt(dn) < p.epsilon) break;                                     // [:407-414]
+        Rt ex, Tn;
+        se3_exp(d, ex);                                                             // [:416-422]
+        rt_mul(T, ex, Tn);
+        double csq = 0.0;                                                           // [:445-456]
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!have[k]) continue;
+            const double r = res_one(Tn, pa[k], pb[k], hd);
+            csq += r * r;
+        }
+        csq = warp_sum_d(csq);
+        const double currE = sqrt(csq);
+        rnorm = currE;
+        if (currE < prevE) {                                                        // [:457-467]
+            prevE = currE;
+            T = Tn;
+            lambda /= 2.0;
+        } else {
+            lambda *= 5.0;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) gT[i * 4 + j] = T.R[i * 3 + j];
+            gT[i * 4 + 3] = T.t[i];
+        }
+        gT[12] = 0.0; gT[13] = 0.0; gT[14] = 0.0; gT[15] = 1.0;
+        p.out[prob].H_norm = Hnorm;
+        p.out[prob].r_norm = rnorm;
+        p.out[prob].lambda = lambda;
+        if (p.iters) p.iters[prob] = iters;
+    }
+}
+
 size_t lm_smem_doubles(int nz, int nr, int D) {
     size_t rt = sizeof(Rt) / sizeof(double);
     return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)LM_TP * (D + 1) + D +
@@ -455,6 +619,11 @@ int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
     if (p.n_zeta < 1 || p.n_zeta > LM_MAX_ZETA)
         EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "n_zeta = %d outside [1, %d]", p.n_zeta, LM_MAX_ZETA);
     if (p.n_rep < 1 || p.N < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_rep = %d, N = %d", p.n_rep, p.N);
+    if (p.single_pair && p.n_zeta == 1 && p.n_rep == 1 && p.N <= 64) {
+        lm_pair_kernel<<<(p.B + LMP_WARPS - 1) / LMP_WARPS, LMP_WARPS * 32, 0, ctx->stream>>>(p);
+        EPV_LAUNCHED(ctx);
+        return EPIVO_OK;
+    }
     LmArgs a;
     a.p = p;
     a.D = 6 * p.n_zeta;

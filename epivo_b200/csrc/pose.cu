@@ -116,9 +116,12 @@ __device__ void decompose_essential(const double* E, double (&R1)[9], double (&R
     for (int i = 0; i < 3; ++i) t[i] = u[2][i];
 }
 
-// cheirality / distance test of one correspondence against one candidate [R | t]
-__device__ __forceinline__ bool triangulate_good(const double* R, const double* t, double a1, double b1, double a2,
-                                                 double b2, double dist) {
+// Cheirality / distance tests of one correspondence against the candidates [R | t] AND [R | -t].
+// The DLT matrix of -t is that of +t with its fourth column negated, so its smallest right
+// singular vector is the same vector with W negated (exactly, IEEE arithmetic being
+// sign-symmetric): one Jacobi solve serves both candidates.  Returns bit 0 = (R,t), bit 1 = (R,-t).
+__device__ __forceinline__ unsigned triangulate_good2(const double* R, const double* t, double a1, double b1,
+                                                      double a2, double b2, double dist) {
     // DLT rows (triangulate.cpp): x*P[2] - P[0], y*P[2] - P[1] for P0 = [I|0], P1 = [R|t]
     double A[4][4] = {{-1.0, 0.0, a1, 0.0},
                       {0.0, -1.0, b1, 0.0},
@@ -148,12 +151,16 @@ __device__ __forceinline__ bool triangulate_good(const double* R, const double* 
         if (k == 3) v = V[i][3];
         Q[i] = v;
     }
-    bool good = (Q[2] * Q[3]) > 0;
+    const double zw = Q[2] * Q[3];
     const double X = Q[0] / Q[3], Y = Q[1] / Q[3], Z = Q[2] / Q[3];
-    good = good && (Z < dist);
-    const double z2 = ((R[6] * X + R[7] * Y) + R[8] * Z) + t[2];
-    good = good && (z2 > 0) && (z2 < dist);
-    return good;
+    const double rz = (R[6] * X + R[7] * Y) + R[8] * Z;
+    // +t: point (X, Y, Z), second-camera depth rz + t2
+    const double z2p = rz + t[2];
+    const bool gp = (zw > 0) && (Z < dist) && (z2p > 0) && (z2p < dist);
+    // -t: W -> -W, i.e. point (-X, -Y, -Z), second-camera depth -rz - t2
+    const double z2n = (-rz) + (-t[2]);
+    const bool gn = (-zw > 0) && (-Z < dist) && (z2n > 0) && (z2n < dist);
+    return (gp ? 1u : 0u) | (gn ? 2u : 0u);
 }
 
 __global__ void __launch_bounds__(PS_THREADS) pose_kernel(PosePlan p) {
@@ -186,16 +193,14 @@ __global__ void __launch_bounds__(PS_THREADS) pose_kernel(PosePlan p) {
     const double* Y2 = X2 + p.stride;
     const uint8_t* im = p.in_mask ? p.in_mask + (int64_t)pair * p.stride : nullptr;
     const double tp[3] = {s_t[0], s_t[1], s_t[2]};
-    const double tn[3] = {-s_t[0], -s_t[1], -s_t[2]};
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     for (int i = tid; i < n; i += PS_THREADS) {
         const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
         unsigned f = 0;
         if (!im || im[i]) {
-            f |= triangulate_good(s_R[0], tp, a1, b1, a2, b2, p.dist_thresh) ? 1u : 0u;
-            f |= triangulate_good(s_R[1], tp, a1, b1, a2, b2, p.dist_thresh) ? 2u : 0u;
-            f |= triangulate_good(s_R[0], tn, a1, b1, a2, b2, p.dist_thresh) ? 4u : 0u;
-            f |= triangulate_good(s_R[1], tn, a1, b1, a2, b2, p.dist_thresh) ? 8u : 0u;
+            const unsigned g1 = triangulate_good2(s_R[0], tp, a1, b1, a2, b2, p.dist_thresh);   // (R1, +-t)
+            const unsigned g2 = triangulate_good2(s_R[1], tp, a1, b1, a2, b2, p.dist_thresh);   // (R2, +-t)
+            f = (g1 & 1u) | ((g2 & 1u) << 1) | ((g1 & 2u) << 1) | ((g2 & 2u) << 2);
         }
         mask[i] = (uint8_t)f;
         c0 += f & 1; c1 += (f >> 1) & 1; c2 += (f >> 2) & 1; c3 += (f >> 3) & 1;

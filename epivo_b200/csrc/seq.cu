@@ -412,6 +412,7 @@ int epivo_seq_run(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair
         lp.out = s->d_lmres + p0;
         lp.iters = s->d_lmiters + p0;
         lp.active = s->d_lmactive + p0;
+        lp.single_pair = 1;
         rc = epv_lm_launch(ctx, lp);
         if (rc) return rc;
         EPV_CUDA(ctx, cudaEventRecord(s->ev[c][5], ctx->stream));

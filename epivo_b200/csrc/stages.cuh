@@ -65,5 +65,6 @@ struct LmPlan {
     epivo_lm_res* out;       // [B]
     int32_t* iters;          // [B]
     const int32_t* active;   // optional [B]: 0 => problem skipped, T0s untouched
+    int single_pair;         // caller asserts reps == {(0,0)}: warp-per-problem kernel when n_zeta == 1, N <= 64
 };
 int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p);
