@@ -16,8 +16,8 @@
 //     lane reads the same train row (shared-memory broadcast, LDS.128).
 //   * keys are dist << 22 | index, so an unsigned min gives "smallest distance, then
 //     lowest index" = OpenCV's first-minimum tie-break.  Row keys stay in registers; column
-//     keys are reduced across the warp with REDUX.MIN, across warps with shared-memory
-//     atomicMin and across CTAs with one global atomicMin per (CTA, train row).
+//     keys are reduced across the warp with REDUX.MIN, across warps through per-warp shared
+//     memory slots and across CTAs with one global atomicMin per (CTA, train row).
 //   * grid = (query blocks, pairs): a batch of frame pairs is one launch.
 #include <algorithm>
 
@@ -69,17 +69,44 @@ __global__ void desc_planes_kernel(const uint32_t* __restrict__ in, uint32_t* __
     out[r * words + half + w] = ((a0 >> 1) & 0x55555555u) | (a1 & 0xAAAAAAAAu);
 }
 
+// 3:2 carry-save compressor: a + b + c = s + 2*carry, bitwise (2 LOP3)
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& carry) {
+    s = a ^ b ^ c;
+    carry = (a & b) | (a & c) | (b & c);
+}
+
+// Distance of one descriptor pair.  POPC runs on the XU pipe at 16 lanes/clk/SM -- a quarter of
+// the ALU (LOP3) rate -- so words are first compressed with carry-save adders and only the
+// compressed words are counted: 3 POPC instead of 4 per 256-bit Hamming2 pair (4 instead of 8
+// for plain Hamming), which balances the XU and ALU pipes.
 template <int WORDS, bool NORM2>
 __device__ __forceinline__ uint32_t desc_dist(const uint32_t (&q)[WORDS], const uint32_t (&t)[WORDS]) {
-    uint32_t d = 0;
+    constexpr int NX = NORM2 ? WORDS / 2 : WORDS;
+    uint32_t x[NX];
     if (NORM2) {
 #pragma unroll
-        for (int w = 0; w < WORDS / 2; ++w) d += __popc((q[w] ^ t[w]) | (q[w + WORDS / 2] ^ t[w + WORDS / 2]));
+        for (int w = 0; w < NX; ++w) x[w] = (q[w] ^ t[w]) | (q[w + NX] ^ t[w + NX]);
     } else {
 #pragma unroll
-        for (int w = 0; w < WORDS; ++w) d += __popc(q[w] ^ t[w]);
+        for (int w = 0; w < NX; ++w) x[w] = q[w] ^ t[w];
     }
-    return d;
+    if (NX == 4) {
+        uint32_t s, c;
+        csa(x[0], x[1], x[2], s, c);
+        return (uint32_t)__popc(s) + (uint32_t)__popc(x[3]) + 2u * (uint32_t)__popc(c);
+    } else if (NX == 8) {
+        uint32_t s0, c0, s1, c1, s2, c2, s3, c3;
+        csa(x[0], x[1], x[2], s0, c0);
+        csa(x[3], x[4], x[5], s1, c1);
+        csa(s0, s1, x[6], s2, c2);
+        csa(c0, c1, c2, s3, c3);
+        return (uint32_t)__popc(s2) + (uint32_t)__popc(x[7]) + 2u * (uint32_t)__popc(s3) + 4u * (uint32_t)__popc(c3);
+    } else {
+        uint32_t d = 0;
+#pragma unroll
+        for (int w = 0; w < NX; ++w) d += __popc(x[w]);
+        return d;
+    }
 }
 
 template <int WORDS, bool NORM2, bool TOP2>
@@ -88,12 +115,12 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
                   int nt, uint32_t* __restrict__ rowkey, uint32_t* __restrict__ rowkey2,
                   uint32_t* __restrict__ colkey, int stride, int tiles_per_split, int64_t part_stride) {
     __shared__ __align__(128) uint32_t s_tile[2][MT_TILE * WORDS];
-    __shared__ uint32_t s_col[2][MT_TILE];
+    __shared__ uint32_t s_col[2][MT_THREADS / 32][MT_TILE];   // per-warp column minima of the tile in flight
     __shared__ __align__(8) uint64_t s_bar[2];
 
     const int pair = blockIdx.y;
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
+    const int lane = tid & 31, warp = tid >> 5;
     const int qbase = blockIdx.x * (MT_THREADS * MT_RQ);
     if (qbase >= nq) return;
     const uint32_t* qrows = desc + (q0 + (int64_t)pair * qs) * WORDS;
@@ -115,7 +142,6 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
         mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * MT_TILE; i += MT_THREADS) (&s_col[0][0])[i] = 0xFFFFFFFFu;
     __syncthreads();
     if (tid == 0) {
         for (int b = 0; b < 2 && b < n_tiles; ++b) {
@@ -168,18 +194,20 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
                 t[4 * w + 3] = v.w;
             }
             uint32_t cmin = 0xFFFFFFFFu;
+            const uint32_t jj = jglob0 + jbase + j;
 #pragma unroll
             for (int r = 0; r < MT_RQ; ++r) {
-                uint32_t d = desc_dist<WORDS, NORM2>(q[r], t);
-                uint32_t rk = (d << EPV_KEY_SHIFT) | (jglob0 + jbase + j);
+                const uint32_t d = desc_dist<WORDS, NORM2>(q[r], t);
+                // keys as multiply-add so that they issue on the FMA pipe (IMAD), not the ALU
+                const uint32_t rk = d * (1u << EPV_KEY_SHIFT) + jj;
                 if (TOP2) {
                     best2[r] = min(best2[r], max(best[r], rk));
                 }
                 best[r] = min(best[r], rk);
-                cmin = min(cmin, (d << EPV_KEY_SHIFT) | qidx[r]);
+                cmin = min(cmin, d * (1u << EPV_KEY_SHIFT) + qidx[r]);
             }
             cmin = __reduce_min_sync(0xFFFFFFFFu, cmin);
-            if (lane == 0) atomicMin(&s_col[buf][j], cmin);
+            if (lane == 0) s_col[buf][warp][j] = cmin;          // plain store: one slot per (warp, train row)
         }
         __syncthreads();                                       // tile + its column keys are complete
         if (tid == 0 && tile + 2 < n_tiles) {
@@ -189,10 +217,12 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
             tma_load_1d(s_tile[buf], trows + (int64_t)(tile + 2) * MT_TILE * WORDS, bytes, &s_bar[buf]);
         }
         for (int j = tid; j < rows; j += MT_THREADS) {
-            atomicMin(&colkey[(int64_t)pair * stride + jbase + j], s_col[buf][j]);
-            s_col[buf][j] = 0xFFFFFFFFu;
+            uint32_t m = s_col[buf][0][j];
+#pragma unroll
+            for (int w = 1; w < MT_THREADS / 32; ++w) m = min(m, s_col[buf][w][j]);
+            atomicMin(&colkey[(int64_t)pair * stride + jbase + j], m);
         }
-        // s_col[buf] is next touched two tiles later, after at least one more __syncthreads
+        // s_col[buf] is next written two tiles later, after at least one more __syncthreads
     }
 
 #pragma unroll
