@@ -71,7 +71,9 @@ SIGNATURES = {
     "epivo_seq_upload": (_i, [_vp, _i, _i, _vp, _vp]),
     "epivo_seq_run": (_i, [_vp, C.POINTER(PipelineParams), _i, _i]),
     "epivo_seq_download": (_i, [_vp, _vp, _i, _i]),
+    "epivo_seq_process": (_i, [_vp, C.POINTER(PipelineParams), _i, _vp, _vp, _vp]),
     "epivo_seq_stage_ms": (_i, [_vp, _vp, _i]),
+    "epivo_seq_set_overlap": (_i, [_vp, _i]),
     "epivo_seq_get_matches": (_i, [_vp, _i, _vp, _vp, _vp, _pi]),
     "epivo_seq_get_masks": (_i, [_vp, _i, _vp, _pi, _vp, _pi]),
     "epivo_microbench": (_i, [_vp, _i, C.POINTER(_d)]),

@@ -318,12 +318,29 @@ class SequencePipeline:
     def run(self, params: PipelineParams, first_pair: int, n_pairs: int):
         self.ctx.check(self.ctx.lib.epivo_seq_run(self.h, C.byref(params), int(first_pair), int(n_pairs)))
 
+    def process(self, params: PipelineParams, kps: np.ndarray, descs: np.ndarray, out=None):
+        """Host buffers in, per-pair results out (the reference-facing call): the upload is pipelined
+        under the matcher; returns after the results are on the host."""
+        assert kps.dtype == np.float32 and descs.dtype == np.uint8
+        assert kps.flags.c_contiguous and descs.flags.c_contiguous
+        F = kps.shape[0]
+        assert kps.shape == (F, self.kp, 2) and descs.shape == (F, self.kp, 32)
+        if out is None:
+            out = np.zeros(F - 1, dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and out.shape[0] >= F - 1
+        self.ctx.check(self.ctx.lib.epivo_seq_process(self.h, C.byref(params), F, _p(kps), _p(descs), _p(out)))
+        return out
+
     def download(self, first_pair: int, n_pairs: int, out=None):
         if out is None:
             out = np.zeros(n_pairs, dtype=RESULT_DTYPE)
         assert out.dtype == RESULT_DTYPE and out.shape[0] >= n_pairs
         self.ctx.check(self.ctx.lib.epivo_seq_download(self.h, _p(out), int(first_pair), int(n_pairs)))
         return out
+
+    def set_overlap(self, on: bool):
+        """Two-stream pipelining of matcher and geometry across pair groups (default off)."""
+        self.ctx.check(self.ctx.lib.epivo_seq_set_overlap(self.h, 1 if on else 0))
 
     def stage_ms(self):
         ms = np.zeros(16, dtype=np.float32)

@@ -13,7 +13,9 @@ OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libepivo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--fmad=false", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# FMA contraction is on: every place that must reproduce OpenCV's un-fused arithmetic bit for bit
+# (Sampson error, K-normalisation) spells its operations with __dmul_rn / __dadd_rn / __fma_rn.
 
 
 def _stale(target: str, deps: list[str]) -> bool:

@@ -87,6 +87,7 @@ struct MatchPlan {
     uint32_t* colkey;          // [n_pairs][stride]
     int stride;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // optional: recorded right around the tile kernel
+    int pad_smem = 0;          // extra dynamic shared memory per CTA (bytes) to cap resident CTAs per SM
 };
 int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass);
 int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt);   // train splits that fill the GPU

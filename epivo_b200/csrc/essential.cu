@@ -63,18 +63,20 @@ __device__ int update_num_iters(double p, double ep, int model_points, int max_i
 }
 
 // EMEstimatorCallback::computeError for one correspondence, OpenCV's operation order
-// (Matx products accumulate left to right from 0; the library is built without FMA
-// contraction, and so is this file: --fmad=false).
+// (Matx products accumulate left to right from 0; OpenCV's calib3d is built without FMA
+// contraction, so every operation here is an explicit round-to-nearest intrinsic).
 __device__ __forceinline__ float sampson_f32(const double* __restrict__ E, double a1, double b1, double a2,
                                              double b2) {
-    const double ex0 = (E[0] * a1 + E[1] * b1) + E[2];
-    const double ex1 = (E[3] * a1 + E[4] * b1) + E[5];
-    const double ex2 = (E[6] * a1 + E[7] * b1) + E[8];
-    const double et0 = (E[0] * a2 + E[3] * b2) + E[6];
-    const double et1 = (E[1] * a2 + E[4] * b2) + E[7];
-    const double x2tEx1 = (a2 * ex0 + b2 * ex1) + ex2;
-    const double den = ((ex0 * ex0 + ex1 * ex1) + et0 * et0) + et1 * et1;
-    return (float)(x2tEx1 * x2tEx1 / den);
+    // explicit round-to-nearest multiplies and adds: never contracted into FMAs
+    const double ex0 = __dadd_rn(__dadd_rn(__dmul_rn(E[0], a1), __dmul_rn(E[1], b1)), E[2]);
+    const double ex1 = __dadd_rn(__dadd_rn(__dmul_rn(E[3], a1), __dmul_rn(E[4], b1)), E[5]);
+    const double ex2 = __dadd_rn(__dadd_rn(__dmul_rn(E[6], a1), __dmul_rn(E[7], b1)), E[8]);
+    const double et0 = __dadd_rn(__dadd_rn(__dmul_rn(E[0], a2), __dmul_rn(E[3], b2)), E[6]);
+    const double et1 = __dadd_rn(__dadd_rn(__dmul_rn(E[1], a2), __dmul_rn(E[4], b2)), E[7]);
+    const double x2tEx1 = __dadd_rn(__dadd_rn(__dmul_rn(a2, ex0), __dmul_rn(b2, ex1)), ex2);
+    const double den = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(ex0, ex0), __dmul_rn(ex1, ex1)), __dmul_rn(et0, et0)),
+                                 __dmul_rn(et1, et1));
+    return (float)__ddiv_rn(__dmul_rn(x2tEx1, x2tEx1), den);
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -119,7 +121,7 @@ struct EssArgs {
     double* xin;                // optional compacted inliers [pair][4][stride] (E3, kitti_E.cpp:106-112)
 };
 
-__global__ void __launch_bounds__(ES_THREADS) essential_kernel(EssArgs a) {
+__global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
     __shared__ double s_models[ES_CHUNK][10][9];
     __shared__ int s_nmodels[ES_CHUNK];
     __shared__ int s_idx[ES_CHUNK][5];
@@ -196,17 +198,30 @@ __global__ void __launch_bounds__(ES_THREADS) essential_kernel(EssArgs a) {
         int done = 0;                                        // samples of this chunk consumed by the replay
         for (int sub = 0; sub * ES_WARPS < ch; ++sub) {
             const int s = sub * ES_WARPS + warp;
-            if (s < ch) {
-                for (int k = 0; k < s_nmodels[s]; ++k) {
-                    const double* E = s_models[s][k];
-                    if (n == 5) continue;
-                    if (!lmeds) {
-                        int cnt = 0;
-                        for (int i = lane; i < n; i += 32)
-                            cnt += (sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]) <= thr32);
-                        cnt = warp_sum(cnt);
-                        if (lane == 0) s_score[s][k] = (float)cnt;
-                    } else {
+            if (s < ch && n != 5) {
+                const int nm = s_nmodels[s];
+                if (!lmeds) {
+                    // point-outer loop: a correspondence is loaded once and scored against every
+                    // model of this warp's sample (models broadcast from shared memory)
+                    int cnt[10];
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) cnt[k] = 0;
+                    for (int i = lane; i < n; i += 32) {
+                        const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
+#pragma unroll
+                        for (int k = 0; k < 10; ++k)
+                            if (k < nm) cnt[k] += (sampson_f32(s_models[s][k], a1, b1, a2, b2) <= thr32);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+                        if (k < nm) {
+                            const int c = warp_sum(cnt[k]);
+                            if (lane == 0) s_score[s][k] = (float)c;
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < nm; ++k) {
+                        const double* E = s_models[s][k];
                         float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
                         for (int i = lane; i < n; i += 32) buf[i] = sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]);
                         __syncwarp();
@@ -339,7 +354,7 @@ __global__ void sample_kernel(int n_pairs, const int32_t* __restrict__ n_arr, in
     rng_out[pair] = rng.state;
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 8)
 presolve_kernel(int n_pairs, int stride, const double* __restrict__ xn, const int32_t* __restrict__ n_arr, int count,
                 int used, const int32_t* __restrict__ idx, const int32_t* __restrict__ shared_samples,
                 double* __restrict__ models, int32_t* __restrict__ nmodels) {

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(MT_THREADS)
 match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int64_t t0, int64_t ts, int nq,
                   int nt, uint32_t* __restrict__ rowkey, uint32_t* __restrict__ rowkey2,
                   uint32_t* __restrict__ colkey, int stride, int tiles_per_split, int64_t part_stride) {
+    extern __shared__ uint32_t s_occupancy_pad[];   // unused: sized by the host to cap CTAs per SM (co-scheduling)
     __shared__ __align__(128) uint32_t s_tile[2][MT_TILE * WORDS];
     __shared__ uint32_t s_col[2][MT_THREADS / 32][MT_TILE];   // per-warp column minima of the tile in flight
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -321,10 +322,14 @@ int launch_words(epivo_ctx* ctx, const MatchPlan& mp, const uint32_t* src) {
     const int64_t part = (int64_t)mp.n_pairs * mp.stride;
     dim3 block(MT_THREADS);
     const bool n2 = mp.norm == EPIVO_NORM_HAMMING2;
-#define EPV_MT(N2, T2)                                                                                    \
-    match_tile_kernel<WORDS, N2, T2><<<grid, block, 0, ctx->stream>>>(src, mp.q0, mp.qs, mp.t0, mp.ts,   \
-                                                                      mp.nq, mp.nt, mp.rowkey, mp.rowkey2, \
-                                                                      mp.colkey, mp.stride, tps, part)
+#define EPV_MT(N2, T2)                                                                                     \
+    do {                                                                                                   \
+        if (mp.pad_smem > 0)                                                                               \
+            cudaFuncSetAttribute(match_tile_kernel<WORDS, N2, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 mp.pad_smem);                                                             \
+        match_tile_kernel<WORDS, N2, T2><<<grid, block, mp.pad_smem, ctx->stream>>>(                       \
+            src, mp.q0, mp.qs, mp.t0, mp.ts, mp.nq, mp.nt, mp.rowkey, mp.rowkey2, mp.colkey, mp.stride, tps, part); \
+    } while (0)
     if (n2 && mp.top2) EPV_MT(true, true);
     else if (n2) EPV_MT(true, false);
     else if (mp.top2) EPV_MT(false, true);

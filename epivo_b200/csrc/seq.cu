@@ -5,6 +5,7 @@
 // of kitti_ba.cpp:641-693 as the correspondence source.  Pairs are processed in chunks so
 // that a chunk's intermediates (keys, matches, normalised points, masks) stay L2-resident;
 // everything is enqueued on the context stream with no host synchronisation in between.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -14,10 +15,11 @@
 #include "stages.cuh"
 
 namespace {
-constexpr int SEQ_CHUNK = 8192;    // pairs per launch group (intermediates are streamed once; no L2 reuse to protect)
+constexpr int SEQ_CHUNK = 8192;          // pairs per launch group (single stream: large groups, fewer tails)
+constexpr int SEQ_CHUNK_OVERLAP = 1024;  // group size when the two-stream pipelining is switched on
 constexpr int SEQ_PRE_MAX = 128;   // max pre-solved samples per pair (4 chunks of 32)
 constexpr int SEQ_STAGES = 7;      // prep, match, finalize, essential, pose, lm, (total)
-constexpr int SEQ_MAX_CHUNKS = 128;
+constexpr int SEQ_MAX_CHUNKS = 256;
 }  // namespace
 
 struct epivo_seq {
@@ -49,7 +51,12 @@ struct epivo_seq {
     cudaEvent_t ev[SEQ_MAX_CHUNKS][SEQ_STAGES] = {};
     cudaEvent_t evk[SEQ_MAX_CHUNKS][2] = {};     // around the matcher tile kernel alone
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    int last_chunks = 0;
+    cudaStream_t stream2 = nullptr;          // geometry stream (FP64 kernels) -- overlaps the integer-bound matcher
+    cudaEvent_t ev_matched[SEQ_MAX_CHUNKS] = {};
+    cudaEvent_t ev_geo_done = nullptr;
+    int overlap = 0;   // measured on B200: co-running the matcher and the FP64 kernels gains nothing
+    int match_pad = 0;
+    int last_mgroups = 0, last_ggroups = 0;
     int last_n_pairs = 0, last_first = 0;
     std::vector<void*> allocs;
 };
@@ -199,7 +206,7 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     s->stride = (kp_per_frame + 31) / 32 * 32;
     const size_t F = max_frames, P = max_frames - 1, st = s->stride, kp = kp_per_frame;
     s->chunk = (int)std::min<size_t>(SEQ_CHUNK, P);
-    const size_t C = s->chunk;
+    const size_t C = P;        // group-scoped buffers are allocated for every pair, so groups never alias
     int rc = 0;
 #define A(ptr, count) if (!rc) rc = seq_alloc(s, &s->ptr, (count))
     A(d_kps, F * kp * 2);
@@ -224,7 +231,16 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
         for (int k = 0; k < SEQ_STAGES; ++k) ev_ok &= cudaEventCreate(&s->ev[c][k]) == cudaSuccess;
         for (int k = 0; k < 2; ++k) ev_ok &= cudaEventCreate(&s->evk[c][k]) == cudaSuccess;
     }
+    for (int c = 0; c < SEQ_MAX_CHUNKS && ev_ok; ++c)
+        ev_ok &= cudaEventCreateWithFlags(&s->ev_matched[c], cudaEventDisableTiming) == cudaSuccess;
     ev_ok = ev_ok && cudaEventCreate(&s->ev_begin) == cudaSuccess && cudaEventCreate(&s->ev_end) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&s->ev_geo_done, cudaEventDisableTiming) == cudaSuccess;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);       // hi = numerically lowest = highest priority
+        (void)hi;
+        ev_ok = ev_ok && cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    }
     if (rc || !ev_ok) {
         epivo_seq_destroy(s);
         if (!rc) EPV_FAIL(ctx, EPIVO_ERR_CUDA, "event creation failed");
@@ -249,6 +265,10 @@ void epivo_seq_destroy(epivo_seq* s) {
     for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
         for (int k = 0; k < 2; ++k)
             if (s->evk[c][k]) cudaEventDestroy(s->evk[c][k]);
+    for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
+        if (s->ev_matched[c]) cudaEventDestroy(s->ev_matched[c]);
+    if (s->ev_geo_done) cudaEventDestroy(s->ev_geo_done);
+    if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
     delete s;
@@ -268,164 +288,257 @@ int epivo_seq_upload(epivo_seq* s, int first_frame, int n_frames, const float* k
     return EPIVO_OK;
 }
 
-int epivo_seq_run(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair, int n_pairs) {
-    if (!s || !prm) return EPIVO_ERR_INVALID;
+int epivo_seq_set_overlap(epivo_seq* s, int overlap) {
+    if (!s) return EPIVO_ERR_INVALID;
+    s->overlap = overlap ? 1 : 0;
+    return EPIVO_OK;
+}
+
+// geometry of one group on the context's CURRENT stream (the caller selects the stream)
+static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int c, int p0, int np) {
+    epivo_ctx* ctx = s->ctx;
+    const int st = s->stride;
+    const size_t o = (size_t)p0;                 // group-scoped buffers are indexed by absolute pair
+    int rc;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev[c][2], ctx->stream));
+    EssentialPlan ep{};
+    ep.n_pairs = np;
+    ep.stride = st;
+    ep.xn = s->d_xn + o * 4 * st;
+    ep.n = s->d_nmatch + p0;
+    ep.method = prm->method;
+    ep.prob = prm->prob;
+    ep.thresh = prm->threshold / ((prm->K[0] + prm->K[4]) / 2.0);
+    ep.max_iters = prm->max_iters;
+    ep.samples = nullptr;
+    ep.m = 0;
+    ep.errbuf = s->d_err + epv_essential_errbuf_floats(p0, st);
+    ep.E = s->d_E + o * 9;
+    ep.mask = s->d_emask + o * st;
+    ep.n_inliers = s->d_ninl + p0;
+    ep.iters = s->d_iters + p0;
+    ep.n_models = s->d_nmodels + p0;
+    ep.status = s->d_status + p0;
+    ep.xin = s->d_xin + o * 4 * st;
+    ep.pre_count = std::min(SEQ_PRE_MAX, epv_essential_pre_count(prm->method, prm->prob, prm->max_iters, 0));
+    ep.pre_models = s->d_pm + o * SEQ_PRE_MAX * 90;
+    ep.pre_nmodels = s->d_pn + o * SEQ_PRE_MAX;
+    ep.pre_idx = s->d_pi + o * SEQ_PRE_MAX * 5;
+    ep.pre_rng = s->d_prng + o;
+    rc = epv_essential_launch(ctx, ep);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev[c][3], ctx->stream));
+    PosePlan pp{};
+    pp.n_pairs = np;
+    pp.stride = st;
+    pp.E = s->d_E + o * 9;
+    pp.xn = s->d_xin + o * 4 * st;
+    pp.n = s->d_ninl + p0;
+    pp.in_mask = nullptr;
+    pp.dist_thresh = prm->dist_thresh;
+    pp.R = s->d_R + o * 9;
+    pp.t = s->d_t + o * 3;
+    pp.mask = s->d_pmask + o * st;
+    pp.n_good = s->d_ngood + p0;
+    pp.skip = s->d_status + p0;
+    rc = epv_pose_launch(ctx, pp);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev[c][4], ctx->stream));
+    lm_prep_kernel<<<np, 64, 0, ctx->stream>>>(np, st, *prm, s->d_R + o * 9, s->d_t + o * 3, s->d_status + p0,
+                                               s->d_ninl + p0, s->d_ngood + p0, s->d_xin + o * 4 * st,
+                                               s->d_T0 + o * 16, s->d_T + o * 16, s->d_lmp + o * 64 * 3,
+                                               s->d_lmq + o * 64 * 3, s->d_w + p0, s->d_lmactive + p0);
+    EPV_LAUNCHED(ctx);
+    LmPlan lp{};
+    lp.B = np;
+    lp.n_zeta = 1;
+    lp.n_rep = 1;
+    lp.N = prm->lm_points;
+    lp.reps = s->d_reps;
+    lp.wreps = s->d_w + p0;
+    lp.epsilon = prm->lm_epsilon;
+    lp.lambda0 = prm->lm_lambda0;
+    lp.huber_delta = prm->huber_delta;
+    lp.max_iters = prm->lm_max_iters;
+    lp.T0s = s->d_T + o * 16;
+    lp.pr = s->d_lmp + o * 64 * 3;
+    lp.p_r = s->d_lmq + o * 64 * 3;
+    lp.out = s->d_lmres + p0;
+    lp.iters = s->d_lmiters + p0;
+    lp.active = s->d_lmactive + p0;
+    lp.single_pair = 1;
+    rc = epv_lm_launch(ctx, lp);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev[c][5], ctx->stream));
+    finish_kernel<<<(np + 127) / 128, 128, 0, ctx->stream>>>(
+        np, *prm, s->d_E + o * 9, s->d_R + o * 9, s->d_t + o * 3, s->d_T0 + o * 16, s->d_T + o * 16, s->d_lmres + p0,
+        s->d_lmiters + p0, s->d_lmactive + p0, s->d_nmatch + p0, s->d_ninl + p0, s->d_ngood + p0, s->d_iters + p0,
+        s->d_nmodels + p0, s->d_results + p0);
+    EPV_LAUNCHED(ctx);
+    EPV_CUDA(ctx, cudaEventRecord(s->ev[c][6], ctx->stream));
+    return EPIVO_OK;
+}
+
+// matcher + finalize of one group on the context stream
+static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, int p0, int np) {
+    epivo_ctx* ctx = s->ctx;
+    const int kp = s->kp, st = s->stride;
+    const size_t o = (size_t)p0;
+    int rc;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev[c][0], ctx->stream));
+    MatchPlan mp{};
+    mp.desc = s->d_desc + o * kp * 8;                     // group-local view: frames p0 .. p0+np
+    mp.planes = s->d_planes + o * kp * 8;
+    // bit planes of the group's frames; the first frame of a later group was already converted as
+    // the last frame of the previous one, converting it again writes the same values
+    mp.total_rows = (int64_t)(np + 1) * kp;
+    mp.words = 8;
+    mp.norm = prm->norm;
+    mp.top2 = prm->match_mode == EPIVO_MATCH_RATIO;
+    mp.n_pairs = np;
+    mp.q0 = 0;
+    mp.qs = kp;
+    mp.t0 = kp;
+    mp.ts = kp;
+    mp.nq = kp;
+    mp.nt = kp;
+    mp.tsplits = 1;
+    mp.rowkey = s->d_rowkey + o * st;
+    mp.rowkey2 = s->d_rowkey2 + o * st;
+    mp.colkey = s->d_colkey + o * st;
+    mp.stride = st;
+    mp.ev0 = s->evk[c][0];
+    mp.ev1 = s->evk[c][1];
+    mp.pad_smem = s->match_pad;
+    rc = epv_match_launch(ctx, mp, true);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev[c][1], ctx->stream));
+    FinalizePlan fp{};
+    fp.n_pairs = np;
+    fp.nq = kp;
+    fp.nt = kp;
+    fp.stride = st;
+    fp.mode = prm->match_mode;
+    fp.tsplits = 1;
+    fp.ratio = prm->ratio;
+    fp.rowkey = s->d_rowkey + o * st;
+    fp.rowkey2 = s->d_rowkey2 + o * st;
+    fp.colkey = s->d_colkey + o * st;
+    fp.mq = s->d_mq + o * st;
+    fp.mt = s->d_mt + o * st;
+    fp.md = s->d_md + o * st;
+    fp.md2 = nullptr;
+    fp.n_matches = s->d_nmatch + p0;
+    fp.kps = s->d_kps + o * kp * 2;
+    fp.q0 = 0;
+    fp.qs = kp;
+    fp.t0 = kp;
+    fp.ts = kp;
+    fp.p0 = nullptr;
+    fp.p1 = nullptr;
+    fp.xn = s->d_xn + o * 4 * st;
+    const double ax = 1.0 / prm->K[0], ay = 1.0 / prm->K[4];
+    fp.ax = ax;
+    fp.bx = -prm->K[2] * ax;
+    fp.ay = ay;
+    fp.by = -prm->K[5] * ay;
+    rc = epv_finalize_launch(ctx, fp);
+    if (rc) return rc;
+    return EPIVO_OK;
+}
+
+// Common executor.  With host buffers (h_kps/h_desc != NULL) the frames are uploaded in pieces on
+// the copy stream and every matcher group starts as soon as its frames have landed, so the
+// host->device transfer hides under the matcher; the geometry then runs once over all pairs.
+static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair, int n_pairs,
+                       const float* h_kps, const uint8_t* h_desc) {
     epivo_ctx* ctx = s->ctx;
     if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
         EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range [%d,+%d) outside [0,%d)", first_pair, n_pairs, s->max_frames - 1);
     if (prm->lm_points < 1 || prm->lm_points > 64) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "lm_points must be in [1,64]");
     if (prm->method != EPIVO_RANSAC && prm->method != EPIVO_LMEDS) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "method");
     if (prm->match_mode < 0 || prm->match_mode > 2) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "match_mode");
+    if (prm->norm != EPIVO_NORM_HAMMING && prm->norm != EPIVO_NORM_HAMMING2) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "norm");
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int kp = s->kp, st = s->stride;
-    const int n_chunks = (n_pairs + s->chunk - 1) / s->chunk;
-    if (n_chunks > SEQ_MAX_CHUNKS) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "too many chunks");
-    s->last_chunks = n_chunks;
+    cudaStream_t main_stream = ctx->stream;
+    const bool upload = h_kps != nullptr;
+    const bool overlap = s->overlap && !upload;
+    // matcher groups / geometry groups (event slots: matcher [0, HALF), geometry [HALF, 2*HALF))
+    constexpr int HALF = SEQ_MAX_CHUNKS / 2;
+    int mchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
+    if (upload) mchunk = std::max(256, (n_pairs + 3) / 4);          // four upload/match pieces
+    const int gchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
+    const int n_m = (n_pairs + mchunk - 1) / mchunk, n_g = (n_pairs + gchunk - 1) / gchunk;
+    if (n_m > HALF || n_g > HALF) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "too many pair groups");
+    s->last_mgroups = n_m;
+    s->last_ggroups = n_g;
     s->last_n_pairs = n_pairs;
     s->last_first = first_pair;
-    EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, ctx->stream));
-    const double ax = 1.0 / prm->K[0], ay = 1.0 / prm->K[4];
-    for (int c = 0; c < n_chunks; ++c) {
-        const int p0 = first_pair + c * s->chunk;
-        const int np = std::min(s->chunk, first_pair + n_pairs - p0);
-        int rc;
-        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][0], ctx->stream));
-        MatchPlan mp{};
-        mp.desc = s->d_desc + (size_t)p0 * kp * 8;          // chunk-local view: frames p0 .. p0+np
-        mp.planes = s->d_planes + (size_t)p0 * kp * 8;
-        // bit planes of the chunk's frames; the first frame of a later chunk was already
-        // converted as the last frame of the previous one, converting it again is idempotent
-        mp.total_rows = (int64_t)(np + 1) * kp;
-        mp.words = 8;
-        mp.norm = prm->norm;
-        mp.top2 = prm->match_mode == EPIVO_MATCH_RATIO;
-        mp.n_pairs = np;
-        mp.q0 = 0;
-        mp.qs = kp;
-        mp.t0 = kp;
-        mp.ts = kp;
-        mp.nq = kp;
-        mp.nt = kp;
-        mp.tsplits = 1;
-        mp.rowkey = s->d_rowkey;
-        mp.rowkey2 = s->d_rowkey2;
-        mp.colkey = s->d_colkey;
-        mp.stride = st;
-        mp.ev0 = s->evk[c][0];
-        mp.ev1 = s->evk[c][1];
-        rc = epv_match_launch(ctx, mp, true);
-        if (rc) return rc;
-        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][1], ctx->stream));
-        FinalizePlan fp{};
-        fp.n_pairs = np;
-        fp.nq = kp;
-        fp.nt = kp;
-        fp.stride = st;
-        fp.mode = prm->match_mode;
-        fp.tsplits = 1;
-        fp.ratio = prm->ratio;
-        fp.rowkey = s->d_rowkey;
-        fp.rowkey2 = s->d_rowkey2;
-        fp.colkey = s->d_colkey;
-        fp.mq = s->d_mq + (size_t)p0 * st;
-        fp.mt = s->d_mt + (size_t)p0 * st;
-        fp.md = s->d_md + (size_t)p0 * st;
-        fp.md2 = nullptr;
-        fp.n_matches = s->d_nmatch + p0;
-        fp.kps = s->d_kps + (size_t)p0 * kp * 2;
-        fp.q0 = 0;
-        fp.qs = kp;
-        fp.t0 = kp;
-        fp.ts = kp;
-        fp.p0 = nullptr;
-        fp.p1 = nullptr;
-        fp.xn = s->d_xn;
-        fp.ax = ax;
-        fp.bx = -prm->K[2] * ax;
-        fp.ay = ay;
-        fp.by = -prm->K[5] * ay;
-        rc = epv_finalize_launch(ctx, fp);
-        if (rc) return rc;
-        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][2], ctx->stream));
-        EssentialPlan ep{};
-        ep.n_pairs = np;
-        ep.stride = st;
-        ep.xn = s->d_xn;
-        ep.n = s->d_nmatch + p0;
-        ep.method = prm->method;
-        ep.prob = prm->prob;
-        ep.thresh = prm->threshold / ((prm->K[0] + prm->K[4]) / 2.0);
-        ep.max_iters = prm->max_iters;
-        ep.samples = nullptr;
-        ep.m = 0;
-        ep.errbuf = s->d_err;
-        ep.E = s->d_E + (size_t)p0 * 9;
-        ep.mask = s->d_emask + (size_t)p0 * st;
-        ep.n_inliers = s->d_ninl + p0;
-        ep.iters = s->d_iters + p0;
-        ep.n_models = s->d_nmodels + p0;
-        ep.status = s->d_status + p0;
-        ep.xin = s->d_xin;
-        ep.pre_count = std::min(SEQ_PRE_MAX, epv_essential_pre_count(prm->method, prm->prob, prm->max_iters, 0));
-        ep.pre_models = s->d_pm;
-        ep.pre_nmodels = s->d_pn;
-        ep.pre_idx = s->d_pi;
-        ep.pre_rng = s->d_prng;
-        rc = epv_essential_launch(ctx, ep);
-        if (rc) return rc;
-        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][3], ctx->stream));
-        PosePlan pp{};
-        pp.n_pairs = np;
-        pp.stride = st;
-        pp.E = s->d_E + (size_t)p0 * 9;
-        pp.xn = s->d_xin;
-        pp.n = s->d_ninl + p0;
-        pp.in_mask = nullptr;
-        pp.dist_thresh = prm->dist_thresh;
-        pp.R = s->d_R + (size_t)p0 * 9;
-        pp.t = s->d_t + (size_t)p0 * 3;
-        pp.mask = s->d_pmask + (size_t)p0 * st;
-        pp.n_good = s->d_ngood + p0;
-        pp.skip = s->d_status + p0;
-        rc = epv_pose_launch(ctx, pp);
-        if (rc) return rc;
-        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][4], ctx->stream));
-        lm_prep_kernel<<<np, 64, 0, ctx->stream>>>(np, st, *prm, s->d_R + (size_t)p0 * 9, s->d_t + (size_t)p0 * 3,
-                                                   s->d_status + p0, s->d_ninl + p0, s->d_ngood + p0, s->d_xin,
-                                                   s->d_T0 + (size_t)p0 * 16, s->d_T + (size_t)p0 * 16, s->d_lmp,
-                                                   s->d_lmq, s->d_w, s->d_lmactive + p0);
-        EPV_LAUNCHED(ctx);
-        LmPlan lp{};
-        lp.B = np;
-        lp.n_zeta = 1;
-        lp.n_rep = 1;
-        lp.N = prm->lm_points;
-        lp.reps = s->d_reps;
-        lp.wreps = s->d_w;
-        lp.epsilon = prm->lm_epsilon;
-        lp.lambda0 = prm->lm_lambda0;
-        lp.huber_delta = prm->huber_delta;
-        lp.max_iters = prm->lm_max_iters;
-        lp.T0s = s->d_T + (size_t)p0 * 16;
-        lp.pr = s->d_lmp;
-        lp.p_r = s->d_lmq;
-        lp.out = s->d_lmres + p0;
-        lp.iters = s->d_lmiters + p0;
-        lp.active = s->d_lmactive + p0;
-        lp.single_pair = 1;
-        rc = epv_lm_launch(ctx, lp);
-        if (rc) return rc;
-        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][5], ctx->stream));
-        finish_kernel<<<(np + 127) / 128, 128, 0, ctx->stream>>>(
-            np, *prm, s->d_E + (size_t)p0 * 9, s->d_R + (size_t)p0 * 9, s->d_t + (size_t)p0 * 3,
-            s->d_T0 + (size_t)p0 * 16, s->d_T + (size_t)p0 * 16, s->d_lmres + p0, s->d_lmiters + p0,
-            s->d_lmactive + p0, s->d_nmatch + p0, s->d_ninl + p0, s->d_ngood + p0, s->d_iters + p0,
-            s->d_nmodels + p0, s->d_results + p0);
-        EPV_LAUNCHED(ctx);
-        EPV_CUDA(ctx, cudaEventRecord(s->ev[c][6], ctx->stream));
+    EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, main_stream));
+    int rc = EPIVO_OK;
+    const size_t kp = s->kp;
+    if (upload) {
+        // all pieces are queued on the copy stream at once; they run back to back at PCIe rate
+        EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
+        for (int c = 0; c < n_m; ++c) {
+            const int p0 = first_pair + c * mchunk;
+            const int np = std::min(mchunk, first_pair + n_pairs - p0);
+            const int f0 = (c == 0) ? p0 : p0 + 1;                  // frame p0 came with the previous piece
+            const int nf = p0 + np + 1 - f0;
+            const size_t ho = (size_t)(f0 - first_pair);            // host arrays start at frame first_pair
+            EPV_CUDA(ctx, cudaMemcpyAsync(s->d_kps + (size_t)f0 * kp * 2, h_kps + ho * kp * 2, (size_t)nf * kp * 8,
+                                          cudaMemcpyHostToDevice, s->stream2));
+            EPV_CUDA(ctx, cudaMemcpyAsync(s->d_desc + (size_t)f0 * kp * 8, h_desc + ho * kp * 32, (size_t)nf * kp * 32,
+                                          cudaMemcpyHostToDevice, s->stream2));
+            EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], s->stream2));
+        }
     }
-    EPV_CUDA(ctx, cudaEventRecord(s->ev_end, ctx->stream));
+    if (overlap) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
+    for (int c = 0; c < n_m && !rc; ++c) {
+        const int p0 = first_pair + c * mchunk;
+        const int np = std::min(mchunk, first_pair + n_pairs - p0);
+        if (upload) EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_matched[c], 0));
+        rc = seq_run_match(s, prm, c, p0, np);
+        if (rc) break;
+        if (overlap) {      // optional two-stream compute: geometry of group c under the matcher of c+1
+            EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], main_stream));
+            EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_matched[c], 0));
+            ctx->stream = s->stream2;
+            rc = seq_run_geometry(s, prm, HALF + c, p0, np);
+            ctx->stream = main_stream;
+        }
+    }
+    ctx->stream = main_stream;
+    if (rc) return rc;
+    if (overlap) {          // later work on the context stream (download) is ordered after the geometry
+        EPV_CUDA(ctx, cudaEventRecord(s->ev_geo_done, s->stream2));
+        EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_geo_done, 0));
+    } else {
+        for (int c = 0; c < n_g && !rc; ++c) {
+            const int p0 = first_pair + c * gchunk;
+            const int np = std::min(gchunk, first_pair + n_pairs - p0);
+            rc = seq_run_geometry(s, prm, HALF + c, p0, np);
+        }
+        if (rc) return rc;
+    }
+    EPV_CUDA(ctx, cudaEventRecord(s->ev_end, main_stream));
     return EPIVO_OK;
+}
+
+int epivo_seq_run(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair, int n_pairs) {
+    if (!s || !prm) return EPIVO_ERR_INVALID;
+    return seq_execute(s, prm, first_pair, n_pairs, nullptr, nullptr);
+}
+
+int epivo_seq_process(epivo_seq* s, const epivo_pipeline_params* prm, int n_frames, const float* kps,
+                      const uint8_t* descs, epivo_pair_result* out) {
+    if (!s || !prm) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (!kps || !descs || !out) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null buffer");
+    if (n_frames < 2 || n_frames > s->max_frames) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_frames %d outside [2,%d]", n_frames, s->max_frames);
+    int rc = seq_execute(s, prm, 0, n_frames - 1, kps, descs);
+    if (rc) return rc;
+    return epivo_seq_download(s, out, 0, n_frames - 1);
 }
 
 int epivo_seq_download(epivo_seq* s, epivo_pair_result* out, int first_pair, int n_pairs) {
@@ -446,22 +559,25 @@ int epivo_seq_stage_ms(epivo_seq* s, float* ms, int n) {
     epivo_ctx* ctx = s->ctx;
     EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int c = 0; c < s->last_chunks; ++c) {
-        for (int k = 0; k < SEQ_STAGES - 1; ++k) {
+    constexpr int HALF = SEQ_MAX_CHUNKS / 2;
+    for (int c = 0; c < s->last_mgroups; ++c) {
+        float t = 0;
+        EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->ev[c][0], s->ev[c][1]));
+        acc[1] += t;                // [1] match: plane pre-pass + key init + tile kernel
+        EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->evk[c][0], s->evk[c][1]));
+        acc[7] += t;                // [7] matcher tile kernel alone, summed over the group launches
+    }
+    for (int c = 0; c < s->last_ggroups; ++c) {
+        for (int k = 2; k < 6; ++k) {   // [3] essential [4] pose [5] lm [6] finish
             float t = 0;
-            EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->ev[c][k], s->ev[c][k + 1]));
-            acc[k + 1] += t;       // [1] match (incl. plane pre-pass + key init) [2] finalize [3] essential [4] pose [5] lm [6] finish
+            EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->ev[HALF + c][k], s->ev[HALF + c][k + 1]));
+            acc[k + 1] += t;
         }
     }
-    for (int c = 0; c < s->last_chunks; ++c) {
-        float t = 0;
-        EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->evk[c][0], s->evk[c][1]));
-        acc[7] += t;                // [7] matcher tile kernel alone, summed over the chunk launches
-    }
     float tot = 0;
-    if (s->last_chunks > 0) EPV_CUDA(ctx, cudaEventElapsedTime(&tot, s->ev_begin, s->ev_end));
+    if (s->last_mgroups > 0) EPV_CUDA(ctx, cudaEventElapsedTime(&tot, s->ev_begin, s->ev_end));
     acc[0] = tot;
-    for (int i = 0; i < n; ++i) ms[i] = i < 8 ? acc[i] : (i == 8 ? (float)s->last_chunks : 0.f);
+    for (int i = 0; i < n; ++i) ms[i] = i < 8 ? acc[i] : (i == 8 ? (float)s->last_mgroups : 0.f);
     return EPIVO_OK;
 }
 

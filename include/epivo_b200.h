@@ -159,11 +159,20 @@ void epivo_seq_destroy(epivo_seq* seq);
 int epivo_seq_upload(epivo_seq* seq, int first_frame, int n_frames, const float* kps, const uint8_t* descs);
 /* enqueue the pipeline for pairs [first_pair, first_pair + n_pairs) (async) */
 int epivo_seq_run(epivo_seq* seq, const epivo_pipeline_params* p, int first_pair, int n_pairs);
+/* The reference-facing call with HOST buffers: upload n_frames frames (kps n_frames x kp x 2 f32,
+ * descs n_frames x kp x 32 u8, ideally pinned), run all n_frames-1 pairs, copy the results back
+ * and synchronise.  The upload is pipelined under the matcher on a second (copy) stream. */
+int epivo_seq_process(epivo_seq* seq, const epivo_pipeline_params* p, int n_frames, const float* kps,
+                      const uint8_t* descs, epivo_pair_result* out);
 /* device -> host copy of the results of the last run and stream sync */
 int epivo_seq_download(epivo_seq* seq, epivo_pair_result* out, int first_pair, int n_pairs);
+/* overlap != 0: groups of pairs are pipelined over two CUDA streams, the integer-bound matcher of
+ * group g+1 running concurrently with the FP64-bound geometry of group g.  Default 0: measured on
+ * B200 the two kernels contend for issue slots and registers and the pipelined run is not faster. */
+int epivo_seq_set_overlap(epivo_seq* seq, int overlap);
 /* per-stage device time of the last run (CUDA events on the context stream), ms:
- * [0] prep [1] match [2] finalize/gather [3] essential [4] pose [5] lm [6] total.
- * n_match_launches/ms_match_kernel give the matcher kernel's launches and summed time. */
+ * [0] total [1] match [2] - [3] essential [4] pose [5] lm [6] finish [7] matcher tile kernel alone
+ * [8] number of pair groups; stage times overlap when the two streams do. */
 int epivo_seq_stage_ms(epivo_seq* seq, float* ms, int n);
 /* debug/parity views of the last run, host copies: matches of one pair */
 int epivo_seq_get_matches(epivo_seq* seq, int pair, int32_t* query_idx, int32_t* train_idx,
