@@ -220,7 +220,7 @@ def main():
         pipe.process(prm, kps_np, desc_np, results)   # H2D (pipelined under the matcher) + run + D2H + sync
         if world > 1:                         # the only collective: per-pair poses -> every rank (NCCL)
             T = torch.from_numpy(np.ascontiguousarray(results["T"])).cuda(non_blocking=True)
-            gathered = torch.empty((world,) + tuple(T.shape), dtype=T.dtype, device="cuda")
+            gathered = torch.empty((world * T.shape[0],) + tuple(T.shape[1:]), dtype=T.dtype, device="cuda")
             dist.all_gather_into_tensor(gathered, T)
     e3.record(stream)
     barrier()

@@ -1,0 +1,83 @@
+"""Multi-GPU sharding of a sequence and the host-side pose chaining that follows the hot path.
+
+Frame pairs are independent (the reference loop kitti_E.cpp:54-201 carries no state between
+iterations until the pose chaining at :225-228), so a sequence is split into contiguous blocks
+of pairs, one block per rank (contiguous so that every frame is uploaded to one GPU only, with a
+halo of one frame), with NO collective on the data path.  The only exchange is one all-gather of
+the fixed-size per-pair pose records at the end (NCCL on GPUs, gloo in the CPU tests), after
+which rank 0 does the inherently sequential chaining cT <- cT * dT^-1 (kitti_E.cpp:218-228).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_pairs: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block [start, stop) of pair indices for `rank`: blocks of
+    ceil(n_pairs / world), the last ranks possibly short or empty."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    per = -(-n_pairs // world)
+    start = min(rank * per, n_pairs)
+    return start, min(start + per, n_pairs)
+
+
+def frames_for(start: int, stop: int) -> tuple[int, int]:
+    """Frames a rank needs for pairs [start, stop): [start, stop] inclusive, i.e. a halo of one."""
+    return (start, stop + 1) if stop > start else (start, start)
+
+
+def gather_poses(local_T: np.ndarray, n_pairs: int, world: int, rank: int, dist=None, device=None) -> np.ndarray:
+    """All-gather the per-pair 4x4 poses of every rank into sequence order.
+
+    local_T: (stop-start, 4, 4) float64 for this rank's block.  Every rank contributes a block
+    padded to ceil(n_pairs/world) records so that a plain all_gather works for ragged tails.
+    `dist` is torch.distributed (None when world == 1); `device` the tensor device to stage on
+    ("cuda" for NCCL, "cpu" for gloo)."""
+    start, stop = shard_range(n_pairs, world, rank)
+    assert local_T.shape == (stop - start, 4, 4)
+    if world == 1 or dist is None:
+        return np.ascontiguousarray(local_T, dtype=np.float64)
+    import torch
+    per = -(-n_pairs // world)
+    buf = np.zeros((per, 4, 4), dtype=np.float64)
+    buf[:stop - start] = local_T
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * per, 4, 4), dtype=t.dtype, device=t.device)     # concatenated along dim 0
+    dist.all_gather_into_tensor(out, t)
+    return out.cpu().numpy()[:n_pairs]
+
+
+def chain_poses(T_pairs: np.ndarray, scales: np.ndarray | None = None) -> np.ndarray:
+    """Host pose chaining of kitti_E.cpp:218-228.
+
+    T_pairs[i] is the refined point transform of pair i (frame i -> i+1).  The reference
+    normalises its translation, rescales it by the ground-truth step length (`scale`,
+    kitti_E.cpp:220-222) and accumulates the camera pose cT <- cT * dT^-1 starting from identity;
+    all_T[i] is the pose BEFORE pair i is applied (kitti_E.cpp:227), so n+1 poses come back."""
+    n = T_pairs.shape[0]
+    scales = np.ones(n) if scales is None else np.asarray(scales, dtype=np.float64)
+    cT = np.eye(4)
+    out = np.empty((n + 1, 4, 4))
+    for i in range(n):
+        out[i] = cT
+        dT = np.eye(4)
+        t = T_pairs[i][:3, 3]
+        nt = np.linalg.norm(t)
+        dT[:3, :3] = T_pairs[i][:3, :3]
+        dT[:3, 3] = (t / nt if nt > 0 else t) * scales[i]
+        cT = cT @ np.linalg.inv(dT)
+    out[n] = cT
+    return out
+
+
+def write_poses(path: str, poses: np.ndarray) -> None:
+    """kitti.T / kitti.GT / euroc.T text format (kitti_E.cpp:271-286): 4x4 blocks separated by a
+    blank line, which the reference's viewers read with np.fromfile(sep=' ') (cloud_pango.py:32-34)."""
+    with open(path, "w") as f:
+        for T in poses:
+            for r in range(4):
+                f.write(" ".join(repr(float(v)) for v in T[r]) + "\n")
+            f.write("\n")

@@ -127,3 +127,61 @@ def test_lm_batch_and_errors(ctx):
         api.Levenberg_Marquardt(2, 1e-8, [(0, 2)], [1.0], 1e-2, T0b[0], prb[0][:1], p_rb[0][:1], ctx=ctx)
     with pytest.raises(ValueError):
         api.Levenberg_Marquardt(2, 1e-8, reps, [1.0], 1e-2, T0b[0], prb[0], p_rb[0], ctx=ctx)
+
+
+def _check_vs_c(ctx, n_zeta, reps, N, seed, delta, iters, w=None):
+    from oracle import clib
+    Ts, T0s, pr, p_r = synth.gen_scene_sequence(seed, N, n_zeta, reps)
+    w = [1.0] * len(reps) if w is None else w
+    To, lo = clib.levenberg_marquardt(n_zeta, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=delta, max_iters=iters)
+    Tg, lg = api.Levenberg_Marquardt(n_zeta, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=delta,
+                                     max_iters=iters, ctx=ctx)
+    assert lg["iters"] == lo["iters"]
+    for k in range(n_zeta):
+        assert rot_angle(Tg[k][:3, :3], To[k][:3, :3]) < ROT_TOL
+        assert np.abs(Tg[k][:3, 3] - To[k][:3, 3]).max() < 1e-6 * max(1.0, np.abs(To[k][:3, 3]).max())
+    assert abs(lg["r_norm"] - lo["r_norm"]) <= 1e-5 * max(lo["r_norm"], 1e-12) + 1e-15
+    return Ts, Tg, lg
+
+
+def test_lm_cfg5_window_full_size(ctx):
+    """BASELINE config 5: n_zeta = 10, reps {(i,i),(0,i)} (test_jac_Rt_gen.cpp:294-297) x N = 250
+    = 5000 correspondences, J 5000 x 60, H 60 x 60; against the plain-C restatement."""
+    Ts, Tg, lg = _check_vs_c(ctx, 10, REPS10, 250, 51, 1.0, 30)
+    for k in range(10):
+        assert np.linalg.norm(Tg[k][:3, :3] - Ts[k][:3, :3]) < 1e-5
+    _check_vs_c(ctx, 10, REPS10, 250, 52, 1e-5, 30)
+
+
+def test_lm_kitti_ba_stereo_window_shape(ctx):
+    """The shape kitti_ba.cpp ships: ws = 3 stereo -> 9 reps x 32 points, n_zeta = 4
+    (kitti_ba.cpp:931-938,969-975,1038): reps below are what those lines build."""
+    reps = [(0, 1), (1, 1), (0, 0), (0, 3), (1, 3), (0, 0), (2, 3), (3, 3), (2, 2)]
+    _check_vs_c(ctx, 4, reps, 32, 61, 1.0, 30)
+    _check_vs_c(ctx, 4, reps, 32, 62, 1e-5, 30)
+    # a '<32 points' rep: weight 0 and all-ones dummy points (kitti_ba.cpp:983-987)
+    from oracle import clib
+    Ts, T0s, pr, p_r = synth.gen_scene_sequence(63, 32, 4, reps)
+    pr[4][:] = 1.0
+    p_r[4][:] = 1.0
+    w = [1.0] * 9
+    w[4] = 0.0
+    To, lo = clib.levenberg_marquardt(4, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=1.0)
+    Tg, lg = api.Levenberg_Marquardt(4, 1e-8, reps, w, 1e-2, T0s, pr, p_r, huber_delta=1.0, ctx=ctx)
+    assert lg["iters"] == lo["iters"] and np.abs(Tg - To).max() < 1e-6
+
+
+def test_lm_window_batch_sharded_like_8_gpus(ctx):
+    """kitti_ba windows are independent: a rank's block of windows is one batched launch."""
+    from epivo_b200 import shard
+    from oracle import clib
+    reps = [(0, 0), (1, 1), (2, 2), (0, 2), (0, 1), (1, 2)]
+    B = 10
+    data = [synth.gen_scene_sequence(200 + b, 32, 3, reps) for b in range(B)]
+    a, b_ = shard.shard_range(B, 8, 1)            # rank 1 of 8
+    Tb, res, its = api.Levenberg_Marquardt_batch(3, 1e-8, reps, [1.0] * 6, 1e-2, np.stack([d[1] for d in data[a:b_]]),
+                                                 np.stack([d[2] for d in data[a:b_]]),
+                                                 np.stack([d[3] for d in data[a:b_]]), huber_delta=1.0, ctx=ctx)
+    for k, d in enumerate(data[a:b_]):
+        To, lo = clib.levenberg_marquardt(3, 1e-8, reps, [1.0] * 6, 1e-2, d[1], d[2], d[3], huber_delta=1.0)
+        assert its[k] == lo["iters"] and np.abs(Tb[k] - To).max() < 1e-6
