@@ -1,0 +1,186 @@
+// epivo_shims.hpp -- header-only C++ shims with the reference drivers' call shapes over the C ABI.
+//
+// The reference (Ronnypetson/epivo) has no plugin interface: its drivers call
+//     cv::BFMatcher(NORM_HAMMING2, true).match(desc0, desc1, matches)        kitti_ba.cpp:602,641
+//     cv::findEssentialMat(p0, p1, cam, method, prob, thr, mask)             kitti_E.cpp:98-104
+//     cv::recoverPose(E, p0, p1, cam, R, t, mask)                            kitti_E.cpp:120
+//     Levenberg_Marquardt(n_zeta, eps, reps, wreps, lambda0, T0s, pr, p_r, lm_res)
+//                                                                            jac_Rt_gen_.cpp:287-296
+// on cv::Mat / std::vector<cv::Point2f> / Eigen::MatrixXd.  Neither OpenCV's nor Eigen's headers
+// exist in this image, so the shims are templates over "anything that looks like" those types:
+//   * a matrix type M with M(rows, cols), .rows(), .cols() and (i, j) element access
+//     (Eigen::MatrixXd qualifies; tests/cpp/shim_test.cpp uses a 20-line stand-in),
+//   * a 2-D point type with public .x and .y floats (cv::Point2f qualifies).
+// A driver switches by including this header, linking libepivo_b200.so and replacing the
+// `cv::` / unqualified calls with `epivo::` ones -- see INTEGRATION.md.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "epivo_b200.h"
+
+// The reference uses `LM_res` (jac_Rt_gen_.cpp:295,473-475; kitti_ba.cpp:876) but defines it
+// nowhere; this is the definition its fields imply.
+struct LM_res {
+    double H_norm = 0.0, r_norm = 0.0, lambda = 0.0;
+};
+
+namespace epivo {
+
+enum { NORM_HAMMING = EPIVO_NORM_HAMMING, NORM_HAMMING2 = EPIVO_NORM_HAMMING2, LMEDS = EPIVO_LMEDS, RANSAC = EPIVO_RANSAC };
+
+// One context per host thread (kitti_ba.cpp:1153-1163 runs association and BA on different
+// threads concurrently: give each its own Context).
+class Context {
+  public:
+    explicit Context(int device = 0) {
+        if (epivo_create(&ctx_, device) != EPIVO_OK || !ctx_)
+            throw std::runtime_error("epivo_create failed: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Context() { epivo_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    epivo_ctx* get() const { return ctx_; }
+    void check(int rc) const {
+        if (rc != EPIVO_OK) throw std::runtime_error(std::string("epivo_b200: ") + epivo_last_error(ctx_));
+    }
+
+  private:
+    epivo_ctx* ctx_ = nullptr;
+};
+
+struct DMatch {               // cv::DMatch
+    int queryIdx = -1, trainIdx = -1, imgIdx = 0;
+    float distance = 0.f;
+};
+
+// cv::BFMatcher(normType, crossCheck); descriptors as a contiguous row-major byte matrix
+class BFMatcher {
+  public:
+    BFMatcher(Context& ctx, int normType = NORM_HAMMING2, bool crossCheck = false)
+        : ctx_(ctx), norm_(normType), cross_(crossCheck) {}
+    // desc0 / desc1: n x desc_bytes, row-major uint8 (cv::Mat::data of an ORB descriptor matrix)
+    void match(const uint8_t* desc0, int n0, const uint8_t* desc1, int n1, int desc_bytes,
+               std::vector<DMatch>& matches) const {
+        std::vector<int32_t> q(n0 > 0 ? n0 : 1), t(q.size()), d(q.size());
+        int n = 0;
+        ctx_.check(epivo_match_hamming(ctx_.get(), desc0, n0, desc1, n1, desc_bytes, norm_,
+                                       cross_ ? EPIVO_MATCH_CROSSCHECK : EPIVO_MATCH_NN, 0.f, q.data(), t.data(),
+                                       d.data(), nullptr, &n));
+        matches.resize(n);
+        for (int i = 0; i < n; ++i) {
+            matches[i].queryIdx = q[i];
+            matches[i].trainIdx = t[i];
+            matches[i].imgIdx = 0;
+            matches[i].distance = (float)d[i];
+        }
+    }
+
+  private:
+    Context& ctx_;
+    int norm_;
+    bool cross_;
+};
+
+namespace detail {
+template <typename Pt>
+std::vector<float> flatten(const std::vector<Pt>& p) {
+    std::vector<float> o(2 * p.size());
+    for (size_t i = 0; i < p.size(); ++i) { o[2 * i] = p[i].x; o[2 * i + 1] = p[i].y; }
+    return o;
+}
+}  // namespace detail
+
+// cv::findEssentialMat(points1, points2, cameraMatrix, method, prob, threshold, mask).
+// cam: 9 doubles, row-major (widen the reference's float Mat: kitti_E.cpp:38).  Returns false where
+// OpenCV returns an empty Mat (fewer than 5 points / no model); E is 3x3 row-major.
+template <typename Pt>
+bool findEssentialMat(Context& ctx, const std::vector<Pt>& points1, const std::vector<Pt>& points2,
+                      const double cam[9], int method, double prob, double threshold, double E[9],
+                      std::vector<unsigned char>& mask, int maxIters = 1000) {
+    if (points1.size() != points2.size()) throw std::invalid_argument("point sets differ in size");
+    const int n = (int)points1.size();
+    std::vector<float> p0 = detail::flatten(points1), p1 = detail::flatten(points2);
+    mask.assign(n, 0);
+    int ninl = 0, iters = 0;
+    int rc = epivo_find_essential(ctx.get(), p0.data(), p1.data(), n, cam, method, prob, threshold, maxIters, nullptr, 0,
+                                  E, mask.data(), &ninl, &iters);
+    if (rc == EPIVO_ERR_NOMODEL) return false;
+    ctx.check(rc);
+    return true;
+}
+
+// cv::recoverPose(E, points1, points2, cameraMatrix, R, t, mask): returns the number of points that
+// pass the cheirality check; mask entries are 0 / 255 (the drivers test == 255, kitti_E.cpp:177).
+template <typename Pt>
+int recoverPose(Context& ctx, const double E[9], const std::vector<Pt>& points1, const std::vector<Pt>& points2,
+                const double cam[9], double R[9], double t[3], std::vector<unsigned char>& mask,
+                double distanceThresh = 50.0) {
+    const int n = (int)points1.size();
+    std::vector<float> p0 = detail::flatten(points1), p1 = detail::flatten(points2);
+    mask.assign(n, 0);
+    int good = 0;
+    ctx.check(epivo_recover_pose(ctx.get(), E, p0.data(), p1.data(), n, cam, distanceThresh, nullptr, R, t,
+                                 mask.data(), &good));
+    return good;
+}
+
+// int Levenberg_Marquardt(const int n_zeta, const double epsilon, const vector<pair<int,int>>& reps,
+//                         const vector<double>& wreps, const double lambda0, vector<MatrixXd>& T0s,
+//                         vector<MatrixXd>& pr, vector<MatrixXd>& p_r, LM_res& lm_res)
+// (jac_Rt_gen_.cpp:287-296).  T0s (4x4 each) is updated in place, as in the reference.
+template <typename M>
+int Levenberg_Marquardt(Context& ctx, const int n_zeta, const double epsilon,
+                        const std::vector<std::pair<int, int> >& reps, const std::vector<double>& wreps,
+                        const double lambda0, std::vector<M>& T0s, std::vector<M>& pr, std::vector<M>& p_r,
+                        LM_res& lm_res, double huber_delta = 1e-5 /* jac_Rt_gen_.cpp:17 */, int max_iters = 30) {
+    if (reps.size() != wreps.size()) throw std::invalid_argument("reps.size() != wreps.size()");   // :297
+    const int n_rep = (int)reps.size();
+    if ((int)T0s.size() != n_zeta || (int)pr.size() != n_rep || (int)p_r.size() != n_rep)
+        throw std::invalid_argument("T0s / pr / p_r sizes do not match n_zeta / reps");
+    const int N = (int)pr[0].rows();                                                               // :299
+    std::vector<int32_t> r(2 * n_rep);
+    for (int j = 0; j < n_rep; ++j) { r[2 * j] = reps[j].first; r[2 * j + 1] = reps[j].second; }
+    std::vector<double> T(16 * (size_t)n_zeta), a(3 * (size_t)n_rep * N), b(a.size());
+    for (int k = 0; k < n_zeta; ++k)
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) T[16 * k + 4 * i + j] = T0s[k](i, j);
+    for (int j = 0; j < n_rep; ++j) {
+        if ((int)pr[j].rows() != N || (int)p_r[j].rows() != N) throw std::invalid_argument("all reps share one N");
+        for (int i = 0; i < N; ++i)
+            for (int c = 0; c < 3; ++c) {
+                a[((size_t)j * N + i) * 3 + c] = pr[j](i, c);
+                b[((size_t)j * N + i) * 3 + c] = p_r[j](i, c);
+            }
+    }
+    epivo_lm_res res;
+    int iters = 0;
+    ctx.check(epivo_lm_rt(ctx.get(), n_zeta, epsilon, r.data(), wreps.data(), n_rep, lambda0, max_iters, huber_delta,
+                          T.data(), a.data(), b.data(), N, &res, &iters));
+    for (int k = 0; k < n_zeta; ++k)
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) T0s[k](i, j) = T[16 * k + 4 * i + j];
+    lm_res.H_norm = res.H_norm;
+    lm_res.r_norm = res.r_norm;
+    lm_res.lambda = res.lambda;
+    return 0;
+}
+
+// The 7-argument form kitti_E.cpp:196 calls -- unit weights, one diagnostic returned.  The reference
+// never defines this overload; of the three candidates it leaves commented out
+// (jac_Rt_gen_.cpp:470-472: H.norm(), r0.norm(), lambda) the residual norm is returned, which is what
+// the caller's `uncert > 1E-9` revert test (kitti_E.cpp:198) is dimensionally consistent with.
+template <typename M>
+double Levenberg_Marquardt(Context& ctx, const int n_zeta, const double epsilon,
+                           const std::vector<std::pair<int, int> >& reps, const double lambda0, std::vector<M>& T0s,
+                           std::vector<M>& pr, std::vector<M>& p_r) {
+    std::vector<double> w(reps.size(), 1.0);
+    LM_res res;
+    Levenberg_Marquardt(ctx, n_zeta, epsilon, reps, w, lambda0, T0s, pr, p_r, res);
+    return res.r_norm;
+}
+
+}  // namespace epivo
