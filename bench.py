@@ -272,7 +272,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline, "pipe": pipe_roof,
             "stages_ms_per_step": {k: float(stage_acc[i] / a.steps) for i, k in
-                                   enumerate(["total", "match", "-", "essential", "pose", "lm", "finish",
+                                   enumerate(["total", "match", "presolve", "essential", "pose", "lm", "finish",
                                               "match_kernel"])},
             "quality": {"mean_matches": float(results["n_matches"].mean()),
                         "mean_inliers": float(results["n_inliers"].mean()),

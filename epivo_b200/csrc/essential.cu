@@ -12,6 +12,7 @@
 // is the model the sequential loop would return; at most CHUNK-1 samples are wasted.
 #include <float.h>
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -79,6 +80,64 @@ __device__ __forceinline__ float sampson_f32(const double* __restrict__ E, doubl
     return (float)__ddiv_rn(__dmul_rn(x2tEx1, x2tEx1), den);
 }
 
+// Inlier test  (float)(num/den) <= thr32  without the FP64 division.
+// Let B be the largest double whose float rounding is <= thr32 (the midpoint between thr32 and the
+// next float up, or its predecessor when the tie would round up).  Then
+//     num/den <= B                =>  RN64(num/den) <= B        => inlier      (RN is monotone)
+//     num/den >  B (1 + 2^-50)    =>  RN64(num/den) >  B        => outlier
+// and the sign of B*den - num is exact in one FMA.  Only quotients within 2^-50 of B (or
+// den == 0 / NaN) take the division; num and den are the same un-fused values OpenCV computes.
+struct SampThr {
+    double B, C;     // C = B * 2^-50
+    float thr32;
+};
+__host__ __device__ inline SampThr make_samp_thr(float thr32) {
+    SampThr t;
+    t.thr32 = thr32;
+    unsigned bits;
+#ifdef __CUDA_ARCH__
+    bits = __float_as_uint(thr32);
+    const float up = __uint_as_float(bits + 1u);
+#else
+    memcpy(&bits, &thr32, 4);
+    const unsigned ub = bits + 1u;
+    float up;
+    memcpy(&up, &ub, 4);
+#endif
+    double mid = 0.5 * ((double)thr32 + (double)up);          // exact: two adjacent floats
+    if ((bits & 1u) && mid > 0.0 && mid < 1e300) {            // odd mantissa: the tie rounds away from thr32
+#ifdef __CUDA_ARCH__
+        mid = __longlong_as_double(__double_as_longlong(mid) - 1);
+#else
+        long long mb;
+        memcpy(&mb, &mid, 8);
+        mb -= 1;
+        memcpy(&mid, &mb, 8);
+#endif
+    }
+    if (!(thr32 >= 0.0f) || !(thr32 < 3e38f)) mid = -1.0;     // negative / NaN / huge: always take the exact path
+    t.B = mid;
+    t.C = mid * 8.881784197001252e-16;                         // 2^-50
+    return t;
+}
+
+__device__ __forceinline__ bool sampson_inlier(const double* __restrict__ E, double a1, double b1, double a2,
+                                               double b2, const SampThr& T) {
+    const double ex0 = __dadd_rn(__dadd_rn(__dmul_rn(E[0], a1), __dmul_rn(E[1], b1)), E[2]);
+    const double ex1 = __dadd_rn(__dadd_rn(__dmul_rn(E[3], a1), __dmul_rn(E[4], b1)), E[5]);
+    const double ex2 = __dadd_rn(__dadd_rn(__dmul_rn(E[6], a1), __dmul_rn(E[7], b1)), E[8]);
+    const double et0 = __dadd_rn(__dadd_rn(__dmul_rn(E[0], a2), __dmul_rn(E[3], b2)), E[6]);
+    const double et1 = __dadd_rn(__dadd_rn(__dmul_rn(E[1], a2), __dmul_rn(E[4], b2)), E[7]);
+    const double x2tEx1 = __dadd_rn(__dadd_rn(__dmul_rn(a2, ex0), __dmul_rn(b2, ex1)), ex2);
+    const double den = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(ex0, ex0), __dmul_rn(ex1, ex1)), __dmul_rn(et0, et0)),
+                                 __dmul_rn(et1, et1));
+    const double num = __dmul_rn(x2tEx1, x2tEx1);
+    const double r = __fma_rn(T.B, den, -num);
+    if (r >= 0.0 && den > 0.0 && T.B > 0.0) return true;
+    if (-r > __dmul_rn(T.C, den) && T.B > 0.0) return false;
+    return (float)__ddiv_rn(num, den) <= T.thr32;
+}
+
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
 // k-th smallest (0-based) of n non-negative floats in buf, by bitwise binary search on the
@@ -125,7 +184,8 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
     __shared__ double s_models[ES_CHUNK][10][9];
     __shared__ int s_nmodels[ES_CHUNK];
     __shared__ int s_idx[ES_CHUNK][5];
-    __shared__ float s_score[ES_CHUNK][10];      // RANSAC: inlier count (exact in float up to 2^24); LMedS: median
+    __shared__ float s_score[ES_CHUNK][10];      // LMedS: median of every model of the chunk
+    __shared__ int s_cnt[ES_WARPS][10];          // RANSAC: inlier counts of the sub-chunk being scored
     __shared__ double s_bestE[9];
     __shared__ int s_niters, s_iter, s_have, s_total_models;
     __shared__ unsigned long long s_rng;
@@ -156,12 +216,15 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
     __syncthreads();
 
     double best_score = lmeds ? DBL_MAX : 0.0;               // thread 0 only
+    const SampThr thrR = make_samp_thr(thr32);
 
     while (true) {
         const int iter0 = s_iter, niters = s_niters;
         if (iter0 >= niters) break;
-        const int ch = min(ES_CHUNK, niters - iter0);
-        const bool presolved = iter0 + ES_CHUNK <= a.pre_count;
+        // a chunk never straddles the end of the pre-solved samples (the in-kernel RNG state
+        // continues from there)
+        const bool presolved = iter0 < a.pre_count;
+        const int ch = min(min(ES_CHUNK, niters - iter0), presolved ? a.pre_count - iter0 : ES_CHUNK);
         if (presolved) {
             // models of this chunk were solved by presolve_kernel at full occupancy
             const double* gm = a.pre_models + ((int64_t)pair * a.pre_count + iter0) * 90;
@@ -193,33 +256,43 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
             }
             __syncthreads();
         }
-        // score + replay in sub-chunks of ES_WARPS samples (warp w owns sample sub*ES_WARPS + w):
-        // RANSAC usually shrinks niters after the first few samples, so later ones are never scored
-        int done = 0;                                        // samples of this chunk consumed by the replay
+        // score + replay in sub-chunks of at most ES_WARPS samples.  RANSAC usually shrinks niters
+        // after the first few samples: samples at or beyond the current niters are never scored,
+        // and when fewer than ES_WARPS samples remain their points are split across the idle warps.
         for (int sub = 0; sub * ES_WARPS < ch; ++sub) {
-            const int s = sub * ES_WARPS + warp;
-            if (s < ch && n != 5) {
-                const int nm = s_nmodels[s];
-                if (!lmeds) {
+            const int sbase = sub * ES_WARPS;
+            const int r = min(ES_WARPS, min(ch, s_niters - iter0) - sbase);     // samples scored now (>= 1)
+            if (!lmeds) {
+                if (tid < ES_WARPS * 10) (&s_cnt[0][0])[tid] = 0;
+                __syncthreads();
+                const int slices = (r >= 5) ? 1 : (r >= 3 ? 2 : (r == 2 ? 4 : 8));   // warps per sample
+                const int q = warp / slices, slice = warp % slices;
+                if (q < r && n != 5) {
+                    const int s = sbase + q;
+                    const int nm = s_nmodels[s];
                     // point-outer loop: a correspondence is loaded once and scored against every
                     // model of this warp's sample (models broadcast from shared memory)
                     int cnt[10];
 #pragma unroll
                     for (int k = 0; k < 10; ++k) cnt[k] = 0;
-                    for (int i = lane; i < n; i += 32) {
+                    for (int i = lane + 32 * slice; i < n; i += 32 * slices) {
                         const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
 #pragma unroll
                         for (int k = 0; k < 10; ++k)
-                            if (k < nm) cnt[k] += (sampson_f32(s_models[s][k], a1, b1, a2, b2) <= thr32);
+                            if (k < nm) cnt[k] += sampson_inlier(s_models[s][k], a1, b1, a2, b2, thrR) ? 1 : 0;
                     }
 #pragma unroll
                     for (int k = 0; k < 10; ++k) {
                         if (k < nm) {
                             const int c = warp_sum(cnt[k]);
-                            if (lane == 0) s_score[s][k] = (float)c;
+                            if (lane == 0) atomicAdd(&s_cnt[q][k], c);
                         }
                     }
-                } else {
+                }
+            } else {
+                const int s = sbase + warp;
+                if (warp < r && n != 5) {
+                    const int nm = s_nmodels[s];
                     for (int k = 0; k < nm; ++k) {
                         const double* E = s_models[s][k];
                         float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
@@ -234,8 +307,8 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
             __syncthreads();
             if (tid == 0) {                                  // sequential bookkeeping of ptsetreg.cpp run()
                 int ni = s_niters;
-                int q = sub * ES_WARPS;
-                const int qend = min(ch, q + ES_WARPS);
+                int q = sbase;
+                const int qend = sbase + r;
                 for (; q < qend; ++q) {
                     if (iter0 + q >= ni) break;
                     for (int k = 0; k < s_nmodels[q]; ++k) {
@@ -248,7 +321,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
                             continue;
                         }
                         if (!lmeds) {
-                            const int good = (int)s_score[q][k];
+                            const int good = s_cnt[q - sbase][k];
                             if (good > max((int)best_score, 4)) {
                                 best_score = good;
                                 s_have = 1;
@@ -269,10 +342,8 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
                 s_niters = ni;
             }
             __syncthreads();
-            done = s_iter - iter0;
             if (s_iter >= s_niters) break;                   // the sequential loop would have stopped here
         }
-        (void)done;
         __syncthreads();
     }
 
@@ -290,7 +361,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
     }
     __syncthreads();
     const bool have = s_have != 0;
-    const float thr = s_thr;
+    const SampThr thrF = make_samp_thr(s_thr);
     uint8_t* mask = a.mask + (int64_t)pair * a.stride;
     double* xin = a.xin ? a.xin + so : nullptr;
     for (int start = 0; start < n; start += ES_THREADS) {
@@ -299,7 +370,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
         double p[4] = {0, 0, 0, 0};
         if (i < n && have) {
             p[0] = X1[i]; p[1] = Y1[i]; p[2] = X2[i]; p[3] = Y2[i];
-            in = (n == 5) ? true : (sampson_f32(s_bestE, p[0], p[1], p[2], p[3]) <= thr);
+            in = (n == 5) ? true : sampson_inlier(s_bestE, p[0], p[1], p[2], p[3], thrF);
         }
         if (i < n) mask[i] = in ? 1 : 0;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
@@ -354,7 +425,10 @@ __global__ void sample_kernel(int n_pairs, const int32_t* __restrict__ n_arr, in
     rng_out[pair] = rng.state;
 }
 
-__global__ void __launch_bounds__(64, 8)
+#ifndef EPV_PRESOLVE_MINBLOCKS
+#define EPV_PRESOLVE_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(64, EPV_PRESOLVE_MINBLOCKS)
 presolve_kernel(int n_pairs, int stride, const double* __restrict__ xn, const int32_t* __restrict__ n_arr, int count,
                 int used, const int32_t* __restrict__ idx, const int32_t* __restrict__ shared_samples,
                 double* __restrict__ models, int32_t* __restrict__ nmodels) {
@@ -421,8 +495,9 @@ score_count_kernel(const double* __restrict__ E, int m, const double* __restrict
     const bool valid = i < n;
     const int ii = valid ? i : 0;
     const double a1 = xn[ii], b1 = xn[stride + ii], a2 = xn[2 * stride + ii], b2 = xn[3 * stride + ii];
+    const SampThr T = make_samp_thr(thr32);
     for (int k = 0; k < mm; ++k) {
-        const bool in = valid && (sampson_f32(s_E[k], a1, b1, a2, b2) <= thr32);
+        const bool in = valid && sampson_inlier(s_E[k], a1, b1, a2, b2, T);
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
         if (lane == 0 && bal) atomicAdd(&s_cnt[k], __popc(bal));
     }
@@ -477,7 +552,7 @@ __global__ void mask_of_model_kernel(const double* __restrict__ E, const int* __
     if (b < 0) { mask[i] = 0; return; }
     double e[9];
     for (int q = 0; q < 9; ++q) e[q] = E[(int64_t)b * 9 + q];
-    mask[i] = sampson_f32(e, xn[i], xn[stride + i], xn[2 * stride + i], xn[3 * stride + i]) <= thr32 ? 1 : 0;
+    mask[i] = sampson_inlier(e, xn[i], xn[stride + i], xn[2 * stride + i], xn[3 * stride + i], make_samp_thr(thr32)) ? 1 : 0;
 }
 
 // pixel -> K-normalised float64 (five-point.cpp: one scale-and-shift per coordinate)
@@ -504,9 +579,10 @@ int epv_normalize_launch(epivo_ctx* ctx, const float* d_p0, const float* d_p1, i
 }
 
 int epv_essential_pre_count(int method, double prob, int max_iters, int m_samples) {
-    // how many leading samples are solved ahead of the per-pair kernel: one chunk for RANSAC (it
-    // nearly always stops within it), every sample for LMedS (its iteration count is fixed)
-    int want = ES_CHUNK;
+    // how many leading samples are solved ahead of the per-pair kernel: two sub-chunks for RANSAC
+    // (on KITTI-like data it stops after ~10 samples; a pair that needs more continues with
+    // in-kernel solves), every sample for LMedS (its iteration count is fixed)
+    int want = 2 * ES_WARPS;
     if (method == EPIVO_LMEDS) {
         double num = log(fmax(1.0 - prob, DBL_MIN)), den = log(1.0 - pow(1.0 - 0.45, 5.0));
         int ni = (int)rint(num / den);
@@ -515,7 +591,7 @@ int epv_essential_pre_count(int method, double prob, int max_iters, int m_sample
     }
     if (m_samples > 0) want = std::min(want, m_samples);
     want = std::min(want, std::max(max_iters, 1));
-    int c = (want + ES_CHUNK - 1) / ES_CHUNK * ES_CHUNK;
+    int c = (want + ES_WARPS - 1) / ES_WARPS * ES_WARPS;
     return std::min(c, 4 * ES_CHUNK);
 }
 
@@ -558,6 +634,7 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
         a.pre_nmodels = p.pre_nmodels;
         a.pre_rng = p.pre_rng;
     }
+    if (p.ev_presolved) EPV_CUDA(ctx, cudaEventRecord(p.ev_presolved, ctx->stream));
     essential_kernel<<<p.n_pairs, ES_THREADS, 0, ctx->stream>>>(a);
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
@@ -594,3 +671,14 @@ int epv_score_launch(epivo_ctx* ctx, const double* d_E, int m, const double* d_x
     }
     return EPIVO_OK;
 }
+
+#ifdef EPV_PROFILE_SOLVE
+// tuning builds only: read and reset the per-phase clock totals of fivept::solve
+extern "C" int epivo_debug_solve_profile(unsigned long long* out8) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(out8, fivept::g_solve_prof, sizeof(z)) != cudaSuccess) return -2;
+    if (cudaMemcpyToSymbol(fivept::g_solve_prof, z, sizeof(z)) != cudaSuccess) return -2;
+    return 0;
+}
+#endif

@@ -21,6 +21,25 @@
 
 namespace fivept {
 
+// Tuning builds only (-DEPV_PROFILE_SOLVE): per-phase clock totals of solve(), read back by
+// epivo_debug_solve_profile().  [0] null space + constraints [1] Gauss-Jordan [2] polynomial
+// [3] Durand-Kerner [4] roots -> E + refinement [5] DK sweeps [6] solves [7] models
+#ifdef EPV_PROFILE_SOLVE
+__device__ unsigned long long g_solve_prof[8];
+#define EPV_PROF_BEGIN long long _pt = clock64()
+#define EPV_PROF(i)                                                       \
+    do {                                                                  \
+        const long long _n = clock64();                                   \
+        atomicAdd(&g_solve_prof[i], (unsigned long long)(_n - _pt));      \
+        _pt = _n;                                                         \
+    } while (0)
+#define EPV_PROF_ADD(i, v) atomicAdd(&g_solve_prof[i], (unsigned long long)(v))
+#else
+#define EPV_PROF_BEGIN
+#define EPV_PROF(i)
+#define EPV_PROF_ADD(i, v)
+#endif
+
 __device__ __forceinline__ void null_space_5x9(const double (&x1)[5][2], const double (&x2)[5][2],
                                                double (&e)[4][9]) {
     // A = Q' (9 x 5), column c = epipolar row of correspondence c
@@ -113,11 +132,57 @@ __device__ __forceinline__ void pmul(const double (&a)[NA + 1], const double (&b
 }
 
 // cv::solvePoly's Durand-Kerner on real coefficients c[0..n] (ascending), n <= 10.
-// Returns the degree actually solved; roots in (re, im).
-__device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)[10], double (&im)[10]) {
-    int n = 10;
-    for (; n > 1; --n)
-        if (fabs(c[n]) > 2.220446049250313e-16) break;      // DBL_EPSILON, as cv::solvePoly
+// dk_sweeps<N>: degree known at compile time, so the roots live in registers and both loops are
+// fully unrolled (the generic version indexes re[]/im[] dynamically, i.e. through local memory).
+// Same start values, same Gauss-Seidel sweep order and same stopping rule as the generic version.
+template <int N>
+__device__ __forceinline__ void dk_sweeps(const double (&c)[11], double (&re)[10], double (&im)[10]) {
+    {
+        double pr = 1.0, pi = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {                        // roots[i] = (1 + 1i)^i
+            re[i] = pr; im[i] = pi;
+            const double t = pr - pi;
+            pi = pr + pi; pr = t;
+        }
+    }
+    double prev2 = 1e300;
+#pragma unroll 1
+    for (int iter = 0; iter < 300; ++iter) {
+        double maxrel2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double xr = re[i], xi = im[i];
+            double nr = c[N], ni = 0.0, dr = c[N], di = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double t = nr * xr - ni * xi + c[N - j - 1];
+                ni = nr * xi + ni * xr;
+                nr = t;
+                if (j != i) {
+                    const double er = xr - re[j], ei = xi - im[j];
+                    const bool nz = (er != 0.0 || ei != 0.0);
+                    const double u = dr * er - di * ei;
+                    const double v = dr * ei + di * er;
+                    di = nz ? v : di;
+                    dr = nz ? u : dr;
+                }
+            }
+            const double s = 1.0 / (dr * dr + di * di);
+            const double qr = (nr * dr + ni * di) * s;
+            const double qi = (ni * dr - nr * di) * s;
+            re[i] = xr - qr; im[i] = xi - qi;
+            maxrel2 = fmax(maxrel2, (qr * qr + qi * qi) / fmax(1.0, xr * xr + xi * xi));
+        }
+        EPV_PROF_ADD(5, 1);
+        if (!(maxrel2 > 1e-26)) break;
+        if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) break;
+        prev2 = maxrel2;
+    }
+}
+
+// Generic degree (the leading coefficients vanished): rare, kept out of line.
+__device__ __noinline__ void dk_sweeps_generic(const double (&c)[11], int n, double (&re)[10], double (&im)[10]) {
     double pr = 1.0, pi = 0.0;
     for (int i = 0; i < n; ++i) {                            // roots[i] = (1 + 1i)^i
         re[i] = pr; im[i] = pi;
@@ -161,6 +226,15 @@ __device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)
         if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) break;
         prev2 = maxrel2;
     }
+}
+
+// Returns the degree actually solved; roots in (re, im).
+__device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)[10], double (&im)[10]) {
+    int n = 10;
+    for (; n > 1; --n)
+        if (fabs(c[n]) > 2.220446049250313e-16) break;      // DBL_EPSILON, as cv::solvePoly
+    if (n == 10) dk_sweeps<10>(c, re, im);
+    else dk_sweeps_generic(c, n, re, im);
     return n;
 }
 
@@ -354,11 +428,14 @@ __device__ __noinline__ void refine_essential(const double (&e)[4][9], double (&
 
 // Solve one sample.  Eout[k] = k-th essential matrix (row-major, unit Frobenius norm).
 __device__ __noinline__ int solve(const double (&x1)[5][2], const double (&x2)[5][2], double (*Eout)[9]) {
+    EPV_PROF_BEGIN;
     double e[4][9];
     null_space_5x9(x1, x2, e);
     double A[10][20];
     fivept_constraints(e, A);
+    EPV_PROF(0);
     if (!gauss_jordan_10x20(A)) return 0;
+    EPV_PROF(1);
     // B(z): entries (j,0),(j,1) cubic, (j,2) quartic; ascending powers.  Row j comes from
     // reduced rows 4+2j ("e - z f"): coefficient layout of the right block per row is
     // [xz^2 xz x | yz^2 yz y | z^3 z^2 z 1] (descending in z inside each group).
@@ -438,8 +515,10 @@ __device__ __noinline__ int solve(const double (&x1)[5][2], const double (&x2)[5
 #pragma unroll
         for (int i = 0; i < 11; ++i) c[i] += t10[i];
     }
+    EPV_PROF(2);
     double re[10], im[10];
     const int n = durand_kerner(c, re, im);
+    EPV_PROF(3);
     int count = 0;
     for (int i = 0; i < n; ++i) {
         if (fabs(im[i]) > 1e-10) continue;
@@ -474,6 +553,9 @@ __device__ __noinline__ int solve(const double (&x1)[5][2], const double (&x2)[5
         for (int k = 0; k < 9; ++k) Eout[count][k] = E[k];
         ++count;
     }
+    EPV_PROF(4);
+    EPV_PROF_ADD(6, 1);
+    EPV_PROF_ADD(7, count);
     return count;
 }
 

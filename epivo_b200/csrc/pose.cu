@@ -8,7 +8,8 @@
 //   E = U diag(s) V'  (V from the Jacobi eigen-decomposition of E'E, U = E V / s,
 //                      third columns by cross product so det U = det V = +1)
 //   R1 = U W V', R2 = U W' V', t = U[:,2];  candidates (R1,t) (R2,t) (R1,-t) (R2,-t)
-//   Q = smallest right singular vector of the DLT matrix (Jacobi on A'A)
+//   Q = smallest right singular vector of the DLT matrix (inverse iteration on A'A from the
+//       first camera's exact ray; cyclic Jacobi only if that does not converge)
 //   good = Qz*Qw > 0 && Qz/Qw < d && 0 < ([R|t] Q/Qw)_z < d   [&& input mask]
 //   winner = first candidate whose count is >= all the others; mask values {0,255}.
 #include "common.cuh"
@@ -116,25 +117,17 @@ __device__ void decompose_essential(const double* E, double (&R1)[9], double (&R
     for (int i = 0; i < 3; ++i) t[i] = u[2][i];
 }
 
-// Cheirality / distance tests of one correspondence against the candidates [R | t] AND [R | -t].
-// The DLT matrix of -t is that of +t with its fourth column negated, so its smallest right
-// singular vector is the same vector with W negated (exactly, IEEE arithmetic being
-// sign-symmetric): one Jacobi solve serves both candidates.  Returns bit 0 = (R,t), bit 1 = (R,-t).
-__device__ __forceinline__ unsigned triangulate_good2(const double* R, const double* t, double a1, double b1,
-                                                      double a2, double b2, double dist) {
-    // DLT rows (triangulate.cpp): x*P[2] - P[0], y*P[2] - P[1] for P0 = [I|0], P1 = [R|t]
-    double A[4][4] = {{-1.0, 0.0, a1, 0.0},
-                      {0.0, -1.0, b1, 0.0},
-                      {a2 * R[6] - R[0], a2 * R[7] - R[1], a2 * R[8] - R[2], a2 * t[2] - t[0]},
-                      {b2 * R[6] - R[3], b2 * R[7] - R[4], b2 * R[8] - R[5], b2 * t[2] - t[1]}};
+// Slow, always-convergent path: cyclic Jacobi on the full 4x4 normal matrix.
+__device__ __noinline__ void smallest_eigvec4_jacobi(const double* m10, double* Q) {
     double M[4][4], V[4][4];
+    int e = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = i; j < 4; ++j) {
-            const double s = A[0][i] * A[0][j] + A[1][i] * A[1][j] + A[2][i] * A[2][j] + A[3][i] * A[3][j];
-            M[i][j] = s;
-            M[j][i] = s;
+            M[i][j] = m10[e];
+            M[j][i] = m10[e];
+            ++e;
         }
     jacobi_eig<4>(M, V);
     int k = 0;
@@ -142,7 +135,6 @@ __device__ __forceinline__ unsigned triangulate_good2(const double* R, const dou
 #pragma unroll
     for (int i = 1; i < 4; ++i)
         if (M[i][i] < best) { best = M[i][i]; k = i; }
-    double Q[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double v = V[i][0];
@@ -151,6 +143,84 @@ __device__ __forceinline__ unsigned triangulate_good2(const double* R, const dou
         if (k == 3) v = V[i][3];
         Q[i] = v;
     }
+}
+
+// Cheirality / distance tests of one correspondence against the candidates [R | t] AND [R | -t].
+// The DLT matrix of -t is that of +t with its fourth column negated, so its smallest right
+// singular vector is the same vector with W negated (exactly, IEEE arithmetic being
+// sign-symmetric): one eigenvector solve serves both candidates.  Returns bit 0 = (R,t), bit 1 = (R,-t).
+__device__ __forceinline__ unsigned triangulate_good2(const double* R, const double* t, double a1, double b1,
+                                                      double a2, double b2, double dist) {
+    // DLT rows (triangulate.cpp): x*P[2] - P[0], y*P[2] - P[1] for P0 = [I|0], P1 = [R|t]:
+    //   (-1, 0, a1, 0), (0, -1, b1, 0), r2 = a2*P1[2] - P1[0], r3 = b2*P1[2] - P1[1]
+    const double r2[4] = {a2 * R[6] - R[0], a2 * R[7] - R[1], a2 * R[8] - R[2], a2 * t[2] - t[0]};
+    const double r3[4] = {b2 * R[6] - R[3], b2 * R[7] - R[4], b2 * R[8] - R[5], b2 * t[2] - t[1]};
+    // M = A'A, upper triangle in row order: 00 01 02 03 11 12 13 22 23 33
+    double m[10];
+    m[0] = 1.0 + (r2[0] * r2[0] + r3[0] * r3[0]);
+    m[1] = r2[0] * r2[1] + r3[0] * r3[1];
+    m[2] = (r2[0] * r2[2] + r3[0] * r3[2]) - a1;
+    m[3] = r2[0] * r2[3] + r3[0] * r3[3];
+    m[4] = 1.0 + (r2[1] * r2[1] + r3[1] * r3[1]);
+    m[5] = (r2[1] * r2[2] + r3[1] * r3[2]) - b1;
+    m[6] = r2[1] * r2[3] + r3[1] * r3[3];
+    m[7] = (a1 * a1 + b1 * b1) + (r2[2] * r2[2] + r3[2] * r3[2]);
+    m[8] = r2[2] * r2[3] + r3[2] * r3[3];
+    m[9] = r2[3] * r2[3] + r3[3] * r3[3];
+    // The smallest right singular vector of A = eigenvector of M for its smallest eigenvalue, by
+    // inverse iteration on M + mu I = L D L' (same eigenvectors; the shift only keeps the
+    // factorisation finite when the point is noise-free and M is singular to working precision).
+    // Start: the least-squares solution inside the subspace X = a1 Z, Y = b1 Z that the first
+    // camera's two rows span exactly; it is within the pixel noise of the answer, so the
+    // iteration contracts by lambda1/lambda2 (~1e-3 .. 1e-6) per step from ~1e-3.
+    const double mu = 1e-15 * ((m[0] + m[4]) + (m[7] + m[9]));
+    const double d0 = m[0] + mu, i0 = 1.0 / d0;
+    const double l10 = m[1] * i0, l20 = m[2] * i0, l30 = m[3] * i0;
+    const double d1 = (m[4] + mu) - l10 * m[1], i1 = 1.0 / d1;
+    const double u21 = m[5] - l20 * m[1], u31 = m[6] - l30 * m[1];
+    const double l21 = u21 * i1, l31 = u31 * i1;
+    const double d2 = ((m[7] + mu) - l20 * m[2]) - l21 * u21, i2 = 1.0 / d2;
+    const double u32 = (m[8] - l30 * m[2]) - l31 * u21;
+    const double l32 = u32 * i2;
+    double d3 = (((m[9] + mu) - l30 * m[3]) - l31 * u31) - l32 * u32;
+    if (d3 == 0.0) d3 = 1e-300;
+    const double i3 = 1.0 / d3;
+    const double c2 = (r2[0] * a1 + r2[1] * b1) + r2[2], c3 = (r3[0] * a1 + r3[1] * b1) + r3[2];
+    double Q[4];
+    {
+        const double z = -(c2 * r2[3] + c3 * r3[3]), w = c2 * c2 + c3 * c3;
+        Q[0] = a1 * z; Q[1] = b1 * z; Q[2] = z; Q[3] = w;
+    }
+    bool converged = false;
+#pragma unroll 1
+    for (int it = 0; it < 12; ++it) {
+        // y = (L D L')^-1 Q
+        const double f0 = Q[0];
+        const double f1 = Q[1] - l10 * f0;
+        const double f2 = (Q[2] - l20 * f0) - l21 * f1;
+        const double f3 = ((Q[3] - l30 * f0) - l31 * f1) - l32 * f2;
+        const double y3 = f3 * i3;
+        const double y2 = f2 * i2 - l32 * y3;
+        const double y1 = (f1 * i1 - l21 * y2) - l31 * y3;
+        const double y0 = ((f0 * i0 - l10 * y1) - l20 * y2) - l30 * y3;
+        // y parallel to Q?  component-wise y (Q.Q) - Q (Q.y): no cancellation below round-off
+        const double qq = (Q[0] * Q[0] + Q[1] * Q[1]) + (Q[2] * Q[2] + Q[3] * Q[3]);
+        const double qy = (Q[0] * y0 + Q[1] * y1) + (Q[2] * y2 + Q[3] * y3);
+        const double yy = (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
+        const double e0 = y0 * qq - Q[0] * qy, e1 = y1 * qq - Q[1] * qy, e2 = y2 * qq - Q[2] * qy,
+                     e3 = y3 * qq - Q[3] * qy;
+        const double err2 = (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+        // rescale by a power of two near 1/|y|_inf to stay in range (exact, direction unchanged)
+        const double big = fmax(fmax(fabs(y0), fabs(y1)), fmax(fabs(y2), fabs(y3)));
+        // sc = 2^-floor(log2 big), assembled from the exponent field (big = 0 gives a harmless 2^1023)
+        const double sc = __hiloint2double(0x7FE00000 - (__double2hiint(big) & 0x7FF00000), 0);
+        Q[0] = y0 * sc; Q[1] = y1 * sc; Q[2] = y2 * sc; Q[3] = y3 * sc;
+        // |sin angle(y, Q)|^2 = err2 / (qq^2 yy): converged once a step moves the direction by
+        // < 2e-15 (the new iterate is then better than that by the contraction factor)
+        if (err2 <= 4e-30 * (qq * qq) * yy) { converged = true; break; }
+        if (!(big == big) || big > 1e300) break;
+    }
+    if (!converged) smallest_eigvec4_jacobi(m, Q);
     const double zw = Q[2] * Q[3];
     const double X = Q[0] / Q[3], Y = Q[1] / Q[3], Z = Q[2] / Q[3];
     const double rz = (R[6] * X + R[7] * Y) + R[8] * Z;

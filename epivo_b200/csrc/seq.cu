@@ -50,6 +50,7 @@ struct epivo_seq {
     // timing
     cudaEvent_t ev[SEQ_MAX_CHUNKS][SEQ_STAGES] = {};
     cudaEvent_t evk[SEQ_MAX_CHUNKS][2] = {};     // around the matcher tile kernel alone
+    cudaEvent_t evp[SEQ_MAX_CHUNKS] = {};        // after sample + presolve
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaStream_t stream2 = nullptr;          // geometry stream (FP64 kernels) -- overlaps the integer-bound matcher
     cudaEvent_t ev_matched[SEQ_MAX_CHUNKS] = {};
@@ -230,6 +231,7 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     {
         for (int k = 0; k < SEQ_STAGES; ++k) ev_ok &= cudaEventCreate(&s->ev[c][k]) == cudaSuccess;
         for (int k = 0; k < 2; ++k) ev_ok &= cudaEventCreate(&s->evk[c][k]) == cudaSuccess;
+        ev_ok &= cudaEventCreate(&s->evp[c]) == cudaSuccess;
     }
     for (int c = 0; c < SEQ_MAX_CHUNKS && ev_ok; ++c)
         ev_ok &= cudaEventCreateWithFlags(&s->ev_matched[c], cudaEventDisableTiming) == cudaSuccess;
@@ -265,6 +267,8 @@ void epivo_seq_destroy(epivo_seq* s) {
     for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
         for (int k = 0; k < 2; ++k)
             if (s->evk[c][k]) cudaEventDestroy(s->evk[c][k]);
+    for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
+        if (s->evp[c]) cudaEventDestroy(s->evp[c]);
     for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
         if (s->ev_matched[c]) cudaEventDestroy(s->ev_matched[c]);
     if (s->ev_geo_done) cudaEventDestroy(s->ev_geo_done);
@@ -325,6 +329,7 @@ static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int 
     ep.pre_nmodels = s->d_pn + o * SEQ_PRE_MAX;
     ep.pre_idx = s->d_pi + o * SEQ_PRE_MAX * 5;
     ep.pre_rng = s->d_prng + o;
+    ep.ev_presolved = s->evp[c];
     rc = epv_essential_launch(ctx, ep);
     if (rc) return rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][3], ctx->stream));
@@ -568,6 +573,11 @@ int epivo_seq_stage_ms(epivo_seq* s, float* ms, int n) {
         acc[7] += t;                // [7] matcher tile kernel alone, summed over the group launches
     }
     for (int c = 0; c < s->last_ggroups; ++c) {
+        {                               // [2] sample + presolve (part of [3])
+            float t = 0;
+            EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->ev[HALF + c][2], s->evp[HALF + c]));
+            acc[2] += t;
+        }
         for (int k = 2; k < 6; ++k) {   // [3] essential [4] pose [5] lm [6] finish
             float t = 0;
             EPV_CUDA(ctx, cudaEventElapsedTime(&t, s->ev[HALF + c][k], s->ev[HALF + c][k + 1]));

@@ -25,6 +25,7 @@ struct EssentialPlan {
     int32_t* pre_nmodels;             // [pair][pre_count]
     int32_t* pre_idx;                 // [pair][pre_count][5]
     unsigned long long* pre_rng;      // [pair]
+    cudaEvent_t ev_presolved = nullptr;   // optional: recorded after the sample + presolve kernels
 };
 int epv_essential_pre_count(int method, double prob, int max_iters, int m_samples);
 int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p);

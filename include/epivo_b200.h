@@ -171,7 +171,7 @@ int epivo_seq_download(epivo_seq* seq, epivo_pair_result* out, int first_pair, i
  * B200 the two kernels contend for issue slots and registers and the pipelined run is not faster. */
 int epivo_seq_set_overlap(epivo_seq* seq, int overlap);
 /* per-stage device time of the last run (CUDA events on the context stream), ms:
- * [0] total [1] match [2] - [3] essential [4] pose [5] lm [6] finish [7] matcher tile kernel alone
+ * [0] total [1] match [2] presolve (part of 3) [3] essential [4] pose [5] lm [6] finish [7] matcher tile kernel alone
  * [8] number of pair groups; stage times overlap when the two streams do. */
 int epivo_seq_stage_ms(epivo_seq* seq, float* ms, int n);
 /* debug/parity views of the last run, host copies: matches of one pair */
