@@ -57,8 +57,14 @@ __device__ __forceinline__ void rt_inv(const Rt& a, Rt& o) {
     o = r;
 }
 
+// Arithmetic note.  FP64 division and square root cost ~20 dependent instructions each on the
+// GPU and the reference's formulas are full of them (||A||/||B||, X/X_z, .../||B||^2 per Jacobian
+// column).  The functions below compute the same quantities from one reciprocal square root per
+// norm and one reciprocal per depth; results differ from the literal formulas in the last bits
+// only (the parity tolerance for the LM is relative 1e-5, tests/test_gpu_pose_lm.py).
+
 // Sophus::SE3<double>::exp(delta), delta = (upsilon, omega)                         [:419]
-__device__ void se3_exp(const double* d, Rt& o) {
+__device__ __forceinline__ void se3_exp(const double* d, Rt& o) {
     const double wx = d[3], wy = d[4], wz = d[5];
     const double th2 = wx * wx + wy * wy + wz * wz;
     const double th = sqrt(th2);
@@ -66,9 +72,12 @@ __device__ void se3_exp(const double* d, Rt& o) {
     if (th < 1e-10) {
         a = 1.0; b = 0.5; c = 1.0 / 6.0;
     } else {
-        a = sin(th) / th;
-        b = (1.0 - cos(th)) / th2;
-        c = (th - sin(th)) / (th2 * th);
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        const double ith = 1.0 / th, ith2 = ith * ith;
+        a = sn * ith;
+        b = (1.0 - cs) * ith2;
+        c = (th - sn) * (ith2 * ith);
     }
     const double Om[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
     double Om2[9];
@@ -95,19 +104,22 @@ __device__ __forceinline__ double res_one(const Rt& T, const double* p, const do
     const double q1 = T.R[3] * p[0] + T.R[4] * p[1] + T.R[5] * p[2];
     const double q2 = T.R[6] * p[0] + T.R[7] * p[1] + T.R[8] * p[2];
     const double B0 = q0 + px * q2, B1 = q1 + py * q2;
-    const double nb = sqrt(B0 * B0 + B1 * B1);
-    double d = 0.0;
-    if (nb > 0) d = sqrt(A0 * A0 + A1 * A1) / nb;
+    const double ATA = A0 * A0 + A1 * A1, BTB = B0 * B0 + B1 * B1;
+    double d = 0.0;                                                                  // ||A|| / ||B||, 0 if ||B|| = 0
+    if (BTB > 0) d = (ATA > 0) ? (ATA * rsqrt(ATA)) * rsqrt(BTB) : 0.0;
     const double X0 = q0 * d + T.t[0], X1 = q1 * d + T.t[1], X2 = q2 * d + T.t[2];
-    const double e0 = p_[0] - X0 / X2, e1 = p_[1] - X1 / X2, e2 = p_[2] - X2 / X2;
-    double r = (e0 * e0 + e1 * e1 + e2 * e2) / 2.0;
-    if (r > hd) r = hd * (sqrt(r) - hd / 2.0);
+    const double iz = 1.0 / X2;
+    const double e0 = p_[0] - X0 * iz, e1 = p_[1] - X1 * iz, e2 = p_[2] - X2 * iz;
+    double r = (e0 * e0 + e1 * e1 + e2 * e2) * 0.5;
+    if (r > hd) r = hd * (sqrt(r) - hd * 0.5);
     return r;
 }
 
 // One row of Dr_Deps: d r / d eps for T = Tl exp(eps) Tr (sign s for reverse reps)   [:109-208]
+// If `res` is non-null the residual of the same correspondence under T0 is returned through it
+// (the single-pair kernel evaluates both at the same transform).
 __device__ __forceinline__ void jac_row(const Rt& Tl, const Rt& Tr, const Rt& T0, double s, const double* p,
-                                        const double* p_, double hd, double* row) {
+                                        const double* p_, double hd, double* row, double* res = nullptr) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) row[j] = 0.0;
     const double px = -p_[0], py = -p_[1];
@@ -117,28 +129,38 @@ __device__ __forceinline__ void jac_row(const Rt& Tl, const Rt& Tr, const Rt& T0
     const double q2 = T0.R[6] * p[0] + T0.R[7] * p[1] + T0.R[8] * p[2];
     const double B0 = q0 + px * q2, B1 = q1 + py * q2;
     const double ATA = A0 * A0 + A1 * A1, BTB = B0 * B0 + B1 * B1;
-    if (ATA == 0 || BTB == 0) return;                                              // [:152-154]
-    const double sa = sqrt(ATA), sb = sqrt(BTB);
-    const double ka = (1.0 / sa) * sb, kb = (1.0 / sb) * sa;
-    const double d0 = sa / sb;
+    const bool degenerate = (ATA == 0 || BTB == 0);                                 // [:152-154]: row stays 0
+    const double isa = degenerate ? 0.0 : rsqrt(ATA), isb = degenerate ? 0.0 : rsqrt(BTB);
+    const double sa = ATA * isa, sb = BTB * isb;                                     // ||A||, ||B||
+    const double ka = isa * sb, kb = isb * sa;
+    const double d0 = (BTB > 0) ? sa * isb : 0.0;                                    // res(): d = 0 when ||B|| = 0
+    const double iBTB = isb * isb;
     const double X0 = q0 * d0 + T0.t[0], X1 = q1 * d0 + T0.t[1], X2 = q2 * d0 + T0.t[2];
+    const double iz = 1.0 / X2;
+    if (res) {
+        const double f0 = p_[0] - X0 * iz, f1 = p_[1] - X1 * iz, f2 = p_[2] - X2 * iz;
+        double r = (f0 * f0 + f1 * f1 + f2 * f2) * 0.5;
+        if (r > hd) r = hd * (sqrt(r) - hd * 0.5);
+        *res = r;
+    }
+    if (degenerate) return;
     // u = Rr p, ut = tr  (the generator acts on Tr [p d0; 1] = Rr p d0 + tr)
     const double u0 = Tr.R[0] * p[0] + Tr.R[1] * p[1] + Tr.R[2] * p[2];
     const double u1 = Tr.R[3] * p[0] + Tr.R[4] * p[1] + Tr.R[5] * p[2];
     const double u2 = Tr.R[6] * p[0] + Tr.R[7] * p[1] + Tr.R[8] * p[2];
-    double e0, e1, e2, j00 = 0, j02 = 0, j12 = 0;   // J_pi rows: (j00, 0, j02), (0, j00, j12), 0
+    double j00 = 0, j02 = 0, j12 = 0;   // J_pi rows: (j00, 0, j02), (0, j00, j12), 0
     if (X2 != 0) {
-        j00 = 1.0 / X2;
-        j02 = -X0 / (X2 * X2);
-        j12 = -X1 / (X2 * X2);
+        j00 = iz;
+        j02 = -X0 * (iz * iz);
+        j12 = -X1 * (iz * iz);
     }
-    e0 = X0 / X2 - p_[0];
-    e1 = X1 / X2 - p_[1];
-    e2 = 1.0 - p_[2];
+    const double e0 = X0 * iz - p_[0];
+    const double e1 = X1 * iz - p_[1];
+    const double e2 = 1.0 - p_[2];
     const double ee = e0 * e0 + e1 * e1 + e2 * e2;
     double g0 = e0, g1 = e1;                                                        // [:203-207]
     if (!(ee <= hd)) {
-        const double k = hd / sqrt(ee);
+        const double k = hd * rsqrt(ee);
         g0 = k * e0;
         g1 = k * e1;
     }
@@ -164,7 +186,7 @@ __device__ __forceinline__ void jac_row(const Rt& Tl, const Rt& Tr, const Rt& T0
         }
         const double dA0 = mt0 + px * mt2, dA1 = mt1 + py * mt2;
         const double dB0 = mp0 + px * mp2, dB1 = mp1 + py * mp2;
-        const double jd = (ka * (A0 * dA0 + A1 * dA1) - kb * (B0 * dB0 + B1 * dB1)) / BTB;   // [:162]
+        const double jd = (ka * (A0 * dA0 + A1 * dA1) - kb * (B0 * dB0 + B1 * dB1)) * iBTB;   // [:162]
         const double dX0 = mp0 * d0 + mt0 + q0 * jd;                                        // [:171,175]
         const double dX1 = mp1 * d0 + mt1 + q1 * jd;
         const double dX2 = mp2 * d0 + mt2 + q2 * jd;
@@ -350,12 +372,12 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                 }
                 __syncthreads();
             }
-            const double piv = sH[(size_t)k * (D + 1) + k];
+            const double ipiv = 1.0 / sH[(size_t)k * (D + 1) + k];
             // eliminate below: element (r, c) for r > k, c > k
             const int rows = D - k - 1, cols = D - k;     // cols k+1..D
             for (int e = tid; e < rows * cols; e += LM_THREADS) {
                 const int r = k + 1 + e / cols, c = k + 1 + e % cols;
-                const double f = sH[(size_t)r * (D + 1) + k] / piv;
+                const double f = sH[(size_t)r * (D + 1) + k] * ipiv;
                 sH[(size_t)r * (D + 1) + c] -= f * sH[(size_t)k * (D + 1) + c];
             }
         }
@@ -446,19 +468,37 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
 // One WARP per problem, everything in registers: each lane owns up to two correspondences,
 // the 6x6 normal equations are reduced with warp shuffles and solved redundantly by every lane,
 // so the 30 dependent iterations need no shared memory and no block barrier.
-constexpr int LMP_WARPS = 4;
+#ifndef EPV_LMP_WARPS
+#define EPV_LMP_WARPS 4
+#endif
+#ifndef EPV_LMP_MINBLOCKS
+#define EPV_LMP_MINBLOCKS 1
+#endif
+constexpr int LMP_WARPS = EPV_LMP_WARPS;
 
-__device__ __forceinline__ double warp_sum_d(double v) {
+// lanes per problem: 32 = one warp per problem (two correspondences per lane); 16 / 8 pack two /
+// four problems into a warp (four / eight correspondences per lane), trading per-problem latency
+// for fewer, fuller warps -- the 30 dependent iterations make this kernel latency bound.
+#ifndef EPV_LM_LPP
+#define EPV_LM_LPP 8
+#endif
+constexpr int LM_LPP = EPV_LM_LPP;
+constexpr int LM_PPL = 64 / LM_LPP;                 // correspondences per lane (N <= 64)
+
+__device__ __forceinline__ double group_sum_d(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    for (int o = LM_LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
 }
 
-__global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
-    const int lane = threadIdx.x & 31;
-    const int prob = blockIdx.x * LMP_WARPS + (threadIdx.x >> 5);
-    if (prob >= p.B) return;
-    if (p.active && !p.active[prob]) return;
+__global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_kernel(LmPlan p) {
+    const int gl = threadIdx.x & (LM_LPP - 1);                                  // lane within the problem's group
+    const int prob_raw = (blockIdx.x * LMP_WARPS * 32 + threadIdx.x) / LM_LPP;
+    const bool exists = prob_raw < p.B;
+    const int prob = exists ? prob_raw : p.B - 1;                               // clamp: shuffles need every lane
+    bool done = !exists || (p.active && !p.active[prob]);
+    const bool skip = done;                                                      // nothing is written for this problem
+    if (__all_sync(0xFFFFFFFFu, done)) return;
     const int N = p.N;
     double* gT = p.T0s + (size_t)prob * 16;
     const double* gpr = p.pr + (size_t)prob * N * 3;
@@ -474,11 +514,11 @@ __global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
         T.t[i] = gT[i * 4 + 3];
     }
     // this lane's correspondences
-    double pa[2][3], pb[2][3];
-    bool have[2];
+    double pa[LM_PPL][3], pb[LM_PPL][3];
+    bool have[LM_PPL];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int i = lane + 32 * k;
+    for (int k = 0; k < LM_PPL; ++k) {
+        const int i = gl + LM_LPP * k;
         have[k] = i < N;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -486,21 +526,23 @@ __global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
             pb[k][c] = have[k] ? gp_r[i * 3 + c] : 1.0;
         }
     }
-    double lambda = p.lambda0, prevE = 1e10, Hnorm = 0.0, rnorm = 0.0;
+    // squared norms are carried; the square roots are taken once at the end
+    double lambda = p.lambda0, prevE2 = 1e20, hs_out = 0.0, rsq_out = 0.0;
     int iters = 0;
     for (int iter = 0; iter < p.max_iters; ++iter) {
-        iters = iter + 1;
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+        if (!done) iters = iter + 1;
         double H[21], b[6], rsq = 0.0;
 #pragma unroll
         for (int i = 0; i < 21; ++i) H[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < 6; ++i) b[i] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < LM_PPL; ++k) {
             if (!have[k]) continue;
-            const double r = w * res_one(T, pa[k], pb[k], hd);                      // [:356-359]
-            double row[6];
-            jac_row(T, I, T, 1.0, pa[k], pb[k], hd, row);                           // [:372-381]
+            double row[6], r;
+            jac_row(T, I, T, 1.0, pa[k], pb[k], hd, row, &r);                       // [:356-359, :372-381]
+            r *= w;
 #pragma unroll
             for (int c = 0; c < 6; ++c) row[c] *= w;
             int e = 0;
@@ -513,11 +555,10 @@ __global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
             rsq += r * r;
         }
 #pragma unroll
-        for (int i = 0; i < 21; ++i) H[i] = warp_sum_d(H[i]);
+        for (int i = 0; i < 21; ++i) H[i] = group_sum_d(H[i]);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) b[i] = warp_sum_d(b[i]);
-        rsq = warp_sum_d(rsq);
-        rnorm = sqrt(rsq);
+        for (int i = 0; i < 6; ++i) b[i] = group_sum_d(b[i]);
+        rsq = group_sum_d(rsq);
         // augmented, damped system  [H + lambda diag(H) | -b]                      [:403-405]
         double A[6][7];
         {
@@ -537,9 +578,9 @@ __global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
         for (int a = 0; a < 6; ++a)
 #pragma unroll
             for (int c = 0; c < 6; ++c) hs += A[a][c] * A[a][c];
-        Hnorm = sqrt(hs);
+        double ip[6];                                       // reciprocal pivots
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {                       // LU, partial pivoting (uniform across lanes)
+        for (int k = 0; k < 6; ++k) {                       // LU, partial pivoting (uniform across the group)
             int pv = k;
             double best = fabs(A[k][k]);
 #pragma unroll
@@ -551,9 +592,10 @@ __global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
 #pragma unroll
                     for (int c = 0; c < 7; ++c) { const double t = A[k][c]; A[k][c] = A[r][c]; A[r][c] = t; }
                 }
+            ip[k] = 1.0 / A[k][k];
 #pragma unroll
             for (int r = k + 1; r < 6; ++r) {
-                const double f = A[r][k] / A[k][k];
+                const double f = A[r][k] * ip[k];
 #pragma unroll
                 for (int c = k + 1; c < 7; ++c) A[r][c] -= f * A[k][c];
             }
@@ -565,33 +607,36 @@ __global__ void __launch_bounds__(LMP_WARPS * 32) lm_pair_kernel(LmPlan p) {
             double s = A[r][6];
 #pragma unroll
             for (int c = r + 1; c < 6; ++c) s -= A[r][c] * d[c];
-            d[r] = s / A[r][r];
+            d[r] = s * ip[r];
             bad |= !(d[r] == d[r]) || isinf(d[r]);
             dn += d[r] * d[r];
         }
-        if (bad || sqrt(dn) < p.epsilon) break;                                     // [:407-414]
+        if (!done) { rsq_out = rsq; hs_out = hs; }
+        if (bad || sqrt(dn) < p.epsilon) done = true;                               // [:407-414]
         Rt ex, Tn;
         se3_exp(d, ex);                                                             // [:416-422]
         rt_mul(T, ex, Tn);
         double csq = 0.0;                                                           // [:445-456]
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < LM_PPL; ++k) {
             if (!have[k]) continue;
             const double r = res_one(Tn, pa[k], pb[k], hd);
             csq += r * r;
         }
-        csq = warp_sum_d(csq);
-        const double currE = sqrt(csq);
-        rnorm = currE;
-        if (currE < prevE) {                                                        // [:457-467]
-            prevE = currE;
-            T = Tn;
-            lambda /= 2.0;
-        } else {
-            lambda *= 5.0;
+        csq = group_sum_d(csq);
+        if (!done) {
+            rsq_out = csq;                                                          // r0 now holds the candidate residuals
+            if (csq < prevE2) {                                                     // [:457-467] (|r| < prev_E, squared)
+                prevE2 = csq;
+                T = Tn;
+                lambda /= 2.0;
+            } else {
+                lambda *= 5.0;
+            }
         }
     }
-    if (lane == 0) {
+    const double Hnorm = sqrt(hs_out), rnorm = sqrt(rsq_out);
+    if (gl == 0 && !skip) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
 #pragma unroll
@@ -620,7 +665,8 @@ int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
         EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "n_zeta = %d outside [1, %d]", p.n_zeta, LM_MAX_ZETA);
     if (p.n_rep < 1 || p.N < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_rep = %d, N = %d", p.n_rep, p.N);
     if (p.single_pair && p.n_zeta == 1 && p.n_rep == 1 && p.N <= 64) {
-        lm_pair_kernel<<<(p.B + LMP_WARPS - 1) / LMP_WARPS, LMP_WARPS * 32, 0, ctx->stream>>>(p);
+        const int per_block = LMP_WARPS * 32 / LM_LPP;       // problems per CTA
+        lm_pair_kernel<<<(p.B + per_block - 1) / per_block, LMP_WARPS * 32, 0, ctx->stream>>>(p);
         EPV_LAUNCHED(ctx);
         return EPIVO_OK;
     }
