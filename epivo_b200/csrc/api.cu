@@ -224,10 +224,10 @@ int epivo_find_essential(epivo_ctx* ctx, const float* p0, const float* p1, int n
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     const int stride = n;
     const size_t nerr = epv_essential_errbuf_floats(1, stride);
-    const int pre = epv_essential_pre_count(method, prob, max_iters, samples ? m : 0);
+    const size_t wbytes = epv_essential_work_bytes(1);
     size_t need = epv_align((size_t)n * 8) * 2 + epv_align((size_t)stride * 32) + epv_align(nerr * 4) +
                   epv_align((size_t)n) + epv_align((size_t)std::max(m, 1) * 20) + 8 * 256 + 4096 +
-                  epv_align((size_t)pre * 720) + epv_align((size_t)pre * 24) + 512;
+                  epv_align(wbytes) + 512;
     int rc = epv_ws_reserve(ctx, need);
     if (rc) return rc;
     float* d_p0 = epv_ws_take<float>(ctx, (size_t)n * 2);
@@ -239,10 +239,7 @@ int epivo_find_essential(epivo_ctx* ctx, const float* p0, const float* p1, int n
     double* d_E = epv_ws_take<double>(ctx, 9);
     int32_t* d_n = epv_ws_take<int32_t>(ctx, 1);
     int32_t* d_out = epv_ws_take<int32_t>(ctx, 4);
-    double* d_pm = epv_ws_take<double>(ctx, (size_t)pre * 90);
-    int32_t* d_pn = epv_ws_take<int32_t>(ctx, pre);
-    int32_t* d_pi = epv_ws_take<int32_t>(ctx, (size_t)pre * 5);
-    unsigned long long* d_pr = epv_ws_take<unsigned long long>(ctx, 1);
+    char* d_work = epv_ws_take<char>(ctx, wbytes);
     EPV_CUDA(ctx, cudaMemcpyAsync(d_p0, p0, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(d_p1, p1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(d_n, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -268,11 +265,8 @@ int epivo_find_essential(epivo_ctx* ctx, const float* p0, const float* p1, int n
     ep.iters = d_out + 1;
     ep.n_models = d_out + 2;
     ep.status = d_out + 3;
-    ep.pre_count = pre;
-    ep.pre_models = d_pm;
-    ep.pre_nmodels = d_pn;
-    ep.pre_idx = d_pi;
-    ep.pre_rng = d_pr;
+    ep.work = d_work;
+    ep.work_bytes = wbytes;
     rc = epv_essential_launch(ctx, ep);
     if (rc) return rc;
     int32_t h_out[4];
@@ -291,16 +285,17 @@ int epivo_five_point(epivo_ctx* ctx, const double* x1, const double* x2, int m, 
     if (m < 0 || (m > 0 && (!x1 || !x2 || !E_out || !n_models))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
     if (m == 0) return EPIVO_OK;
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = epv_ws_reserve(ctx, (size_t)m * (80 * 2 + 720 + 4) + 4096);
+    int rc = epv_ws_reserve(ctx, (size_t)m * (80 * 2 + 720 + 4 + 96 * 8) + 8192);
     if (rc) return rc;
     double* d_x1 = epv_ws_take<double>(ctx, (size_t)m * 10);
     double* d_x2 = epv_ws_take<double>(ctx, (size_t)m * 10);
     double* d_E = epv_ws_take<double>(ctx, (size_t)m * 90);
     int32_t* d_nm = epv_ws_take<int32_t>(ctx, m);
+    double* d_rec = epv_ws_take<double>(ctx, (size_t)m * 96);
     EPV_CUDA(ctx, cudaMemcpyAsync(d_x1, x1, (size_t)m * 80, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(d_x2, x2, (size_t)m * 80, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemsetAsync(d_E, 0, (size_t)m * 720, ctx->stream));
-    rc = epv_five_point_launch(ctx, d_x1, d_x2, m, d_E, d_nm);
+    rc = epv_five_point_launch(ctx, d_x1, d_x2, m, d_rec, d_E, d_nm);
     if (rc) return rc;
     EPV_CUDA(ctx, cudaMemcpyAsync(E_out, d_E, (size_t)m * 720, cudaMemcpyDeviceToHost, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(n_models, d_nm, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,15 +1,15 @@
-// E1/E2: cv::findEssentialMat(RANSAC | LMEDS) on the GPU, one CTA per frame pair.
+// E1/E2: cv::findEssentialMat(RANSAC | LMEDS) on the GPU, batched over frame pairs.
 //
 // Replaces kitti.cpp:98-104, kitti_E.cpp:98-104, euroc_E.cpp:202-208, kitti_ba.cpp:232,308,702.
 // OpenCV's estimator (modules/calib3d/src/ptsetreg.cpp) is a sequential loop
 //     sample 5 -> solve (<= 10 models) -> score every model -> keep strictly better -> shrink niters
-// whose sample stream does not depend on the data (cv::RNG seeded with -1).  The kernel
-// keeps those semantics exactly but evaluates CHUNK samples at a time: thread 0 draws the
-// next CHUNK samples from the same RNG, CHUNK threads solve them (fivept.cuh), the warps
-// score all their models (Sampson error in OpenCV's operation order, float32 compare), and
-// thread 0 replays the sequential "strictly better / update niters" bookkeeping over the
-// chunk in sample order, stopping where the sequential loop would have stopped.  The result
-// is the model the sequential loop would return; at most CHUNK-1 samples are wasted.
+// whose sample stream does not depend on the data (cv::RNG seeded with -1).  Those semantics are
+// kept exactly, but the work is done in rounds (see "Rounds" below): the next R samples of every
+// running pair are drawn from the same RNG stream and solved at full occupancy (fivept.cuh), then
+// one CTA per pair scores the models (Sampson error in OpenCV's operation order, float32
+// compare) and replays the sequential "strictly better / update niters" bookkeeping in sample
+// order, stopping where the sequential loop would have stopped.  The result is the model the
+// sequential loop returns.
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -24,7 +24,6 @@ namespace {
 
 constexpr int ES_THREADS = 256;
 constexpr int ES_WARPS = ES_THREADS / 32;
-constexpr int ES_CHUNK = 32;
 
 struct CvRng {   // cv::RNG: multiply-with-carry
     unsigned long long state;
@@ -154,6 +153,64 @@ __device__ float warp_select(const float* buf, int n, int k, int lane) {
     return __uint_as_float(result);
 }
 
+// =====================================================================================
+// Rounds.  OpenCV's estimator is a sequential loop whose sample stream does not depend on
+// the data, so samples can be solved ahead of the bookkeeping.  A round r handles the next
+// R_r samples of every pair that is still running:
+//     ess_sample_kernel   one thread per running pair draws the samples (cv::RNG stream)
+//     solve_a_kernel      one lane per (pair, sample): null space, constraints, elimination
+//     solve_b_kernel      one lane per (pair, sample): polynomial, roots, models, refinement
+//     ess_round_kernel    one CTA per running pair: scores the models, replays the sequential
+//                         "strictly better -> update niters" bookkeeping in sample order, and
+//                         either finishes the pair (mask, compaction) or queues it for round r+1
+// Pairs that have stopped drop out of the work list; samples at or beyond a pair's current
+// niters are never solved or scored.  The host enqueues enough rounds to cover max_iters;
+// rounds with an empty work list cost a few microseconds (grid-stride kernels, small grids).
+// =====================================================================================
+constexpr int ES_RMAX = 128;         // samples per pair per round, at most
+constexpr int ES_MAX_ROUNDS = 40;
+
+struct RansacState {
+    double best_score;
+    double bestE[9];
+    unsigned long long rng;
+    int iter, niters, have, total_models;
+};
+
+struct EssWork {
+    RansacState* state;      // [n_pairs]
+    int32_t* wl[2];          // work lists (pair indices), ping-pong
+    int32_t* ctl;            // [ES_MAX_ROUNDS + 1] running pairs per round
+    int32_t* idx;            // [n_pairs * ES_RMAX][5]
+    double* rec;             // [EB_DOUBLES][cap]  stage A -> stage B records, SoA
+    double* models;          // [cap][10][9]
+    int32_t* nmodels;        // [cap]
+    size_t cap;              // n_pairs * ES_RMAX slots
+};
+
+size_t ess_work_carve(EssWork* w, char* base, int n_pairs) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += epv_align(bytes);
+        return p;
+    };
+    const size_t cap = (size_t)n_pairs * ES_RMAX;
+    RansacState* st = reinterpret_cast<RansacState*>(take((size_t)n_pairs * sizeof(RansacState)));
+    int32_t* wl0 = reinterpret_cast<int32_t*>(take((size_t)n_pairs * 4));
+    int32_t* wl1 = reinterpret_cast<int32_t*>(take((size_t)n_pairs * 4));
+    int32_t* ctl = reinterpret_cast<int32_t*>(take((ES_MAX_ROUNDS + 1) * 4));
+    int32_t* idx = reinterpret_cast<int32_t*>(take(cap * 5 * 4));
+    double* rec = reinterpret_cast<double*>(take(cap * fivept::EB_DOUBLES * 8));
+    double* models = reinterpret_cast<double*>(take(cap * 90 * 8));
+    int32_t* nm = reinterpret_cast<int32_t*>(take(cap * 4));
+    if (w) {
+        w->state = st; w->wl[0] = wl0; w->wl[1] = wl1; w->ctl = ctl; w->idx = idx; w->rec = rec;
+        w->models = models; w->nmodels = nm; w->cap = cap;
+    }
+    return off;
+}
+
 struct EssArgs {
     int n_pairs;
     int stride;                 // per-pair row stride of xn / masks
@@ -165,11 +222,7 @@ struct EssArgs {
     const int32_t* samples;     // optional injected samples [m][5] (shared by all pairs) or nullptr
     int m;
     float* errbuf;              // LMedS scratch [pair][ES_WARPS][stride]
-    // pre-solved first samples (presolve_kernel): models of samples [0, pre_count) of every pair
-    int pre_count;              // multiple of ES_CHUNK (0 = none)
-    const double* pre_models;   // [pair][pre_count][10][9]
-    const int32_t* pre_nmodels; // [pair][pre_count]
-    const unsigned long long* pre_rng;   // [pair] RNG state after pre_count samples
+    EssWork w;
     // outputs
     double* E;                  // [pair][9]
     uint8_t* mask;              // [pair][stride] {0,1}
@@ -180,138 +233,251 @@ struct EssArgs {
     double* xin;                // optional compacted inliers [pair][4][stride] (E3, kitti_E.cpp:106-112)
 };
 
-__global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
-    __shared__ double s_models[ES_CHUNK][10][9];
-    __shared__ int s_nmodels[ES_CHUNK];
-    __shared__ int s_idx[ES_CHUNK][5];
-    __shared__ float s_score[ES_CHUNK][10];      // LMedS: median of every model of the chunk
-    __shared__ int s_cnt[ES_WARPS][10];          // RANSAC: inlier counts of the sub-chunk being scored
+__global__ void ess_init_kernel(EssArgs a) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair == 0) {
+        a.w.ctl[0] = a.n_pairs;
+        for (int r = 1; r <= ES_MAX_ROUNDS; ++r) a.w.ctl[r] = 0;
+    }
+    if (pair >= a.n_pairs) return;
+    const int n = a.n[pair];
+    const bool lmeds = a.method == EPIVO_LMEDS;
+    RansacState s;
+    s.best_score = lmeds ? DBL_MAX : 0.0;
+    for (int i = 0; i < 9; ++i) s.bestE[i] = 0.0;
+    s.rng = 0xFFFFFFFFFFFFFFFFULL;                                      // RNG rng((uint64)-1)
+    s.iter = 0;
+    s.have = 0;
+    s.total_models = 0;
+    int ni = lmeds ? max(update_num_iters(a.prob, 0.45, 5, a.max_iters), 3) : max(a.max_iters, 1);
+    if (a.samples) ni = min(ni, a.m);
+    if (n < 5) ni = 0;
+    if (n == 5) ni = 1;                                                 // count == modelPoints: one solve on all points
+    s.niters = ni;
+    a.w.state[pair] = s;
+    a.w.wl[0][pair] = pair;
+}
+
+// one thread per running pair: the next min(R, niters - iter) samples of its stream
+__global__ void ess_sample_kernel(EssArgs a, int round, int R) {
+    const int count = a.w.ctl[round];
+    const int32_t* wl = a.w.wl[round & 1];
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
+        const int pair = wl[w];
+        RansacState& st = a.w.state[pair];
+        const int n = a.n[pair];
+        const int ns = min(R, st.niters - st.iter);
+        int32_t* out = a.w.idx + (size_t)w * R * 5;
+        if (n == 5) {
+            for (int s = 0; s < ns; ++s)
+                for (int k = 0; k < 5; ++k) out[s * 5 + k] = k;
+        } else if (a.samples) {
+            for (int s = 0; s < ns; ++s)
+                for (int k = 0; k < 5; ++k) out[s * 5 + k] = a.samples[(size_t)(st.iter + s) * 5 + k];
+        } else {
+            CvRng rng{st.rng};
+            for (int s = 0; s < ns; ++s) {
+                int v[5];
+                draw_subset(rng, n, v);
+                for (int k = 0; k < 5; ++k) out[s * 5 + k] = v[k];
+            }
+            st.rng = rng.state;
+        }
+    }
+}
+
+// ---- stage A: one warp = 32 hypotheses, 10x20 matrices lane-strided in shared memory -------
+constexpr int SA_SMEM = 10 * 20 * 32 * 8;   // 51200 bytes per warp
+
+__global__ void __launch_bounds__(32) solve_a_kernel(EssArgs a, int round, int R) {
+    extern __shared__ __align__(16) double s_A[];
+    const int lane = threadIdx.x;
+    const int count = a.w.ctl[round];
+    const int32_t* wl = a.w.wl[round & 1];
+    const long long total = (long long)count * R;
+    for (long long g = blockIdx.x; g * 32 < total; g += gridDim.x) {
+        const long long slot = g * 32 + lane;
+        bool valid = slot < total;
+        int pair = 0, s = 0;
+        if (valid) {
+            const int w = (int)(slot / R);
+            s = (int)(slot % R);
+            pair = wl[w];
+            const RansacState& st = a.w.state[pair];
+            valid = st.iter + s < st.niters;
+        }
+        if (valid) {
+            const int32_t* id = a.w.idx + slot * 5;
+            const double* X1 = a.xn + (size_t)pair * 4 * a.stride;
+            double x1[5][2], x2[5][2];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int i = id[k];
+                x1[k][0] = X1[i]; x1[k][1] = X1[a.stride + i];
+                x2[k][0] = X1[2 * a.stride + i]; x2[k][1] = X1[3 * a.stride + i];
+            }
+            fivept::stage_a(x1, x2, fivept::SmemMat{s_A + lane}, a.w.rec + slot, a.w.cap);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- stage B: one lane per hypothesis, registers + a 75-double shared scratch ---------------
+constexpr int SB_THREADS = 64;
+#ifndef EPV_SB_MINBLOCKS
+#define EPV_SB_MINBLOCKS 4
+#endif
+
+__global__ void __launch_bounds__(SB_THREADS, EPV_SB_MINBLOCKS) solve_b_kernel(EssArgs a, int round, int R) {
+    __shared__ double s_sh[fivept::SB_SCRATCH * SB_THREADS];
+    const int count = a.w.ctl[round];
+    const int32_t* wl = a.w.wl[round & 1];
+    const long long total = (long long)count * R;
+    for (long long base = (long long)blockIdx.x * SB_THREADS; base < total; base += (long long)gridDim.x * SB_THREADS) {
+        const long long slot = base + threadIdx.x;
+        if (slot >= total) continue;
+        const int w = (int)(slot / R), s = (int)(slot % R);
+        const RansacState& st = a.w.state[wl[w]];
+        if (st.iter + s >= st.niters) continue;
+        a.w.nmodels[slot] = fivept::stage_b(a.w.rec + slot, a.w.cap, s_sh + threadIdx.x, SB_THREADS, a.w.models + slot * 90);
+    }
+}
+
+// ---- scoring + sequential replay + finish: one CTA per running pair -------------------------
+__global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int round, int R, int last_round) {
+    __shared__ double s_models[ES_WARPS][10][9];  // models of the sub-chunk being scored
+    __shared__ int s_nm[ES_WARPS];
+    __shared__ unsigned char s_item[ES_WARPS * 10];   // flattened (sample << 4 | model) list of the sub-chunk
+    __shared__ int s_nitems;
+    __shared__ float s_score[ES_WARPS][10];       // LMedS: medians
+    __shared__ int s_cnt[ES_WARPS][10];           // RANSAC: inlier counts
     __shared__ double s_bestE[9];
+    __shared__ double s_best_score;
     __shared__ int s_niters, s_iter, s_have, s_total_models;
-    __shared__ unsigned long long s_rng;
     __shared__ int s_warpcnt[ES_WARPS];
     __shared__ int s_base;
+    __shared__ float s_thr;
 
-    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = a.n[pair];
-    const int64_t so = (int64_t)pair * 4 * a.stride;
-    const double* X1 = a.xn + so;
-    const double* Y1 = X1 + a.stride;
-    const double* X2 = Y1 + a.stride;
-    const double* Y2 = X2 + a.stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int count = a.w.ctl[round];
+    const int32_t* wl = a.w.wl[round & 1];
     const bool lmeds = a.method == EPIVO_LMEDS;
     const float thr32 = (float)(a.thresh * a.thresh);
-
-    if (tid == 0) {
-        s_rng = a.pre_count > 0 && !a.samples ? a.pre_rng[pair] : 0xFFFFFFFFFFFFFFFFULL;   // RNG rng((uint64)-1)
-        s_iter = 0;
-        s_have = 0;
-        s_total_models = 0;
-        int ni = lmeds ? max(update_num_iters(a.prob, 0.45, 5, a.max_iters), 3) : max(a.max_iters, 1);
-        if (a.samples) ni = min(ni, a.m);
-        if (n < 5) ni = 0;
-        if (n == 5) ni = 1;                                  // count == modelPoints: one solve on all points
-        s_niters = ni;
-    }
-    __syncthreads();
-
-    double best_score = lmeds ? DBL_MAX : 0.0;               // thread 0 only
     const SampThr thrR = make_samp_thr(thr32);
 
-    while (true) {
-        const int iter0 = s_iter, niters = s_niters;
-        if (iter0 >= niters) break;
-        // a chunk never straddles the end of the pre-solved samples (the in-kernel RNG state
-        // continues from there)
-        const bool presolved = iter0 < a.pre_count;
-        const int ch = min(min(ES_CHUNK, niters - iter0), presolved ? a.pre_count - iter0 : ES_CHUNK);
-        if (presolved) {
-            // models of this chunk were solved by presolve_kernel at full occupancy
-            const double* gm = a.pre_models + ((int64_t)pair * a.pre_count + iter0) * 90;
-            const int32_t* gn = a.pre_nmodels + (int64_t)pair * a.pre_count + iter0;
-            for (int i = tid; i < ch * 90; i += ES_THREADS) (&s_models[0][0][0])[i] = gm[i];
-            for (int i = tid; i < ch; i += ES_THREADS) s_nmodels[i] = gn[i];
-        } else if (tid == 0) {
-            if (n == 5) {
-                for (int k = 0; k < 5; ++k) s_idx[0][k] = k;
-            } else if (a.samples) {
-                for (int s = 0; s < ch; ++s)
-                    for (int k = 0; k < 5; ++k) s_idx[s][k] = a.samples[(int64_t)(iter0 + s) * 5 + k];
-            } else {
-                CvRng rng{s_rng};
-                for (int s = 0; s < ch; ++s) draw_subset(rng, n, s_idx[s]);
-                s_rng = rng.state;
-            }
+    for (int w = blockIdx.x; w < count; w += gridDim.x) {
+        const int pair = wl[w];
+        const int n = a.n[pair];
+        const int64_t so = (int64_t)pair * 4 * a.stride;
+        const double* X1 = a.xn + so;
+        const double* Y1 = X1 + a.stride;
+        const double* X2 = Y1 + a.stride;
+        const double* Y2 = X2 + a.stride;
+        RansacState& st = a.w.state[pair];
+        __syncthreads();                                     // previous pair of this CTA is completely done
+        if (tid == 0) {
+            s_iter = st.iter;
+            s_niters = st.niters;
+            s_have = st.have;
+            s_total_models = st.total_models;
+            s_best_score = st.best_score;
         }
+        if (tid < 9) s_bestE[tid] = st.bestE[tid];
         __syncthreads();
-        if (!presolved) {
-            if (tid < ch) {
-                double x1[5][2], x2[5][2];
-                for (int k = 0; k < 5; ++k) {
-                    const int i = s_idx[tid][k];
-                    x1[k][0] = X1[i]; x1[k][1] = Y1[i];
-                    x2[k][0] = X2[i]; x2[k][1] = Y2[i];
+        const int iter0 = s_iter;
+        const int ch = min(R, s_niters - iter0);             // samples solved for this pair in this round
+        const double* gmodels = a.w.models + (size_t)w * R * 90;
+        const int32_t* gnm = a.w.nmodels + (size_t)w * R;
+
+        // sub-chunks of at most ES_WARPS samples: score, then replay.  RANSAC usually shrinks niters
+        // after the first few samples; samples at or beyond the current niters are never scored.
+        for (int sbase = 0; sbase < ch; sbase += ES_WARPS) {
+            const int r = min(ES_WARPS, min(ch, s_niters - iter0) - sbase);     // samples scored now (>= 1)
+            // stage the models of these samples and flatten them into a work list
+            for (int i = tid; i < r * 90; i += ES_THREADS) (&s_models[0][0][0])[i] = gmodels[(size_t)sbase * 90 + i];
+            if (tid < ES_WARPS * 10) (&s_cnt[0][0])[tid] = 0;
+            if (warp == 0) {
+                const int c = lane < r ? gnm[sbase + lane] : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < ES_WARPS; o <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
                 }
-                s_nmodels[tid] = fivept::solve(x1, x2, s_models[tid]);
+                if (lane < r) {
+                    s_nm[lane] = c;
+                    for (int k = 0; k < c; ++k) s_item[incl - c + k] = (unsigned char)(lane << 4 | k);
+                }
+                if (lane == ES_WARPS - 1) s_nitems = incl;
             }
             __syncthreads();
-        }
-        // score + replay in sub-chunks of at most ES_WARPS samples.  RANSAC usually shrinks niters
-        // after the first few samples: samples at or beyond the current niters are never scored,
-        // and when fewer than ES_WARPS samples remain their points are split across the idle warps.
-        for (int sub = 0; sub * ES_WARPS < ch; ++sub) {
-            const int sbase = sub * ES_WARPS;
-            const int r = min(ES_WARPS, min(ch, s_niters - iter0) - sbase);     // samples scored now (>= 1)
-            if (!lmeds) {
-                if (tid < ES_WARPS * 10) (&s_cnt[0][0])[tid] = 0;
-                __syncthreads();
-                const int slices = (r >= 5) ? 1 : (r >= 3 ? 2 : (r == 2 ? 4 : 8));   // warps per sample
-                const int q = warp / slices, slice = warp % slices;
-                if (q < r && n != 5) {
-                    const int s = sbase + q;
-                    const int nm = s_nmodels[s];
-                    // point-outer loop: a correspondence is loaded once and scored against every
-                    // model of this warp's sample (models broadcast from shared memory)
-                    int cnt[10];
+            const int M = s_nitems;
+            if (n != 5 && M > 0) {
+                if (!lmeds) {
+                    if (M >= ES_WARPS) {
+                        // warp w scores items w, w + 8, ...: a correspondence is loaded once and tested
+                        // against every model of the warp (models broadcast from shared memory)
+                        const double* Ep[10];
+                        int mine = 0;
 #pragma unroll
-                    for (int k = 0; k < 10; ++k) cnt[k] = 0;
-                    for (int i = lane + 32 * slice; i < n; i += 32 * slices) {
-                        const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
+                        for (int j = 0; j < 10; ++j) {
+                            const int it = warp + ES_WARPS * j;
+                            const int code = it < M ? s_item[it] : 0;
+                            Ep[j] = s_models[code >> 4][code & 15];
+                            mine += it < M;
+                        }
+                        int cnt[10];
 #pragma unroll
-                        for (int k = 0; k < 10; ++k)
-                            if (k < nm) cnt[k] += sampson_inlier(s_models[s][k], a1, b1, a2, b2, thrR) ? 1 : 0;
-                    }
+                        for (int j = 0; j < 10; ++j) cnt[j] = 0;
+                        for (int i = lane; i < n; i += 32) {
+                            const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
 #pragma unroll
-                    for (int k = 0; k < 10; ++k) {
-                        if (k < nm) {
-                            const int c = warp_sum(cnt[k]);
-                            if (lane == 0) atomicAdd(&s_cnt[q][k], c);
+                            for (int j = 0; j < 10; ++j)
+                                if (j < mine) cnt[j] += sampson_inlier(Ep[j], a1, b1, a2, b2, thrR) ? 1 : 0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 10; ++j) {
+                            if (j < mine) {
+                                const int c = warp_sum(cnt[j]);
+                                const int code = s_item[warp + ES_WARPS * j];
+                                if (lane == 0) s_cnt[code >> 4][code & 15] = c;
+                            }
+                        }
+                    } else {
+                        // fewer models than warps: split the correspondences of each model over several warps
+                        const int slices = ES_WARPS / M;
+                        const int it = warp / slices, slice = warp % slices;
+                        if (it < M) {
+                            const int code = s_item[it];
+                            const double* E = s_models[code >> 4][code & 15];
+                            int cnt = 0;
+                            for (int i = lane + 32 * slice; i < n; i += 32 * slices)
+                                cnt += sampson_inlier(E, X1[i], Y1[i], X2[i], Y2[i], thrR) ? 1 : 0;
+                            cnt = warp_sum(cnt);
+                            if (lane == 0) atomicAdd(&s_cnt[code >> 4][code & 15], cnt);
                         }
                     }
-                }
-            } else {
-                const int s = sbase + warp;
-                if (warp < r && n != 5) {
-                    const int nm = s_nmodels[s];
-                    for (int k = 0; k < nm; ++k) {
-                        const double* E = s_models[s][k];
-                        float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
+                } else {
+                    float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
+                    for (int it = warp; it < M; it += ES_WARPS) {
+                        const int code = s_item[it];
+                        const double* E = s_models[code >> 4][code & 15];
                         for (int i = lane; i < n; i += 32) buf[i] = sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]);
                         __syncwarp();
                         const float med = warp_select(buf, n, n / 2, lane);
                         __syncwarp();
-                        if (lane == 0) s_score[s][k] = med;
+                        if (lane == 0) s_score[code >> 4][code & 15] = med;
                     }
                 }
             }
             __syncthreads();
             if (tid == 0) {                                  // sequential bookkeeping of ptsetreg.cpp run()
                 int ni = s_niters;
-                int q = sbase;
-                const int qend = sbase + r;
-                for (; q < qend; ++q) {
-                    if (iter0 + q >= ni) break;
-                    for (int k = 0; k < s_nmodels[q]; ++k) {
+                double best_score = s_best_score;
+                int q = 0;
+                for (; q < r; ++q) {
+                    if (iter0 + sbase + q >= ni) break;
+                    for (int k = 0; k < s_nm[q]; ++k) {
                         s_total_models++;
                         if (n == 5) {                        // minimal case: first solution, all inliers
                             if (!s_have) {
@@ -321,7 +487,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
                             continue;
                         }
                         if (!lmeds) {
-                            const int good = s_cnt[q - sbase][k];
+                            const int good = s_cnt[q][k];
                             if (good > max((int)best_score, 4)) {
                                 best_score = good;
                                 s_have = 1;
@@ -338,139 +504,113 @@ __global__ void __launch_bounds__(ES_THREADS, 2) essential_kernel(EssArgs a) {
                         }
                     }
                 }
-                s_iter = iter0 + q;
+                s_iter = iter0 + sbase + q;
                 s_niters = ni;
+                s_best_score = best_score;
             }
             __syncthreads();
             if (s_iter >= s_niters) break;                   // the sequential loop would have stopped here
         }
         __syncthreads();
-    }
 
-    // final mask (ptsetreg.cpp findInliers on the best model), inlier compaction
-    __shared__ float s_thr;
-    if (tid == 0) {
-        float t = thr32;
-        if (lmeds && s_have && n > 5) {
-            double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 5)) * sqrt(best_score);
-            sigma = fmax(sigma, 0.001);
-            t = (float)(sigma * sigma);
+        if (s_iter < s_niters && !last_round) {
+            // not finished: save the state and queue the pair for the next round
+            if (tid == 0) {
+                st.iter = s_iter;
+                st.niters = s_niters;
+                st.have = s_have;
+                st.total_models = s_total_models;
+                st.best_score = s_best_score;
+                const int pos = atomicAdd(&a.w.ctl[round + 1], 1);
+                a.w.wl[(round + 1) & 1][pos] = pair;
+            }
+            if (tid < 9) st.bestE[tid] = s_bestE[tid];
+            continue;
         }
-        s_thr = t;
-        s_base = 0;
-    }
-    __syncthreads();
-    const bool have = s_have != 0;
-    const SampThr thrF = make_samp_thr(s_thr);
-    uint8_t* mask = a.mask + (int64_t)pair * a.stride;
-    double* xin = a.xin ? a.xin + so : nullptr;
-    for (int start = 0; start < n; start += ES_THREADS) {
-        const int i = start + tid;
-        bool in = false;
-        double p[4] = {0, 0, 0, 0};
-        if (i < n && have) {
-            p[0] = X1[i]; p[1] = Y1[i]; p[2] = X2[i]; p[3] = Y2[i];
-            in = (n == 5) ? true : sampson_inlier(s_bestE, p[0], p[1], p[2], p[3], thrF);
-        }
-        if (i < n) mask[i] = in ? 1 : 0;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
-        if (lane == 0) s_warpcnt[warp] = __popc(bal);
-        __syncthreads();
-        int off = s_base;
-        for (int w = 0; w < warp; ++w) off += s_warpcnt[w];
-        if (in && xin) {
-            const int k = off + __popc(bal & ((1u << lane) - 1));
-            xin[k] = p[0];
-            xin[a.stride + k] = p[1];
-            xin[2 * a.stride + k] = p[2];
-            xin[3 * a.stride + k] = p[3];
-        }
-        __syncthreads();
+
+        // final mask (ptsetreg.cpp findInliers on the best model), inlier compaction
         if (tid == 0) {
-            int tot = 0;
-            for (int w = 0; w < ES_WARPS; ++w) tot += s_warpcnt[w];
-            s_base += tot;
+            float t = thr32;
+            if (lmeds && s_have && n > 5) {
+                double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 5)) * sqrt(s_best_score);
+                sigma = fmax(sigma, 0.001);
+                t = (float)(sigma * sigma);
+            }
+            s_thr = t;
+            s_base = 0;
         }
         __syncthreads();
-    }
-    if (tid == 0) {
-        a.n_inliers[pair] = s_base;
-        a.iters[pair] = s_iter;
-        a.n_models[pair] = s_total_models;
-        a.status[pair] = have ? 0 : EPIVO_ERR_NOMODEL;
-    }
-    if (tid < 9) a.E[(int64_t)pair * 9 + tid] = have ? s_bestE[tid] : 0.0;
-}
-
-// ---- first samples of every pair, solved at full occupancy --------------------------------
-// sample_kernel: one thread per pair draws the first `count` samples of OpenCV's stream;
-// presolve_kernel: one thread per (pair, sample) runs the 5-point solver.
-__global__ void sample_kernel(int n_pairs, const int32_t* __restrict__ n_arr, int count, int32_t* __restrict__ idx,
-                              unsigned long long* __restrict__ rng_out) {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pair >= n_pairs) return;
-    const int n = n_arr[pair];
-    CvRng rng{0xFFFFFFFFFFFFFFFFULL};
-    int32_t* out = idx + (int64_t)pair * count * 5;
-    if (n > 5) {
-        for (int s = 0; s < count; ++s) {
-            int v[5];
-            draw_subset(rng, n, v);
-            for (int k = 0; k < 5; ++k) out[s * 5 + k] = v[k];
+        const bool have = s_have != 0;
+        const SampThr thrF = make_samp_thr(s_thr);
+        uint8_t* mask = a.mask + (int64_t)pair * a.stride;
+        double* xin = a.xin ? a.xin + so : nullptr;
+        for (int start = 0; start < n; start += ES_THREADS) {
+            const int i = start + tid;
+            bool in = false;
+            double p[4] = {0, 0, 0, 0};
+            if (i < n && have) {
+                p[0] = X1[i]; p[1] = Y1[i]; p[2] = X2[i]; p[3] = Y2[i];
+                in = (n == 5) ? true : sampson_inlier(s_bestE, p[0], p[1], p[2], p[3], thrF);
+            }
+            if (i < n) mask[i] = in ? 1 : 0;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
+            if (lane == 0) s_warpcnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = s_base;
+            for (int ww = 0; ww < warp; ++ww) off += s_warpcnt[ww];
+            if (in && xin) {
+                const int k = off + __popc(bal & ((1u << lane) - 1));
+                xin[k] = p[0];
+                xin[a.stride + k] = p[1];
+                xin[2 * a.stride + k] = p[2];
+                xin[3 * a.stride + k] = p[3];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int ww = 0; ww < ES_WARPS; ++ww) tot += s_warpcnt[ww];
+                s_base += tot;
+            }
+            __syncthreads();
         }
-    } else {
-        for (int s = 0; s < count; ++s)
-            for (int k = 0; k < 5; ++k) out[s * 5 + k] = (n == 5) ? k : -1;
+        if (tid == 0) {
+            a.n_inliers[pair] = s_base;
+            a.iters[pair] = s_iter;
+            a.n_models[pair] = s_total_models;
+            a.status[pair] = have ? 0 : EPIVO_ERR_NOMODEL;
+        }
+        if (tid < 9) a.E[(int64_t)pair * 9 + tid] = have ? s_bestE[tid] : 0.0;
     }
-    rng_out[pair] = rng.state;
 }
 
-#ifndef EPV_PRESOLVE_MINBLOCKS
-#define EPV_PRESOLVE_MINBLOCKS 8
-#endif
-__global__ void __launch_bounds__(64, EPV_PRESOLVE_MINBLOCKS)
-presolve_kernel(int n_pairs, int stride, const double* __restrict__ xn, const int32_t* __restrict__ n_arr, int count,
-                int used, const int32_t* __restrict__ idx, const int32_t* __restrict__ shared_samples,
-                double* __restrict__ models, int32_t* __restrict__ nmodels) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (int64_t)n_pairs * count) return;
-    const int pair = (int)(g / count), s = (int)(g % count);
-    const int n = n_arr[pair];
-    int32_t* nm = nmodels + g;
-    if (n < 5 || s >= used || (n == 5 && s > 0)) { *nm = 0; return; }
-    const int32_t* id = shared_samples ? shared_samples + (int64_t)s * 5 : idx + g * 5;
-    const double* X1 = xn + (int64_t)pair * 4 * stride;
-    double x1[5][2], x2[5][2];
-    for (int k = 0; k < 5; ++k) {
-        const int i = (n == 5) ? k : id[k];
-        x1[k][0] = X1[i]; x1[k][1] = X1[stride + i];
-        x2[k][0] = X1[2 * stride + i]; x2[k][1] = X1[3 * stride + i];
+// ---- K2 alone: m hypotheses given as coordinates (x1, x2: m x 5 x 2) -------------------------
+__global__ void __launch_bounds__(32) five_point_a_kernel(const double* __restrict__ x1, const double* __restrict__ x2,
+                                                          int m, double* __restrict__ rec) {
+    extern __shared__ __align__(16) double s_A[];
+    const int lane = threadIdx.x;
+    for (long long g = blockIdx.x; g * 32 < m; g += gridDim.x) {
+        const long long i = g * 32 + lane;
+        if (i < m) {
+            double a[5][2], b[5][2];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                a[k][0] = x1[(i * 5 + k) * 2];
+                a[k][1] = x1[(i * 5 + k) * 2 + 1];
+                b[k][0] = x2[(i * 5 + k) * 2];
+                b[k][1] = x2[(i * 5 + k) * 2 + 1];
+            }
+            fivept::stage_a(a, b, fivept::SmemMat{s_A + lane}, rec + i, (size_t)m);
+        }
+        __syncwarp();
     }
-    double E[10][9];
-    const int c = fivept::solve(x1, x2, E);
-    *nm = c;
-    double* out = models + g * 90;
-    for (int k = 0; k < c; ++k)
-        for (int q = 0; q < 9; ++q) out[k * 9 + q] = E[k][q];
 }
 
-// ---- K2 alone: one thread per sample ------------------------------------------------
-__global__ void __launch_bounds__(64) five_point_kernel(const double* __restrict__ x1, const double* __restrict__ x2,
-                                                        int m, double* __restrict__ Eout, int32_t* __restrict__ nm) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(SB_THREADS, EPV_SB_MINBLOCKS)
+five_point_b_kernel(const double* __restrict__ rec, int m, double* __restrict__ Eout, int32_t* __restrict__ nm) {
+    __shared__ double s_sh[fivept::SB_SCRATCH * SB_THREADS];
+    const long long i = (long long)blockIdx.x * SB_THREADS + threadIdx.x;
     if (i >= m) return;
-    double a[5][2], b[5][2];
-    for (int k = 0; k < 5; ++k) {
-        a[k][0] = x1[(i * 5 + k) * 2];
-        a[k][1] = x1[(i * 5 + k) * 2 + 1];
-        b[k][0] = x2[(i * 5 + k) * 2];
-        b[k][1] = x2[(i * 5 + k) * 2 + 1];
-    }
-    double E[10][9];
-    const int n = fivept::solve(a, b, E);
-    nm[i] = n;
-    for (int k = 0; k < n; ++k)
-        for (int q = 0; q < 9; ++q) Eout[((int64_t)i * 10 + k) * 9 + q] = E[k][q];
+    nm[i] = fivept::stage_b(rec + i, (size_t)m, s_sh + threadIdx.x, SB_THREADS, Eout + i * 90);
 }
 
 // ---- K3 alone: fixed hypothesis set, m models x n correspondences ----------------------
@@ -578,25 +718,38 @@ int epv_normalize_launch(epivo_ctx* ctx, const float* d_p0, const float* d_p1, i
     return EPIVO_OK;
 }
 
-int epv_essential_pre_count(int method, double prob, int max_iters, int m_samples) {
-    // how many leading samples are solved ahead of the per-pair kernel: two sub-chunks for RANSAC
-    // (on KITTI-like data it stops after ~10 samples; a pair that needs more continues with
-    // in-kernel solves), every sample for LMedS (its iteration count is fixed)
-    int want = 2 * ES_WARPS;
+size_t epv_essential_work_bytes(int n_pairs) { return ess_work_carve(nullptr, nullptr, std::max(n_pairs, 1)); }
+
+// round sizes: a short first round for RANSAC (on KITTI-like data it stops after ~10 samples), then
+// doubling up to ES_RMAX; LMedS has a fixed iteration count and takes it in ES_RMAX pieces
+static int ess_round_sizes(int method, double prob, int max_iters, int m_samples, int* R) {
+    int total;
+    int first;
     if (method == EPIVO_LMEDS) {
         double num = log(fmax(1.0 - prob, DBL_MIN)), den = log(1.0 - pow(1.0 - 0.45, 5.0));
         int ni = (int)rint(num / den);
-        ni = std::max(std::min(ni, max_iters), 3);
-        want = ni;
+        total = std::max(std::min(ni, max_iters), 3);
+        first = ES_RMAX;
+    } else {
+        total = std::max(max_iters, 1);
+        first = 2 * ES_WARPS;
     }
-    if (m_samples > 0) want = std::min(want, m_samples);
-    want = std::min(want, std::max(max_iters, 1));
-    int c = (want + ES_WARPS - 1) / ES_WARPS * ES_WARPS;
-    return std::min(c, 4 * ES_CHUNK);
+    if (m_samples > 0) total = std::min(total, m_samples);
+    int nr = 0, done = 0, r = first;
+    while (done < total && nr < ES_MAX_ROUNDS) {
+        const bool last_slot = nr == ES_MAX_ROUNDS - 1;
+        R[nr] = last_slot ? std::min(total - done, ES_RMAX) : std::min(r, total - done);
+        done += R[nr];
+        ++nr;
+        r = std::min(2 * r, ES_RMAX);
+    }
+    return done >= total ? nr : -1;
 }
 
 int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
     if (p.n_pairs <= 0) return EPIVO_OK;
+    if (!p.work || p.work_bytes < epv_essential_work_bytes(p.n_pairs))
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "essential work buffer too small");
     EssArgs a{};
     a.n_pairs = p.n_pairs;
     a.stride = p.stride;
@@ -616,35 +769,55 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
     a.n_models = p.n_models;
     a.status = p.status;
     a.xin = p.xin;
-    a.pre_count = 0;
-    if (p.pre_count > 0 && p.pre_models && p.pre_nmodels && p.pre_idx && p.pre_rng) {
-        const int count = p.pre_count;
-        int used = count;
-        if (p.samples) used = std::min(count, p.m);
-        if (!p.samples) {
-            sample_kernel<<<(p.n_pairs + 127) / 128, 128, 0, ctx->stream>>>(p.n_pairs, p.n, count, p.pre_idx, p.pre_rng);
-            EPV_LAUNCHED(ctx);
-        }
-        const int64_t total = (int64_t)p.n_pairs * count;
-        presolve_kernel<<<(unsigned)((total + 63) / 64), 64, 0, ctx->stream>>>(
-            p.n_pairs, p.stride, p.xn, p.n, count, used, p.pre_idx, p.samples, p.pre_models, p.pre_nmodels);
-        EPV_LAUNCHED(ctx);
-        a.pre_count = count;
-        a.pre_models = p.pre_models;
-        a.pre_nmodels = p.pre_nmodels;
-        a.pre_rng = p.pre_rng;
+    ess_work_carve(&a.w, reinterpret_cast<char*>(p.work), p.n_pairs);
+    int R[ES_MAX_ROUNDS];
+    const int nr = ess_round_sizes(p.method, p.prob, p.max_iters, p.samples ? p.m : 0, R);
+    if (nr < 0)
+        EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "max_iters = %d needs more than %d rounds of %d samples", p.max_iters,
+                 ES_MAX_ROUNDS, ES_RMAX);
+    static bool attr_set = false;
+    if (!attr_set) {
+        EPV_CUDA(ctx, cudaFuncSetAttribute(solve_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
+        EPV_CUDA(ctx, cudaFuncSetAttribute(five_point_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
+        attr_set = true;
     }
-    if (p.ev_presolved) EPV_CUDA(ctx, cudaEventRecord(p.ev_presolved, ctx->stream));
-    essential_kernel<<<p.n_pairs, ES_THREADS, 0, ctx->stream>>>(a);
+    ess_init_kernel<<<(p.n_pairs + 127) / 128, 128, 0, ctx->stream>>>(a);
     EPV_LAUNCHED(ctx);
+    // Round 0 runs on every pair; later rounds usually see a short (often empty) work list, so their
+    // grids are small and loop (grid-stride) -- an empty round is four near-empty launches.
+    const int sms = ctx->sm_count;
+    for (int r = 0; r < nr; ++r) {
+        const long long pairs_ub = p.n_pairs;
+        const long long slots_ub = pairs_ub * R[r];
+        const bool full = r == 0;
+        const unsigned g_pairs = (unsigned)std::min<long long>(pairs_ub, full ? pairs_ub : 2LL * sms);
+        const unsigned g_samp = (unsigned)std::min<long long>((pairs_ub + 127) / 128, full ? (1LL << 30) : sms);
+        const unsigned g_a = (unsigned)std::min<long long>((slots_ub + 31) / 32, full ? (1LL << 30) : 4LL * sms);
+        const unsigned g_b = (unsigned)std::min<long long>((slots_ub + SB_THREADS - 1) / SB_THREADS,
+                                                           full ? (1LL << 30) : 4LL * sms);
+        ess_sample_kernel<<<g_samp, 128, 0, ctx->stream>>>(a, r, R[r]);
+        EPV_LAUNCHED(ctx);
+        solve_a_kernel<<<g_a, 32, SA_SMEM, ctx->stream>>>(a, r, R[r]);
+        EPV_LAUNCHED(ctx);
+        solve_b_kernel<<<g_b, SB_THREADS, 0, ctx->stream>>>(a, r, R[r]);
+        EPV_LAUNCHED(ctx);
+        if (r == 0 && p.ev_presolved) EPV_CUDA(ctx, cudaEventRecord(p.ev_presolved, ctx->stream));
+        ess_round_kernel<<<g_pairs, ES_THREADS, 0, ctx->stream>>>(a, r, R[r], r == nr - 1 ? 1 : 0);
+        EPV_LAUNCHED(ctx);
+    }
     return EPIVO_OK;
 }
 
 size_t epv_essential_errbuf_floats(int n_pairs, int stride) { return (size_t)n_pairs * ES_WARPS * stride; }
 
-int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_E, int32_t* d_nm) {
+// d_rec: m * 96 doubles of scratch
+int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_rec, double* d_E,
+                          int32_t* d_nm) {
     if (m <= 0) return EPIVO_OK;
-    five_point_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>(d_x1, d_x2, m, d_E, d_nm);
+    EPV_CUDA(ctx, cudaFuncSetAttribute(five_point_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
+    five_point_a_kernel<<<(m + 31) / 32, 32, SA_SMEM, ctx->stream>>>(d_x1, d_x2, m, d_rec);
+    EPV_LAUNCHED(ctx);
+    five_point_b_kernel<<<(m + SB_THREADS - 1) / SB_THREADS, SB_THREADS, 0, ctx->stream>>>(d_rec, m, d_E, d_nm);
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
 }
@@ -671,14 +844,3 @@ int epv_score_launch(epivo_ctx* ctx, const double* d_E, int m, const double* d_x
     }
     return EPIVO_OK;
 }
-
-#ifdef EPV_PROFILE_SOLVE
-// tuning builds only: read and reset the per-phase clock totals of fivept::solve
-extern "C" int epivo_debug_solve_profile(unsigned long long* out8) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
-    if (cudaMemcpyFromSymbol(out8, fivept::g_solve_prof, sizeof(z)) != cudaSuccess) return -2;
-    if (cudaMemcpyToSymbol(fivept::g_solve_prof, z, sizeof(z)) != cudaSuccess) return -2;
-    return 0;
-}
-#endif

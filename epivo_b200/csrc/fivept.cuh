@@ -1,4 +1,4 @@
-// K2: Nister 5-point minimal solver, one hypothesis per thread, FP64.
+// K2: Nister 5-point minimal solver, FP64, one hypothesis per lane, in two stages.
 //
 // Restates the algorithm of cv::findEssentialMat's EMEstimatorCallback::runKernel
 // (OpenCV modules/calib3d/src/five-point.cpp; called from kitti.cpp:98, kitti_E.cpp:98,
@@ -7,7 +7,8 @@
 //      (OpenCV: full SVD; here: Householder QR of the transpose -- any orthonormal basis of
 //      the same null space yields the same set of essential matrices),
 //   2. the ten cubic constraints -> Nister's 10x20 matrix (fivept_gen.cuh),
-//   3. Gauss-Jordan with partial pivoting on the left 10x10 block (OpenCV: inv() * right),
+//   3. elimination with partial pivoting on the left 10x10 block (OpenCV: inv() * right); only
+//      rows 4..9 of inv(left) * right are needed, so the back substitution stops there,
 //   4. B(z) = {rows 4,6,8} - z {rows 5,7,9}, det B(z) = degree-10 polynomial,
 //   5. all complex roots by the Durand-Kerner iteration of cv::solvePoly (same start
 //      values (1+i)^k, same Gauss-Seidel sweep, 300 sweeps at most; stops early once every
@@ -16,29 +17,25 @@
 //      third component is < 1e-10 in magnitude), E = x E0 + y E1 + z E2 + E3, normalised,
 //   7. (not in OpenCV) each solution is refined by Gauss-Newton on the ten constraints inside the
 //      null space (refine_essential below), which removes the basis-dependent loss of accuracy.
+//
+// Stage A (steps 1-3) needs the 10x20 matrix, which only fits on chip in shared memory: one warp
+// = 32 hypotheses, the matrix lane-strided (element (r,c) of lane l at [(r*20+c)*32 + l], bank =
+// lane, conflict free even though every lane pivots on a different row).  Its product is 96
+// doubles per hypothesis (null-space basis + six reduced rows).  Stage B (steps 4-7) is
+// register/shared only.  A thread-private 10x20 array would live in local memory, and with tens
+// of thousands of hypotheses in flight that traffic goes to HBM.
 #pragma once
 #include "fivept_gen.cuh"
 
 namespace fivept {
 
-// Tuning builds only (-DEPV_PROFILE_SOLVE): per-phase clock totals of solve(), read back by
-// epivo_debug_solve_profile().  [0] null space + constraints [1] Gauss-Jordan [2] polynomial
-// [3] Durand-Kerner [4] roots -> E + refinement [5] DK sweeps [6] solves [7] models
-#ifdef EPV_PROFILE_SOLVE
-__device__ unsigned long long g_solve_prof[8];
-#define EPV_PROF_BEGIN long long _pt = clock64()
-#define EPV_PROF(i)                                                       \
-    do {                                                                  \
-        const long long _n = clock64();                                   \
-        atomicAdd(&g_solve_prof[i], (unsigned long long)(_n - _pt));      \
-        _pt = _n;                                                         \
-    } while (0)
-#define EPV_PROF_ADD(i, v) atomicAdd(&g_solve_prof[i], (unsigned long long)(v))
-#else
-#define EPV_PROF_BEGIN
-#define EPV_PROF(i)
-#define EPV_PROF_ADD(i, v)
-#endif
+constexpr int EB_DOUBLES = 96;     // stage A -> stage B record: e[4][9] then rows 4..9 x 10 right-hand columns
+
+// this lane's 10x20 matrix inside a warp-wide, lane-strided shared-memory block
+struct SmemMat {
+    double* base;       // already offset by the lane
+    __device__ __forceinline__ double& operator()(int r, int c) const { return base[(r * 20 + c) * 32]; }
+};
 
 __device__ __forceinline__ void null_space_5x9(const double (&x1)[5][2], const double (&x2)[5][2],
                                                double (&e)[4][9]) {
@@ -95,29 +92,72 @@ __device__ __forceinline__ void null_space_5x9(const double (&x1)[5][2], const d
     }
 }
 
-// Gauss-Jordan with partial pivoting: left 10x10 -> I, right 10x10 -> inv(left) * right.
-__device__ __forceinline__ bool gauss_jordan_10x20(double (&A)[10][20]) {
+// Rows 4..9 of inv(left 10x10) * (right 10x10): forward elimination with partial pivoting to a
+// unit upper-triangular left block, then back substitution of rows 9..4 only.  The result
+// overwrites A(4..9, 10..19).  Returns false if the left block is singular.
+template <class Mat>
+__device__ __forceinline__ bool reduce_rows_4_9(Mat& A) {
     for (int k = 0; k < 10; ++k) {
         int p = k;
-        double best = fabs(A[k][k]);
+        double best = fabs(A(k, k));
         for (int r = k + 1; r < 10; ++r) {
-            const double v = fabs(A[r][k]);
+            const double v = fabs(A(r, k));
             if (v > best) { best = v; p = r; }
         }
         if (!(best > 1e-300)) return false;
-        if (p != k) {
-            for (int c = k; c < 20; ++c) { const double t = A[k][c]; A[k][c] = A[p][c]; A[p][c] = t; }
+        // pivot row -> registers, scaled; the old row k goes where the pivot row was
+        double row[20];
+        const double inv = 1.0 / A(p, k);
+        if (p != k) A(p, k) = A(k, k);                 // multiplier column of the displaced row
+#pragma unroll
+        for (int c = 0; c < 20; ++c) {
+            if (c > k) {                               // columns <= k of the pivot row are never read again
+                const double v = A(p, c);
+                if (p != k) A(p, c) = A(k, c);
+                row[c] = v * inv;
+                A(k, c) = row[c];
+            }
         }
-        const double inv = 1.0 / A[k][k];
-        for (int c = k; c < 20; ++c) A[k][c] *= inv;
-        for (int r = 0; r < 10; ++r) {
-            if (r == k) continue;
-            const double f = A[r][k];
+        for (int r = k + 1; r < 10; ++r) {
+            const double f = A(r, k);
             if (f == 0.0) continue;
-            for (int c = k; c < 20; ++c) A[r][c] -= f * A[k][c];
+#pragma unroll
+            for (int c = 0; c < 20; ++c)
+                if (c > k) A(r, c) -= f * row[c];
         }
     }
+    // X_i = Y_i - sum_{j > i} U_ij X_j, rows 9 (already final) down to 4
+    for (int i = 8; i >= 4; --i) {
+        double acc[10];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) acc[c] = A(i, 10 + c);
+        for (int j = i + 1; j < 10; ++j) {
+            const double u = A(i, j);
+#pragma unroll
+            for (int c = 0; c < 10; ++c) acc[c] -= u * A(j, 10 + c);
+        }
+#pragma unroll
+        for (int c = 0; c < 10; ++c) A(i, 10 + c) = acc[c];
+    }
     return true;
+}
+
+// ---- stage A: correspondences -> null-space basis + reduced rows ------------------------------
+// out[k * out_stride], k < EB_DOUBLES.  A singular system is flagged by a NaN in out[36].
+__device__ __forceinline__ void stage_a(const double (&x1)[5][2], const double (&x2)[5][2], SmemMat A, double* out,
+                                        size_t out_stride) {
+    double e[4][9];
+    null_space_5x9(x1, x2, e);
+    fivept_constraints(e, A);
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int r = 0; r < 9; ++r) out[(size_t)(b * 9 + r) * out_stride] = e[b][r];
+    const bool ok = reduce_rows_4_9(A);
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int c = 0; c < 10; ++c)
+            out[(size_t)(36 + i * 10 + c) * out_stride] = ok ? A(4 + i, 10 + c) : __longlong_as_double(0x7FF8000000000000LL);
 }
 
 // ascending-power polynomial product: out[0..na+nb] = a[0..na] * b[0..nb]
@@ -133,8 +173,16 @@ __device__ __forceinline__ void pmul(const double (&a)[NA + 1], const double (&b
 
 // cv::solvePoly's Durand-Kerner on real coefficients c[0..n] (ascending), n <= 10.
 // dk_sweeps<N>: degree known at compile time, so the roots live in registers and both loops are
-// fully unrolled (the generic version indexes re[]/im[] dynamically, i.e. through local memory).
-// Same start values, same Gauss-Seidel sweep order and same stopping rule as the generic version.
+// fully unrolled.  Same start values and Gauss-Seidel sweep order as cv::solvePoly.
+// cv::solvePoly only stops when a sweep's update is exactly zero, which practically never
+// happens: it runs all 300 sweeps while the roots jitter at round-off level.  Stopping once
+// every update is below 1e-13 of the root leaves the roots equal to OpenCV's up to that jitter
+// (the solutions are refined on the constraints afterwards anyway).  Clustered roots never get
+// below their own noise floor (1e-12 .. 1e-9): once the update is small and no longer
+// shrinking by 10x per sweep (the quadratic phase is over), more sweeps only re-draw the
+// noise -- and would stall the whole warp.
+// The relative update of a sweep is tracked as a fraction (numerator, denominator) compared by
+// cross-multiplication, so a sweep costs one division per root, not two.
 template <int N>
 __device__ __forceinline__ void dk_sweeps(const double (&c)[11], double (&re)[10], double (&im)[10]) {
     {
@@ -149,14 +197,14 @@ __device__ __forceinline__ void dk_sweeps(const double (&c)[11], double (&re)[10
     double prev2 = 1e300;
 #pragma unroll 1
     for (int iter = 0; iter < 300; ++iter) {
-        double maxrel2 = 0.0;
+        double mnum = 0.0, mden = 1.0;                       // max over roots of |update|^2 / max(1, |root|^2)
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const double xr = re[i], xi = im[i];
             double nr = c[N], ni = 0.0, dr = c[N], di = 0.0;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const double t = nr * xr - ni * xi + c[N - j - 1];
+                const double t = nr * xr - ni * xi + c[N - j - 1];     // num = num * x + c[N-j-1]
                 ni = nr * xi + ni * xr;
                 nr = t;
                 if (j != i) {
@@ -172,9 +220,10 @@ __device__ __forceinline__ void dk_sweeps(const double (&c)[11], double (&re)[10
             const double qr = (nr * dr + ni * di) * s;
             const double qi = (ni * dr - nr * di) * s;
             re[i] = xr - qr; im[i] = xi - qi;
-            maxrel2 = fmax(maxrel2, (qr * qr + qi * qi) / fmax(1.0, xr * xr + xi * xi));
+            const double q2 = qr * qr + qi * qi, m = fmax(1.0, xr * xr + xi * xi);
+            if (q2 * mden > mnum * m || !(q2 == q2)) { mnum = q2; mden = m; }
         }
-        EPV_PROF_ADD(5, 1);
+        const double maxrel2 = mnum / mden;
         if (!(maxrel2 > 1e-26)) break;
         if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) break;
         prev2 = maxrel2;
@@ -184,19 +233,18 @@ __device__ __forceinline__ void dk_sweeps(const double (&c)[11], double (&re)[10
 // Generic degree (the leading coefficients vanished): rare, kept out of line.
 __device__ __noinline__ void dk_sweeps_generic(const double (&c)[11], int n, double (&re)[10], double (&im)[10]) {
     double pr = 1.0, pi = 0.0;
-    for (int i = 0; i < n; ++i) {                            // roots[i] = (1 + 1i)^i
+    for (int i = 0; i < n; ++i) {
         re[i] = pr; im[i] = pi;
         const double t = pr - pi;
         pi = pr + pi; pr = t;
     }
     double prev2 = 1e300;
     for (int iter = 0; iter < 300; ++iter) {
-        double maxrel2 = 0.0;                                // max |update|^2 / max(1, |root|^2) of the sweep
+        double maxrel2 = 0.0;
         for (int i = 0; i < n; ++i) {
             const double xr = re[i], xi = im[i];
             double nr = c[n], ni = 0.0, dr = c[n], di = 0.0;
             for (int j = 0; j < n; ++j) {
-                // num = num * p + c[n-j-1]
                 const double t = nr * xr - ni * xi + c[n - j - 1];
                 ni = nr * xi + ni * xr;
                 nr = t;
@@ -215,32 +263,10 @@ __device__ __noinline__ void dk_sweeps_generic(const double (&c)[11], int n, dou
             re[i] = xr - qr; im[i] = xi - qi;
             maxrel2 = fmax(maxrel2, (qr * qr + qi * qi) / fmax(1.0, xr * xr + xi * xi));
         }
-        // cv::solvePoly only stops when a sweep's update is exactly zero, which practically never
-        // happens: it runs all 300 sweeps while the roots jitter at round-off level.  Stopping
-        // once every update is below 1e-13 of the root leaves the roots equal to OpenCV's up to
-        // that jitter (the solutions are refined on the constraints afterwards anyway).
-        // Clustered roots never get below their own noise floor (1e-12 .. 1e-9): once the
-        // update is small and no longer shrinking by 10x per sweep (the quadratic phase is
-        // over), more sweeps only re-draw the noise -- and would stall the whole warp.
         if (!(maxrel2 > 1e-26)) break;
         if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) break;
         prev2 = maxrel2;
     }
-}
-
-// Returns the degree actually solved; roots in (re, im).
-__device__ __forceinline__ int durand_kerner(const double (&c)[11], double (&re)[10], double (&im)[10]) {
-    int n = 10;
-    for (; n > 1; --n)
-        if (fabs(c[n]) > 2.220446049250313e-16) break;      // DBL_EPSILON, as cv::solvePoly
-    if (n == 10) dk_sweeps<10>(c, re, im);
-    else dk_sweeps_generic(c, n, re, im);
-    return n;
-}
-
-__device__ __forceinline__ double det3(const double (&M)[3][3]) {
-    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
-           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
 }
 
 // Unit null vector of a (near) rank-2 3x3 matrix: the largest of the row cross products.
@@ -255,7 +281,7 @@ __device__ __forceinline__ void null_vec3(const double (&M)[3][3], double (&v)[3
         const double n2 = cx * cx + cy * cy + cz * cz;
         if (n2 > best) { best = n2; v[0] = cx; v[1] = cy; v[2] = cz; }
     }
-    const double inv = best > 0 ? 1.0 / sqrt(best) : 0.0;
+    const double inv = best > 0 ? rsqrt(best) : 0.0;
     v[0] *= inv; v[1] *= inv; v[2] *= inv;
 }
 
@@ -298,27 +324,31 @@ __device__ __forceinline__ double constraints10(const double* E, double* F) {
     return fmax(m, fabs(F[9]));
 }
 
-__device__ __noinline__ void refine_essential(const double (&e)[4][9], double (&E)[9]) {
+// e: the null-space basis, element i of basis matrix k at e[(k * 9 + i) * es] (es = element stride,
+// so the basis can stay in a thread-strided shared-memory block)
+__device__ __noinline__ void refine_essential(const double* e, int es, double (&E)[9]) {
     double c[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) s += E[i] * e[k][i];
+        for (int i = 0; i < 9; ++i) s += E[i] * e[(k * 9 + i) * es];
         c[k] = s;
     }
     {
-        const double n = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3]);
-        if (!(n > 0)) return;
+        const double n2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3];
+        if (!(n2 > 0)) return;
+        const double in = rsqrt(n2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c[k] /= n;
+        for (int k = 0; k < 4; ++k) c[k] *= in;
     }
     double Ec[9], F[10];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Ec[i] = c[0] * e[0][i] + c[1] * e[1][i] + c[2] * e[2][i] + c[3] * e[3][i];
+    for (int i = 0; i < 9; ++i)
+        Ec[i] = c[0] * e[i * es] + c[1] * e[(9 + i) * es] + c[2] * e[(18 + i) * es] + c[3] * e[(27 + i) * es];
     double fmaxv = constraints10(Ec, F);
     for (int it = 0; it < 6; ++it) {
-        // Jacobian columns: dF along each basis matrix
+        // J column k = dF along basis matrix k
         double J[10][4];
         double G[9], EtE[9], cof[9];
         mat3_mul_nt(Ec, Ec, G);                 // E E'
@@ -333,7 +363,9 @@ __device__ __noinline__ void refine_essential(const double (&e)[4][9], double (&
             }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double* D = e[k];
+            double D[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) D[i] = e[(k * 9 + i) * es];
             double A1[9], A2[9], A3[9], T[9];
             mat3_mul(D, EtE, A1);               // D E'E
             mat3_mul_nt(Ec, D, T);              // E D'
@@ -370,8 +402,9 @@ __device__ __noinline__ void refine_essential(const double (&e)[4][9], double (&
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) N[a][b] += mu * c[a] * c[b];
-        // 4x4 Gaussian elimination with partial pivoting
+        // 4x4 Gaussian elimination with partial pivoting (reciprocal pivots)
         bool ok = true;
+        double ip[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int p = k;
@@ -386,9 +419,10 @@ __device__ __noinline__ void refine_essential(const double (&e)[4][9], double (&
 #pragma unroll
                     for (int q = 0; q < 5; ++q) { const double t = N[k][q]; N[k][q] = N[r][q]; N[r][q] = t; }
                 }
+            ip[k] = 1.0 / N[k][k];
 #pragma unroll
             for (int r = k + 1; r < 4; ++r) {
-                const double f = N[r][k] / N[k][k];
+                const double f = N[r][k] * ip[k];
 #pragma unroll
                 for (int q = k; q < 5; ++q) N[r][q] -= f * N[k][q];
             }
@@ -400,17 +434,18 @@ __device__ __noinline__ void refine_essential(const double (&e)[4][9], double (&
             double s = N[r][4];
 #pragma unroll
             for (int q = r + 1; q < 4; ++q) s -= N[r][q] * d[q];
-            d[r] = s / N[r][r];
+            d[r] = s * ip[r];
         }
         double c2[4], n2 = 0.0, dn = 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) { c2[k] = c[k] + d[k]; n2 += c2[k] * c2[k]; dn += d[k] * d[k]; }
-        n2 = sqrt(n2);
+        const double in2 = rsqrt(n2);
         double E2[9], F2[10];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c2[k] /= n2;
+        for (int k = 0; k < 4; ++k) c2[k] *= in2;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) E2[i] = c2[0] * e[0][i] + c2[1] * e[1][i] + c2[2] * e[2][i] + c2[3] * e[3][i];
+        for (int i = 0; i < 9; ++i)
+            E2[i] = c2[0] * e[i * es] + c2[1] * e[(9 + i) * es] + c2[2] * e[(18 + i) * es] + c2[3] * e[(27 + i) * es];
         const double f2 = constraints10(E2, F2);
         if (!(f2 < fmaxv)) break;                // NaN or no improvement: keep the current iterate
         fmaxv = f2;
@@ -420,48 +455,59 @@ __device__ __noinline__ void refine_essential(const double (&e)[4][9], double (&
         for (int i = 0; i < 9; ++i) Ec[i] = E2[i];
 #pragma unroll
         for (int i = 0; i < 10; ++i) F[i] = F2[i];
-        if (sqrt(dn) < 1e-14) break;
+        if (dn < 1e-28) break;                   // |step| < 1e-14
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) E[i] = Ec[i];
 }
 
-// Solve one sample.  Eout[k] = k-th essential matrix (row-major, unit Frobenius norm).
-__device__ __noinline__ int solve(const double (&x1)[5][2], const double (&x2)[5][2], double (*Eout)[9]) {
-    EPV_PROF_BEGIN;
-    double e[4][9];
-    null_space_5x9(x1, x2, e);
-    double A[10][20];
-    fivept_constraints(e, A);
-    EPV_PROF(0);
-    if (!gauss_jordan_10x20(A)) return 0;
-    EPV_PROF(1);
-    // B(z): entries (j,0),(j,1) cubic, (j,2) quartic; ascending powers.  Row j comes from
-    // reduced rows 4+2j ("e - z f"): coefficient layout of the right block per row is
+// ---- stage B: reduced rows -> degree-10 polynomial -> roots -> essential matrices -------------
+// rec[k * rs]: the stage-A record (k < EB_DOUBLES).  sh: this thread's scratch in shared memory,
+// element i at sh[i * ss], SB_SCRATCH doubles: [0, 36) the basis, [36, 75) the B(z) coefficients
+// (4 + 4 + 5 per row of B).  Eout[k * 9 + i]: k-th essential matrix (row-major, unit Frobenius
+// norm).  Returns the number of solutions.
+constexpr int SB_SCRATCH = 36 + 39;
+
+__device__ __forceinline__ int stage_b(const double* rec, size_t rs, double* sh, int ss, double* Eout) {
+    if (!(rec[36 * rs] == rec[36 * rs])) return 0;            // stage A flagged a singular system
+#pragma unroll
+    for (int i = 0; i < 36; ++i) sh[i * ss] = rec[(size_t)i * rs];
+    // B(z): entries (j,0),(j,1) cubic, (j,2) quartic; ascending powers.  Row j comes from reduced
+    // rows 4+2j ("e - z f"): coefficient layout of the right block per row is
     // [xz^2 xz x | yz^2 yz y | z^3 z^2 z 1] (descending in z inside each group).
     double B[3][3][5];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const double* r1 = &A[4 + 2 * j][10];
-        const double* r2 = &A[5 + 2 * j][10];
+        double r1[10], r2[10];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+            r1[c] = rec[(size_t)(36 + (2 * j) * 10 + c) * rs];
+            r2[c] = rec[(size_t)(36 + (2 * j + 1) * 10 + c) * rs];
+        }
         // group g (x: 0..2, y: 3..5) -> cubic: r1 contributes z^2..z^0, -z*r2 contributes z^3..z^1
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const double* a = r1 + 3 * g;
-            const double* b = r2 + 3 * g;
-            B[j][g][0] = a[2];
-            B[j][g][1] = a[1] - b[2];
-            B[j][g][2] = a[0] - b[1];
-            B[j][g][3] = -b[0];
+            B[j][g][0] = r1[3 * g + 2];
+            B[j][g][1] = r1[3 * g + 1] - r2[3 * g + 2];
+            B[j][g][2] = r1[3 * g + 0] - r2[3 * g + 1];
+            B[j][g][3] = -r2[3 * g + 0];
             B[j][g][4] = 0.0;
         }
-        const double* a = r1 + 6;
-        const double* b = r2 + 6;
-        B[j][2][0] = a[3];
-        B[j][2][1] = a[2] - b[3];
-        B[j][2][2] = a[1] - b[2];
-        B[j][2][3] = a[0] - b[1];
-        B[j][2][4] = -b[0];
+        B[j][2][0] = r1[9];
+        B[j][2][1] = r1[8] - r2[9];
+        B[j][2][2] = r1[7] - r2[8];
+        B[j][2][3] = r1[6] - r2[7];
+        B[j][2][4] = -r2[6];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {                            // stash B for the per-root evaluation
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sh[(36 + j * 13 + k) * ss] = B[j][0][k];
+            sh[(36 + j * 13 + 4 + k) * ss] = B[j][1][k];
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sh[(36 + j * 13 + 8 + k) * ss] = B[j][2][k];
     }
     double c[11];
     {
@@ -515,47 +561,47 @@ __device__ __noinline__ int solve(const double (&x1)[5][2], const double (&x2)[5
 #pragma unroll
         for (int i = 0; i < 11; ++i) c[i] += t10[i];
     }
-    EPV_PROF(2);
     double re[10], im[10];
-    const int n = durand_kerner(c, re, im);
-    EPV_PROF(3);
+    int n = 10;
+    for (; n > 1; --n)
+        if (fabs(c[n]) > 2.220446049250313e-16) break;      // DBL_EPSILON, as cv::solvePoly
+    if (n == 10) dk_sweeps<10>(c, re, im);
+    else dk_sweeps_generic(c, n, re, im);
     int count = 0;
-    for (int i = 0; i < n; ++i) {
-        if (fabs(im[i]) > 1e-10) continue;
-        const double z = re[i];
-        double Bz[3][3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+    for (int i = 0; i < 10; ++i) {                           // unrolled: re/im stay in registers
+        if (i < n && !(fabs(im[i]) > 1e-10)) {
+            const double z = re[i];
+            double Bz[3][3];
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                double acc = B[j][g][4];
+            for (int j = 0; j < 3; ++j) {
+                const double* bj = sh + (36 + j * 13) * ss;
+                Bz[j][0] = ((bj[3 * ss] * z + bj[2 * ss]) * z + bj[1 * ss]) * z + bj[0];
+                Bz[j][1] = ((bj[7 * ss] * z + bj[6 * ss]) * z + bj[5 * ss]) * z + bj[4 * ss];
+                Bz[j][2] = (((bj[12 * ss] * z + bj[11 * ss]) * z + bj[10 * ss]) * z + bj[9 * ss]) * z + bj[8 * ss];
+            }
+            double v[3];
+            null_vec3(Bz, v);
+            if (fabs(v[2]) >= 1e-10) {
+                const double iv = 1.0 / v[2];
+                const double x = v[0] * iv, y = v[1] * iv;
+                double s = 0.0;
+                double E[9];
 #pragma unroll
-                for (int k = 3; k >= 0; --k) acc = acc * z + B[j][g][k];
-                Bz[j][g] = acc;
+                for (int k = 0; k < 9; ++k) {
+                    E[k] = sh[k * ss] * x + sh[(9 + k) * ss] * y + sh[(18 + k) * ss] * z + sh[(27 + k) * ss];
+                    s += E[k] * E[k];
+                }
+                const double inv = rsqrt(s);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) E[k] *= inv;
+                refine_essential(sh, ss, E);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Eout[count * 9 + k] = E[k];
+                ++count;
             }
         }
-        double v[3];
-        null_vec3(Bz, v);
-        if (!(fabs(v[2]) >= 1e-10)) continue;
-        const double x = v[0] / v[2], y = v[1] / v[2];
-        double s = 0.0;
-        double E[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            E[k] = e[0][k] * x + e[1][k] * y + e[2][k] * z + e[3][k];
-            s += E[k] * E[k];
-        }
-        const double inv = 1.0 / sqrt(s);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) E[k] *= inv;
-        refine_essential(e, E);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Eout[count][k] = E[k];
-        ++count;
     }
-    EPV_PROF(4);
-    EPV_PROF_ADD(6, 1);
-    EPV_PROF_ADD(7, count);
     return count;
 }
 

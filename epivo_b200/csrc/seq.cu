@@ -17,7 +17,6 @@
 namespace {
 constexpr int SEQ_CHUNK = 8192;          // pairs per launch group (single stream: large groups, fewer tails)
 constexpr int SEQ_CHUNK_OVERLAP = 1024;  // group size when the two-stream pipelining is switched on
-constexpr int SEQ_PRE_MAX = 128;   // max pre-solved samples per pair (4 chunks of 32)
 constexpr int SEQ_STAGES = 7;      // prep, match, finalize, essential, pose, lm, (total)
 constexpr int SEQ_MAX_CHUNKS = 256;
 }  // namespace
@@ -42,9 +41,8 @@ struct epivo_seq {
     double *d_xn = nullptr, *d_xin = nullptr, *d_lmp = nullptr, *d_lmq = nullptr, *d_w = nullptr;
     float* d_err = nullptr;
     int32_t* d_reps = nullptr;
-    double* d_pm = nullptr;
-    int32_t *d_pn = nullptr, *d_pi = nullptr;
-    unsigned long long* d_prng = nullptr;
+    char* d_esswork = nullptr;      // essential-stage scratch for one pair group
+    size_t esswork_bytes = 0;
     // host staging for results
     epivo_pair_result* h_results = nullptr;
     // timing
@@ -223,7 +221,8 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     A(d_lmp, C * 64 * 3); A(d_lmq, C * 64 * 3); A(d_w, C);
     A(d_err, epv_essential_errbuf_floats((int)C, (int)st));
     A(d_reps, 2);
-    A(d_pm, C * SEQ_PRE_MAX * 90); A(d_pn, C * SEQ_PRE_MAX); A(d_pi, C * SEQ_PRE_MAX * 5); A(d_prng, C);
+    s->esswork_bytes = epv_essential_work_bytes((int)std::min<size_t>(P, SEQ_CHUNK));
+    A(d_esswork, s->esswork_bytes);
 #undef A
     if (!rc && cudaMallocHost(&s->h_results, P * sizeof(epivo_pair_result)) != cudaSuccess) rc = EPIVO_ERR_CUDA;
     bool ev_ok = true;
@@ -324,11 +323,8 @@ static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int 
     ep.n_models = s->d_nmodels + p0;
     ep.status = s->d_status + p0;
     ep.xin = s->d_xin + o * 4 * st;
-    ep.pre_count = std::min(SEQ_PRE_MAX, epv_essential_pre_count(prm->method, prm->prob, prm->max_iters, 0));
-    ep.pre_models = s->d_pm + o * SEQ_PRE_MAX * 90;
-    ep.pre_nmodels = s->d_pn + o * SEQ_PRE_MAX;
-    ep.pre_idx = s->d_pi + o * SEQ_PRE_MAX * 5;
-    ep.pre_rng = s->d_prng + o;
+    ep.work = s->d_esswork;          // one group at a time uses it: groups are stream-ordered
+    ep.work_bytes = s->esswork_bytes;
     ep.ev_presolved = s->evp[c];
     rc = epv_essential_launch(ctx, ep);
     if (rc) return rc;

@@ -18,21 +18,17 @@ struct EssentialPlan {
     uint8_t* mask;           // [pair][stride]
     int32_t *n_inliers, *iters, *n_models, *status;   // [pair]
     double* xin;             // optional [pair][4][stride]
-    // optional buffers for solving the first pre_count samples of every pair ahead of the per-pair
-    // kernel (pre_count from epv_essential_pre_count; all four must be given)
-    int pre_count;
-    double* pre_models;               // [pair][pre_count][10][9]
-    int32_t* pre_nmodels;             // [pair][pre_count]
-    int32_t* pre_idx;                 // [pair][pre_count][5]
-    unsigned long long* pre_rng;      // [pair]
-    cudaEvent_t ev_presolved = nullptr;   // optional: recorded after the sample + presolve kernels
+    void* work;              // device scratch of epv_essential_work_bytes(n_pairs) bytes
+    size_t work_bytes;
+    cudaEvent_t ev_presolved = nullptr;   // optional: recorded after the first round's sample + solve kernels
 };
-int epv_essential_pre_count(int method, double prob, int max_iters, int m_samples);
+size_t epv_essential_work_bytes(int n_pairs);
 int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p);
 size_t epv_essential_errbuf_floats(int n_pairs, int stride);
 int epv_normalize_launch(epivo_ctx* ctx, const float* d_p0, const float* d_p1, int n, int stride, const double K[9],
                          double* d_xn);
-int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_E, int32_t* d_nm);
+int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_rec /* m x 96 */,
+                          double* d_E, int32_t* d_nm);
 int epv_score_launch(epivo_ctx* ctx, const double* d_E, int m, const double* d_xn, int stride, int n, double thresh,
                      int32_t* d_counts, float* d_medians, float* d_errbuf, int* d_best, uint8_t* d_mask);
 
