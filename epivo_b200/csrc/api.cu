@@ -285,21 +285,35 @@ int epivo_five_point(epivo_ctx* ctx, const double* x1, const double* x2, int m, 
     if (m < 0 || (m > 0 && (!x1 || !x2 || !E_out || !n_models))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
     if (m == 0) return EPIVO_OK;
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = epv_ws_reserve(ctx, (size_t)m * (80 * 2 + 720 + 4 + 96 * 8) + 8192);
+    int rc = epv_ws_reserve(ctx, (size_t)m * (80 * 2 + 720 + 4 + 96 * 8 + 40 + 80) + 16384);
+    if (rc) return rc;
+    rc = epv_pin_reserve(ctx, (size_t)m * (720 + 4) + 1024);
     if (rc) return rc;
     double* d_x1 = epv_ws_take<double>(ctx, (size_t)m * 10);
     double* d_x2 = epv_ws_take<double>(ctx, (size_t)m * 10);
     double* d_E = epv_ws_take<double>(ctx, (size_t)m * 90);
-    int32_t* d_nm = epv_ws_take<int32_t>(ctx, m);
+    uint32_t* d_flags = epv_ws_take<uint32_t>(ctx, m);
     double* d_rec = epv_ws_take<double>(ctx, (size_t)m * 96);
+    uint32_t* d_items = epv_ws_take<uint32_t>(ctx, (size_t)m * 10);
+    double* d_item_z = epv_ws_take<double>(ctx, (size_t)m * 10);
+    int32_t* d_count = epv_ws_take<int32_t>(ctx, 1);
+    double* h_E = epv_pin_take<double>(ctx, (size_t)m * 90);
+    uint32_t* h_flags = epv_pin_take<uint32_t>(ctx, m);
     EPV_CUDA(ctx, cudaMemcpyAsync(d_x1, x1, (size_t)m * 80, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(d_x2, x2, (size_t)m * 80, cudaMemcpyHostToDevice, ctx->stream));
-    EPV_CUDA(ctx, cudaMemsetAsync(d_E, 0, (size_t)m * 720, ctx->stream));
-    rc = epv_five_point_launch(ctx, d_x1, d_x2, m, d_rec, d_E, d_nm);
+    rc = epv_five_point_launch(ctx, d_x1, d_x2, m, d_rec, d_items, d_item_z, d_count, d_E, d_flags);
     if (rc) return rc;
-    EPV_CUDA(ctx, cudaMemcpyAsync(E_out, d_E, (size_t)m * 720, cudaMemcpyDeviceToHost, ctx->stream));
-    EPV_CUDA(ctx, cudaMemcpyAsync(n_models, d_nm, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(h_E, d_E, (size_t)m * 720, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(h_flags, d_flags, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // valid models, in root order, packed to the front of each sample's block of ten
+    memset(E_out, 0, (size_t)m * 720);
+    for (int i = 0; i < m; ++i) {
+        int c = 0;
+        for (int j = 0; j < 10; ++j)
+            if (h_flags[i] >> j & 1u) memcpy(E_out + ((size_t)i * 10 + c++) * 9, h_E + ((size_t)i * 10 + j) * 9, 72);
+        n_models[i] = c;
+    }
     return EPIVO_OK;
 }
 

@@ -183,8 +183,11 @@ struct EssWork {
     int32_t* ctl;            // [ES_MAX_ROUNDS + 1] running pairs per round
     int32_t* idx;            // [n_pairs * ES_RMAX][5]
     double* rec;             // [EB_DOUBLES][cap]  stage A -> stage B records, SoA
-    double* models;          // [cap][10][9]
-    int32_t* nmodels;        // [cap]
+    double* models;          // [cap][10][9], model j of a slot is valid iff bit j of mflags[slot]
+    uint32_t* mflags;        // [cap]
+    uint32_t* items;         // [cap * 10] real roots of the round, compacted: slot << 4 | root index
+    double* item_z;          // [cap * 10] the root itself
+    int32_t* nitems;         // [ES_MAX_ROUNDS] roots per round
     size_t cap;              // n_pairs * ES_RMAX slots
 };
 
@@ -203,10 +206,13 @@ size_t ess_work_carve(EssWork* w, char* base, int n_pairs) {
     int32_t* idx = reinterpret_cast<int32_t*>(take(cap * 5 * 4));
     double* rec = reinterpret_cast<double*>(take(cap * fivept::EB_DOUBLES * 8));
     double* models = reinterpret_cast<double*>(take(cap * 90 * 8));
-    int32_t* nm = reinterpret_cast<int32_t*>(take(cap * 4));
+    uint32_t* mf = reinterpret_cast<uint32_t*>(take(cap * 4));
+    uint32_t* items = reinterpret_cast<uint32_t*>(take(cap * 10 * 4));
+    double* item_z = reinterpret_cast<double*>(take(cap * 10 * 8));
+    int32_t* nitems = reinterpret_cast<int32_t*>(take(ES_MAX_ROUNDS * 4));
     if (w) {
         w->state = st; w->wl[0] = wl0; w->wl[1] = wl1; w->ctl = ctl; w->idx = idx; w->rec = rec;
-        w->models = models; w->nmodels = nm; w->cap = cap;
+        w->models = models; w->mflags = mf; w->items = items; w->item_z = item_z; w->nitems = nitems; w->cap = cap;
     }
     return off;
 }
@@ -238,6 +244,7 @@ __global__ void ess_init_kernel(EssArgs a) {
     if (pair == 0) {
         a.w.ctl[0] = a.n_pairs;
         for (int r = 1; r <= ES_MAX_ROUNDS; ++r) a.w.ctl[r] = 0;
+        for (int r = 0; r < ES_MAX_ROUNDS; ++r) a.w.nitems[r] = 0;
     }
     if (pair >= a.n_pairs) return;
     const int n = a.n[pair];
@@ -322,31 +329,86 @@ __global__ void __launch_bounds__(32) solve_a_kernel(EssArgs a, int round, int R
     }
 }
 
-// ---- stage B: one lane per hypothesis, registers + a 75-double shared scratch ---------------
-constexpr int SB_THREADS = 64;
-#ifndef EPV_SB_MINBLOCKS
-#define EPV_SB_MINBLOCKS 4
+// ---- stage B1: one lane per hypothesis (polynomial + roots); real roots -> compact work list ----
+constexpr int SB1_THREADS = 128;
+#ifndef EPV_SB1_MINBLOCKS
+#define EPV_SB1_MINBLOCKS 4
 #endif
 
-__global__ void __launch_bounds__(SB_THREADS, EPV_SB_MINBLOCKS) solve_b_kernel(EssArgs a, int round, int R) {
-    __shared__ double s_sh[fivept::SB_SCRATCH * SB_THREADS];
+// the warp's real roots are appended to the round's item list with one atomic per warp
+__device__ __forceinline__ void append_roots(int count, const double (&zs)[10], uint32_t slot, uint32_t* items,
+                                             double* item_z, int32_t* total) {
+    const int lane = threadIdx.x & 31;
+    int incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    int base = 0;
+    if (lane == 31 && warp_total > 0) base = atomicAdd(total, warp_total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    const int off = base + incl - count;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (k < count) {
+            items[off + k] = slot << 4 | (uint32_t)k;
+            item_z[off + k] = zs[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SB1_THREADS, EPV_SB1_MINBLOCKS) solve_b1_kernel(EssArgs a, int round, int R) {
     const int count = a.w.ctl[round];
     const int32_t* wl = a.w.wl[round & 1];
     const long long total = (long long)count * R;
-    for (long long base = (long long)blockIdx.x * SB_THREADS; base < total; base += (long long)gridDim.x * SB_THREADS) {
+    // whole warps iterate together (the append is a warp collective)
+    for (long long base = (long long)blockIdx.x * SB1_THREADS; base < total; base += (long long)gridDim.x * SB1_THREADS) {
         const long long slot = base + threadIdx.x;
-        if (slot >= total) continue;
-        const int w = (int)(slot / R), s = (int)(slot % R);
-        const RansacState& st = a.w.state[wl[w]];
-        if (st.iter + s >= st.niters) continue;
-        a.w.nmodels[slot] = fivept::stage_b(a.w.rec + slot, a.w.cap, s_sh + threadIdx.x, SB_THREADS, a.w.models + slot * 90);
+        bool valid = slot < total;
+        if (valid) {
+            const int w = (int)(slot / R), s = (int)(slot % R);
+            const RansacState& st = a.w.state[wl[w]];
+            valid = st.iter + s < st.niters;
+        }
+        double zs[10];
+        int nz = 0;
+        if (valid) {
+            nz = fivept::stage_b1(a.w.rec + slot, a.w.cap, zs);
+            a.w.mflags[slot] = 0;
+        }
+        append_roots(nz, zs, (uint32_t)slot, a.w.items, a.w.item_z, a.w.nitems + round);
+    }
+}
+
+// ---- stage B2: one lane per real root: model + refinement -----------------------------------------
+constexpr int SB2_THREADS = 64;
+#ifndef EPV_SB2_MINBLOCKS
+#define EPV_SB2_MINBLOCKS 4
+#endif
+
+__global__ void __launch_bounds__(SB2_THREADS, EPV_SB2_MINBLOCKS) solve_b2_kernel(EssArgs a, int round) {
+    __shared__ double s_sh[36 * SB2_THREADS];
+    const int n_items = a.w.nitems[round];
+    for (int it = blockIdx.x * SB2_THREADS + threadIdx.x; it < n_items; it += gridDim.x * SB2_THREADS) {
+        const uint32_t code = a.w.items[it];
+        const size_t slot = code >> 4;
+        const int j = code & 15;
+        double E[9];
+        if (fivept::stage_b2(a.w.rec + slot, a.w.cap, a.w.item_z[it], s_sh + threadIdx.x, SB2_THREADS, E)) {
+            double* out = a.w.models + slot * 90 + j * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out[k] = E[k];
+            atomicOr(&a.w.mflags[slot], 1u << j);
+        }
     }
 }
 
 // ---- scoring + sequential replay + finish: one CTA per running pair -------------------------
 __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int round, int R, int last_round) {
     __shared__ double s_models[ES_WARPS][10][9];  // models of the sub-chunk being scored
-    __shared__ int s_nm[ES_WARPS];
+    __shared__ unsigned s_flags[ES_WARPS];         // valid-model bit masks of the sub-chunk's samples
     __shared__ unsigned char s_item[ES_WARPS * 10];   // flattened (sample << 4 | model) list of the sub-chunk
     __shared__ int s_nitems;
     __shared__ float s_score[ES_WARPS][10];       // LMedS: medians
@@ -387,7 +449,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
         const int iter0 = s_iter;
         const int ch = min(R, s_niters - iter0);             // samples solved for this pair in this round
         const double* gmodels = a.w.models + (size_t)w * R * 90;
-        const int32_t* gnm = a.w.nmodels + (size_t)w * R;
+        const uint32_t* gfl = a.w.mflags + (size_t)w * R;
 
         // sub-chunks of at most ES_WARPS samples: score, then replay.  RANSAC usually shrinks niters
         // after the first few samples; samples at or beyond the current niters are never scored.
@@ -397,7 +459,8 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
             for (int i = tid; i < r * 90; i += ES_THREADS) (&s_models[0][0][0])[i] = gmodels[(size_t)sbase * 90 + i];
             if (tid < ES_WARPS * 10) (&s_cnt[0][0])[tid] = 0;
             if (warp == 0) {
-                const int c = lane < r ? gnm[sbase + lane] : 0;
+                const unsigned fl = lane < r ? gfl[sbase + lane] : 0u;
+                const int c = __popc(fl);
                 int incl = c;
 #pragma unroll
                 for (int o = 1; o < ES_WARPS; o <<= 1) {
@@ -405,8 +468,10 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     if (lane >= o) incl += v;
                 }
                 if (lane < r) {
-                    s_nm[lane] = c;
-                    for (int k = 0; k < c; ++k) s_item[incl - c + k] = (unsigned char)(lane << 4 | k);
+                    s_flags[lane] = fl;
+                    int pos = incl - c;
+                    for (int j = 0; j < 10; ++j)
+                        if (fl >> j & 1u) s_item[pos++] = (unsigned char)(lane << 4 | j);
                 }
                 if (lane == ES_WARPS - 1) s_nitems = incl;
             }
@@ -477,7 +542,8 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                 int q = 0;
                 for (; q < r; ++q) {
                     if (iter0 + sbase + q >= ni) break;
-                    for (int k = 0; k < s_nm[q]; ++k) {
+                    for (int k = 0; k < 10; ++k) {             // valid models in root order
+                        if (!(s_flags[q] >> k & 1u)) continue;
                         s_total_models++;
                         if (n == 5) {                        // minimal case: first solution, all inliers
                             if (!s_have) {
@@ -605,12 +671,39 @@ __global__ void __launch_bounds__(32) five_point_a_kernel(const double* __restri
     }
 }
 
-__global__ void __launch_bounds__(SB_THREADS, EPV_SB_MINBLOCKS)
-five_point_b_kernel(const double* __restrict__ rec, int m, double* __restrict__ Eout, int32_t* __restrict__ nm) {
-    __shared__ double s_sh[fivept::SB_SCRATCH * SB_THREADS];
-    const long long i = (long long)blockIdx.x * SB_THREADS + threadIdx.x;
-    if (i >= m) return;
-    nm[i] = fivept::stage_b(rec + i, (size_t)m, s_sh + threadIdx.x, SB_THREADS, Eout + i * 90);
+// stage B1 + B2 for the stand-alone solver: flags[i] = valid-model mask, models at fixed positions
+__global__ void __launch_bounds__(SB1_THREADS, EPV_SB1_MINBLOCKS)
+five_point_b1_kernel(const double* __restrict__ rec, int m, uint32_t* __restrict__ flags, uint32_t* __restrict__ items,
+                     double* __restrict__ item_z, int32_t* __restrict__ n_items) {
+    for (long long base = (long long)blockIdx.x * SB1_THREADS; base < m; base += (long long)gridDim.x * SB1_THREADS) {
+        const long long i = base + threadIdx.x;
+        double zs[10];
+        int nz = 0;
+        if (i < m) {
+            nz = fivept::stage_b1(rec + i, (size_t)m, zs);
+            flags[i] = 0;
+        }
+        append_roots(nz, zs, (uint32_t)i, items, item_z, n_items);
+    }
+}
+
+__global__ void __launch_bounds__(SB2_THREADS, EPV_SB2_MINBLOCKS)
+five_point_b2_kernel(const double* __restrict__ rec, int m, const uint32_t* __restrict__ items,
+                     const double* __restrict__ item_z, const int32_t* __restrict__ n_items, double* __restrict__ Eout,
+                     uint32_t* __restrict__ flags) {
+    __shared__ double s_sh[36 * SB2_THREADS];
+    const int n = *n_items;
+    for (int it = blockIdx.x * SB2_THREADS + threadIdx.x; it < n; it += gridDim.x * SB2_THREADS) {
+        const uint32_t code = items[it];
+        const size_t i = code >> 4;
+        const int j = code & 15;
+        double E[9];
+        if (fivept::stage_b2(rec + i, (size_t)m, item_z[it], s_sh + threadIdx.x, SB2_THREADS, E)) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Eout[i * 90 + j * 9 + k] = E[k];
+            atomicOr(&flags[i], 1u << j);
+        }
+    }
 }
 
 // ---- K3 alone: fixed hypothesis set, m models x n correspondences ----------------------
@@ -793,13 +886,18 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
         const unsigned g_pairs = (unsigned)std::min<long long>(pairs_ub, full ? pairs_ub : 2LL * sms);
         const unsigned g_samp = (unsigned)std::min<long long>((pairs_ub + 127) / 128, full ? (1LL << 30) : sms);
         const unsigned g_a = (unsigned)std::min<long long>((slots_ub + 31) / 32, full ? (1LL << 30) : 4LL * sms);
-        const unsigned g_b = (unsigned)std::min<long long>((slots_ub + SB_THREADS - 1) / SB_THREADS,
-                                                           full ? (1LL << 30) : 4LL * sms);
+        const unsigned g_b1 = (unsigned)std::min<long long>((slots_ub + SB1_THREADS - 1) / SB1_THREADS,
+                                                            full ? (1LL << 30) : 4LL * sms);
+        // stage B2 sees ~4.3 real roots per hypothesis; its grid-stride loop absorbs the rest
+        const unsigned g_b2 = (unsigned)std::min<long long>((slots_ub * 5 + SB2_THREADS - 1) / SB2_THREADS,
+                                                            full ? (1LL << 30) : 4LL * sms);
         ess_sample_kernel<<<g_samp, 128, 0, ctx->stream>>>(a, r, R[r]);
         EPV_LAUNCHED(ctx);
         solve_a_kernel<<<g_a, 32, SA_SMEM, ctx->stream>>>(a, r, R[r]);
         EPV_LAUNCHED(ctx);
-        solve_b_kernel<<<g_b, SB_THREADS, 0, ctx->stream>>>(a, r, R[r]);
+        solve_b1_kernel<<<g_b1, SB1_THREADS, 0, ctx->stream>>>(a, r, R[r]);
+        EPV_LAUNCHED(ctx);
+        solve_b2_kernel<<<g_b2, SB2_THREADS, 0, ctx->stream>>>(a, r);
         EPV_LAUNCHED(ctx);
         if (r == 0 && p.ev_presolved) EPV_CUDA(ctx, cudaEventRecord(p.ev_presolved, ctx->stream));
         ess_round_kernel<<<g_pairs, ES_THREADS, 0, ctx->stream>>>(a, r, R[r], r == nr - 1 ? 1 : 0);
@@ -810,14 +908,21 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
 
 size_t epv_essential_errbuf_floats(int n_pairs, int stride) { return (size_t)n_pairs * ES_WARPS * stride; }
 
-// d_rec: m * 96 doubles of scratch
-int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_rec, double* d_E,
-                          int32_t* d_nm) {
+// d_rec: m * 96 doubles; d_items: m * 10 u32; d_item_z: m * 10 doubles; d_count: 1 int (scratch).
+// d_E: m x 10 x 9 with model j of sample i valid iff bit j of d_flags[i].
+int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_rec,
+                          uint32_t* d_items, double* d_item_z, int32_t* d_count, double* d_E, uint32_t* d_flags) {
     if (m <= 0) return EPIVO_OK;
     EPV_CUDA(ctx, cudaFuncSetAttribute(five_point_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
+    EPV_CUDA(ctx, cudaMemsetAsync(d_count, 0, 4, ctx->stream));
     five_point_a_kernel<<<(m + 31) / 32, 32, SA_SMEM, ctx->stream>>>(d_x1, d_x2, m, d_rec);
     EPV_LAUNCHED(ctx);
-    five_point_b_kernel<<<(m + SB_THREADS - 1) / SB_THREADS, SB_THREADS, 0, ctx->stream>>>(d_rec, m, d_E, d_nm);
+    five_point_b1_kernel<<<(m + SB1_THREADS - 1) / SB1_THREADS, SB1_THREADS, 0, ctx->stream>>>(d_rec, m, d_flags, d_items,
+                                                                                            d_item_z, d_count);
+    EPV_LAUNCHED(ctx);
+    const long long ub = (long long)m * 5;
+    five_point_b2_kernel<<<(unsigned)((ub + SB2_THREADS - 1) / SB2_THREADS), SB2_THREADS, 0, ctx->stream>>>(
+        d_rec, m, d_items, d_item_z, d_count, d_E, d_flags);
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
 }

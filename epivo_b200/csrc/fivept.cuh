@@ -21,9 +21,11 @@
 // Stage A (steps 1-3) needs the 10x20 matrix, which only fits on chip in shared memory: one warp
 // = 32 hypotheses, the matrix lane-strided (element (r,c) of lane l at [(r*20+c)*32 + l], bank =
 // lane, conflict free even though every lane pivots on a different row).  Its product is 96
-// doubles per hypothesis (null-space basis + six reduced rows).  Stage B (steps 4-7) is
-// register/shared only.  A thread-private 10x20 array would live in local memory, and with tens
-// of thousands of hypotheses in flight that traffic goes to HBM.
+// doubles per hypothesis (null-space basis + six reduced rows).  A thread-private 10x20 array
+// would live in local memory, and with tens of thousands of hypotheses in flight that traffic
+// goes to HBM.  Stage B1 (steps 4-5) is one lane per hypothesis, registers only.  Stage B2
+// (steps 6-7) is one lane per REAL ROOT: hypotheses have 0..10 real roots (4.3 on average), so
+// the roots are compacted into a work list first instead of idling the lanes of a warp.
 #pragma once
 #include "fivept_gen.cuh"
 
@@ -461,54 +463,40 @@ __device__ __noinline__ void refine_essential(const double* e, int es, double (&
     for (int i = 0; i < 9; ++i) E[i] = Ec[i];
 }
 
-// ---- stage B: reduced rows -> degree-10 polynomial -> roots -> essential matrices -------------
-// rec[k * rs]: the stage-A record (k < EB_DOUBLES).  sh: this thread's scratch in shared memory,
-// element i at sh[i * ss], SB_SCRATCH doubles: [0, 36) the basis, [36, 75) the B(z) coefficients
-// (4 + 4 + 5 per row of B).  Eout[k * 9 + i]: k-th essential matrix (row-major, unit Frobenius
-// norm).  Returns the number of solutions.
-constexpr int SB_SCRATCH = 36 + 39;
-
-__device__ __forceinline__ int stage_b(const double* rec, size_t rs, double* sh, int ss, double* Eout) {
-    if (!(rec[36 * rs] == rec[36 * rs])) return 0;            // stage A flagged a singular system
+// ---- stage B1: reduced rows -> degree-10 polynomial -> roots -----------------------------------
+// rec[k * rs]: the stage-A record.  zs[0..count): the real roots (|imag| <= 1e-10) in cv::solvePoly's
+// root order.  Returns their number (0 if stage A flagged a singular system).
+// Row j of B(z) comes from reduced rows 4+2j ("e - z f"): the coefficient layout of the right block per
+// row is [xz^2 xz x | yz^2 yz y | z^3 z^2 z 1] (descending in z inside each group); entries (j,0),(j,1)
+// are cubic, (j,2) quartic, ascending powers.
+__device__ __forceinline__ void build_B_row(const double* rec, size_t rs, int j, double (&B)[3][5]) {
+    double r1[10], r2[10];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) sh[i * ss] = rec[(size_t)i * rs];
-    // B(z): entries (j,0),(j,1) cubic, (j,2) quartic; ascending powers.  Row j comes from reduced
-    // rows 4+2j ("e - z f"): coefficient layout of the right block per row is
-    // [xz^2 xz x | yz^2 yz y | z^3 z^2 z 1] (descending in z inside each group).
+    for (int c = 0; c < 10; ++c) {
+        r1[c] = rec[(size_t)(36 + (2 * j) * 10 + c) * rs];
+        r2[c] = rec[(size_t)(36 + (2 * j + 1) * 10 + c) * rs];
+    }
+    // group g (x: 0..2, y: 3..5) -> cubic: r1 contributes z^2..z^0, -z*r2 contributes z^3..z^1
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        B[g][0] = r1[3 * g + 2];
+        B[g][1] = r1[3 * g + 1] - r2[3 * g + 2];
+        B[g][2] = r1[3 * g + 0] - r2[3 * g + 1];
+        B[g][3] = -r2[3 * g + 0];
+        B[g][4] = 0.0;
+    }
+    B[2][0] = r1[9];
+    B[2][1] = r1[8] - r2[9];
+    B[2][2] = r1[7] - r2[8];
+    B[2][3] = r1[6] - r2[7];
+    B[2][4] = -r2[6];
+}
+
+__device__ __forceinline__ int stage_b1(const double* rec, size_t rs, double (&zs)[10]) {
+    if (!(rec[36 * rs] == rec[36 * rs])) return 0;            // stage A flagged a singular system
     double B[3][3][5];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        double r1[10], r2[10];
-#pragma unroll
-        for (int c = 0; c < 10; ++c) {
-            r1[c] = rec[(size_t)(36 + (2 * j) * 10 + c) * rs];
-            r2[c] = rec[(size_t)(36 + (2 * j + 1) * 10 + c) * rs];
-        }
-        // group g (x: 0..2, y: 3..5) -> cubic: r1 contributes z^2..z^0, -z*r2 contributes z^3..z^1
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            B[j][g][0] = r1[3 * g + 2];
-            B[j][g][1] = r1[3 * g + 1] - r2[3 * g + 2];
-            B[j][g][2] = r1[3 * g + 0] - r2[3 * g + 1];
-            B[j][g][3] = -r2[3 * g + 0];
-            B[j][g][4] = 0.0;
-        }
-        B[j][2][0] = r1[9];
-        B[j][2][1] = r1[8] - r2[9];
-        B[j][2][2] = r1[7] - r2[8];
-        B[j][2][3] = r1[6] - r2[7];
-        B[j][2][4] = -r2[6];
-    }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {                            // stash B for the per-root evaluation
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            sh[(36 + j * 13 + k) * ss] = B[j][0][k];
-            sh[(36 + j * 13 + 4 + k) * ss] = B[j][1][k];
-        }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) sh[(36 + j * 13 + 8 + k) * ss] = B[j][2][k];
-    }
+    for (int j = 0; j < 3; ++j) build_B_row(rec, rs, j, B[j]);
     double c[11];
     {
         double c3a[4], c3b[4], q4[5], m7a[8], m7b[8], m6a[7], m6b[7], t10[11];
@@ -570,39 +558,47 @@ __device__ __forceinline__ int stage_b(const double* rec, size_t rs, double* sh,
     int count = 0;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {                           // unrolled: re/im stay in registers
-        if (i < n && !(fabs(im[i]) > 1e-10)) {
-            const double z = re[i];
-            double Bz[3][3];
+        const bool real = i < n && !(fabs(im[i]) > 1e-10);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double* bj = sh + (36 + j * 13) * ss;
-                Bz[j][0] = ((bj[3 * ss] * z + bj[2 * ss]) * z + bj[1 * ss]) * z + bj[0];
-                Bz[j][1] = ((bj[7 * ss] * z + bj[6 * ss]) * z + bj[5 * ss]) * z + bj[4 * ss];
-                Bz[j][2] = (((bj[12 * ss] * z + bj[11 * ss]) * z + bj[10 * ss]) * z + bj[9 * ss]) * z + bj[8 * ss];
-            }
-            double v[3];
-            null_vec3(Bz, v);
-            if (fabs(v[2]) >= 1e-10) {
-                const double iv = 1.0 / v[2];
-                const double x = v[0] * iv, y = v[1] * iv;
-                double s = 0.0;
-                double E[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    E[k] = sh[k * ss] * x + sh[(9 + k) * ss] * y + sh[(18 + k) * ss] * z + sh[(27 + k) * ss];
-                    s += E[k] * E[k];
-                }
-                const double inv = rsqrt(s);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) E[k] *= inv;
-                refine_essential(sh, ss, E);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) Eout[count * 9 + k] = E[k];
-                ++count;
-            }
-        }
+        for (int k = 0; k < 10; ++k)
+            if (k <= i && real && k == count) zs[k] = re[i];  // zs[count] = re[i] with static indices
+        count += real ? 1 : 0;
     }
     return count;
+}
+
+// ---- stage B2: one real root -> one essential matrix ------------------------------------------
+// sh: this thread's scratch in shared memory for the null-space basis (36 doubles, element i at sh[i * ss]).
+// E: row-major, unit Frobenius norm, refined.  Returns false if OpenCV would skip this root (the null
+// vector of B(z) has a third component below 1e-10).
+__device__ __forceinline__ bool stage_b2(const double* rec, size_t rs, double z, double* sh, int ss, double (&E)[9]) {
+    double Bz[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double B[3][5];
+        build_B_row(rec, rs, j, B);
+        Bz[j][0] = ((B[0][3] * z + B[0][2]) * z + B[0][1]) * z + B[0][0];
+        Bz[j][1] = ((B[1][3] * z + B[1][2]) * z + B[1][1]) * z + B[1][0];
+        Bz[j][2] = (((B[2][4] * z + B[2][3]) * z + B[2][2]) * z + B[2][1]) * z + B[2][0];
+    }
+    double v[3];
+    null_vec3(Bz, v);
+    if (!(fabs(v[2]) >= 1e-10)) return false;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) sh[i * ss] = rec[(size_t)i * rs];
+    const double iv = 1.0 / v[2];
+    const double x = v[0] * iv, y = v[1] * iv;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        E[k] = sh[k * ss] * x + sh[(9 + k) * ss] * y + sh[(18 + k) * ss] * z + sh[(27 + k) * ss];
+        s += E[k] * E[k];
+    }
+    const double inv = rsqrt(s);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E[k] *= inv;
+    refine_essential(sh, ss, E);
+    return true;
 }
 
 }  // namespace fivept

@@ -28,7 +28,8 @@ size_t epv_essential_errbuf_floats(int n_pairs, int stride);
 int epv_normalize_launch(epivo_ctx* ctx, const float* d_p0, const float* d_p1, int n, int stride, const double K[9],
                          double* d_xn);
 int epv_five_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_rec /* m x 96 */,
-                          double* d_E, int32_t* d_nm);
+                          uint32_t* d_items /* m x 10 */, double* d_item_z /* m x 10 */, int32_t* d_count /* 1 */,
+                          double* d_E /* m x 10 x 9 */, uint32_t* d_flags /* m */);
 int epv_score_launch(epivo_ctx* ctx, const double* d_E, int m, const double* d_xn, int stride, int n, double thresh,
                      int32_t* d_counts, float* d_medians, float* d_errbuf, int* d_best, uint8_t* d_mask);
 
