@@ -55,7 +55,13 @@ __device__ int update_num_iters(double p, double ep, int model_points, int max_i
     ep = fmax(ep, 0.0);
     ep = fmin(ep, 1.0);
     double num = fmax(1.0 - p, DBL_MIN);
-    double denom = 1.0 - pow(1.0 - ep, (double)model_points);
+    double denom;
+    if (model_points == 5) {                   // the only call shape here; x^5 by multiplication instead of pow()
+        const double x = 1.0 - ep, x2 = x * x;
+        denom = 1.0 - x2 * x2 * x;
+    } else {
+        denom = 1.0 - pow(1.0 - ep, (double)model_points);
+    }
     if (denom < DBL_MIN) return 0;
     num = log(num);
     denom = log(denom);
@@ -135,6 +141,30 @@ __device__ __forceinline__ bool sampson_inlier(const double* __restrict__ E, dou
     if (r >= 0.0 && den > 0.0 && T.B > 0.0) return true;
     if (-r > __dmul_rn(T.C, den) && T.B > 0.0) return false;
     return (float)__ddiv_rn(num, den) <= T.thr32;
+}
+
+// The same test for UNIT-NORM models (what the solver emits), with a fused pre-filter: the Sampson
+// numerator and denominator are first evaluated with FMAs (22 instructions instead of 36).  With
+// |E_ij| <= 1 and S1 = |a1|+|b1|+1, S2 = |a2|+|b2|+1 the fused s = x2'Ex1 is within 12 u S1 S2 of
+// the exact value (u = 2^-53) and den within a relative 24 u S sqrt(2/den) + 4u.  A decision is taken
+// from the fused values only if it is clear by a relative 1e-6 and the quantities are far from
+// degenerate (den > 1e-8, B den > 1e-10; then the bounds above are below 1e-9 for any realistic
+// field of view); everything else -- including every borderline point -- runs the exact
+// OpenCV-order evaluation, so the result is always that of sampson_inlier().
+__device__ __forceinline__ bool sampson_inlier_unit(const double* __restrict__ E, double a1, double b1, double a2,
+                                                    double b2, const SampThr& T) {
+    const double ex0 = fma(E[0], a1, fma(E[1], b1, E[2]));
+    const double ex1 = fma(E[3], a1, fma(E[4], b1, E[5]));
+    const double ex2 = fma(E[6], a1, fma(E[7], b1, E[8]));
+    const double et0 = fma(E[0], a2, fma(E[3], b2, E[6]));
+    const double et1 = fma(E[1], a2, fma(E[4], b2, E[7]));
+    const double sx = fma(a2, ex0, fma(b2, ex1, ex2));
+    const double den = fma(ex0, ex0, fma(ex1, ex1, fma(et0, et0, et1 * et1)));
+    const double num = sx * sx;
+    const double t = T.B * den;
+    const double r = t - num;
+    if (fabs(r) > 1e-6 * (t + num) && den > 1e-8 && t > 1e-10) return r > 0.0;
+    return sampson_inlier(E, a1, b1, a2, b2, T);
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -498,7 +528,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                             const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
 #pragma unroll
                             for (int j = 0; j < 10; ++j)
-                                if (j < mine) cnt[j] += sampson_inlier(Ep[j], a1, b1, a2, b2, thrR) ? 1 : 0;
+                                if (j < mine) cnt[j] += sampson_inlier_unit(Ep[j], a1, b1, a2, b2, thrR) ? 1 : 0;
                         }
 #pragma unroll
                         for (int j = 0; j < 10; ++j) {
@@ -517,7 +547,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                             const double* E = s_models[code >> 4][code & 15];
                             int cnt = 0;
                             for (int i = lane + 32 * slice; i < n; i += 32 * slices)
-                                cnt += sampson_inlier(E, X1[i], Y1[i], X2[i], Y2[i], thrR) ? 1 : 0;
+                                cnt += sampson_inlier_unit(E, X1[i], Y1[i], X2[i], Y2[i], thrR) ? 1 : 0;
                             cnt = warp_sum(cnt);
                             if (lane == 0) atomicAdd(&s_cnt[code >> 4][code & 15], cnt);
                         }
@@ -536,43 +566,85 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                 }
             }
             __syncthreads();
-            if (tid == 0) {                                  // sequential bookkeeping of ptsetreg.cpp run()
-                int ni = s_niters;
-                double best_score = s_best_score;
-                int q = 0;
-                for (; q < r; ++q) {
-                    if (iter0 + sbase + q >= ni) break;
-                    for (int k = 0; k < 10; ++k) {             // valid models in root order
-                        if (!(s_flags[q] >> k & 1u)) continue;
-                        s_total_models++;
-                        if (n == 5) {                        // minimal case: first solution, all inliers
-                            if (!s_have) {
-                                s_have = 1;
-                                for (int c = 0; c < 9; ++c) s_bestE[c] = s_models[q][k][c];
-                            }
-                            continue;
+            // Bookkeeping of ptsetreg.cpp run(), which is sequential over (sample, model):
+            //     RANSAC: if (good > max(best, 4)) { best = good; E = model; niters = update(ep, niters); }
+            //     LMedS : if (median < best)       { best = median; E = model; }
+            //     stop as soon as iter >= niters.
+            // Replayed by warp 0 with lane q = sample q of the sub-chunk.  "Strictly better" makes the
+            // winner the FIRST model that attains the best score, and RANSACUpdateNumIters is a
+            // min(niters, f(best)) with f non-increasing in the count, so niters after sample q depends
+            // only on the best count among samples <= q: one update per lane, all lanes in parallel.
+            if (warp == 0) {
+                const int q = lane;
+                const bool live = q < r;
+                const unsigned fl = live ? s_flags[q] : 0u;
+                const int ni_in = s_niters;
+                if (n == 5) {                                // minimal case: first solution, all inliers
+                    if (lane == 0) {
+                        if (!s_have && fl) {
+                            const int k = __ffs(fl) - 1;
+                            s_have = 1;
+                            for (int c = 0; c < 9; ++c) s_bestE[c] = s_models[0][k][c];
                         }
-                        if (!lmeds) {
-                            const int good = s_cnt[q][k];
-                            if (good > max((int)best_score, 4)) {
-                                best_score = good;
-                                s_have = 1;
-                                for (int c = 0; c < 9; ++c) s_bestE[c] = s_models[q][k][c];
-                                ni = update_num_iters(a.prob, (double)(n - good) / n, 5, ni);
-                            }
-                        } else {
-                            const double med = (double)s_score[q][k];
-                            if (med < best_score) {
-                                best_score = med;
-                                s_have = 1;
-                                for (int c = 0; c < 9; ++c) s_bestE[c] = s_models[q][k][c];
-                            }
-                        }
+                        s_total_models += __popc(fl);
+                        s_iter = iter0 + sbase + r;
+                    }
+                } else if (!lmeds) {
+                    const int b_in = (int)s_best_score;
+                    int m = 0, kb = 0;                       // best count of this sample and its first model
+                    for (int k = 0; k < 10; ++k)
+                        if ((fl >> k & 1u) && s_cnt[q][k] > m) { m = s_cnt[q][k]; kb = k; }
+                    const int c = m > 4 ? m : 0;             // a count <= 4 never wins
+                    int pa = max(c, b_in);                   // inclusive prefix maximum: best after sample q
+#pragma unroll
+                    for (int o = 1; o < ES_WARPS; o <<= 1) pa = max(pa, __shfl_up_sync(0xFFFFFFFFu, pa, o, ES_WARPS));
+                    const int ni_after = pa > b_in ? update_num_iters(a.prob, (double)(n - pa) / n, 5, ni_in) : ni_in;
+                    int ni_before = __shfl_up_sync(0xFFFFFFFFu, ni_after, 1, ES_WARPS);
+                    if (q == 0) ni_before = ni_in;
+                    const bool stop_here = live && !(iter0 + sbase + q < ni_before);
+                    const unsigned stops = __ballot_sync(0xFFFFFFFFu, stop_here) & ((1u << ES_WARPS) - 1);
+                    const int qstop = stops ? __ffs(stops) - 1 : r;          // samples [0, qstop) are counted
+                    const int B = __shfl_sync(0xFFFFFFFFu, pa, max(qstop - 1, 0));
+                    const int ni_out = __shfl_sync(0xFFFFFFFFu, ni_after, max(qstop - 1, 0));
+                    const unsigned winners = __ballot_sync(0xFFFFFFFFu, live && q < qstop && c == B && B > b_in);
+                    int nmod = (live && q < qstop) ? __popc(fl) : 0;
+                    nmod = warp_sum(nmod);
+                    if (winners && q == __ffs(winners) - 1) {
+                        s_best_score = (double)B;
+                        s_have = 1;
+                        for (int cc = 0; cc < 9; ++cc) s_bestE[cc] = s_models[q][kb][cc];
+                    }
+                    if (lane == 0) {
+                        s_total_models += nmod;
+                        s_iter = iter0 + sbase + qstop;
+                        s_niters = qstop > 0 ? ni_out : ni_in;
+                    }
+                } else {
+                    float m = 3.0e38f;                       // smallest median of this sample and its first model
+                    int kb = -1;
+                    for (int k = 0; k < 10; ++k)
+                        if ((fl >> k & 1u) && (kb < 0 || s_score[q][k] < m)) { m = s_score[q][k]; kb = k; }
+                    // first (lowest q) sample with the smallest median
+                    float mm = kb >= 0 ? m : 3.0e38f;
+                    unsigned long long key = ((unsigned long long)__float_as_uint(mm) << 32) | (unsigned)q;   // medians are >= 0
+                    if (kb < 0) key = ~0ULL;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+                        key = other < key ? other : key;
+                    }
+                    int nmod = live ? __popc(fl) : 0;
+                    nmod = warp_sum(nmod);
+                    if (key != ~0ULL && q == (int)(key & 0xFFFFFFFFu) && (double)m < s_best_score) {
+                        s_best_score = (double)m;
+                        s_have = 1;
+                        for (int cc = 0; cc < 9; ++cc) s_bestE[cc] = s_models[q][kb][cc];
+                    }
+                    if (lane == 0) {
+                        s_total_models += nmod;
+                        s_iter = iter0 + sbase + r;
                     }
                 }
-                s_iter = iter0 + sbase + q;
-                s_niters = ni;
-                s_best_score = best_score;
             }
             __syncthreads();
             if (s_iter >= s_niters) break;                   // the sequential loop would have stopped here
@@ -616,7 +688,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
             double p[4] = {0, 0, 0, 0};
             if (i < n && have) {
                 p[0] = X1[i]; p[1] = Y1[i]; p[2] = X2[i]; p[3] = Y2[i];
-                in = (n == 5) ? true : sampson_inlier(s_bestE, p[0], p[1], p[2], p[3], thrF);
+                in = (n == 5) ? true : sampson_inlier_unit(s_bestE, p[0], p[1], p[2], p[3], thrF);
             }
             if (i < n) mask[i] = in ? 1 : 0;
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
