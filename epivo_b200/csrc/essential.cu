@@ -94,6 +94,7 @@ __device__ __forceinline__ float sampson_f32(const double* __restrict__ E, doubl
 // den == 0 / NaN) take the division; num and den are the same un-fused values OpenCV computes.
 struct SampThr {
     double B, C;     // C = B * 2^-50
+    double Blo, Bhi, dmin;   // pre-filter of sampson_inlier_unit: B (1 -+ 2e-6); smallest trusted denominator
     float thr32;
 };
 __host__ __device__ inline SampThr make_samp_thr(float thr32) {
@@ -123,6 +124,9 @@ __host__ __device__ inline SampThr make_samp_thr(float thr32) {
     if (!(thr32 >= 0.0f) || !(thr32 < 3e38f)) mid = -1.0;     // negative / NaN / huge: always take the exact path
     t.B = mid;
     t.C = mid * 8.881784197001252e-16;                         // 2^-50
+    t.Blo = mid * (1.0 - 2e-6);
+    t.Bhi = mid * (1.0 + 2e-6);
+    t.dmin = mid > 0.0 ? fmax(1e-8, 1e-10 / mid) : 1e300;     // invalid threshold: the pre-filter never decides
     return t;
 }
 
@@ -143,13 +147,20 @@ __device__ __forceinline__ bool sampson_inlier(const double* __restrict__ E, dou
     return (float)__ddiv_rn(num, den) <= T.thr32;
 }
 
+// out-of-line copy for the pre-filter's fallback: a call keeps the compiler from predicating the
+// 36-instruction exact path into the fast path (where it would be issued, masked off, every time)
+__device__ __noinline__ bool sampson_inlier_slow(const double* E, double a1, double b1, double a2, double b2,
+                                                 const SampThr& T) {
+    return sampson_inlier(E, a1, b1, a2, b2, T);
+}
+
 // The same test for UNIT-NORM models (what the solver emits), with a fused pre-filter: the Sampson
 // numerator and denominator are first evaluated with FMAs (22 instructions instead of 36).  With
 // |E_ij| <= 1 and S1 = |a1|+|b1|+1, S2 = |a2|+|b2|+1 the fused s = x2'Ex1 is within 12 u S1 S2 of
 // the exact value (u = 2^-53) and den within a relative 24 u S sqrt(2/den) + 4u.  A decision is taken
 // from the fused values only if it is clear by a relative 1e-6 and the quantities are far from
 // degenerate (den > 1e-8, B den > 1e-10; then the bounds above are below 1e-9 for any realistic
-// field of view); everything else -- including every borderline point -- runs the exact
+// field of view) -- "clear" means num outside [B (1 - 2e-6) den, B (1 + 2e-6) den]; everything else -- including every borderline point -- runs the exact
 // OpenCV-order evaluation, so the result is always that of sampson_inlier().
 __device__ __forceinline__ bool sampson_inlier_unit(const double* __restrict__ E, double a1, double b1, double a2,
                                                     double b2, const SampThr& T) {
@@ -161,10 +172,11 @@ __device__ __forceinline__ bool sampson_inlier_unit(const double* __restrict__ E
     const double sx = fma(a2, ex0, fma(b2, ex1, ex2));
     const double den = fma(ex0, ex0, fma(ex1, ex1, fma(et0, et0, et1 * et1)));
     const double num = sx * sx;
-    const double t = T.B * den;
-    const double r = t - num;
-    if (fabs(r) > 1e-6 * (t + num) && den > 1e-8 && t > 1e-10) return r > 0.0;
-    return sampson_inlier(E, a1, b1, a2, b2, T);
+    // clear by a relative 2e-6 on either side, and far from degenerate (T.dmin folds den > 1e-8 and
+    // B den > 1e-10).  Branch-free: the three comparisons feed one (practically never taken) branch.
+    const bool in = num < den * T.Blo, out = num > den * T.Bhi;
+    if ((in || out) && den > T.dmin) return in;
+    return sampson_inlier_slow(E, a1, b1, a2, b2, T);
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -435,8 +447,34 @@ __global__ void __launch_bounds__(SB2_THREADS, EPV_SB2_MINBLOCKS) solve_b2_kerne
     }
 }
 
+// inlier counts of one or two unit-norm models over correspondences [first, n) in steps of `step`;
+// P: pointer type of the point rows (the caller passes the shared-memory array itself when the
+// points are staged there, so the loads compile to LDS rather than generic loads)
+template <class P>
+__device__ __forceinline__ void count_two(P X1, int stride, int n, int first, int step, const double (&E0)[9],
+                                          const double (&E1)[9], const SampThr& T, int& c0, int& c1) {
+    for (int i = first; i < n; i += step) {
+        const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
+        c0 += sampson_inlier_unit(E0, a1, b1, a2, b2, T) ? 1 : 0;
+        c1 += sampson_inlier_unit(E1, a1, b1, a2, b2, T) ? 1 : 0;
+    }
+}
+template <class P>
+__device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int step, const double (&E)[9],
+                                         const SampThr& T) {
+    int c = 0;
+    for (int i = first; i < n; i += step)
+        c += sampson_inlier_unit(E, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T) ? 1 : 0;
+    return c;
+}
+
 // ---- scoring + sequential replay + finish: one CTA per running pair -------------------------
-__global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int round, int R, int last_round) {
+// pts_in_smem: the pair's correspondences (4 x stride doubles) are staged in dynamic shared memory
+// once and every scoring pass reads them from there; they are read 3+ times per pair and the
+// whole batch (45 KB per pair) does not stay in L2.  Off when they do not fit.
+__global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int round, int R, int last_round,
+                                                                  int pts_in_smem) {
+    extern __shared__ __align__(16) double s_pts[];
     __shared__ double s_models[ES_WARPS][10][9];  // models of the sub-chunk being scored
     __shared__ unsigned s_flags[ES_WARPS];         // valid-model bit masks of the sub-chunk's samples
     __shared__ unsigned char s_item[ES_WARPS * 10];   // flattened (sample << 4 | model) list of the sub-chunk
@@ -461,12 +499,21 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
         const int pair = wl[w];
         const int n = a.n[pair];
         const int64_t so = (int64_t)pair * 4 * a.stride;
-        const double* X1 = a.xn + so;
+        const double* X1 = pts_in_smem ? s_pts : a.xn + so;
         const double* Y1 = X1 + a.stride;
         const double* X2 = Y1 + a.stride;
         const double* Y2 = X2 + a.stride;
         RansacState& st = a.w.state[pair];
         __syncthreads();                                     // previous pair of this CTA is completely done
+        if (pts_in_smem) {
+            const double* g = a.xn + so;
+            for (int i = tid; i < n; i += ES_THREADS) {
+                s_pts[i] = g[i];
+                s_pts[a.stride + i] = g[a.stride + i];
+                s_pts[2 * a.stride + i] = g[2 * a.stride + i];
+                s_pts[3 * a.stride + i] = g[3 * a.stride + i];
+            }
+        }
         if (tid == 0) {
             s_iter = st.iter;
             s_niters = st.niters;
@@ -510,32 +557,31 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
             if (n != 5 && M > 0) {
                 if (!lmeds) {
                     if (M >= ES_WARPS) {
-                        // warp w scores items w, w + 8, ...: a correspondence is loaded once and tested
-                        // against every model of the warp (models broadcast from shared memory)
-                        const double* Ep[10];
-                        int mine = 0;
+                        // warp w scores items w, w + 8, ... two at a time: both models live in registers
+                        // and every correspondence (shared memory) is tested against both
+                        for (int j0 = warp; j0 < M; j0 += 2 * ES_WARPS) {
+                            const int code0 = s_item[j0];
+                            const bool two = j0 + ES_WARPS < M;
+                            const int code1 = two ? s_item[j0 + ES_WARPS] : code0;
+                            double E0[9], E1[9];
 #pragma unroll
-                        for (int j = 0; j < 10; ++j) {
-                            const int it = warp + ES_WARPS * j;
-                            const int code = it < M ? s_item[it] : 0;
-                            Ep[j] = s_models[code >> 4][code & 15];
-                            mine += it < M;
-                        }
-                        int cnt[10];
-#pragma unroll
-                        for (int j = 0; j < 10; ++j) cnt[j] = 0;
-                        for (int i = lane; i < n; i += 32) {
-                            const double a1 = X1[i], b1 = Y1[i], a2 = X2[i], b2 = Y2[i];
-#pragma unroll
-                            for (int j = 0; j < 10; ++j)
-                                if (j < mine) cnt[j] += sampson_inlier_unit(Ep[j], a1, b1, a2, b2, thrR) ? 1 : 0;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 10; ++j) {
-                            if (j < mine) {
-                                const int c = warp_sum(cnt[j]);
-                                const int code = s_item[warp + ES_WARPS * j];
-                                if (lane == 0) s_cnt[code >> 4][code & 15] = c;
+                            for (int c = 0; c < 9; ++c) {
+                                E0[c] = s_models[code0 >> 4][code0 & 15][c];
+                                E1[c] = s_models[code1 >> 4][code1 & 15][c];
+                            }
+                            int c0 = 0, c1 = 0;
+                            if (two) {
+                                if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, E0, E1, thrR, c0, c1);
+                                else count_two(a.xn + so, a.stride, n, lane, 32, E0, E1, thrR, c0, c1);
+                            } else {
+                                c0 = pts_in_smem ? count_one(s_pts, a.stride, n, lane, 32, E0, thrR)
+                                                 : count_one(a.xn + so, a.stride, n, lane, 32, E0, thrR);
+                            }
+                            c0 = warp_sum(c0);
+                            c1 = warp_sum(c1);
+                            if (lane == 0) {
+                                s_cnt[code0 >> 4][code0 & 15] = c0;
+                                if (two) s_cnt[code1 >> 4][code1 & 15] = c1;
                             }
                         }
                     } else {
@@ -544,10 +590,11 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                         const int it = warp / slices, slice = warp % slices;
                         if (it < M) {
                             const int code = s_item[it];
-                            const double* E = s_models[code >> 4][code & 15];
-                            int cnt = 0;
-                            for (int i = lane + 32 * slice; i < n; i += 32 * slices)
-                                cnt += sampson_inlier_unit(E, X1[i], Y1[i], X2[i], Y2[i], thrR) ? 1 : 0;
+                            double E[9];
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) E[c] = s_models[code >> 4][code & 15][c];
+                            int cnt = pts_in_smem ? count_one(s_pts, a.stride, n, lane + 32 * slice, 32 * slices, E, thrR)
+                                                  : count_one(a.xn + so, a.stride, n, lane + 32 * slice, 32 * slices, E, thrR);
                             cnt = warp_sum(cnt);
                             if (lane == 0) atomicAdd(&s_cnt[code >> 4][code & 15], cnt);
                         }
@@ -946,6 +993,11 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
         EPV_CUDA(ctx, cudaFuncSetAttribute(five_point_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
         attr_set = true;
     }
+    // correspondences staged in shared memory when two CTAs per SM still fit (<= 100 KB each)
+    const size_t pts_bytes = (size_t)p.stride * 4 * sizeof(double);
+    const size_t pts_smem = pts_bytes <= 100 * 1024 ? pts_bytes : 0;
+    if (pts_smem > 0)
+        EPV_CUDA(ctx, cudaFuncSetAttribute(ess_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pts_smem));
     ess_init_kernel<<<(p.n_pairs + 127) / 128, 128, 0, ctx->stream>>>(a);
     EPV_LAUNCHED(ctx);
     // Round 0 runs on every pair; later rounds usually see a short (often empty) work list, so their
@@ -972,7 +1024,7 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
         solve_b2_kernel<<<g_b2, SB2_THREADS, 0, ctx->stream>>>(a, r);
         EPV_LAUNCHED(ctx);
         if (r == 0 && p.ev_presolved) EPV_CUDA(ctx, cudaEventRecord(p.ev_presolved, ctx->stream));
-        ess_round_kernel<<<g_pairs, ES_THREADS, 0, ctx->stream>>>(a, r, R[r], r == nr - 1 ? 1 : 0);
+        ess_round_kernel<<<g_pairs, ES_THREADS, pts_smem, ctx->stream>>>(a, r, R[r], r == nr - 1 ? 1 : 0, pts_smem > 0);
         EPV_LAUNCHED(ctx);
     }
     return EPIVO_OK;
