@@ -347,6 +347,28 @@ class SequencePipeline:
         self.ctx.check(self.ctx.lib.epivo_seq_stage_ms(self.h, _p(ms), 16))
         return ms
 
+    def cloud(self, scales=None, first_pair: int = 0, n_pairs: int | None = None, with_points: bool = True):
+        """Pose chain + depth / point cloud of the last run (kitti_E.cpp:203-254).
+
+        Returns (poses (n+1, 4, 4) -- the reference's all_T plus the final pose, points (m, 3),
+        limits (n,) -- cloud points before each pair).  scales: GT step lengths (kitti_E.cpp:220)."""
+        n = (self.max_frames - 1 - first_pair) if n_pairs is None else int(n_pairs)
+        poses = np.zeros((n + 1, 4, 4), dtype=np.float64)
+        limits = np.zeros(max(n, 1), dtype=np.int64)
+        total = C.c_int64(0)
+        sc = None
+        if scales is not None:
+            sc = np.ascontiguousarray(scales, dtype=np.float64)
+            assert sc.shape == (n,)
+        lib = self.ctx.lib
+        self.ctx.check(lib.epivo_seq_cloud(self.h, _p(sc) if sc is not None else None, int(first_pair), n,
+                                           _p(poses), None, 0, _p(limits), C.byref(total)))
+        points = np.zeros((total.value, 3), dtype=np.float64)
+        if with_points and total.value > 0:
+            self.ctx.check(lib.epivo_seq_cloud(self.h, _p(sc) if sc is not None else None, int(first_pair), n,
+                                               _p(poses), _p(points), total.value, _p(limits), C.byref(total)))
+        return poses, points, limits[:n]
+
     def matches(self, pair: int):
         qi = np.zeros(self.kp, dtype=np.int32)
         ti = np.zeros(self.kp, dtype=np.int32)

@@ -10,7 +10,7 @@
 //     every row as bit planes (L = even bits, H = odd bits, two source words interleaved
 //     per output word) so that the 2-bit-group distance is popc((Lq^Lt) | (Hq^Ht)):
 //     4 POPC per 256-bit pair instead of 8 XOR/SHF/LOP/POPC groups.
-//   * a CTA owns THREADS*RQ query rows (RQ rows per thread, held in registers, loaded with
+//   * a CTA owns THREADS*RQ = 128*8 query rows (RQ rows per thread, held in registers, loaded with
 //     128-bit coalesced loads) and streams ALL train rows through shared memory in tiles of
 //     TILE rows, double-buffered by TMA 1-D bulk copies (cp.async.bulk + mbarrier).  Every
 //     lane reads the same train row (shared-memory broadcast, LDS.128).
@@ -25,8 +25,17 @@
 
 namespace {
 
-constexpr int MT_THREADS = 256;
-constexpr int MT_RQ = 4;
+#ifndef EPV_MT_THREADS
+#define EPV_MT_THREADS 128
+#endif
+#ifndef EPV_MT_RQ
+#define EPV_MT_RQ 8
+#endif
+#ifndef EPV_MT_MINBLOCKS
+#define EPV_MT_MINBLOCKS 1
+#endif
+constexpr int MT_THREADS = EPV_MT_THREADS;
+constexpr int MT_RQ = EPV_MT_RQ;
 constexpr int MT_TILE = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -110,7 +119,7 @@ __device__ __forceinline__ uint32_t desc_dist(const uint32_t (&q)[WORDS], const 
 }
 
 template <int WORDS, bool NORM2, bool TOP2>
-__global__ void __launch_bounds__(MT_THREADS)
+__global__ void __launch_bounds__(MT_THREADS, EPV_MT_MINBLOCKS)
 match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int64_t t0, int64_t ts, int nq,
                   int nt, uint32_t* __restrict__ rowkey, uint32_t* __restrict__ rowkey2,
                   uint32_t* __restrict__ colkey, int stride, int tiles_per_split, int64_t part_stride) {

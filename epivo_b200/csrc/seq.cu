@@ -555,6 +555,58 @@ int epivo_seq_download(epivo_seq* s, epivo_pair_result* out, int first_pair, int
     return EPIVO_OK;
 }
 
+int epivo_seq_cloud(epivo_seq* s, const double* scales, int first_pair, int n_pairs, double* poses, double* points,
+                    int64_t cap, int64_t* limits, int64_t* n_points) {
+    if (!s) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range [%d,+%d) outside [0,%d)", first_pair, n_pairs, s->max_frames - 1);
+    if (first_pair < s->last_first || first_pair + n_pairs > s->last_first + s->last_n_pairs)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pairs [%d,+%d) were not part of the last run", first_pair, n_pairs);
+    if (n_points) *n_points = 0;
+    if (n_pairs == 0) {
+        if (poses) { for (int i = 0; i < 16; ++i) poses[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+        return EPIVO_OK;
+    }
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t np = (size_t)n_pairs;
+    if (cap < 0 || !points) cap = 0;
+    size_t need = epv_align(np * 8) + epv_align((np + 1) * 128) + epv_align(np * 4) + epv_align((np + 1) * 8) +
+                  epv_align((size_t)cap * 24) + 4096;
+    int rc = epv_ws_reserve(ctx, need);
+    if (rc) return rc;
+    double* d_scales = scales ? epv_ws_take<double>(ctx, np) : nullptr;
+    double* d_poses = epv_ws_take<double>(ctx, (np + 1) * 16);
+    int32_t* d_counts = epv_ws_take<int32_t>(ctx, np);
+    int64_t* d_limits = epv_ws_take<int64_t>(ctx, np + 1);
+    double* d_points = cap > 0 ? epv_ws_take<double>(ctx, (size_t)cap * 3) : nullptr;
+    if (scales) EPV_CUDA(ctx, cudaMemcpyAsync(d_scales, scales, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t o = (size_t)first_pair;
+    rc = epv_chain_launch(ctx, s->d_results + o, d_scales, n_pairs, d_poses);
+    if (rc) return rc;
+    rc = epv_cloud_launch(ctx, n_pairs, s->stride, s->d_results + o, d_scales, d_poses, s->d_xin + o * 4 * s->stride,
+                          s->d_ninl + o, d_counts, d_limits, nullptr, 0, 0);
+    if (rc) return rc;
+    if (cap > 0) {
+        rc = epv_cloud_launch(ctx, n_pairs, s->stride, s->d_results + o, d_scales, d_poses,
+                              s->d_xin + o * 4 * s->stride, s->d_ninl + o, d_counts, d_limits, d_points, cap, 1);
+        if (rc) return rc;
+    }
+    std::vector<int64_t> h_limits(np + 1);
+    EPV_CUDA(ctx, cudaMemcpyAsync(h_limits.data(), d_limits, (np + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (poses) EPV_CUDA(ctx, cudaMemcpyAsync(poses, d_poses, (np + 1) * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t total = h_limits[np];
+    if (limits) memcpy(limits, h_limits.data(), np * 8);
+    if (n_points) *n_points = total;
+    if (cap > 0) {
+        const int64_t w = std::min<int64_t>(total, cap);
+        EPV_CUDA(ctx, cudaMemcpyAsync(points, d_points, (size_t)w * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return EPIVO_OK;
+}
+
 int epivo_seq_stage_ms(epivo_seq* s, float* ms, int n) {
     if (!s || !ms) return EPIVO_ERR_INVALID;
     epivo_ctx* ctx = s->ctx;

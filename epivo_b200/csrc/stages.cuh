@@ -66,3 +66,9 @@ struct LmPlan {
     int single_pair;         // caller asserts reps == {(0,0)}: warp-per-problem kernel when n_zeta == 1, N <= 64
 };
 int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p);
+
+// ---- cloud.cu (N2: pose chain + per-inlier depth / point cloud, kitti_E.cpp:203-254) ------
+int epv_chain_launch(epivo_ctx* ctx, const epivo_pair_result* d_res, const double* d_scales, int n, double* d_poses);
+int epv_cloud_launch(epivo_ctx* ctx, int n_pairs, int stride, const epivo_pair_result* d_res, const double* d_scales,
+                     const double* d_poses, const double* d_xin, const int32_t* d_ninl, int32_t* d_counts,
+                     int64_t* d_limits, double* d_points, int64_t cap, int pass);

@@ -74,10 +74,6 @@ def chain_poses(T_pairs: np.ndarray, scales: np.ndarray | None = None) -> np.nda
 
 
 def write_poses(path: str, poses: np.ndarray) -> None:
-    """kitti.T / kitti.GT / euroc.T text format (kitti_E.cpp:271-286): 4x4 blocks separated by a
-    blank line, which the reference's viewers read with np.fromfile(sep=' ') (cloud_pango.py:32-34)."""
-    with open(path, "w") as f:
-        for T in poses:
-            for r in range(4):
-                f.write(" ".join(repr(float(v)) for v in T[r]) + "\n")
-            f.write("\n")
+    """kitti.T / kitti.GT / euroc.T text format (kitti_E.cpp:271-286); see epivo_b200.io."""
+    from . import io
+    io.write_poses(path, poses)

@@ -179,6 +179,18 @@ int epivo_seq_get_matches(epivo_seq* seq, int pair, int32_t* query_idx, int32_t*
                           int32_t* dist, int* n_out);
 int epivo_seq_get_masks(epivo_seq* seq, int pair, uint8_t* e_mask, int* n_e, uint8_t* pose_mask, int* n_pose);
 
+/* ---- N2: pose chain + depth / point cloud of the last run (kitti_E.cpp:203-254, euroc_E.cpp:303-349) ----
+ * For the pairs [first_pair, +n_pairs) of the last epivo_seq_run / epivo_seq_process:
+ *   dT_i     = [R_i | t_i/|t_i| * scales[i]]   (refined pose, GT-scaled translation; scales NULL = 1)
+ *   poses[i] = the chained camera pose BEFORE pair i (all_T, kitti_E.cpp:227), poses[n_pairs] the last
+ *              one: (n_pairs + 1) x 16 doubles, starting from identity, cT <- cT * dT^-1
+ *   points   = for every E-inlier of every pair, in order, the reference's depth-from-parallax point
+ *              X = poses[i] * (d * K^-1 x0) with d = |P t| / |P R K^-1 x0|, kept iff |P R K^-1 x0| > 1e-2
+ *   limits[i]= number of cloud points before pair i (the reference's `limits`), n_pairs entries
+ * points may be NULL (or cap 0) to get only poses / limits / *n_points; at most cap points are written. */
+int epivo_seq_cloud(epivo_seq* seq, const double* scales, int first_pair, int n_pairs, double* poses,
+                    double* points, int64_t cap, int64_t* limits, int64_t* n_points);
+
 /* ---- pipe micro-benchmarks (roofline denominators MEASURED_PEAKS.json lacks) ----------
  * which: 0 POPC.32, 1 LOP3, 2 FP64 FMA, 3 FP32 FMA, 4 IADD3; result = thread-ops / s on the whole GPU */
 int epivo_microbench(epivo_ctx* ctx, int which, double* ops_per_sec);

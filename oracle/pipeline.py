@@ -54,3 +54,39 @@ def pair_pipeline(kp0, desc0, kp1, desc1, K, method=O.RANSAC, prob=0.99, thr=1.0
             out["T"] = Tout[0]
         out["T_lm"] = Tout[0]
     return out
+
+
+def chain_and_cloud(T_pairs, inliers0, inliers1, K, scales=None):
+    """CPU restatement of the reference's post-LM loop body, kitti_E.cpp:203-254, run over a sequence.
+
+    T_pairs[i]: refined 4x4 point transform of pair i; inliers0/1[i]: the E-inlier pixel
+    coordinates (cpt0, cpt1_; kitti_E.cpp:106-112) of pair i; scales[i]: ground-truth step length
+    (kitti_E.cpp:220).  Returns (all_T (n+1,4,4) incl. the final pose, X (m,3), limits (n,))."""
+    n = len(T_pairs)
+    scales = np.ones(n) if scales is None else np.asarray(scales, dtype=np.float64)
+    Kf = np.asarray(K, dtype=np.float32)
+    cT = np.eye(4)
+    all_T, X, limits = [], [], []
+    for i in range(n):
+        T = np.asarray(T_pairs[i], dtype=np.float64)
+        dT = np.eye(4)
+        t = T[:3, 3] / np.linalg.norm(T[:3, 3])                              # :221
+        dT[:3, 3] = t * scales[i]                                            # :222
+        dT[:3, :3] = T[:3, :3]                                               # :223
+        pT_ = cT.copy()                                                      # :225
+        all_T.append(cT.copy())                                              # :227
+        cT = cT @ np.linalg.inv(dT)                                          # :228
+        R, tt = dT[:3, :3], dT[:3, 3]                                        # :232-233
+        limits.append(len(X))                                                # :238
+        c0 = O.normalize_points(inliers0[i], Kf)                             # cam_ * (u, v, 1): :240-243
+        c1 = O.normalize_points(inliers1[i], Kf)
+        for j in range(len(c0)):
+            cp = np.array([c0[j, 0], c0[j, 1], 1.0])
+            P = np.array([[1.0, 0.0, -c1[j, 0]], [0.0, 1.0, -c1[j, 1]]])     # :245
+            A = P @ tt
+            B = P @ R @ cp
+            if np.linalg.norm(B) > 1e-2:                                     # :248
+                d = np.linalg.norm(A) / np.linalg.norm(B)
+                X.append(pT_[:3, :3] @ (d * cp) + pT_[:3, 3])                # :250-252
+    all_T.append(cT.copy())
+    return np.array(all_T), np.array(X).reshape(-1, 3), np.array(limits, dtype=np.int64)
