@@ -269,3 +269,58 @@ def gen_scene_sequence(seed: int, N: int, n_zeta: int, reps, noise_rot=1e-1, noi
     for i, (z0, z1) in enumerate(reps):
         _, pr[i], p_r[i] = gen_points(rng, N, compose_rep(Ts, z0, z1))
     return Ts, T0s, pr, p_r
+
+
+# ---- kitti_ba windows: synthetic reprojection map ---------------------------------------------
+def make_reprojs(seed: int, num_frames: int, window, K: np.ndarray = KITTI_K, n_pts: int = 48, stereo: bool = False,
+                 few_points_at=(), baseline: float = 0.54, pose_noise: float = 2e-3):
+    """A `reprojs` map like the one robust_ass / robust_ass_stereo fill (kitti_ba.cpp:178-582) for a
+    synthetic drive: smooth forward motion, landmarks 6..40 m ahead, pixel noise 0.2, and per
+    consecutive node pair the relative pose with a unit translation (what recoverPose returns) plus
+    a little noise.  Mono nodes are frames; stereo nodes are 2f (left) / 2f+1 (right) with the
+    right camera `baseline` to the side and weight 0 on the left->right reprojection (frozen
+    extrinsics, kitti_ba.cpp:171-172).  Keys in `few_points_at` get fewer than 32 points."""
+    from .ba import Reproj, expand_stereo_window
+
+    rng = np.random.default_rng(seed)
+    nodes = 2 * num_frames if stereo else num_frames
+    # world pose of every node (camera-from-world), frames move ~1 m forward with small rotations
+    cam_T = [np.eye(4)]
+    for _ in range(num_frames - 1):
+        d = np.eye(4)
+        d[:3, :3] = rodrigues(rng.normal(0, 0.01, 3))
+        d[:3, 3] = np.array([0.02, -0.01, -1.0]) + rng.normal(0, 0.02, 3)      # point transform: scene moves backwards
+        cam_T.append(d @ cam_T[-1])
+    node_T = []
+    for f in range(num_frames):
+        node_T.append(cam_T[f])
+        if stereo:
+            e = np.eye(4)
+            e[0, 3] = -baseline
+            node_T.append(e @ cam_T[f])
+    win = expand_stereo_window(window) if stereo else list(window)
+    step = 2 if stereo else 1
+    span = max(max(a, b) for a, b in win)
+    keys = set()
+    for i in range(0, num_frames):
+        if step * i + span >= nodes:
+            break
+        for a, b in win:
+            keys.add((step * i + a, step * i + b))
+    lo = min(min(a, b) for a, b in win)
+    for j in range(nodes - 1):
+        keys.add((j, j + 1))
+    out = {}
+    for (i0, i1) in sorted(keys):
+        rel = node_T[i1] @ np.linalg.inv(node_T[i0])                            # point transform i0 -> i1
+        n = n_pts if (i0, i1) not in few_points_at else 20
+        X0 = np.column_stack([rng.uniform(-8, 8, n), rng.uniform(-2, 2, n), rng.uniform(6, 40, n)])
+        X1 = (rel[:3, :3] @ X0.T).T + rel[:3, 3]
+        p0 = _project(K, X0) + rng.normal(0, 0.2, (n, 2))
+        p1 = _project(K, X1) + rng.normal(0, 0.2, (n, 2))
+        t = rel[:3, 3] / max(np.linalg.norm(rel[:3, 3]), 1e-12)
+        R = rel[:3, :3] @ rodrigues(rng.normal(0, pose_noise, 3))
+        t = t + rng.normal(0, pose_noise, 3)
+        w = 0.0 if (stereo and i0 % 2 == 0 and i1 == i0 + 1) else 1.0
+        out[(i0, i1)] = Reproj(p0.astype(np.float32), p1.astype(np.float32), R, t, w)
+    return out

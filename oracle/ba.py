@@ -1,0 +1,75 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  Sequential restatement of the reference's window loops,
+`bundle_adjustment` (kitti_ba.cpp:757-905) and `bundle_adjustment_stereo` (kitti_ba.cpp:908-1068),
+one `Levenberg_Marquardt` call per window in the reference's order.  The thread polling
+(kitti_ba.cpp:793-797) has no CPU counterpart: every reprojection is already in `reprojs`."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as O
+
+MIN_PT = 32
+
+
+def bundle_adjustment(reprojs, window, stride, num_frames, K, stereo=False, huber_delta=1e-5, lm=None):
+    lm_fn = lm or O.levenberg_marquardt
+    nodes = 2 * num_frames if stereo else num_frames
+    mul = 2 if stereo else 1
+    if stereo:                                                       # kitti_ba.cpp:934-941
+        win = []
+        for i0, i1 in window:
+            win += [(2 * i0, 2 * i1), (2 * i0 + 1, 2 * i1), (2 * i0, 2 * i0 + 1)]
+    else:
+        win = list(window)
+    opt_T = [np.eye(4) for _ in range(nodes)]
+    optimized = [False] * nodes
+    Kinv = np.linalg.inv(np.asarray(K, dtype=np.float64))
+    lms, reverted, starts = [], [], []
+    for i in range(0, num_frames, stride):                           # :780 / :943
+        w0, w1, stop = nodes + 1, -1, False
+        for a, b in win:
+            i0, i1 = mul * i + a, mul * i + b
+            w0, w1 = min(w0, i0, i1), max(w1, i0, i1)
+            if max(i0, i1) >= nodes:                                 # :790-793
+                stop = True
+                break
+        if stop:
+            break
+        reps, pr, p_r, wreps = [], [], [], []
+        for a, b in win:
+            i0, i1 = mul * i + a, mul * i + b
+            reps.append((a, b - 1) if i1 > i0 else (a - 1, b))       # :810-815
+            r = reprojs[(i0, i1)]
+            if len(r.p0) < MIN_PT:                                   # :819-824
+                wreps.append(0.0)
+                pr.append(np.ones((MIN_PT, 3)))
+                p_r.append(np.ones((MIN_PT, 3)))
+            else:
+                wreps.append(r.w if stereo else 1.0)                 # :829-835 / :1000-1008
+                h0 = np.column_stack([np.asarray(r.p0[:MIN_PT], dtype=np.float64), np.ones(MIN_PT)])
+                h1 = np.column_stack([np.asarray(r.p1[:MIN_PT], dtype=np.float64), np.ones(MIN_PT)])
+                pr.append(h0 @ Kinv.T)                               # :838-845
+                p_r.append(h1 @ Kinv.T)
+        scale = 1.0
+        if not stereo and optimized[w0]:                             # :853-856
+            scale = np.linalg.norm(opt_T[w0][:3, 3])
+        T0s = []
+        for j in range(w0, w1):                                      # :857-870
+            r = reprojs[(j, j + 1)]
+            T = np.eye(4)
+            T[:3, :3] = r.R
+            T[:3, 3] = np.asarray(r.t).reshape(3)
+            T0s.append(T)
+        bT0s = [T.copy() for T in T0s]
+        Tout, lm = lm_fn(w1 - w0, 1e-8, reps, wreps, 1e-2, T0s, pr, p_r, huber_delta=huber_delta)   # :881
+        rev = bool(lm["r_norm"] > 1e-2)                              # :889-891
+        Ts = bT0s if rev else list(Tout)
+        for j in range(w0, w1):                                      # :895-902
+            opt_T[j] = np.array(Ts[j - w0], dtype=np.float64)
+            if not stereo:
+                opt_T[j][:3, 3] /= scale
+            optimized[j] = True
+        lms.append([lm["H_norm"], lm["r_norm"], lm["lambda"]])
+        reverted.append(rev)
+        starts.append(i)
+    return np.array(opt_T), np.array(lms).reshape(-1, 3), np.array(reverted, dtype=bool), starts

@@ -1,0 +1,81 @@
+"""N3: windowed bundle adjustment (kitti_ba.cpp:757-1068) -- all windows in one batched launch vs
+the sequential CPU restatement of the reference loop."""
+import numpy as np
+import pytest
+
+from epivo_b200 import ba, synth
+from oracle import ba as OBA
+from oracle import clib
+
+pytestmark = pytest.mark.gpu
+
+
+def window_ws(ws):
+    """main(): kitti_ba.cpp:1131-1144."""
+    w = []
+    for i in range(ws - 1):
+        w.append((i, i + 1))
+        if i < ws - 2:
+            w.append((i, i + 2))
+    return w
+
+
+def _compare(ctx, reprojs, window, stride, F, stereo, delta):
+    opt, lm, rev, starts = ba.bundle_adjustment(reprojs, window, stride, F, synth.KITTI_K, stereo, delta, ctx=ctx)
+    o_opt, o_lm, o_rev, o_starts = OBA.bundle_adjustment(reprojs, window, stride, F, synth.KITTI_K, stereo, delta,
+                                                        lm=clib.levenberg_marquardt)
+    assert starts == o_starts and len(starts) > 0
+    assert np.array_equal(rev, o_rev)
+    assert opt.shape == o_opt.shape
+    # The overall scale of a window's translations is a gauge freedom of the reprojection error
+    # (res() is invariant to it), so LM drifts along it at round-off level and magnitudes are only
+    # loosely pinned (the C and numpy restatements differ from each other by ~1e-4 relative here):
+    # compare with north_star's tolerances -- rotation <= 1e-4 rad, translation direction <= 1e-3 rad.
+    for k in range(len(opt)):
+        Rg, Ro, tg, to = opt[k][:3, :3], o_opt[k][:3, :3], opt[k][:3, 3], o_opt[k][:3, 3]
+        assert np.arccos(np.clip((np.trace(Rg.T @ Ro) - 1) / 2, -1, 1)) < 1e-4
+        if np.linalg.norm(to) > 0:
+            c = tg @ to / (np.linalg.norm(tg) * np.linalg.norm(to))
+            assert np.arccos(np.clip(c, -1, 1)) < 1e-3
+            assert abs(np.linalg.norm(tg) / np.linalg.norm(to) - 1) < 5e-3
+        else:
+            assert np.linalg.norm(tg) == 0
+    ok = np.isfinite(o_lm[:, 1])
+    assert np.allclose(lm[ok, 1], o_lm[ok, 1], rtol=1e-4, atol=1e-15)          # r_norm
+    # lambda: the same accept/reject history up to a flip or two once the residual sits at its round-off floor
+    assert np.abs(np.log10(lm[ok, 2] / o_lm[ok, 2])).max() <= 2.0
+    return opt, lm, rev, starts
+
+
+@pytest.mark.parametrize("delta", [1.0, 1e-5])
+def test_mono_windows_ws3(ctx, delta):
+    """The mono driver shape: ws = 3 -> window {(0,1),(0,2),(1,2)}, stride ws-1 (kitti_ba.cpp:1131-1160)."""
+    F, window = 21, window_ws(3)
+    reprojs = synth.make_reprojs(70, F, window)
+    opt, lm, rev, starts = _compare(ctx, reprojs, window, 2, F, False, delta)
+    assert starts == list(range(0, F - 2, 2))
+    # scale carry (kitti_ba.cpp:853-856,898-901): the first window is divided by 1
+    assert np.isfinite(opt).all()
+
+
+def test_mono_overlapping_windows_and_bad_points(ctx):
+    """stride 1 makes windows overlap (later windows overwrite, the scale is carried); one reprojection
+    has fewer than 32 points -> dummy ones with weight 0 (kitti_ba.cpp:819-824)."""
+    F, window = 12, window_ws(4)
+    reprojs = synth.make_reprojs(71, F, window, few_points_at={(3, 5)})
+    _compare(ctx, reprojs, window, 1, F, False, 1.0)
+
+
+@pytest.mark.parametrize("delta", [1.0, 1e-5])
+def test_stereo_windows_ws3(ctx, delta):
+    """The shipped driver: bundle_adjustment_stereo, ws = 3, stride 2: 9 reps x 32 points, n_zeta = 4,
+    weight 0 on the left->right reprojections (kitti_ba.cpp:931-941, 1153-1160)."""
+    F, window = 13, window_ws(3)
+    reprojs = synth.make_reprojs(72, F, window, stereo=True)
+    opt, lm, rev, starts = _compare(ctx, reprojs, window, 2, F, True, delta)
+    assert opt.shape == (2 * F, 4, 4)
+
+
+def test_no_window_fits(ctx):
+    opt, lm, rev, starts = ba.bundle_adjustment({}, window_ws(3), 2, 2, synth.KITTI_K, ctx=ctx)
+    assert starts == [] and opt.shape == (2, 4, 4)
