@@ -249,17 +249,24 @@ def main():
     # needs nq*nt*4 -- report against the instruction count the kernel actually needs (4)
     popc_per_pair = kp * kp * 4
     achieved_popc = popc_per_pair * P / (ms_match * 1e-3)
+    # DRAM traffic of one matcher launch over the default workload, from the `ncu --set full` capture in
+    # profiles/r1_ncu_full_top_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum = 328.8 + 61.3 MB).
+    # It is BELOW the algorithmic bytes because consecutive pairs share a frame (train set of pair i =
+    # query set of pair i+1) and that frame is still in L2.  Only valid for the profiled shape.
+    traffic = 390.1e6 if (a.frames == 4541 and a.kp == 2000 and n_chunk_launches == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "match_tile_kernel<8,HAMMING2>", "launches_per_step": n_chunk_launches,
+                "algorithmic_bytes_per_launch": bytes_per_pair * P / max(n_chunk_launches, 1),
                 "ms_per_step_in_kernel": ms_match,
-                "note": "the matcher is bound by the integer POPC pipe, not HBM (AI ~ 100 popc/byte): see pipe"}
+                "note": "the matcher is bound by the integer pipes (POPC on XU, LOP3 on ALU), not HBM "
+                        "(AI ~ 100 popc/byte, so the HBM fraction is < 1 % by construction): see pipe"}
     pipe_roof = {"bound": "popc32 (XU pipe) / LOP3 (ALU pipe)", "achieved": achieved_popc / 1e9,
                  "peak": popc_peak / 1e9, "unit": "Gpopc/s", "frac": achieved_popc / popc_peak,
                  "alu_peak_Gops": lop_peak / 1e9,
                  "work": "nq*nt*4 POPC.32 per pair (Hamming2 on bit planes), one direction + fused column minima",
                  "note": "carry-save compression issues 3 POPC per 4 algorithmic ones, so frac can exceed 1; "
-                         "ncu (profiles/): ALU pipe 85 %, XU (POPC) pipe 81 % of peak"}
+                         "ncu (profiles/r1_ncu_full_top_kernels.csv): ALU pipe 87 %, XU (POPC) pipe 83 % of peak"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
