@@ -91,6 +91,7 @@ struct MatchPlan {
 };
 int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass);
 int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt);   // train splits that fill the GPU
+int epv_match_pairs_per_wave(const epivo_ctx* ctx, int nq);                // pairs per full wave of matcher CTAs
 
 struct FinalizePlan {
     int n_pairs, nq, nt, stride, mode, tsplits;

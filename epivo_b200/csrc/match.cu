@@ -362,6 +362,17 @@ int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt) {
     return (int)std::max<int64_t>(1, (n_tiles + tps - 1) / tps);   // splits actually launched (no empty part)
 }
 
+// frame pairs whose matcher CTAs fill the GPU exactly once (one "wave"): launches sized in whole
+// waves lose nothing to a partially filled last wave
+int epv_match_pairs_per_wave(const epivo_ctx* ctx, int nq) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_tile_kernel<8, true, false>, MT_THREADS, 0) != cudaSuccess ||
+        occ < 1)
+        occ = 2;
+    const int qblocks = std::max(1, (nq + MT_THREADS * MT_RQ - 1) / (MT_THREADS * MT_RQ));
+    return std::max(1, ctx->sm_count * occ / qblocks);
+}
+
 int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass) {
     if (mp.tsplits < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "tsplits < 1");
     if (mp.words != 4 && mp.words != 8 && mp.words != 16)

@@ -466,10 +466,26 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     const bool overlap = s->overlap && !upload;
     // matcher groups / geometry groups (event slots: matcher [0, HALF), geometry [HALF, 2*HALF))
     constexpr int HALF = SEQ_MAX_CHUNKS / 2;
-    int mchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
-    if (upload) mchunk = std::max(256, (n_pairs + 3) / 4);          // four upload/match pieces
+    // matcher groups.  Resident data: uniform groups.  Host buffers: the upload is cut into pieces of
+    // 1, 2, 4 ... waves of matcher CTAs (the PCIe copy is ~2x faster than the matcher consumes frames,
+    // so a small first piece starts the matcher early and the growing pieces never starve it).
+    std::vector<std::pair<int, int> > mg;     // (first pair, pairs)
+    {
+        const int mchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
+        int wave = upload ? epv_match_pairs_per_wave(ctx, s->kp) : mchunk;
+        int p0 = first_pair, left = n_pairs, waves = 1;
+        while (left > 0) {
+            int np = upload ? wave * waves : mchunk;
+            if (upload && ((int)mg.size() >= 3 || left - np < wave)) np = left;    // the fourth piece takes the rest
+            np = std::min(np, left);
+            mg.push_back(std::make_pair(p0, np));
+            p0 += np;
+            left -= np;
+            waves *= 2;
+        }
+    }
     const int gchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
-    const int n_m = (n_pairs + mchunk - 1) / mchunk, n_g = (n_pairs + gchunk - 1) / gchunk;
+    const int n_m = (int)mg.size(), n_g = (n_pairs + gchunk - 1) / gchunk;
     if (n_m > HALF || n_g > HALF) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "too many pair groups");
     s->last_mgroups = n_m;
     s->last_ggroups = n_g;
@@ -482,8 +498,7 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
         // all pieces are queued on the copy stream at once; they run back to back at PCIe rate
         EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
         for (int c = 0; c < n_m; ++c) {
-            const int p0 = first_pair + c * mchunk;
-            const int np = std::min(mchunk, first_pair + n_pairs - p0);
+            const int p0 = mg[c].first, np = mg[c].second;
             const int f0 = (c == 0) ? p0 : p0 + 1;                  // frame p0 came with the previous piece
             const int nf = p0 + np + 1 - f0;
             const size_t ho = (size_t)(f0 - first_pair);            // host arrays start at frame first_pair
@@ -496,8 +511,7 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     }
     if (overlap) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
     for (int c = 0; c < n_m && !rc; ++c) {
-        const int p0 = first_pair + c * mchunk;
-        const int np = std::min(mchunk, first_pair + n_pairs - p0);
+        const int p0 = mg[c].first, np = mg[c].second;
         if (upload) EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_matched[c], 0));
         rc = seq_run_match(s, prm, c, p0, np);
         if (rc) break;
