@@ -189,8 +189,10 @@ def fivePoint(x1, x2, ctx: Context | None = None):
     return [E[i, :nm[i]].reshape(-1, 3, 3) for i in range(m)]
 
 
-def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None):
-    """K3 alone: (counts (m,), medians (m,) f32, best index, mask of best (n,) {0,1})."""
+def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None,
+                 medians: bool = True):
+    """K3 alone: (counts (m,), medians (m,) f32, best index, mask of best (n,) {0,1}).
+    medians=False skips the LMedS medians (they cost a select over all points per model)."""
     ctx = ctx or default_context()
     Es = np.ascontiguousarray(Es, dtype=np.float64).reshape(-1, 9)
     p0, p1 = _pts(points1), _pts(points2)
@@ -201,7 +203,7 @@ def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Cont
     mask = np.zeros(max(n, 1), dtype=np.uint8)
     best = C.c_int(-1)
     ctx.check(ctx.lib.epivo_score_sampson(ctx.h, _p(Es), m, _p(p0), _p(p1), n, _p(K), float(threshold),
-                                          _p(counts), _p(med), C.byref(best), _p(mask)))
+                                          _p(counts), _p(med) if medians else None, C.byref(best), _p(mask)))
     return counts[:m], med[:m], best.value, mask[:n]
 
 

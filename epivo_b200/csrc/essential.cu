@@ -162,8 +162,12 @@ __device__ __noinline__ bool sampson_inlier_slow(const double* E, double a1, dou
 // degenerate (den > 1e-8, B den > 1e-10; then the bounds above are below 1e-9 for any realistic
 // field of view) -- "clear" means num outside [B (1 - 2e-6) den, B (1 + 2e-6) den]; everything else -- including every borderline point -- runs the exact
 // OpenCV-order evaluation, so the result is always that of sampson_inlier().
-__device__ __forceinline__ bool sampson_inlier_unit(const double* __restrict__ E, double a1, double b1, double a2,
-                                                    double b2, const SampThr& T) {
+// dmin: smallest denominator the pre-filter trusts = T.dmin * |E|_F^2 (T.dmin for the unit-norm models
+// the solver emits; every quantity of the test is homogeneous in the scale of E)
+// E: the model in registers; Emem: the same nine values in (shared / global) memory, read only by the
+// out-of-line fallback -- passing the register copy there would force it onto the stack.
+__device__ __forceinline__ bool sampson_inlier_scaled(const double (&E)[9], const double* Emem, double a1, double b1,
+                                                      double a2, double b2, const SampThr& T, double dmin) {
     const double ex0 = fma(E[0], a1, fma(E[1], b1, E[2]));
     const double ex1 = fma(E[3], a1, fma(E[4], b1, E[5]));
     const double ex2 = fma(E[6], a1, fma(E[7], b1, E[8]));
@@ -175,8 +179,13 @@ __device__ __forceinline__ bool sampson_inlier_unit(const double* __restrict__ E
     // clear by a relative 2e-6 on either side, and far from degenerate (T.dmin folds den > 1e-8 and
     // B den > 1e-10).  Branch-free: the three comparisons feed one (practically never taken) branch.
     const bool in = num < den * T.Blo, out = num > den * T.Bhi;
-    if ((in || out) && den > T.dmin) return in;
-    return sampson_inlier_slow(E, a1, b1, a2, b2, T);
+    if ((in || out) && den > dmin) return in;
+    return sampson_inlier_slow(Emem, a1, b1, a2, b2, T);
+}
+
+__device__ __forceinline__ bool sampson_inlier_unit(const double (&E)[9], const double* Emem, double a1, double b1,
+                                                    double a2, double b2, const SampThr& T) {
+    return sampson_inlier_scaled(E, Emem, a1, b1, a2, b2, T, T.dmin);
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -451,20 +460,25 @@ __global__ void __launch_bounds__(SB2_THREADS, EPV_SB2_MINBLOCKS) solve_b2_kerne
 // P: pointer type of the point rows (the caller passes the shared-memory array itself when the
 // points are staged there, so the loads compile to LDS rather than generic loads)
 template <class P>
-__device__ __forceinline__ void count_two(P X1, int stride, int n, int first, int step, const double (&E0)[9],
-                                          const double (&E1)[9], const SampThr& T, int& c0, int& c1) {
+__device__ __forceinline__ void count_two(P X1, int stride, int n, int first, int step, const double* M0,
+                                          const double* M1, const SampThr& T, int& c0, int& c1) {
+    double E0[9], E1[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) { E0[c] = M0[c]; E1[c] = M1[c]; }
     for (int i = first; i < n; i += step) {
         const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
-        c0 += sampson_inlier_unit(E0, a1, b1, a2, b2, T) ? 1 : 0;
-        c1 += sampson_inlier_unit(E1, a1, b1, a2, b2, T) ? 1 : 0;
+        c0 += sampson_inlier_unit(E0, M0, a1, b1, a2, b2, T) ? 1 : 0;
+        c1 += sampson_inlier_unit(E1, M1, a1, b1, a2, b2, T) ? 1 : 0;
     }
 }
 template <class P>
-__device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int step, const double (&E)[9],
-                                         const SampThr& T) {
+__device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int step, const double* M, const SampThr& T) {
+    double E[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) E[c] = M[c];
     int c = 0;
     for (int i = first; i < n; i += step)
-        c += sampson_inlier_unit(E, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T) ? 1 : 0;
+        c += sampson_inlier_unit(E, M, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T) ? 1 : 0;
     return c;
 }
 
@@ -563,19 +577,15 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                             const int code0 = s_item[j0];
                             const bool two = j0 + ES_WARPS < M;
                             const int code1 = two ? s_item[j0 + ES_WARPS] : code0;
-                            double E0[9], E1[9];
-#pragma unroll
-                            for (int c = 0; c < 9; ++c) {
-                                E0[c] = s_models[code0 >> 4][code0 & 15][c];
-                                E1[c] = s_models[code1 >> 4][code1 & 15][c];
-                            }
+                            const double* M0 = s_models[code0 >> 4][code0 & 15];
+                            const double* M1 = s_models[code1 >> 4][code1 & 15];
                             int c0 = 0, c1 = 0;
                             if (two) {
-                                if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, E0, E1, thrR, c0, c1);
-                                else count_two(a.xn + so, a.stride, n, lane, 32, E0, E1, thrR, c0, c1);
+                                if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, M0, M1, thrR, c0, c1);
+                                else count_two(a.xn + so, a.stride, n, lane, 32, M0, M1, thrR, c0, c1);
                             } else {
-                                c0 = pts_in_smem ? count_one(s_pts, a.stride, n, lane, 32, E0, thrR)
-                                                 : count_one(a.xn + so, a.stride, n, lane, 32, E0, thrR);
+                                c0 = pts_in_smem ? count_one(s_pts, a.stride, n, lane, 32, M0, thrR)
+                                                 : count_one(a.xn + so, a.stride, n, lane, 32, M0, thrR);
                             }
                             c0 = warp_sum(c0);
                             c1 = warp_sum(c1);
@@ -590,9 +600,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                         const int it = warp / slices, slice = warp % slices;
                         if (it < M) {
                             const int code = s_item[it];
-                            double E[9];
-#pragma unroll
-                            for (int c = 0; c < 9; ++c) E[c] = s_models[code >> 4][code & 15][c];
+                            const double* E = s_models[code >> 4][code & 15];
                             int cnt = pts_in_smem ? count_one(s_pts, a.stride, n, lane + 32 * slice, 32 * slices, E, thrR)
                                                   : count_one(a.xn + so, a.stride, n, lane + 32 * slice, 32 * slices, E, thrR);
                             cnt = warp_sum(cnt);
@@ -727,6 +735,9 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
         __syncthreads();
         const bool have = s_have != 0;
         const SampThr thrF = make_samp_thr(s_thr);
+        double bestE[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) bestE[c] = s_bestE[c];
         uint8_t* mask = a.mask + (int64_t)pair * a.stride;
         double* xin = a.xin ? a.xin + so : nullptr;
         for (int start = 0; start < n; start += ES_THREADS) {
@@ -735,7 +746,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
             double p[4] = {0, 0, 0, 0};
             if (i < n && have) {
                 p[0] = X1[i]; p[1] = Y1[i]; p[2] = X2[i]; p[3] = Y2[i];
-                in = (n == 5) ? true : sampson_inlier_unit(s_bestE, p[0], p[1], p[2], p[3], thrF);
+                in = (n == 5) ? true : sampson_inlier_unit(bestE, s_bestE, p[0], p[1], p[2], p[3], thrF);
             }
             if (i < n) mask[i] = in ? 1 : 0;
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
@@ -826,32 +837,53 @@ five_point_b2_kernel(const double* __restrict__ rec, int m, const uint32_t* __re
 }
 
 // ---- K3 alone: fixed hypothesis set, m models x n correspondences ----------------------
-// Every thread keeps one correspondence in registers; the CTA walks a block of models staged
+// Every thread keeps four correspondences in registers; the CTA walks a block of models staged
 // in shared memory (broadcast reads); votes are counted per warp with ballot + popc, per CTA
 // in shared memory and per model with one global atomicAdd per (CTA, model).
 constexpr int SC_THREADS = 256;
-constexpr int SC_MODELS = 128;
+constexpr int SC_PPT = 4;                    // correspondences per thread, in registers
+constexpr int SC_MODELS = 128;               // models per CTA tile, at most
 
 __global__ void __launch_bounds__(SC_THREADS)
-score_count_kernel(const double* __restrict__ E, int m, const double* __restrict__ xn, int stride, int n,
+score_count_kernel(const double* __restrict__ E, int m, int mtile, const double* __restrict__ xn, int stride, int n,
                    float thr32, int32_t* __restrict__ counts) {
     __shared__ double s_E[SC_MODELS][9];
+    __shared__ double s_dmin[SC_MODELS];
     __shared__ int s_cnt[SC_MODELS];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int m0 = blockIdx.y * SC_MODELS;
-    const int mm = min(SC_MODELS, m - m0);
+    const int m0 = blockIdx.y * mtile;
+    const int mm = min(mtile, m - m0);
+    const SampThr T = make_samp_thr(thr32);
     for (int i = tid; i < mm * 9; i += SC_THREADS) (&s_E[0][0])[i] = E[(int64_t)m0 * 9 + i];
     for (int i = tid; i < mm; i += SC_THREADS) s_cnt[i] = 0;
     __syncthreads();
-    const int i = blockIdx.x * SC_THREADS + tid;
-    const bool valid = i < n;
-    const int ii = valid ? i : 0;
-    const double a1 = xn[ii], b1 = xn[stride + ii], a2 = xn[2 * stride + ii], b2 = xn[3 * stride + ii];
-    const SampThr T = make_samp_thr(thr32);
+    for (int k = tid; k < mm; k += SC_THREADS) {
+        double f2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) f2 += s_E[k][c] * s_E[k][c];
+        s_dmin[k] = T.dmin * f2;             // NaN / inf scale: the pre-filter never decides
+    }
+    double a1[SC_PPT], b1[SC_PPT], a2[SC_PPT], b2[SC_PPT];
+    bool valid[SC_PPT];
+#pragma unroll
+    for (int q = 0; q < SC_PPT; ++q) {
+        const int i = (blockIdx.x * SC_PPT + q) * SC_THREADS + tid;
+        valid[q] = i < n;
+        const int ii = valid[q] ? i : 0;
+        a1[q] = xn[ii]; b1[q] = xn[stride + ii]; a2[q] = xn[2 * stride + ii]; b2[q] = xn[3 * stride + ii];
+    }
+    __syncthreads();
     for (int k = 0; k < mm; ++k) {
-        const bool in = valid && sampson_inlier(s_E[k], a1, b1, a2, b2, T);
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
-        if (lane == 0 && bal) atomicAdd(&s_cnt[k], __popc(bal));
+        double e[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) e[c] = s_E[k][c];
+        const double dmin = s_dmin[k];
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < SC_PPT; ++q)
+            c += (valid[q] && sampson_inlier_scaled(e, s_E[k], a1[q], b1[q], a2[q], b2[q], T, dmin)) ? 1 : 0;
+        c = warp_sum(c);
+        if (lane == 0 && c) atomicAdd(&s_cnt[k], c);
     }
     __syncthreads();
     for (int k = tid; k < mm; k += SC_THREADS)
@@ -1056,8 +1088,13 @@ int epv_score_launch(epivo_ctx* ctx, const double* d_E, int m, const double* d_x
     const float thr32 = (float)(thresh * thresh);
     EPV_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)std::max(m, 1) * 4, ctx->stream));
     if (m > 0 && n > 0) {
-        dim3 grid((n + SC_THREADS - 1) / SC_THREADS, (m + SC_MODELS - 1) / SC_MODELS);
-        score_count_kernel<<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, m, d_xn, stride, n, thr32, d_counts);
+        // model tile: as large as possible (fewer re-loads of the correspondences) while the grid still
+        // covers the GPU about four times
+        const int pblocks = (n + SC_THREADS * SC_PPT - 1) / (SC_THREADS * SC_PPT);
+        int mtile = SC_MODELS;
+        while (mtile > 8 && (long long)pblocks * ((m + mtile - 1) / mtile) < 4LL * ctx->sm_count) mtile /= 2;
+        dim3 grid(pblocks, (m + mtile - 1) / mtile);
+        score_count_kernel<<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, m, mtile, d_xn, stride, n, thr32, d_counts);
         EPV_LAUNCHED(ctx);
         if (d_medians) {
             score_median_kernel<<<(m * 32 + 255) / 256, 256, 0, ctx->stream>>>(d_E, m, d_xn, stride, n, d_errbuf,
