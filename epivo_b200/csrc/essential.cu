@@ -608,15 +608,46 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                         }
                     }
                 } else {
+                    // LMedS.  A model can only become the best if its median is below the best median of
+                    // the PREVIOUS sub-chunks, i.e. if more than n/2 of its errors are below it -- a RANSAC
+                    // style count with threshold "largest float < best" (no division, no selection).  Only
+                    // the few models that pass (and everything before a first best exists) pay for the
+                    // exact median: errors to scratch, bitwise radix select.
                     float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
-                    for (int it = warp; it < M; it += ES_WARPS) {
-                        const int code = s_item[it];
-                        const double* E = s_models[code >> 4][code & 15];
-                        for (int i = lane; i < n; i += 32) buf[i] = sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]);
-                        __syncwarp();
-                        const float med = warp_select(buf, n, n / 2, lane);
-                        __syncwarp();
-                        if (lane == 0) s_score[code >> 4][code & 15] = med;
+                    const bool have_best = s_best_score < 1e300;
+                    const float bestf = (float)s_best_score;                 // exact: medians are floats
+                    const bool can_filter = have_best && bestf > 0.0f;
+                    const SampThr thrL = make_samp_thr(can_filter ? __uint_as_float(__float_as_uint(bestf) - 1u) : 0.0f);
+                    const int need = n / 2 + 1;                              // errors that must lie below the best
+                    for (int j0 = warp; j0 < M; j0 += 2 * ES_WARPS) {
+                        const int code0 = s_item[j0];
+                        const bool two = j0 + ES_WARPS < M;
+                        const int code1 = two ? s_item[j0 + ES_WARPS] : code0;
+                        const double* M0 = s_models[code0 >> 4][code0 & 15];
+                        const double* M1 = s_models[code1 >> 4][code1 & 15];
+                        int c0 = need, c1 = need;                            // no best yet: every model needs its median
+                        if (have_best && !can_filter) {
+                            c0 = c1 = 0;                                     // best median is 0: nothing can beat it
+                        } else if (can_filter) {
+                            c0 = c1 = 0;
+                            if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, M0, M1, thrL, c0, c1);
+                            else count_two(a.xn + so, a.stride, n, lane, 32, M0, M1, thrL, c0, c1);
+                            c0 = warp_sum(c0);
+                            c1 = warp_sum(c1);
+                        }
+#pragma unroll 1
+                        for (int h = 0; h < (two ? 2 : 1); ++h) {
+                            const int code = h ? code1 : code0;
+                            const double* E = h ? M1 : M0;
+                            float med = 3.0e38f;                             // cannot win
+                            if ((h ? c1 : c0) >= need) {
+                                for (int i = lane; i < n; i += 32) buf[i] = sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]);
+                                __syncwarp();
+                                med = warp_select(buf, n, n / 2, lane);
+                                __syncwarp();
+                            }
+                            if (lane == 0) s_score[code >> 4][code & 15] = med;
+                        }
                     }
                 }
             }
