@@ -20,8 +20,14 @@
 
 namespace {
 
-constexpr int LM_THREADS = 128;
-constexpr int LM_TP = 64;          // points per Jacobian tile
+#ifndef EPV_LM_THREADS
+#define EPV_LM_THREADS 128
+#endif
+#ifndef EPV_LM_TP
+#define EPV_LM_TP 64
+#endif
+constexpr int LM_THREADS = EPV_LM_THREADS;
+constexpr int LM_TP = EPV_LM_TP;   // points per Jacobian tile
 constexpr int LM_MAX_ZETA = 16;
 
 struct Rt { double R[9]; double t[3]; };
@@ -213,8 +219,9 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     Rt* sInv = sMem + nz * nz;                     // [nz*nz] inverses
     Rt* sRep = sInv + nz * nz;                     // [nr] per-rep transform
     double* sH = reinterpret_cast<double*>(sRep + nr);   // [D][D+1] augmented
-    double* sJ = sH + (size_t)D * (D + 1);         // [LM_TP][D+1] tile: J columns of the span + residual
-    double* sDelta = sJ + (size_t)LM_TP * (D + 1);  // [D]
+    const int JS = (D + 1 + 3) / 4 * 4;            // tile row stride: a multiple of 4 so that 4-wide blocks never straddle a row
+    double* sJ = sH + (size_t)D * (D + 1);         // [LM_TP][JS] tile: J columns of the span + residual, zero padded
+    double* sDelta = sJ + (size_t)LM_TP * JS;      // [D]
     double* sRed = sDelta + D;                     // [LM_THREADS]
     __shared__ double s_lambda, s_prevE, s_Hnorm, s_rnorm;
     __shared__ int s_stop, s_iters, s_piv;
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                     const int pt = it / (span + 1), zi = it % (span + 1);
                     const double* pp = gpr + ((size_t)j * N + base + pt) * 3;
                     const double* pq = gp_r + ((size_t)j * N + base + pt) * 3;
-                    double* dst = sJ + (size_t)pt * (D + 1);
+                    double* dst = sJ + (size_t)pt * JS;
                     if (zi == span) {
                         dst[W] = wj * res_one(sRep[j], pp, pq, hd);                  // [:356-359]
                     } else {
@@ -299,19 +306,66 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                     }
                 }
                 __syncthreads();
-                // accumulate the (W+1) x (W+1) upper block: columns 0..W-1 -> H, column W -> b
-                const int ncol = W + 1;
-                for (int e = tid; e < W * ncol; e += LM_THREADS) {
-                    const int r = e / ncol, c = e % ncol;
-                    if (c < r) continue;
-                    double acc = 0.0;
-                    for (int pt = 0; pt < np; ++pt) acc += sJ[(size_t)pt * (D + 1) + r] * sJ[(size_t)pt * (D + 1) + c];
-                    const int gr = 6 * lo + r;
-                    if (c == W) sH[(size_t)gr * (D + 1) + D] += acc;
-                    else sH[(size_t)gr * (D + 1) + 6 * lo + c] += acc;
+                // Accumulate the upper triangle of the (W+1) x (W+1) Gram block of the tile: columns
+                // 0..W-1 -> H, column W (the residual) -> b.  4 x 4 register blocks: per point a thread loads
+                // 4 + 4 tile values for 16 FMAs.  When there are fewer blocks than threads (short spans) the
+                // points of a block are split over nsl adjacent lanes and merged by a shuffle butterfly
+                // (deterministic summation order: no atomics).
+                {
+                    const int nrb = (W + 3) / 4, ncb = (W + 1 + 3) / 4;              // row blocks, column blocks
+                    const int nblk = nrb * ncb - nrb * (nrb - 1) / 2;                // pairs (rb, cb >= rb)
+                    int nsl = 1;                                                     // point slices per block (power of 2)
+                    while (nsl < 32 && nblk * nsl * 2 <= LM_THREADS) nsl *= 2;
+                    const int passes = (nsl > 1) ? 1 : (nblk + LM_THREADS - 1) / LM_THREADS;
+                    for (int ps = 0; ps < passes; ++ps) {
+                        const int e = ps * LM_THREADS + tid;
+                        const int blk = e / nsl, sl = e % nsl;
+                        const bool active = blk < nblk;
+                        int rb = 0, rem = active ? blk : 0;                          // blk -> (rb, cb): row rb holds ncb - rb blocks
+                        while (rem >= ncb - rb) { rem -= ncb - rb; ++rb; }
+                        const int cb = rb + rem;
+                        double acc[4][4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+                        if (active) {
+                            for (int pt = sl; pt < np; pt += nsl) {
+                                const double* row = sJ + (size_t)pt * JS;
+                                double ra[4], cv[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) { ra[i] = row[4 * rb + i]; cv[i] = row[4 * cb + i]; }
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc[i][j] += ra[i] * cv[j];
+                            }
+                        }
+                        for (int o = nsl >> 1; o > 0; o >>= 1) {                     // uniform across the block: nsl is
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xFFFFFFFFu, acc[i][j], o);
+                        }
+                        if (active && sl == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = 4 * rb + i;
+                                if (r >= W) continue;
+                                const int gr = 6 * lo + r;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int c = 4 * cb + j;
+                                    if (c < r || c > W) continue;
+                                    if (c == W) sH[(size_t)gr * (D + 1) + D] += acc[i][j];
+                                    else sH[(size_t)gr * (D + 1) + 6 * lo + c] += acc[i][j];
+                                }
+                            }
+                        }
+                    }
                 }
                 for (int pt = tid; pt < np; pt += LM_THREADS) {
-                    const double r = sJ[(size_t)pt * (D + 1) + W];
+                    const double r = sJ[(size_t)pt * JS + W];
                     rsq += r * r;
                 }
                 __syncthreads();
@@ -353,14 +407,20 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
         // ---- solve H delta = -b: LU with partial pivoting on the augmented matrix  [:405]
         for (int k = 0; k < D; ++k) {
             __syncthreads();
-            if (tid == 0) {
+            if (tid < 32) {                                  // pivot search by warp 0: first row with the largest |value|
+                double best = -1.0;
                 int pv = k;
-                double best = fabs(sH[(size_t)k * (D + 1) + k]);
-                for (int r = k + 1; r < D; ++r) {
+                for (int r = k + tid; r < D; r += 32) {
                     const double v = fabs(sH[(size_t)r * (D + 1) + k]);
-                    if (v > best) { best = v; pv = r; }
+                    if (v > best) { best = v; pv = r; }      // NaN never wins, as in the sequential search
                 }
-                s_piv = pv;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+                    const int op = __shfl_xor_sync(0xFFFFFFFFu, pv, o);
+                    if (ob > best || (ob == best && op < pv)) { best = ob; pv = op; }
+                }
+                if (tid == 0) s_piv = pv;
             }
             __syncthreads();
             const int pv = s_piv;
@@ -373,12 +433,11 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                 __syncthreads();
             }
             const double ipiv = 1.0 / sH[(size_t)k * (D + 1) + k];
-            // eliminate below: element (r, c) for r > k, c > k
-            const int rows = D - k - 1, cols = D - k;     // cols k+1..D
-            for (int e = tid; e < rows * cols; e += LM_THREADS) {
-                const int r = k + 1 + e / cols, c = k + 1 + e % cols;
+            // eliminate below: warp w takes rows k+1+w, k+1+w+4, ...; lanes take the columns k+1..D
+            for (int r = k + 1 + (tid >> 5); r < D; r += LM_THREADS / 32) {
                 const double f = sH[(size_t)r * (D + 1) + k] * ipiv;
-                sH[(size_t)r * (D + 1) + c] -= f * sH[(size_t)k * (D + 1) + c];
+                for (int c = k + 1 + (tid & 31); c <= D; c += 32)
+                    sH[(size_t)r * (D + 1) + c] -= f * sH[(size_t)k * (D + 1) + c];
             }
         }
         __syncthreads();
@@ -653,7 +712,7 @@ __global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_ker
 
 size_t lm_smem_doubles(int nz, int nr, int D) {
     size_t rt = sizeof(Rt) / sizeof(double);
-    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)LM_TP * (D + 1) + D +
+    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)LM_TP * ((D + 1 + 3) / 4 * 4) + D +
            LM_THREADS;
 }
 

@@ -26,16 +26,3 @@ import signal; signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 print("iters: mean %.2f  <=8 %.3f  <=12 %.3f  <=16 %.3f  <=24 %.3f  <=32 %.3f  max %d" %
       (it.mean(), (it <= 8).mean(), (it <= 12).mean(), (it <= 16).mean(), (it <= 24).mean(), (it <= 32).mean(), it.max()))
 print("models/pair mean %.1f" % res["n_models"].mean())
-if os.environ.get("EPIVO_VARIANT", "") == "prof":
-    import ctypes as C
-    from epivo_b200 import _lib
-    lib = _lib.load()
-    out = (C.c_ulonglong * 8)()
-    lib.epivo_debug_solve_profile(out)          # reset
-    pipe.run(prm, 0, seq.n_pairs)
-    ctx.sync()
-    lib.epivo_debug_solve_profile(out)
-    v = np.array(list(out), dtype=np.float64)
-    ns = v[6]
-    print("solve profile (clocks per solve): nullspace+constraints %.0f  gauss-jordan %.0f  poly %.0f  DK %.0f  roots+refine %.0f"
-          "  | DK sweeps/solve %.1f  models/solve %.2f  solves %d" % (v[0]/ns, v[1]/ns, v[2]/ns, v[3]/ns, v[4]/ns, v[5]/ns, v[7]/ns, ns))
