@@ -24,6 +24,7 @@ namespace {
 
 constexpr int ES_THREADS = 256;
 constexpr int ES_WARPS = ES_THREADS / 32;
+constexpr int ES_SUB = 16;           // samples per scoring sub-chunk, at most (<= 16: s_item packs sample << 4 | model)
 
 struct CvRng {   // cv::RNG: multiply-with-carry
     unsigned long long state;
@@ -126,7 +127,7 @@ __host__ __device__ inline SampThr make_samp_thr(float thr32) {
     t.C = mid * 8.881784197001252e-16;                         // 2^-50
     t.Blo = mid * (1.0 - 2e-6);
     t.Bhi = mid * (1.0 + 2e-6);
-    t.dmin = mid > 0.0 ? fmax(1e-8, 1e-10 / mid) : 1e300;     // invalid threshold: the pre-filter never decides
+    t.dmin = mid > 0.0 ? fmax(1e-8, 1e-13 / mid) : 1e300;     // invalid threshold: the pre-filter never decides
     return t;
 }
 
@@ -156,12 +157,14 @@ __device__ __noinline__ bool sampson_inlier_slow(const double* E, double a1, dou
 
 // The same test for UNIT-NORM models (what the solver emits), with a fused pre-filter: the Sampson
 // numerator and denominator are first evaluated with FMAs (22 instructions instead of 36).  With
-// |E_ij| <= 1 and S1 = |a1|+|b1|+1, S2 = |a2|+|b2|+1 the fused s = x2'Ex1 is within 12 u S1 S2 of
-// the exact value (u = 2^-53) and den within a relative 24 u S sqrt(2/den) + 4u.  A decision is taken
-// from the fused values only if it is clear by a relative 1e-6 and the quantities are far from
-// degenerate (den > 1e-8, B den > 1e-10; then the bounds above are below 1e-9 for any realistic
-// field of view) -- "clear" means num outside [B (1 - 2e-6) den, B (1 + 2e-6) den]; everything else -- including every borderline point -- runs the exact
-// OpenCV-order evaluation, so the result is always that of sampson_inlier().
+// |E_ij| <= 1 and S1 = |a1|+|b1|+1, S2 = |a2|+|b2|+1 the fused s = x2'Ex1 is within eps_s = 12 u S1 S2
+// of the exact value (u = 2^-53) and den within a relative 24 u S sqrt(2/den) + 4u.  A decision is
+// taken from the fused values only if num lies outside [B (1 - 2e-6) den, B (1 + 2e-6) den] -- i.e. |s|
+// differs from the boundary sqrt(B den) by a relative 1e-6 -- and the quantities are far from
+// degenerate: den > 1e-8 (relative error of den below 1e-9 for S <= 20) and B den > 1e-13 (then
+// eps_s < 5e-7 sqrt(B den) for S1 S2 <= 130, i.e. normalised coordinates up to ~10: any real camera).
+// Everything else -- every borderline point included -- runs the exact OpenCV-order evaluation, so
+// the result is always that of sampson_inlier().
 // dmin: smallest denominator the pre-filter trusts = T.dmin * |E|_F^2 (T.dmin for the unit-norm models
 // the solver emits; every quantity of the test is homogeneous in the scale of E)
 // E: the model in registers; Emem: the same nine values in (shared / global) memory, read only by the
@@ -177,7 +180,7 @@ __device__ __forceinline__ bool sampson_inlier_scaled(const double (&E)[9], cons
     const double den = fma(ex0, ex0, fma(ex1, ex1, fma(et0, et0, et1 * et1)));
     const double num = sx * sx;
     // clear by a relative 2e-6 on either side, and far from degenerate (T.dmin folds den > 1e-8 and
-    // B den > 1e-10).  Branch-free: the three comparisons feed one (practically never taken) branch.
+    // B den > 1e-13).  Branch-free: the three comparisons feed one (practically never taken) branch.
     const bool in = num < den * T.Blo, out = num > den * T.Bhi;
     if ((in || out) && den > dmin) return in;
     return sampson_inlier_slow(Emem, a1, b1, a2, b2, T);
@@ -186,6 +189,21 @@ __device__ __forceinline__ bool sampson_inlier_scaled(const double (&E)[9], cons
 __device__ __forceinline__ bool sampson_inlier_unit(const double (&E)[9], const double* Emem, double a1, double b1,
                                                     double a2, double b2, const SampThr& T) {
     return sampson_inlier_scaled(E, Emem, a1, b1, a2, b2, T, T.dmin);
+}
+
+// Pre-filter alone: returns true if the fused evaluation decides the test (then `in` is the answer).
+__device__ __forceinline__ bool sampson_fast(const double (&E)[9], double a1, double b1, double a2, double b2,
+                                             const SampThr& T, double dmin, bool& in) {
+    const double ex0 = fma(E[0], a1, fma(E[1], b1, E[2]));
+    const double ex1 = fma(E[3], a1, fma(E[4], b1, E[5]));
+    const double ex2 = fma(E[6], a1, fma(E[7], b1, E[8]));
+    const double et0 = fma(E[0], a2, fma(E[3], b2, E[6]));
+    const double et1 = fma(E[1], a2, fma(E[4], b2, E[7]));
+    const double sx = fma(a2, ex0, fma(b2, ex1, ex2));
+    const double den = fma(ex0, ex0, fma(ex1, ex1, fma(et0, et0, et1 * et1)));
+    const double num = sx * sx;
+    in = num < den * T.Blo;
+    return (in || num > den * T.Bhi) && den > dmin;
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -459,16 +477,32 @@ __global__ void __launch_bounds__(SB2_THREADS, EPV_SB2_MINBLOCKS) solve_b2_kerne
 // inlier counts of one or two unit-norm models over correspondences [first, n) in steps of `step`;
 // P: pointer type of the point rows (the caller passes the shared-memory array itself when the
 // points are staged there, so the loads compile to LDS rather than generic loads)
+// The hot loop is branch-free (pre-filter only); points it cannot decide -- practically none -- are
+// recounted with the exact test in a second loop that is normally skipped.
 template <class P>
 __device__ __forceinline__ void count_two(P X1, int stride, int n, int first, int step, const double* M0,
                                           const double* M1, const SampThr& T, int& c0, int& c1) {
     double E0[9], E1[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) { E0[c] = M0[c]; E1[c] = M1[c]; }
+    bool undecided = false;
+#pragma unroll 2
     for (int i = first; i < n; i += step) {
         const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
-        c0 += sampson_inlier_unit(E0, M0, a1, b1, a2, b2, T) ? 1 : 0;
-        c1 += sampson_inlier_unit(E1, M1, a1, b1, a2, b2, T) ? 1 : 0;
+        bool in0, in1;
+        const bool d0 = sampson_fast(E0, a1, b1, a2, b2, T, T.dmin, in0);
+        const bool d1 = sampson_fast(E1, a1, b1, a2, b2, T, T.dmin, in1);
+        c0 += (d0 && in0) ? 1 : 0;
+        c1 += (d1 && in1) ? 1 : 0;
+        undecided |= !(d0 && d1);
+    }
+    if (undecided) {
+        for (int i = first; i < n; i += step) {
+            const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
+            bool in0, in1;
+            if (!sampson_fast(E0, a1, b1, a2, b2, T, T.dmin, in0)) c0 += sampson_inlier_slow(M0, a1, b1, a2, b2, T) ? 1 : 0;
+            if (!sampson_fast(E1, a1, b1, a2, b2, T, T.dmin, in1)) c1 += sampson_inlier_slow(M1, a1, b1, a2, b2, T) ? 1 : 0;
+        }
     }
 }
 template <class P>
@@ -477,8 +511,21 @@ __device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int
 #pragma unroll
     for (int c = 0; c < 9; ++c) E[c] = M[c];
     int c = 0;
-    for (int i = first; i < n; i += step)
-        c += sampson_inlier_unit(E, M, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T) ? 1 : 0;
+    bool undecided = false;
+#pragma unroll 2
+    for (int i = first; i < n; i += step) {
+        bool in;
+        const bool d = sampson_fast(E, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T, T.dmin, in);
+        c += (d && in) ? 1 : 0;
+        undecided |= !d;
+    }
+    if (undecided) {
+        for (int i = first; i < n; i += step) {
+            const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
+            bool in;
+            if (!sampson_fast(E, a1, b1, a2, b2, T, T.dmin, in)) c += sampson_inlier_slow(M, a1, b1, a2, b2, T) ? 1 : 0;
+        }
+    }
     return c;
 }
 
@@ -489,12 +536,12 @@ __device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int
 __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int round, int R, int last_round,
                                                                   int pts_in_smem) {
     extern __shared__ __align__(16) double s_pts[];
-    __shared__ double s_models[ES_WARPS][10][9];  // models of the sub-chunk being scored
-    __shared__ unsigned s_flags[ES_WARPS];         // valid-model bit masks of the sub-chunk's samples
-    __shared__ unsigned char s_item[ES_WARPS * 10];   // flattened (sample << 4 | model) list of the sub-chunk
+    __shared__ double s_models[ES_SUB][10][9];    // models of the sub-chunk being scored
+    __shared__ unsigned s_flags[ES_SUB];           // valid-model bit masks of the sub-chunk's samples
+    __shared__ unsigned char s_item[ES_SUB * 10];     // flattened (sample << 4 | model) list of the sub-chunk
     __shared__ int s_nitems;
-    __shared__ float s_score[ES_WARPS][10];       // LMedS: medians
-    __shared__ int s_cnt[ES_WARPS][10];           // RANSAC: inlier counts
+    __shared__ float s_score[ES_SUB][10];         // LMedS: medians
+    __shared__ int s_cnt[ES_SUB][10];             // RANSAC: inlier counts
     __shared__ double s_bestE[9];
     __shared__ double s_best_score;
     __shared__ int s_niters, s_iter, s_have, s_total_models;
@@ -542,19 +589,21 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
         const double* gmodels = a.w.models + (size_t)w * R * 90;
         const uint32_t* gfl = a.w.mflags + (size_t)w * R;
 
-        // sub-chunks of at most ES_WARPS samples: score, then replay.  RANSAC usually shrinks niters
-        // after the first few samples; samples at or beyond the current niters are never scored.
-        for (int sbase = 0; sbase < ch; sbase += ES_WARPS) {
-            const int r = min(ES_WARPS, min(ch, s_niters - iter0) - sbase);     // samples scored now (>= 1)
+        // Sub-chunks: score, then replay.  RANSAC usually shrinks niters after the first few samples, so the
+        // first two sub-chunks of a pair are 8 samples (samples at or beyond the current niters are never
+        // scored); after that 16 at a time, which balances the models better over the 8 warps.
+        for (int sbase = 0, sub = 0; sbase < ch; sbase += sub) {
+            sub = (iter0 + sbase < 2 * ES_WARPS) ? ES_WARPS : ES_SUB;
+            const int r = min(sub, min(ch, s_niters - iter0) - sbase);          // samples scored now (>= 1)
             // stage the models of these samples and flatten them into a work list
             for (int i = tid; i < r * 90; i += ES_THREADS) (&s_models[0][0][0])[i] = gmodels[(size_t)sbase * 90 + i];
-            if (tid < ES_WARPS * 10) (&s_cnt[0][0])[tid] = 0;
+            if (tid < ES_SUB * 10) (&s_cnt[0][0])[tid] = 0;
             if (warp == 0) {
                 const unsigned fl = lane < r ? gfl[sbase + lane] : 0u;
                 const int c = __popc(fl);
                 int incl = c;
 #pragma unroll
-                for (int o = 1; o < ES_WARPS; o <<= 1) {
+                for (int o = 1; o < ES_SUB; o <<= 1) {
                     const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                     if (lane >= o) incl += v;
                 }
@@ -564,7 +613,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     for (int j = 0; j < 10; ++j)
                         if (fl >> j & 1u) s_item[pos++] = (unsigned char)(lane << 4 | j);
                 }
-                if (lane == ES_WARPS - 1) s_nitems = incl;
+                if (lane == ES_SUB - 1) s_nitems = incl;
             }
             __syncthreads();
             const int M = s_nitems;
@@ -683,12 +732,12 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     const int c = m > 4 ? m : 0;             // a count <= 4 never wins
                     int pa = max(c, b_in);                   // inclusive prefix maximum: best after sample q
 #pragma unroll
-                    for (int o = 1; o < ES_WARPS; o <<= 1) pa = max(pa, __shfl_up_sync(0xFFFFFFFFu, pa, o, ES_WARPS));
+                    for (int o = 1; o < ES_SUB; o <<= 1) pa = max(pa, __shfl_up_sync(0xFFFFFFFFu, pa, o, ES_SUB));
                     const int ni_after = pa > b_in ? update_num_iters(a.prob, (double)(n - pa) / n, 5, ni_in) : ni_in;
-                    int ni_before = __shfl_up_sync(0xFFFFFFFFu, ni_after, 1, ES_WARPS);
+                    int ni_before = __shfl_up_sync(0xFFFFFFFFu, ni_after, 1, ES_SUB);
                     if (q == 0) ni_before = ni_in;
                     const bool stop_here = live && !(iter0 + sbase + q < ni_before);
-                    const unsigned stops = __ballot_sync(0xFFFFFFFFu, stop_here) & ((1u << ES_WARPS) - 1);
+                    const unsigned stops = __ballot_sync(0xFFFFFFFFu, stop_here) & ((1u << ES_SUB) - 1);
                     const int qstop = stops ? __ffs(stops) - 1 : r;          // samples [0, qstop) are counted
                     const int B = __shfl_sync(0xFFFFFFFFu, pa, max(qstop - 1, 0));
                     const int ni_out = __shfl_sync(0xFFFFFFFFu, ni_after, max(qstop - 1, 0));

@@ -9,7 +9,8 @@ seq = synth.make_sequence(frames, 2000, seed=synth.seed_for(3, 0))
 ctx = api.Context(0)
 pipe = api.SequencePipeline(seq.n_frames, 2000, ctx=ctx)
 pipe.upload(seq.kps, seq.descs)
-prm = api.default_params(seq.K.astype(np.float32))
+prm = api.default_params(seq.K.astype(np.float32), threshold=float(os.environ.get("THR", "1.0")),
+                         method=api.LMEDS if os.environ.get("LMEDS") else api.RANSAC)
 if os.environ.get("EPIVO_OVERLAP"):
     pipe.set_overlap(True)
 for _ in range(3):
