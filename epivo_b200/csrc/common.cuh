@@ -13,6 +13,7 @@ struct epivo_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
+    bool func_attrs_set = false;   // per-device opt-in attributes (large dynamic shared memory) applied for this context's device
     // grow-only device workspace, carved by a bump pointer per call
     char* ws = nullptr;
     size_t ws_bytes = 0;

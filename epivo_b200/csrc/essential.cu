@@ -1099,17 +1099,15 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
     if (nr < 0)
         EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "max_iters = %d needs more than %d rounds of %d samples", p.max_iters,
                  ES_MAX_ROUNDS, ES_RMAX);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->func_attrs_set) {                  // function attributes are per device: once per context
         EPV_CUDA(ctx, cudaFuncSetAttribute(solve_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
         EPV_CUDA(ctx, cudaFuncSetAttribute(five_point_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
-        attr_set = true;
+        EPV_CUDA(ctx, cudaFuncSetAttribute(ess_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ctx->func_attrs_set = true;
     }
     // correspondences staged in shared memory when two CTAs per SM still fit (<= 100 KB each)
     const size_t pts_bytes = (size_t)p.stride * 4 * sizeof(double);
     const size_t pts_smem = pts_bytes <= 100 * 1024 ? pts_bytes : 0;
-    if (pts_smem > 0)
-        EPV_CUDA(ctx, cudaFuncSetAttribute(ess_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pts_smem));
     ess_init_kernel<<<(p.n_pairs + 127) / 128, 128, 0, ctx->stream>>>(a);
     EPV_LAUNCHED(ctx);
     // Round 0 runs on every pair; later rounds usually see a short (often empty) work list, so their
