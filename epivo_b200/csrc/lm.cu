@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     Rt* sInv = sMem + nz * nz;                     // [nz*nz] inverses
     Rt* sRep = sInv + nz * nz;                     // [nr] per-rep transform
     double* sH = reinterpret_cast<double*>(sRep + nr);   // [D][D+1] augmented
-    const int JS = (D + 1 + 3) / 4 * 4;            // tile row stride: a multiple of 4 so that 4-wide blocks never straddle a row
-    double* sJ = sH + (size_t)D * (D + 1);         // [LM_TP][JS] tile: J columns of the span + residual, zero padded
+    const int JS = (D + 1) | 1;                    // tile row stride, odd: lanes that own consecutive points hit distinct banks
+    double* sJ = sH + (size_t)D * (D + 1);         // [LM_TP][JS] tile: J columns of the span + residual
     double* sDelta = sJ + (size_t)LM_TP * JS;      // [D]
     double* sRed = sDelta + D;                     // [LM_THREADS]
     __shared__ double s_lambda, s_prevE, s_Hnorm, s_rnorm;
@@ -278,9 +278,10 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
             const double wj = w[j];
             for (int base = 0; base < N; base += LM_TP) {
                 const int np = min(LM_TP, N - base);
-                // work item = (point, zeta in span)
+                // work item = (zeta in span | residual, point), point fastest: the lanes of a warp share the zeta
+                // (chain transforms are broadcast reads, no residual/Jacobian divergence inside a warp)
                 for (int it = tid; it < np * (span + 1); it += LM_THREADS) {
-                    const int pt = it / (span + 1), zi = it % (span + 1);
+                    const int pt = it % np, zi = it / np;
                     const double* pp = gpr + ((size_t)j * N + base + pt) * 3;
                     const double* pq = gp_r + ((size_t)j * N + base + pt) * 3;
                     double* dst = sJ + (size_t)pt * JS;
@@ -306,14 +307,17 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                     }
                 }
                 __syncthreads();
-                // Accumulate the upper triangle of the (W+1) x (W+1) Gram block of the tile: columns
-                // 0..W-1 -> H, column W (the residual) -> b.  4 x 4 register blocks: per point a thread loads
-                // 4 + 4 tile values for 16 FMAs.  When there are fewer blocks than threads (short spans) the
-                // points of a block are split over nsl adjacent lanes and merged by a shuffle butterfly
-                // (deterministic summation order: no atomics).
+                // Accumulate the upper triangle of the (W+1) x (W+1) Gram matrix of the tile: columns
+                // 0..W-1 -> H, column W (the residual) -> b.  Register blocks of 4 x 4 products, but a block
+                // owns the RESIDUE CLASSES (a, b) mod Mdl of the column index, i.e. columns a + Mdl*i and
+                // b + Mdl*j, so that consecutive lanes read consecutive tile columns (no bank conflicts).
+                // Only class pairs a <= b are enumerated; a product that lands below the diagonal is the
+                // mirror of an upper element no other block computes.  When there are fewer blocks than
+                // threads (short spans) the points of a block are split over nsl adjacent lanes and merged
+                // by a shuffle butterfly (deterministic summation order: no atomics).
                 {
-                    const int nrb = (W + 3) / 4, ncb = (W + 1 + 3) / 4;              // row blocks, column blocks
-                    const int nblk = nrb * ncb - nrb * (nrb - 1) / 2;                // pairs (rb, cb >= rb)
+                    const int Mdl = (W + 1 + 3) / 4;                                 // classes; i, j < 4 cover W + 1 columns
+                    const int nblk = Mdl * (Mdl + 1) / 2;
                     int nsl = 1;                                                     // point slices per block (power of 2)
                     while (nsl < 32 && nblk * nsl * 2 <= LM_THREADS) nsl *= 2;
                     const int passes = (nsl > 1) ? 1 : (nblk + LM_THREADS - 1) / LM_THREADS;
@@ -321,9 +325,9 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                         const int e = ps * LM_THREADS + tid;
                         const int blk = e / nsl, sl = e % nsl;
                         const bool active = blk < nblk;
-                        int rb = 0, rem = active ? blk : 0;                          // blk -> (rb, cb): row rb holds ncb - rb blocks
-                        while (rem >= ncb - rb) { rem -= ncb - rb; ++rb; }
-                        const int cb = rb + rem;
+                        int ca = 0, rem = active ? blk : 0;                          // blk -> (ca, cb): row ca holds Mdl - ca blocks
+                        while (rem >= Mdl - ca) { rem -= Mdl - ca; ++ca; }
+                        const int cb = ca + rem;
                         double acc[4][4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
@@ -334,14 +338,17 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                                 const double* row = sJ + (size_t)pt * JS;
                                 double ra[4], cv[4];
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) { ra[i] = row[4 * rb + i]; cv[i] = row[4 * cb + i]; }
+                                for (int i = 0; i < 4; ++i) {                        // columns beyond W are never stored: skip the read
+                                    ra[i] = (ca + Mdl * i <= W) ? row[ca + Mdl * i] : 0.0;
+                                    cv[i] = (cb + Mdl * i <= W) ? row[cb + Mdl * i] : 0.0;
+                                }
 #pragma unroll
                                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) acc[i][j] += ra[i] * cv[j];
                             }
                         }
-                        for (int o = nsl >> 1; o > 0; o >>= 1) {                     // uniform across the block: nsl is
+                        for (int o = nsl >> 1; o > 0; o >>= 1) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -350,15 +357,15 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                         if (active && sl == 0) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int r = 4 * rb + i;
-                                if (r >= W) continue;
-                                const int gr = 6 * lo + r;
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const int c = 4 * cb + j;
-                                    if (c < r || c > W) continue;
-                                    if (c == W) sH[(size_t)gr * (D + 1) + D] += acc[i][j];
-                                    else sH[(size_t)gr * (D + 1) + 6 * lo + c] += acc[i][j];
+                                    if (ca == cb && j < i) continue;                 // same class: (i, j) and (j, i) are one element
+                                    const int r0 = ca + Mdl * i, c0 = cb + Mdl * j;
+                                    const int u = min(r0, c0), v = max(r0, c0);      // mirror into the upper triangle
+                                    if (v > W || u == W) continue;
+                                    const int gr = 6 * lo + u;
+                                    if (v == W) sH[(size_t)gr * (D + 1) + D] += acc[i][j];
+                                    else sH[(size_t)gr * (D + 1) + 6 * lo + v] += acc[i][j];
                                 }
                             }
                         }
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_ker
 
 size_t lm_smem_doubles(int nz, int nr, int D) {
     size_t rt = sizeof(Rt) / sizeof(double);
-    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)LM_TP * ((D + 1 + 3) / 4 * 4) + D +
+    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)LM_TP * ((D + 1) | 1) + D +
            LM_THREADS;
 }
 
