@@ -20,14 +20,8 @@
 
 namespace {
 
-#ifndef EPV_LM_THREADS
-#define EPV_LM_THREADS 128
-#endif
-#ifndef EPV_LM_TP
-#define EPV_LM_TP 64
-#endif
-constexpr int LM_THREADS = EPV_LM_THREADS;
-constexpr int LM_TP = EPV_LM_TP;   // points per Jacobian tile
+// The window kernel is instantiated for three CTA shapes <threads, points per Jacobian tile>; the launcher picks
+// one by problem size (measured on B200: small windows want many small CTAs, large ones wider CTAs).
 constexpr int LM_MAX_ZETA = 16;
 
 struct Rt { double R[9]; double t[3]; };
@@ -206,6 +200,7 @@ struct LmArgs {
     size_t smem_doubles;
 };
 
+template <int LM_THREADS, int LM_TP>
 __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     extern __shared__ __align__(16) double sm[];
     const LmPlan& p = a.p;
@@ -717,10 +712,22 @@ __global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_ker
     }
 }
 
-size_t lm_smem_doubles(int nz, int nr, int D) {
+size_t lm_smem_doubles(int nz, int nr, int D, int threads, int tp) {
     size_t rt = sizeof(Rt) / sizeof(double);
-    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)LM_TP * ((D + 1) | 1) + D +
-           LM_THREADS;
+    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)tp * ((D + 1) | 1) + D + threads;
+}
+
+template <int THREADS, int TP>
+int lm_launch_shape(epivo_ctx* ctx, LmArgs& a) {
+    a.smem_doubles = lm_smem_doubles(a.p.n_zeta, a.p.n_rep, a.D, THREADS, TP);
+    const size_t bytes = a.smem_doubles * sizeof(double);
+    if (bytes > 220 * 1024)
+        EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "LM problem needs %zu bytes of shared memory (n_zeta=%d, n_rep=%d)", bytes,
+                 a.p.n_zeta, a.p.n_rep);
+    EPV_CUDA(ctx, cudaFuncSetAttribute(lm_kernel<THREADS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    lm_kernel<THREADS, TP><<<a.p.B, THREADS, bytes, ctx->stream>>>(a);
+    EPV_LAUNCHED(ctx);
+    return EPIVO_OK;
 }
 
 }  // namespace
@@ -739,13 +746,7 @@ int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
     LmArgs a;
     a.p = p;
     a.D = 6 * p.n_zeta;
-    a.smem_doubles = lm_smem_doubles(p.n_zeta, p.n_rep, a.D);
-    const size_t bytes = a.smem_doubles * sizeof(double);
-    if (bytes > 220 * 1024)
-        EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "LM problem needs %zu bytes of shared memory (n_zeta=%d, n_rep=%d)",
-                 bytes, p.n_zeta, p.n_rep);
-    EPV_CUDA(ctx, cudaFuncSetAttribute(lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    lm_kernel<<<p.B, LM_THREADS, bytes, ctx->stream>>>(a);
-    EPV_LAUNCHED(ctx);
-    return EPIVO_OK;
+    if (p.N <= 32) return lm_launch_shape<64, 32>(ctx, a);          // e.g. the shipped kitti_ba shape: 9 reps x 32 points
+    if (p.N >= 96) return lm_launch_shape<192, 96>(ctx, a);         // e.g. cfg5: 20 reps x 250 points
+    return lm_launch_shape<128, 64>(ctx, a);
 }
