@@ -32,11 +32,18 @@ namespace {
 #define EPV_MT_RQ 8
 #endif
 #ifndef EPV_MT_MINBLOCKS
-#define EPV_MT_MINBLOCKS 1
+#define EPV_MT_MINBLOCKS 4
 #endif
 constexpr int MT_THREADS = EPV_MT_THREADS;
 constexpr int MT_RQ = EPV_MT_RQ;
-constexpr int MT_TILE = 128;
+#ifndef EPV_MT_TILE
+#define EPV_MT_TILE 128
+#endif
+#ifndef EPV_MT_UNROLL
+#define EPV_MT_UNROLL 1
+#endif
+constexpr int MT_TILE = EPV_MT_TILE;
+constexpr int MT_UNROLL = EPV_MT_UNROLL;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -192,7 +199,7 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
         const int rows = min(MT_TILE, nt - tile * MT_TILE);
         const uint32_t jbase = (uint32_t)(tile * MT_TILE);
         const uint4* trow4 = reinterpret_cast<const uint4*>(s_tile[buf]);
-#pragma unroll 2
+#pragma unroll MT_UNROLL
         for (int j = 0; j < rows; ++j) {
             uint32_t t[WORDS];
 #pragma unroll
