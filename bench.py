@@ -250,10 +250,10 @@ def main():
     popc_per_pair = kp * kp * 4
     achieved_popc = popc_per_pair * P / (ms_match * 1e-3)
     # DRAM traffic of one matcher launch over the default workload, from the `ncu --set full` capture in
-    # profiles/r1_ncu_full_top_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum = 328.8 + 61.3 MB).
+    # profiles/r1_ncu_full_top_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum = 327.8 + 59.0 MB).
     # It is BELOW the algorithmic bytes because consecutive pairs share a frame (train set of pair i =
     # query set of pair i+1) and that frame is still in L2.  Only valid for the profiled shape.
-    traffic = 390.1e6 if (a.frames == 4541 and a.kp == 2000 and n_chunk_launches == 1) else None
+    traffic = 386.8e6 if (a.frames == 4541 and a.kp == 2000 and n_chunk_launches == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "match_tile_kernel<8,HAMMING2>", "launches_per_step": n_chunk_launches,
@@ -266,7 +266,7 @@ def main():
                  "alu_peak_Gops": lop_peak / 1e9,
                  "work": "nq*nt*4 POPC.32 per pair (Hamming2 on bit planes), one direction + fused column minima",
                  "note": "carry-save compression issues 3 POPC per 4 algorithmic ones, so frac can exceed 1; "
-                         "ncu (profiles/r1_ncu_full_top_kernels.csv): ALU pipe 87 %, XU (POPC) pipe 83 % of peak"}
+                         "ncu (profiles/r1_ncu_full_top_kernels.csv): ALU pipe 89 %, XU (POPC) pipe 88 % of peak"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

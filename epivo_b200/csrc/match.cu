@@ -126,7 +126,7 @@ __device__ __forceinline__ uint32_t desc_dist(const uint32_t (&q)[WORDS], const 
 }
 
 template <int WORDS, bool NORM2, bool TOP2>
-__global__ void __launch_bounds__(MT_THREADS, EPV_MT_MINBLOCKS)
+__global__ void __launch_bounds__(MT_THREADS, WORDS <= 8 ? EPV_MT_MINBLOCKS : 1)   // 64-byte descriptors need the registers
 match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int64_t t0, int64_t ts, int nq,
                   int nt, uint32_t* __restrict__ rowkey, uint32_t* __restrict__ rowkey2,
                   uint32_t* __restrict__ colkey, int stride, int tiles_per_split, int64_t part_stride) {
