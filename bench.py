@@ -184,7 +184,9 @@ def main():
     method = api.RANSAC if a.method == "ransac" else api.LMEDS
     prm = api.default_params(seq.K.astype(np.float32), method=method, threshold=a.thr)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-    results = np.zeros(P, dtype=api.RESULT_DTYPE)
+    # results land in pinned host memory too (the library DMAs straight into a pinned caller buffer)
+    h_res = torch.zeros(P * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    results = h_res.numpy().view(api.RESULT_DTYPE)
 
     pipe.upload(kps_np, desc_np)
     for _ in range(a.warmup):
@@ -286,6 +288,7 @@ def main():
                         "mean_good": float(results["n_good"].mean()),
                         "mean_ransac_iters": float(results["ransac_iters"].mean()),
                         "lm_ran_frac": float(results["lm_ran"].mean()),
+                        "lm_reverted_frac": float(results["lm_reverted"].mean()),   # kitti_E.cpp:198-200 reverts when r_norm > 1e-9
                         "median_rot_err_rad": float(np.median([np.arccos(np.clip((np.trace(results["R"][i].T @ seq.R[i]) - 1) / 2, -1, 1))
                                                                for i in range(0, P, max(1, P // 256))]))}}
 

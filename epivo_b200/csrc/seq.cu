@@ -562,10 +562,15 @@ int epivo_seq_download(epivo_seq* s, epivo_pair_result* out, int first_pair, int
     if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
         EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range");
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
-    EPV_CUDA(ctx, cudaMemcpyAsync(s->h_results, s->d_results + first_pair, (size_t)n_pairs * sizeof(epivo_pair_result),
+    // a pinned caller buffer takes the DMA directly; pageable memory goes through the pinned staging copy
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) (void)cudaGetLastError();
+    epivo_pair_result* dst = pinned ? out : s->h_results;
+    EPV_CUDA(ctx, cudaMemcpyAsync(dst, s->d_results + first_pair, (size_t)n_pairs * sizeof(epivo_pair_result),
                                   cudaMemcpyDeviceToHost, ctx->stream));
     EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(out, s->h_results, (size_t)n_pairs * sizeof(epivo_pair_result));
+    if (!pinned) memcpy(out, s->h_results, (size_t)n_pairs * sizeof(epivo_pair_result));
     return EPIVO_OK;
 }
 
