@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--kp", type=int, default=2000)
     ap.add_argument("--method", default="ransac", choices=["ransac", "lmeds"])
     ap.add_argument("--thr", type=float, default=1.0)
+    ap.add_argument("--match", default="crosscheck", choices=["crosscheck", "ratio"],
+                    help="crosscheck = BFMatcher(norm, true).match (the reference, kitti_ba.cpp:602); "
+                         "ratio = knnMatch(k=2) + Lowe ratio 0.8 (north_star's matcher mode)")
+    ap.add_argument("--norm", default="hamming2", choices=["hamming", "hamming2"])
     ap.add_argument("--cpu-pairs", type=int, default=128, help="bounded CPU-baseline sample (pairs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -54,7 +58,8 @@ def parse():
 
 def workload_name(a):
     return (f"kitti_E synthetic seq-00-length run: {a.frames} frames x {a.kp} kp x 256-bit descriptors, "
-            f"{a.frames - 1} pairs per GPU; BFMatcher(HAMMING2, crossCheck) + findEssentialMat("
+            f"{a.frames - 1} pairs per GPU; BFMatcher({a.norm.upper()}, "
+            f"{'crossCheck' if a.match == 'crosscheck' else 'knnMatch k=2 + ratio 0.8'}) + findEssentialMat("
             f"{a.method.upper()}, 0.99, {a.thr}) + recoverPose + 48-pt LM")
 
 
@@ -117,7 +122,8 @@ def run_reference(a):
     seq = synth.make_sequence(min(a.frames, per_step + 1), a.kp, seed=synth.seed_for(3, 0))
     method = 8 if a.method == "ransac" else 4
     cores = os.cpu_count() or 1
-    pool = R.CpuPool(seq.kps, seq.descs, seq.K, method, 0.99, a.thr, cores=cores)
+    pool = R.CpuPool(seq.kps, seq.descs, seq.K, method, 0.99, a.thr, cores=cores,
+                     norm=7 if a.norm == "hamming2" else 6, ratio=None if a.match == "crosscheck" else 0.8)
     idx = list(range(seq.n_pairs))
     for _ in range(a.warmup):
         pool.run(idx[:max(cores, 8)])
@@ -182,7 +188,9 @@ def main():
     ctx = api.Context(local)
     pipe = api.SequencePipeline(F, kp, ctx=ctx)
     method = api.RANSAC if a.method == "ransac" else api.LMEDS
-    prm = api.default_params(seq.K.astype(np.float32), method=method, threshold=a.thr)
+    prm = api.default_params(seq.K.astype(np.float32), method=method, threshold=a.thr,
+                             match_mode=1 if a.match == "crosscheck" else 2, ratio=0.8,
+                             norm=api.NORM_HAMMING2 if a.norm == "hamming2" else api.NORM_HAMMING)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     # results land in pinned host memory too (the library DMAs straight into a pinned caller buffer)
     h_res = torch.zeros(P * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
@@ -249,16 +257,17 @@ def main():
     lop_peak = ctx.microbench(4)
     # algorithmic POPC.32 per pair: nq*nt*(256/32) for plain Hamming; the Hamming2 bit-plane form
     # needs nq*nt*4 -- report against the instruction count the kernel actually needs (4)
-    popc_per_pair = kp * kp * 4
+    popc_per_pair = kp * kp * (4 if a.norm == "hamming2" else 8)
     achieved_popc = popc_per_pair * P / (ms_match * 1e-3)
     # DRAM traffic of one matcher launch over the default workload, from the `ncu --set full` capture in
     # profiles/r1_ncu_full_top_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum = 327.8 + 59.0 MB).
     # It is BELOW the algorithmic bytes because consecutive pairs share a frame (train set of pair i =
     # query set of pair i+1) and that frame is still in L2.  Only valid for the profiled shape.
-    traffic = 386.8e6 if (a.frames == 4541 and a.kp == 2000 and n_chunk_launches == 1) else None
+    traffic = 386.8e6 if (a.frames == 4541 and a.kp == 2000 and n_chunk_launches == 1 and a.norm == "hamming2"
+                          and a.match == "crosscheck") else None
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "match_tile_kernel<8,HAMMING2>", "launches_per_step": n_chunk_launches,
+                "kernel": "match_tile_kernel<8,%s%s>" % (a.norm.upper(), ",TOP2" if a.match == "ratio" else ""), "launches_per_step": n_chunk_launches,
                 "algorithmic_bytes_per_launch": bytes_per_pair * P / max(n_chunk_launches, 1),
                 "ms_per_step_in_kernel": ms_match,
                 "note": "the matcher is bound by the integer pipes (POPC on XU, LOP3 on ALU), not HBM "
@@ -266,7 +275,8 @@ def main():
     pipe_roof = {"bound": "popc32 (XU pipe) / LOP3 (ALU pipe)", "achieved": achieved_popc / 1e9,
                  "peak": popc_peak / 1e9, "unit": "Gpopc/s", "frac": achieved_popc / popc_peak,
                  "alu_peak_Gops": lop_peak / 1e9,
-                 "work": "nq*nt*4 POPC.32 per pair (Hamming2 on bit planes), one direction + fused column minima",
+                 "work": "nq*nt*%d POPC.32 per pair (%s), one direction + fused column minima" % (
+                     (4, "Hamming2 on bit planes") if a.norm == "hamming2" else (8, "plain Hamming")),
                  "note": "carry-save compression issues 3 POPC per 4 algorithmic ones, so frac can exceed 1; "
                          "ncu (profiles/r1_ncu_full_top_kernels.csv): ALU pipe 89 %, XU (POPC) pipe 88 % of peak"}
 
@@ -297,7 +307,7 @@ def main():
         n = max(8, min(a.cpu_pairs, P))
         cores = os.cpu_count() or 1
         pool = R.CpuPool(seq.kps[:n + 1], seq.descs[:n + 1], seq.K, 8 if a.method == "ransac" else 4, 0.99, a.thr,
-                         cores=cores)
+                         cores=cores, norm=7 if a.norm == "hamming2" else 6, ratio=None if a.match == "crosscheck" else 0.8)
         pool.run(range(min(n, cores)))
         v, res = pool.run(range(n))
         pool.close()

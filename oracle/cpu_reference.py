@@ -26,9 +26,14 @@ from . import oracle as O
 _SEQ = {}
 
 
-def pair_cv2(kp0, d0, kp1, d1, Kf, method=8, prob=0.99, thr=1.0, lm_points=48, huber_delta=1e-5):
-    """One frame pair through the reference's CPU path.  Returns (T 4x4, n_matches, n_inliers, n_good)."""
-    ms = cv2.BFMatcher(cv2.NORM_HAMMING2, True).match(d0, d1)             # kitti_ba.cpp:602,641
+def pair_cv2(kp0, d0, kp1, d1, Kf, method=8, prob=0.99, thr=1.0, lm_points=48, huber_delta=1e-5,
+             norm=7, ratio=None):
+    """One frame pair through the reference's CPU path.  Returns (T 4x4, n_matches, n_inliers, n_good).
+    ratio=None: BFMatcher(norm, crossCheck=true).match (kitti_ba.cpp:602,641); else knnMatch(k=2) + Lowe ratio."""
+    if ratio is None:
+        ms = cv2.BFMatcher(norm, True).match(d0, d1)
+    else:
+        ms = [a for a, b in cv2.BFMatcher(norm, False).knnMatch(d0, d1, k=2) if a.distance < ratio * b.distance]
     qi = np.fromiter((m.queryIdx for m in ms), dtype=np.int64, count=len(ms))
     ti = np.fromiter((m.trainIdx for m in ms), dtype=np.int64, count=len(ms))
     p0, p1 = kp0[qi], kp1[ti]                                             # kitti_ba.cpp:684-693
@@ -67,8 +72,9 @@ def pair_numpy(kp0, d0, kp1, d1, Kf, method=8, prob=0.99, thr=1.0, **kw):
     return o["T"], len(o["matches"][0]), int(o["e_mask"].sum()), int(o["n_good"])
 
 
-def _init(kps, descs, Kf, method, prob, thr):
+def _init(kps, descs, Kf, method, prob, thr, norm=7, ratio=None):
     _SEQ["kps"], _SEQ["descs"], _SEQ["K"], _SEQ["args"] = kps, descs, Kf, (method, prob, thr)
+    _SEQ["match"] = (norm, ratio)
     if HAVE_CV2:
         cv2.setNumThreads(1)                                # pair-parallel: one core per pair
     clib.lib()
@@ -77,8 +83,11 @@ def _init(kps, descs, Kf, method, prob, thr):
 def _work(i):
     kps, descs, Kf = _SEQ["kps"], _SEQ["descs"], _SEQ["K"]
     method, prob, thr = _SEQ["args"]
-    fn = pair_cv2 if HAVE_CV2 else pair_numpy
-    T, nm, ni, ng = fn(kps[i], descs[i], kps[i + 1], descs[i + 1], Kf, method, prob, thr)
+    if HAVE_CV2:
+        norm, ratio = _SEQ["match"]
+        T, nm, ni, ng = pair_cv2(kps[i], descs[i], kps[i + 1], descs[i + 1], Kf, method, prob, thr, norm=norm, ratio=ratio)
+    else:
+        T, nm, ni, ng = pair_numpy(kps[i], descs[i], kps[i + 1], descs[i + 1], Kf, method, prob, thr)
     return i, T, nm, ni, ng
 
 
@@ -86,13 +95,13 @@ class CpuPool:
     """Pair-parallel CPU workers (how a CPU user would saturate the box): `cores` processes,
     cv2.setNumThreads(1) each.  The sequence is inherited by fork, not pickled per task."""
 
-    def __init__(self, kps, descs, K, method=8, prob=0.99, thr=1.0, cores=None):
+    def __init__(self, kps, descs, K, method=8, prob=0.99, thr=1.0, cores=None, norm=7, ratio=None):
         import multiprocessing as mp
         self.cores = cores or (os.cpu_count() or 1)
         clib.build()
         Kf = np.asarray(K, dtype=np.float32)
         self.pool = mp.get_context("fork").Pool(self.cores, initializer=_init,
-                                                initargs=(kps, descs, Kf, method, prob, thr))
+                                                initargs=(kps, descs, Kf, method, prob, thr, norm, ratio))
 
     def run(self, pair_indices):
         """-> (pairs/s, results)"""

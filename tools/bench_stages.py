@@ -41,6 +41,8 @@ F = int(os.environ.get("FRAMES", "1025"))
 kitti = synth.make_sequence(F, 2000, seed=synth.seed_for(3, 0))
 seq_rate("cfg3_ransac_1.0", kitti, 2000)
 seq_rate("cfg1_lmeds", kitti, 2000, method=api.LMEDS, threshold=0.01)
+seq_rate("cfg3_ratio0.8_hamming_knn2", kitti, 2000, match_mode=2, norm=api.NORM_HAMMING, ratio=0.8)   # north_star's matcher mode
+seq_rate("cfg3_crosscheck_hamming", kitti, 2000, norm=api.NORM_HAMMING)
 seq_rate("hard_ransac_0.05", kitti, 2000, threshold=0.05)
 euroc = synth.make_sequence(F, 1500, seed=synth.seed_for(2, 0), K=synth.EUROC_K, size=synth.EUROC_SIZE, depth=(1.0, 8.0),
                             px_sigma=0.3, outlier_frac=0.25)
