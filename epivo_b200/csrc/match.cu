@@ -221,10 +221,12 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
                     best2[r] = min(best2[r], max(best[r], rk));
                 }
                 best[r] = min(best[r], rk);
-                cmin = min(cmin, d * (1u << EPV_KEY_SHIFT) + qidx[r]);
+                if (!TOP2) cmin = min(cmin, d * (1u << EPV_KEY_SHIFT) + qidx[r]);
             }
-            cmin = __reduce_min_sync(0xFFFFFFFFu, cmin);
-            if (lane == 0) s_col[buf][warp][j] = cmin;          // plain store: one slot per (warp, train row)
+            if (!TOP2) {     // column minima feed the cross-check only; the top-2 (ratio / knn) modes never read them
+                cmin = __reduce_min_sync(0xFFFFFFFFu, cmin);
+                if (lane == 0) s_col[buf][warp][j] = cmin;      // plain store: one slot per (warp, train row)
+            }
         }
         __syncthreads();                                       // tile + its column keys are complete
         if (tid == 0 && tile + 2 < n_tiles) {
@@ -233,7 +235,7 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
             mbar_expect_tx(&s_bar[buf], bytes);
             tma_load_1d(s_tile[buf], trows + (int64_t)(tile + 2) * MT_TILE * WORDS, bytes, &s_bar[buf]);
         }
-        for (int j = tid; j < rows; j += MT_THREADS) {
+        for (int j = tid; j < rows && !TOP2; j += MT_THREADS) {
             uint32_t m = s_col[buf][0][j];
 #pragma unroll
             for (int w = 1; w < MT_THREADS / 32; ++w) m = min(m, s_col[buf][w][j]);
