@@ -228,13 +228,15 @@ __device__ float warp_select(const float* buf, int n, int k, int lane) {
 // R_r samples of every pair that is still running:
 //     ess_sample_kernel   one thread per running pair draws the samples (cv::RNG stream)
 //     solve_a_kernel      one lane per (pair, sample): null space, constraints, elimination
-//     solve_b_kernel      one lane per (pair, sample): polynomial, roots, models, refinement
+//     solve_b1_kernel     one lane per (pair, sample): polynomial, roots -> compact list of real roots
+//     solve_b2_kernel     one lane per real root: model + refinement
 //     ess_round_kernel    one CTA per running pair: scores the models, replays the sequential
 //                         "strictly better -> update niters" bookkeeping in sample order, and
 //                         either finishes the pair (mask, compaction) or queues it for round r+1
 // Pairs that have stopped drop out of the work list; samples at or beyond a pair's current
 // niters are never solved or scored.  The host enqueues enough rounds to cover max_iters;
-// rounds with an empty work list cost a few microseconds (grid-stride kernels, small grids).
+// rounds with an empty work list cost a few microseconds (grid-stride kernels, small grids:
+// five ~3 us launches per empty round).
 // =====================================================================================
 constexpr int ES_RMAX = 128;         // samples per pair per round, at most
 constexpr int ES_MAX_ROUNDS = 40;

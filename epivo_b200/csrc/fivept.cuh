@@ -1,4 +1,4 @@
-// K2: Nister 5-point minimal solver, FP64, one hypothesis per lane, in two stages.
+// K2: Nister 5-point minimal solver, FP64, in three stages (A, B1: one hypothesis per lane; B2: one real root per lane).
 //
 // Restates the algorithm of cv::findEssentialMat's EMEstimatorCallback::runKernel
 // (OpenCV modules/calib3d/src/five-point.cpp; called from kitti.cpp:98, kitti_E.cpp:98,
