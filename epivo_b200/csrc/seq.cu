@@ -237,10 +237,11 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     ev_ok = ev_ok && cudaEventCreate(&s->ev_begin) == cudaSuccess && cudaEventCreate(&s->ev_end) == cudaSuccess;
     ev_ok = ev_ok && cudaEventCreateWithFlags(&s->ev_geo_done, cudaEventDisableTiming) == cudaSuccess;
     {
+        // the second stream carries the H2D pieces of the host-buffer path and, in overlap mode, the geometry
+        // kernels: highest priority, so that their short CTAs take the SM slots the long matcher CTAs free up
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);       // hi = numerically lowest = highest priority
-        (void)hi;
-        ev_ok = ev_ok && cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking) == cudaSuccess;
+        ev_ok = ev_ok && cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
     }
     if (rc || !ev_ok) {
         epivo_seq_destroy(s);
