@@ -174,3 +174,19 @@ def test_stress_sweep_properties(ctx):
     sel = rng.choice(M, 32, replace=False)
     oc, _ = O.score_models(Es[sel], x1, x2, O.ransac_threshold(2.0, pr.K))
     assert np.array_equal(counts[sel], oc)
+
+
+def test_find_essential_large_n_matches_oracle(ctx):
+    """cfg4 upper size, N = 20000 correspondences (beyond what the round kernel stages in shared memory, so
+    the scoring reads global memory): the whole call against the oracle's restatement of OpenCV's loop."""
+    pr = synth.make_pair(seed=40_002, n=20000, outlier_frac=0.3)
+    gt = pr.gt_match
+    keep = gt >= 0
+    p0, p1 = pr.kp0[keep], pr.kp1[gt[keep]]
+    assert len(p0) > 13000
+    for method, thr in ((api.RANSAC, 1.0), (api.LMEDS, 0.01)):
+        E, mask, info = api.findEssentialMat(p0, p1, pr.K, method, 0.99, thr, ctx=ctx, return_info=True)
+        Eo, mo, io = O.find_essential_mat(p0, p1, pr.K.astype(np.float32), method, 0.99, thr, 1000)
+        assert info["iters"] == io["iters"]
+        assert np.array_equal(mask, mo)                    # bit-exact over > 13000 correspondences
+        assert esame(E, Eo) < 1e-6                         # the winning minimal sample is conditioned ~1e8 here
