@@ -179,6 +179,12 @@ def findEssentialMat(points1, points2, cameraMatrix, method: int = RANSAC, prob:
 
 def fivePoint(x1, x2, ctx: Context | None = None):
     """The minimal solver alone on m samples (m,5,2) of K-normalised points -> list of (k,3,3)."""
+    E, nm = fivePointRaw(x1, x2, ctx)
+    return [E[i, :nm[i]] for i in range(E.shape[0])]
+
+
+def fivePointRaw(x1, x2, ctx: Context | None = None):
+    """As fivePoint, without the per-sample Python list: (E (m,10,3,3) with the first n_models[i] valid, n_models (m,))."""
     ctx = ctx or default_context()
     x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(-1, 5, 2)
     x2 = np.ascontiguousarray(x2, dtype=np.float64).reshape(-1, 5, 2)
@@ -186,7 +192,7 @@ def fivePoint(x1, x2, ctx: Context | None = None):
     E = np.zeros((m, 10, 9), dtype=np.float64)
     nm = np.zeros(m, dtype=np.int32)
     ctx.check(ctx.lib.epivo_five_point(ctx.h, _p(x1), _p(x2), m, _p(E), _p(nm)))
-    return [E[i, :nm[i]].reshape(-1, 3, 3) for i in range(m)]
+    return E.reshape(m, 10, 3, 3), nm
 
 
 def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None,

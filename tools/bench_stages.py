@@ -57,10 +57,9 @@ for N, M, outl in [(2000, 4096, 0.3), (8000, 16384, 0.5), (20000, 65536, 0.7)]:
     x0, x1 = O.normalize_points(p.kp0, Kf), O.normalize_points(p.kp1, Kf)
     idx = np.stack([rng.choice(N, 5, replace=False) for _ in range(M)])
     X1, X2 = x0[idx], x1[idx]
-    dt = timed(lambda: api.fivePoint(X1, X2, ctx=ctx), reps=2)
-    sols = api.fivePoint(X1, X2, ctx=ctx)
-    nm = np.array([len(e) for e in sols])
-    models = np.concatenate(sols).reshape(-1, 9)[: M]
+    dt = timed(lambda: api.fivePointRaw(X1, X2, ctx=ctx), reps=2)
+    Es, nm = api.fivePointRaw(X1, X2, ctx=ctx)
+    models = np.concatenate([Es[i, :nm[i]] for i in range(M)]).reshape(-1, 9)[: M]
     dt2 = timed(lambda: api.scoreSampson(models, p.kp0, p.kp1, Kf, 1.0, ctx=ctx, medians=False), reps=2)
     out[f"cfg4_N{N}_M{M}"] = {"k2_samples_per_s": M / dt, "k3_hyp_points_per_s": len(models) * N / dt2,
                               "k3_gflops": len(models) * N * 34 / dt2 / 1e9, "models": int(nm.sum())}
