@@ -115,55 +115,71 @@ __device__ __forceinline__ double res_one(const Rt& T, const double* p, const do
     return r;
 }
 
-// One row of Dr_Deps: d r / d eps for T = Tl exp(eps) Tr (sign s for reverse reps)   [:109-208]
-// If `res` is non-null the residual of the same correspondence under T0 is returned through it
-// (the single-pair kernel evaluates both at the same transform).
-__device__ __forceinline__ void jac_row(const Rt& Tl, const Rt& Tr, const Rt& T0, double s, const double* p,
-                                        const double* p_, double hd, double* row, double* res = nullptr) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) row[j] = 0.0;
-    const double px = -p_[0], py = -p_[1];
-    const double A0 = T0.t[0] + px * T0.t[2], A1 = T0.t[1] + py * T0.t[2];
-    const double q0 = T0.R[0] * p[0] + T0.R[1] * p[1] + T0.R[2] * p[2];
-    const double q1 = T0.R[3] * p[0] + T0.R[4] * p[1] + T0.R[5] * p[2];
-    const double q2 = T0.R[6] * p[0] + T0.R[7] * p[1] + T0.R[8] * p[2];
-    const double B0 = q0 + px * q2, B1 = q1 + py * q2;
-    const double ATA = A0 * A0 + A1 * A1, BTB = B0 * B0 + B1 * B1;
-    const bool degenerate = (ATA == 0 || BTB == 0);                                 // [:152-154]: row stays 0
-    const double isa = degenerate ? 0.0 : rsqrt(ATA), isb = degenerate ? 0.0 : rsqrt(BTB);
+// Dr_Deps [:109-208] in two parts.  Everything that depends only on the correspondence and on the rep's
+// full transform T0 = Tl Tr (the same for every zeta of the rep's span) is computed once per point:
+struct JacCommon {
+    double px, py, A0, A1, q0, q1, q2, B0, B1, ka, kb, d0, iBTB, j00, j02, j12, g0, g1;
+    double res;          // res() of the same correspondence under T0 [:230-258]
+    bool degenerate;     // |A| == 0 or |B| == 0: the row stays zero [:152-154]
+};
+
+__device__ __forceinline__ void jac_common(const Rt& T0, const double* p, const double* p_, double hd, JacCommon& c) {
+    c.px = -p_[0];
+    c.py = -p_[1];
+    c.A0 = T0.t[0] + c.px * T0.t[2];
+    c.A1 = T0.t[1] + c.py * T0.t[2];
+    c.q0 = T0.R[0] * p[0] + T0.R[1] * p[1] + T0.R[2] * p[2];
+    c.q1 = T0.R[3] * p[0] + T0.R[4] * p[1] + T0.R[5] * p[2];
+    c.q2 = T0.R[6] * p[0] + T0.R[7] * p[1] + T0.R[8] * p[2];
+    c.B0 = c.q0 + c.px * c.q2;
+    c.B1 = c.q1 + c.py * c.q2;
+    const double ATA = c.A0 * c.A0 + c.A1 * c.A1, BTB = c.B0 * c.B0 + c.B1 * c.B1;
+    c.degenerate = (ATA == 0 || BTB == 0);
+    const double isa = c.degenerate ? 0.0 : rsqrt(ATA), isb = c.degenerate ? 0.0 : rsqrt(BTB);
     const double sa = ATA * isa, sb = BTB * isb;                                     // ||A||, ||B||
-    const double ka = isa * sb, kb = isb * sa;
-    const double d0 = (BTB > 0) ? sa * isb : 0.0;                                    // res(): d = 0 when ||B|| = 0
-    const double iBTB = isb * isb;
-    const double X0 = q0 * d0 + T0.t[0], X1 = q1 * d0 + T0.t[1], X2 = q2 * d0 + T0.t[2];
+    c.ka = isa * sb;
+    c.kb = isb * sa;
+    c.d0 = (BTB > 0) ? sa * isb : 0.0;                                               // res(): d = 0 when ||B|| = 0
+    c.iBTB = isb * isb;
+    const double X0 = c.q0 * c.d0 + T0.t[0], X1 = c.q1 * c.d0 + T0.t[1], X2 = c.q2 * c.d0 + T0.t[2];
     const double iz = 1.0 / X2;
-    if (res) {
+    {
         const double f0 = p_[0] - X0 * iz, f1 = p_[1] - X1 * iz, f2 = p_[2] - X2 * iz;
         double r = (f0 * f0 + f1 * f1 + f2 * f2) * 0.5;
         if (r > hd) r = hd * (sqrt(r) - hd * 0.5);
-        *res = r;
+        c.res = r;
     }
-    if (degenerate) return;
-    // u = Rr p, ut = tr  (the generator acts on Tr [p d0; 1] = Rr p d0 + tr)
-    const double u0 = Tr.R[0] * p[0] + Tr.R[1] * p[1] + Tr.R[2] * p[2];
-    const double u1 = Tr.R[3] * p[0] + Tr.R[4] * p[1] + Tr.R[5] * p[2];
-    const double u2 = Tr.R[6] * p[0] + Tr.R[7] * p[1] + Tr.R[8] * p[2];
-    double j00 = 0, j02 = 0, j12 = 0;   // J_pi rows: (j00, 0, j02), (0, j00, j12), 0
+    c.j00 = 0; c.j02 = 0; c.j12 = 0;          // J_pi rows: (j00, 0, j02), (0, j00, j12), 0
     if (X2 != 0) {
-        j00 = iz;
-        j02 = -X0 * (iz * iz);
-        j12 = -X1 * (iz * iz);
+        c.j00 = iz;
+        c.j02 = -X0 * (iz * iz);
+        c.j12 = -X1 * (iz * iz);
     }
     const double e0 = X0 * iz - p_[0];
     const double e1 = X1 * iz - p_[1];
     const double e2 = 1.0 - p_[2];
     const double ee = e0 * e0 + e1 * e1 + e2 * e2;
-    double g0 = e0, g1 = e1;                                                        // [:203-207]
+    c.g0 = e0;                                                                      // [:203-207]
+    c.g1 = e1;
     if (!(ee <= hd)) {
         const double k = hd * rsqrt(ee);
-        g0 = k * e0;
-        g1 = k * e1;
+        c.g0 = k * e0;
+        c.g1 = k * e1;
     }
+}
+
+// ... and the six columns of one zeta: d r / d eps for T = Tl exp(eps) Tr (sign s for reverse reps)
+__device__ __forceinline__ void jac_zeta(const JacCommon& c, const Rt& Tl, const Rt& Tr, double s, const double* p,
+                                         double* row) {
+    if (c.degenerate) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) row[j] = 0.0;
+        return;
+    }
+    // u = Rr p, ut = tr  (the generator acts on Tr [p d0; 1] = Rr p d0 + tr)
+    const double u0 = Tr.R[0] * p[0] + Tr.R[1] * p[1] + Tr.R[2] * p[2];
+    const double u1 = Tr.R[3] * p[0] + Tr.R[4] * p[1] + Tr.R[5] * p[2];
+    const double u2 = Tr.R[6] * p[0] + Tr.R[7] * p[1] + Tr.R[8] * p[2];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double mt0, mt1, mt2;          // M_j[:3,3]
@@ -184,14 +200,23 @@ __device__ __forceinline__ void jac_row(const Rt& Tl, const Rt& Tr, const Rt& T0
             mt1 = s * (Tl.R[3] * h0 + Tl.R[4] * h1 + Tl.R[5] * h2);
             mt2 = s * (Tl.R[6] * h0 + Tl.R[7] * h1 + Tl.R[8] * h2);
         }
-        const double dA0 = mt0 + px * mt2, dA1 = mt1 + py * mt2;
-        const double dB0 = mp0 + px * mp2, dB1 = mp1 + py * mp2;
-        const double jd = (ka * (A0 * dA0 + A1 * dA1) - kb * (B0 * dB0 + B1 * dB1)) * iBTB;   // [:162]
-        const double dX0 = mp0 * d0 + mt0 + q0 * jd;                                        // [:171,175]
-        const double dX1 = mp1 * d0 + mt1 + q1 * jd;
-        const double dX2 = mp2 * d0 + mt2 + q2 * jd;
-        row[j] = g0 * (j00 * dX0 + j02 * dX2) + g1 * (j00 * dX1 + j12 * dX2);
+        const double dA0 = mt0 + c.px * mt2, dA1 = mt1 + c.py * mt2;
+        const double dB0 = mp0 + c.px * mp2, dB1 = mp1 + c.py * mp2;
+        const double jd = (c.ka * (c.A0 * dA0 + c.A1 * dA1) - c.kb * (c.B0 * dB0 + c.B1 * dB1)) * c.iBTB;   // [:162]
+        const double dX0 = mp0 * c.d0 + mt0 + c.q0 * jd;                                                    // [:171,175]
+        const double dX1 = mp1 * c.d0 + mt1 + c.q1 * jd;
+        const double dX2 = mp2 * c.d0 + mt2 + c.q2 * jd;
+        row[j] = c.g0 * (c.j00 * dX0 + c.j02 * dX2) + c.g1 * (c.j00 * dX1 + c.j12 * dX2);
     }
+}
+
+// One row of Dr_Deps plus (optionally) the residual at the same transform: the single-pair kernel's form.
+__device__ __forceinline__ void jac_row(const Rt& Tl, const Rt& Tr, const Rt& T0, double s, const double* p,
+                                        const double* p_, double hd, double* row, double* res = nullptr) {
+    JacCommon c;
+    jac_common(T0, p, p_, hd, c);
+    if (res) *res = c.res;
+    jac_zeta(c, Tl, Tr, s, p, row);
 }
 
 struct LmArgs {
@@ -220,6 +245,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     double* sRed = sDelta + D;                     // [LM_THREADS]
     __shared__ double s_lambda, s_prevE, s_Hnorm, s_rnorm;
     __shared__ int s_stop, s_iters, s_piv;
+    __shared__ Rt s_identity;
 
     double* gT = p.T0s + (size_t)prob * nz * 16;
     const double* gpr = p.pr + (size_t)prob * nr * N * 3;
@@ -234,6 +260,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
         }
     }
     if (tid == 0) {
+        rt_identity(s_identity);
         s_lambda = p.lambda0;
         s_prevE = 1e10;                                                            // [:322]
         s_stop = 0;
@@ -273,30 +300,30 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
             const double wj = w[j];
             for (int base = 0; base < N; base += LM_TP) {
                 const int np = min(LM_TP, N - base);
-                // work item = (zeta in span | residual, point), point fastest: the lanes of a warp share the zeta
-                // (chain transforms are broadcast reads, no residual/Jacobian divergence inside a warp)
-                for (int it = tid; it < np * (span + 1); it += LM_THREADS) {
-                    const int pt = it % np, zi = it / np;
+                // work item = (point, lane group g): the per-point part of Dr_Deps (everything that depends only on
+                // the rep's full transform) is computed once and reused for the zetas g, g + LM_G, ... of the span;
+                // point fastest, so the lanes of a warp share g and the chain transforms are broadcast reads.
+                // The reference forms T0 = Tl * Tr per zeta [:96]; here every zeta of a rep uses the rep's own
+                // product sRep[j], which is the same matrix up to the association order of the chain.
+                constexpr int LM_G = 2;
+                for (int it = tid; it < np * LM_G; it += LM_THREADS) {
+                    const int pt = it % np, g = it / np;
                     const double* pp = gpr + ((size_t)j * N + base + pt) * 3;
                     const double* pq = gp_r + ((size_t)j * N + base + pt) * 3;
                     double* dst = sJ + (size_t)pt * JS;
-                    if (zi == span) {
-                        dst[W] = wj * res_one(sRep[j], pp, pq, hd);                  // [:356-359]
-                    } else {
+                    JacCommon cm;
+                    jac_common(sRep[j], pp, pq, hd, cm);
+                    if (g == 0) dst[W] = wj * cm.res;                                // [:356-359]
+                    for (int zi = g; zi < span; zi += LM_G) {
                         const int k = lo + zi;
-                        Rt Tl, Tr;
-                        rt_identity(Tr);
-                        if (fwd) {                                                  // [:271-275]
-                            if (z0 < k) Tr = sMem[z0 * nz + (k - 1)];
-                            Tl = sMem[k * nz + z1];
-                        } else {                                                    // [:276-281]
-                            if (z0 > k) Tr = sInv[(k + 1) * nz + z0];
-                            Tl = sInv[z1 * nz + k];
-                        }
-                        Rt T0;
-                        rt_mul(Tl, Tr, T0);                                         // [:96]
                         double row[6];
-                        jac_row(Tl, Tr, T0, fwd ? 1.0 : -1.0, pp, pq, hd, row);
+                        if (fwd) {                                                  // [:271-275]
+                            if (z0 < k) jac_zeta(cm, sMem[k * nz + z1], sMem[z0 * nz + (k - 1)], 1.0, pp, row);
+                            else jac_zeta(cm, sMem[k * nz + z1], s_identity, 1.0, pp, row);
+                        } else {                                                    // [:276-281]
+                            if (z0 > k) jac_zeta(cm, sInv[z1 * nz + k], sInv[(k + 1) * nz + z0], -1.0, pp, row);
+                            else jac_zeta(cm, sInv[z1 * nz + k], s_identity, -1.0, pp, row);
+                        }
 #pragma unroll
                         for (int c = 0; c < 6; ++c) dst[6 * zi + c] = wj * row[c];  // [:381,397]
                     }
