@@ -323,6 +323,11 @@ class SequencePipeline:
         assert kps.shape == (F, self.kp, 2) and descs.shape == (F, self.kp, 32)
         self.ctx.check(self.ctx.lib.epivo_seq_upload(self.h, int(first_frame), F, _p(kps), _p(descs)))
 
+    def set_counts(self, counts, first_frame: int = 0):
+        """Keypoints actually present per frame slot (<= kp_per_frame); the remainder of a slot is ignored."""
+        c = np.ascontiguousarray(counts, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.epivo_seq_set_counts(self.h, int(first_frame), int(c.shape[0]), _p(c)))
+
     def run(self, params: PipelineParams, first_pair: int, n_pairs: int):
         self.ctx.check(self.ctx.lib.epivo_seq_run(self.h, C.byref(params), int(first_pair), int(n_pairs)))
 

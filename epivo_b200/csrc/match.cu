@@ -125,11 +125,12 @@ __device__ __forceinline__ uint32_t desc_dist(const uint32_t (&q)[WORDS], const 
     }
 }
 
-template <int WORDS, bool NORM2, bool TOP2>
+template <int WORDS, bool NORM2, bool TOP2, bool COUNTS>
 __global__ void __launch_bounds__(MT_THREADS, WORDS <= 8 ? EPV_MT_MINBLOCKS : 1)   // 64-byte descriptors need the registers
 match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int64_t t0, int64_t ts, int nq,
                   int nt, uint32_t* __restrict__ rowkey, uint32_t* __restrict__ rowkey2,
-                  uint32_t* __restrict__ colkey, int stride, int tiles_per_split, int64_t part_stride) {
+                  uint32_t* __restrict__ colkey, int stride, int tiles_per_split, int64_t part_stride,
+                  const int32_t* __restrict__ counts) {
     extern __shared__ uint32_t s_occupancy_pad[];   // unused: sized by the host to cap CTAs per SM (co-scheduling)
     __shared__ __align__(128) uint32_t s_tile[2][MT_TILE * WORDS];
     __shared__ uint32_t s_col[2][MT_THREADS / 32][MT_TILE];   // per-warp column minima of the tile in flight
@@ -139,6 +140,10 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int qbase = blockIdx.x * (MT_THREADS * MT_RQ);
+    if (COUNTS) {                       // frame sequences with a different number of keypoints per frame:
+        nq = counts[pair];              // pair p matches frame p (query) against frame p + 1 (train)
+        nt = counts[pair + 1];
+    }
     if (qbase >= nq) return;
     const uint32_t* qrows = desc + (q0 + (int64_t)pair * qs) * WORDS;
     const uint32_t* trows = desc + (t0 + (int64_t)pair * ts) * WORDS;
@@ -268,6 +273,10 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(FinalizePlan fp) {
     const int pair = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t o = (int64_t)pair * fp.stride;
+    if (fp.counts) {
+        fp.nq = fp.counts[pair];
+        fp.nt = fp.counts[pair + 1];
+    }
     if (tid == 0) s_base = 0;
     __syncthreads();
     for (int start = 0; start < fp.nq; start += 256) {
@@ -340,18 +349,25 @@ int launch_words(epivo_ctx* ctx, const MatchPlan& mp, const uint32_t* src) {
     const int64_t part = (int64_t)mp.n_pairs * mp.stride;
     dim3 block(MT_THREADS);
     const bool n2 = mp.norm == EPIVO_NORM_HAMMING2;
-#define EPV_MT(N2, T2)                                                                                     \
+#define EPV_MT(N2, T2, CN)                                                                                 \
     do {                                                                                                   \
         if (mp.pad_smem > 0)                                                                               \
-            cudaFuncSetAttribute(match_tile_kernel<WORDS, N2, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            cudaFuncSetAttribute(match_tile_kernel<WORDS, N2, T2, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  mp.pad_smem);                                                             \
-        match_tile_kernel<WORDS, N2, T2><<<grid, block, mp.pad_smem, ctx->stream>>>(                       \
-            src, mp.q0, mp.qs, mp.t0, mp.ts, mp.nq, mp.nt, mp.rowkey, mp.rowkey2, mp.colkey, mp.stride, tps, part); \
+        match_tile_kernel<WORDS, N2, T2, CN><<<grid, block, mp.pad_smem, ctx->stream>>>(                   \
+            src, mp.q0, mp.qs, mp.t0, mp.ts, mp.nq, mp.nt, mp.rowkey, mp.rowkey2, mp.colkey, mp.stride, tps, part, \
+            mp.counts);                                                                                    \
     } while (0)
-    if (n2 && mp.top2) EPV_MT(true, true);
-    else if (n2) EPV_MT(true, false);
-    else if (mp.top2) EPV_MT(false, true);
-    else EPV_MT(false, false);
+#define EPV_MT2(N2, T2)                     \
+    do {                                    \
+        if (mp.counts) EPV_MT(N2, T2, true); \
+        else EPV_MT(N2, T2, false);         \
+    } while (0)
+    if (n2 && mp.top2) EPV_MT2(true, true);
+    else if (n2) EPV_MT2(true, false);
+    else if (mp.top2) EPV_MT2(false, true);
+    else EPV_MT2(false, false);
+#undef EPV_MT2
 #undef EPV_MT
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
@@ -375,7 +391,7 @@ int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt) {
 // waves lose nothing to a partially filled last wave
 int epv_match_pairs_per_wave(const epivo_ctx* ctx, int nq) {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_tile_kernel<8, true, false>, MT_THREADS, 0) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_tile_kernel<8, true, false, false>, MT_THREADS, 0) != cudaSuccess ||
         occ < 1)
         occ = 2;
     const int qblocks = std::max(1, (nq + MT_THREADS * MT_RQ - 1) / (MT_THREADS * MT_RQ));

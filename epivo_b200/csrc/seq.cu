@@ -28,6 +28,8 @@ struct epivo_seq {
     float* d_kps = nullptr;
     uint32_t* d_desc = nullptr;
     uint32_t* d_planes = nullptr;
+    int32_t* d_counts = nullptr;     // keypoints actually present in every frame slot (<= kp)
+    bool counts_set = false;
     // per pair, whole sequence
     int32_t *d_mq = nullptr, *d_mt = nullptr, *d_md = nullptr, *d_nmatch = nullptr;
     uint8_t *d_emask = nullptr, *d_pmask = nullptr;
@@ -211,6 +213,7 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     A(d_kps, F * kp * 2);
     A(d_desc, F * kp * 8);
     A(d_planes, F * kp * 8);
+    A(d_counts, F);
     A(d_mq, P * st); A(d_mt, P * st); A(d_md, P * st); A(d_nmatch, P);
     A(d_emask, P * st); A(d_pmask, P * st);
     A(d_E, P * 9); A(d_R, P * 9); A(d_t, P * 3); A(d_T, P * 16); A(d_T0, P * 16);
@@ -250,6 +253,11 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     }
     const int32_t reps[2] = {0, 0};
     EPV_CUDA(ctx, cudaMemcpyAsync(s->d_reps, reps, 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        std::vector<int32_t> full((size_t)max_frames, kp_per_frame);
+        EPV_CUDA(ctx, cudaMemcpyAsync(s->d_counts, full.data(), full.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = s;
     return EPIVO_OK;
@@ -289,6 +297,21 @@ int epivo_seq_upload(epivo_seq* s, int first_frame, int n_frames, const float* k
                                   cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(s->d_desc + (size_t)first_frame * kp * 8, descs, (size_t)n_frames * kp * 32,
                                   cudaMemcpyHostToDevice, ctx->stream));
+    return EPIVO_OK;
+}
+
+int epivo_seq_set_counts(epivo_seq* s, int first_frame, int n_frames, const int32_t* counts) {
+    if (!s) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (first_frame < 0 || n_frames < 0 || first_frame + n_frames > s->max_frames || (n_frames > 0 && !counts))
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "frame range [%d,+%d) outside [0,%d)", first_frame, n_frames, s->max_frames);
+    for (int i = 0; i < n_frames; ++i)
+        if (counts[i] < 0 || counts[i] > s->kp) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "counts[%d] = %d outside [0,%d]", i, counts[i], s->kp);
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    // pageable source: the copy is staged before the call returns, so the caller's array may go away
+    EPV_CUDA(ctx, cudaMemcpyAsync(s->d_counts + first_frame, counts, (size_t)n_frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s->counts_set = true;
     return EPIVO_OK;
 }
 
@@ -412,6 +435,7 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
     mp.ev0 = s->evk[c][0];
     mp.ev1 = s->evk[c][1];
     mp.pad_smem = s->match_pad;
+    mp.counts = s->counts_set ? s->d_counts + p0 : nullptr;
     rc = epv_match_launch(ctx, mp, true);
     if (rc) return rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][1], ctx->stream));
@@ -444,6 +468,7 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
     fp.bx = -prm->K[2] * ax;
     fp.ay = ay;
     fp.by = -prm->K[5] * ay;
+    fp.counts = s->counts_set ? s->d_counts + p0 : nullptr;
     rc = epv_finalize_launch(ctx, fp);
     if (rc) return rc;
     return EPIVO_OK;

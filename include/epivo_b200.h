@@ -157,6 +157,9 @@ void epivo_seq_destroy(epivo_seq* seq);
 /* host -> device copy of n_frames frames starting at frame slot first_frame (async on the
  * context stream; kps n_frames x kp x 2 f32, descs n_frames x kp x 32 u8) */
 int epivo_seq_upload(epivo_seq* seq, int first_frame, int n_frames, const float* kps, const uint8_t* descs);
+/* Real detectors return a different number of keypoints per frame: counts[i] (<= kp_per_frame) keypoints of
+ * frame slot first_frame + i are valid (the rest of the slot is ignored).  Default: every slot is full. */
+int epivo_seq_set_counts(epivo_seq* seq, int first_frame, int n_frames, const int32_t* counts);
 /* enqueue the pipeline for pairs [first_pair, first_pair + n_pairs) (async) */
 int epivo_seq_run(epivo_seq* seq, const epivo_pipeline_params* p, int first_pair, int n_pairs);
 /* The reference-facing call with HOST buffers: upload n_frames frames (kps n_frames x kp x 2 f32,

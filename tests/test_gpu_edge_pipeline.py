@@ -96,3 +96,31 @@ def test_fewer_than_five_matches(ctx):
     assert np.allclose(res[0]["T"][:3, :3], np.eye(3)) and np.allclose(res[0]["T"][:3, 3], (0.1, 0.1, -0.9))
     _compare(pipe, res, kps, descs, synth.KITTI_K, 0)
     pipe.close()
+
+
+def test_variable_keypoint_counts_per_frame(ctx):
+    """Real detectors return a different number of keypoints per frame (kitti_ba.cpp:128 asks ORB for up to
+    10000): frames live in fixed-capacity slots and epivo_seq_set_counts says how much of each slot is valid."""
+    seq = synth.make_sequence(n_frames=6, n=900, seed=synth.seed_for(3, 45))
+    counts = np.array([900, 641, 777, 900, 512, 833], dtype=np.int32)
+    pipe = api.SequencePipeline(seq.n_frames, 900, ctx=ctx)
+    pipe.set_counts(counts)
+    prm = api.default_params(seq.K.astype(np.float32))
+    # poison the unused tail of every slot: it must not influence anything
+    kps, descs = seq.kps.copy(), seq.descs.copy()
+    for f, c in enumerate(counts):
+        kps[f, c:] = 1e6
+        descs[f, c:] = descs[f, :1]                        # exact duplicates of a valid descriptor would win matches
+    res = pipe.process(prm, kps, descs).copy()
+    for i in range(seq.n_pairs):
+        a, b = counts[i], counts[i + 1]
+        o = OP.pair_pipeline(seq.kps[i][:a], seq.descs[i][:a], seq.kps[i + 1][:b], seq.descs[i + 1][:b], seq.K)
+        qi, ti, d = pipe.matches(i)
+        assert np.array_equal(qi, o["matches"][0]) and np.array_equal(ti, o["matches"][1]) and np.array_equal(d, o["matches"][2])
+        em, pm = pipe.masks(i)
+        assert np.array_equal(em, o["e_mask"]) and np.array_equal(pm, o["pose_mask"])
+        assert res[i]["n_matches"] == len(qi) and res[i]["ransac_iters"] == o["e_info"]["iters"]
+        assert np.abs(res[i]["T"] - o["T"]).max() < 1e-6
+    with pytest.raises(api.EpivoError):
+        pipe.set_counts(np.array([901], dtype=np.int32))
+    pipe.close()
