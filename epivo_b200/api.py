@@ -295,11 +295,15 @@ def default_params(K=None, **kw) -> PipelineParams:
 class SequencePipeline:
     """Device-resident frame sequence + the fused per-pair pipeline (`epivo_seq`)."""
 
-    def __init__(self, max_frames: int, kp_per_frame: int, ctx: Context | None = None):
+    def __init__(self, max_frames: int, kp_per_frame: int, ctx: Context | None = None, max_pairs: int | None = None):
         self.ctx = ctx or default_context()
         self.max_frames, self.kp = int(max_frames), int(kp_per_frame)
+        self.max_pairs = self.max_frames - 1 if max_pairs is None else int(max_pairs)
+        self.n_pairs = self.max_frames - 1
+        self._pair_list = False
         h = C.c_void_p()
-        self.ctx.check(self.ctx.lib.epivo_seq_create(self.ctx.h, C.byref(h), self.max_frames, self.kp))
+        self.ctx.check(self.ctx.lib.epivo_seq_create_pairs(self.ctx.h, C.byref(h), self.max_frames, self.kp,
+                                                           self.max_pairs))
         self.h = h
         self.ctx._children.add(self)
 
@@ -328,6 +332,21 @@ class SequencePipeline:
         c = np.ascontiguousarray(counts, dtype=np.int32)
         self.ctx.check(self.ctx.lib.epivo_seq_set_counts(self.h, int(first_frame), int(c.shape[0]), _p(c)))
 
+    def set_pairs(self, fq=None, ft=None):
+        """Explicit pair list: pair p matches frame fq[p] (query) against ft[p] (train), as the window walk of
+        kitti_ba.cpp:603-607 does; None restores the consecutive pairs (p, p + 1)."""
+        if fq is None or ft is None or len(fq) == 0:
+            self.ctx.check(self.ctx.lib.epivo_seq_set_pairs(self.h, 0, None, None))
+            self.n_pairs = self.max_frames - 1
+            self._pair_list = False
+            return
+        a = np.ascontiguousarray(fq, dtype=np.int32)
+        b = np.ascontiguousarray(ft, dtype=np.int32)
+        assert a.shape == b.shape and a.ndim == 1
+        self.ctx.check(self.ctx.lib.epivo_seq_set_pairs(self.h, int(a.shape[0]), _p(a), _p(b)))
+        self.n_pairs = int(a.shape[0])
+        self._pair_list = True
+
     def run(self, params: PipelineParams, first_pair: int, n_pairs: int):
         self.ctx.check(self.ctx.lib.epivo_seq_run(self.h, C.byref(params), int(first_pair), int(n_pairs)))
 
@@ -338,9 +357,10 @@ class SequencePipeline:
         assert kps.flags.c_contiguous and descs.flags.c_contiguous
         F = kps.shape[0]
         assert kps.shape == (F, self.kp, 2) and descs.shape == (F, self.kp, 32)
+        n_out = self.n_pairs if self._pair_list else F - 1
         if out is None:
-            out = np.zeros(F - 1, dtype=RESULT_DTYPE)
-        assert out.dtype == RESULT_DTYPE and out.shape[0] >= F - 1
+            out = np.zeros(n_out, dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and out.shape[0] >= n_out
         self.ctx.check(self.ctx.lib.epivo_seq_process(self.h, C.byref(params), F, _p(kps), _p(descs), _p(out)))
         return out
 

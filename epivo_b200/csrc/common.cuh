@@ -89,7 +89,12 @@ struct MatchPlan {
     int stride;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // optional: recorded right around the tile kernel
     int pad_smem = 0;          // extra dynamic shared memory per CTA (bytes) to cap resident CTAs per SM
-    const int32_t* counts = nullptr;   // optional per-frame row counts (device): pair p uses counts[p] x counts[p+1] <= nq x nt
+    // optional general addressing (device arrays; all three or none): pair p matches frame fq[p] against frame
+    // ft[p] of a frame array with qs (= ts) rows per slot, counts[frame] of them valid; q0 / t0 are ignored
+    const int32_t* fq = nullptr;
+    const int32_t* ft = nullptr;
+    const int32_t* counts = nullptr;
+    int64_t prepass_row0 = 0;  // first row of desc / planes the HAMMING2 plane pre-pass converts (total_rows rows)
 };
 int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass);
 int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt);   // train splits that fill the GPU
@@ -114,6 +119,8 @@ struct FinalizePlan {
     float* p1;
     double* xn;                // [n_pairs][4][stride]: x1, y1, x2, y2 normalised
     double ax, bx, ay, by;     // x = u*ax + bx
-    const int32_t* counts = nullptr;   // optional per-frame row counts (device), as in MatchPlan
+    const int32_t* fq = nullptr;       // optional general addressing, as in MatchPlan
+    const int32_t* ft = nullptr;
+    const int32_t* counts = nullptr;
 };
 int epv_finalize_launch(epivo_ctx* ctx, const FinalizePlan& fp);

@@ -923,7 +923,10 @@ five_point_b2_kernel(const double* __restrict__ rec, int m, const uint32_t* __re
 // in shared memory (broadcast reads); votes are counted per warp with ballot + popc, per CTA
 // in shared memory and per model with one global atomicAdd per (CTA, model).
 constexpr int SC_THREADS = 256;
-constexpr int SC_PPT = 4;                    // correspondences per thread, in registers
+#ifndef EPV_SC_PPT
+#define EPV_SC_PPT 4
+#endif
+constexpr int SC_PPT = EPV_SC_PPT;           // correspondences per thread, in registers
 constexpr int SC_MODELS = 128;               // models per CTA tile, at most
 
 __global__ void __launch_bounds__(SC_THREADS)

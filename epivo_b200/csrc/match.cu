@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(MT_THREADS, WORDS <= 8 ? EPV_MT_MINBLOCKS : 1)
 match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int64_t t0, int64_t ts, int nq,
                   int nt, uint32_t* __restrict__ rowkey, uint32_t* __restrict__ rowkey2,
                   uint32_t* __restrict__ colkey, int stride, int tiles_per_split, int64_t part_stride,
-                  const int32_t* __restrict__ counts) {
+                  const int32_t* __restrict__ fq, const int32_t* __restrict__ ft, const int32_t* __restrict__ counts) {
     extern __shared__ uint32_t s_occupancy_pad[];   // unused: sized by the host to cap CTAs per SM (co-scheduling)
     __shared__ __align__(128) uint32_t s_tile[2][MT_TILE * WORDS];
     __shared__ uint32_t s_col[2][MT_THREADS / 32][MT_TILE];   // per-warp column minima of the tile in flight
@@ -140,13 +140,19 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int qbase = blockIdx.x * (MT_THREADS * MT_RQ);
-    if (COUNTS) {                       // frame sequences with a different number of keypoints per frame:
-        nq = counts[pair];              // pair p matches frame p (query) against frame p + 1 (train)
-        nt = counts[pair + 1];
+    // GENERAL variant (template flag COUNTS): pair p matches frame fq[p] (query) against frame ft[p] (train) of a
+    // frame array with qs rows per frame slot, of which counts[frame] are valid
+    int64_t qrow0 = q0 + (int64_t)pair * qs, trow0 = t0 + (int64_t)pair * ts;
+    if (COUNTS) {
+        const int f0 = fq[pair], f1 = ft[pair];
+        nq = counts[f0];
+        nt = counts[f1];
+        qrow0 = (int64_t)f0 * qs;
+        trow0 = (int64_t)f1 * ts;
     }
     if (qbase >= nq) return;
-    const uint32_t* qrows = desc + (q0 + (int64_t)pair * qs) * WORDS;
-    const uint32_t* trows = desc + (t0 + (int64_t)pair * ts) * WORDS;
+    const uint32_t* qrows = desc + qrow0 * WORDS;
+    const uint32_t* trows = desc + trow0 * WORDS;
     // this CTA's share of the train tiles (blockIdx.z splits the train set so that a single
     // small pair still fills the GPU; a batch of pairs uses one split)
     const int tile0 = blockIdx.z * tiles_per_split;
@@ -273,9 +279,13 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(FinalizePlan fp) {
     const int pair = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t o = (int64_t)pair * fp.stride;
-    if (fp.counts) {
-        fp.nq = fp.counts[pair];
-        fp.nt = fp.counts[pair + 1];
+    int64_t qrow0 = fp.q0 + (int64_t)pair * fp.qs, trow0 = fp.t0 + (int64_t)pair * fp.ts;   // keypoint rows of the pair
+    if (fp.fq) {
+        const int f0 = fp.fq[pair], f1 = fp.ft[pair];
+        fp.nq = fp.counts[f0];
+        fp.nt = fp.counts[f1];
+        qrow0 = (int64_t)f0 * fp.qs;
+        trow0 = (int64_t)f1 * fp.ts;
     }
     if (tid == 0) s_base = 0;
     __syncthreads();
@@ -315,8 +325,8 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(FinalizePlan fp) {
             if (fp.md) fp.md[o + k] = (int)(rk >> EPV_KEY_SHIFT);
             if (fp.md2 && fp.mode == EPIVO_MATCH_RATIO) fp.md2[o + k] = (int)(rk2 >> EPV_KEY_SHIFT);
             if (fp.kps) {
-                const float2 a = reinterpret_cast<const float2*>(fp.kps)[fp.q0 + (int64_t)pair * fp.qs + qi];
-                const float2 b = reinterpret_cast<const float2*>(fp.kps)[fp.t0 + (int64_t)pair * fp.ts + t];
+                const float2 a = reinterpret_cast<const float2*>(fp.kps)[qrow0 + qi];
+                const float2 b = reinterpret_cast<const float2*>(fp.kps)[trow0 + t];
                 if (fp.p0) {
                     reinterpret_cast<float2*>(fp.p0)[o + k] = a;
                     reinterpret_cast<float2*>(fp.p1)[o + k] = b;
@@ -356,11 +366,11 @@ int launch_words(epivo_ctx* ctx, const MatchPlan& mp, const uint32_t* src) {
                                  mp.pad_smem);                                                             \
         match_tile_kernel<WORDS, N2, T2, CN><<<grid, block, mp.pad_smem, ctx->stream>>>(                   \
             src, mp.q0, mp.qs, mp.t0, mp.ts, mp.nq, mp.nt, mp.rowkey, mp.rowkey2, mp.colkey, mp.stride, tps, part, \
-            mp.counts);                                                                                    \
+            mp.fq, mp.ft, mp.counts);                                                                      \
     } while (0)
 #define EPV_MT2(N2, T2)                     \
     do {                                    \
-        if (mp.counts) EPV_MT(N2, T2, true); \
+        if (mp.fq) EPV_MT(N2, T2, true);    \
         else EPV_MT(N2, T2, false);         \
     } while (0)
     if (n2 && mp.top2) EPV_MT2(true, true);
@@ -411,7 +421,8 @@ int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass) {
     if (mp.norm == EPIVO_NORM_HAMMING2) {
         if (run_prepass) {
             int64_t n = mp.total_rows * (mp.words / 2);
-            desc_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mp.desc, mp.planes,
+            const int64_t off = mp.prepass_row0 * mp.words;
+            desc_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mp.desc + off, mp.planes + off,
                                                                                      mp.total_rows, mp.words);
             EPV_LAUNCHED(ctx);
         }

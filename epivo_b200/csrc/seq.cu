@@ -30,6 +30,12 @@ struct epivo_seq {
     uint32_t* d_planes = nullptr;
     int32_t* d_counts = nullptr;     // keypoints actually present in every frame slot (<= kp)
     bool counts_set = false;
+    // pair list: pair p matches frame fq[p] (query) against frame ft[p] (train); the default is (p, p + 1).
+    // kitti_ba.cpp:603-607 walks (i + window[j].first, i + window[j].second) -- an arbitrary list of this kind
+    int32_t *d_fq = nullptr, *d_ft = nullptr;
+    bool pairs_set = false;
+    int max_pairs = 0, n_list = 0;   // capacity / pairs currently addressable
+    int frames_hi = 0;               // frames [0, frames_hi) have been uploaded (plane pre-pass range in list mode)
     // per pair, whole sequence
     int32_t *d_mq = nullptr, *d_mt = nullptr, *d_md = nullptr, *d_nmatch = nullptr;
     uint8_t *d_emask = nullptr, *d_pmask = nullptr;
@@ -195,9 +201,14 @@ void epivo_pipeline_params_default(epivo_pipeline_params* p) {
 }
 
 int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per_frame) {
+    return epivo_seq_create_pairs(ctx, out, max_frames, kp_per_frame, max_frames - 1);
+}
+
+int epivo_seq_create_pairs(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per_frame, int max_pairs) {
     if (!ctx || !out) return EPIVO_ERR_INVALID;
     *out = nullptr;
     if (max_frames < 2 || kp_per_frame < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "need >= 2 frames and >= 1 keypoint");
+    if (max_pairs < max_frames - 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "max_pairs %d < max_frames - 1", max_pairs);
     if (kp_per_frame > (int)EPV_IDX_MASK) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "too many keypoints per frame");
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     epivo_seq* s = new epivo_seq();
@@ -205,7 +216,9 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     s->max_frames = max_frames;
     s->kp = kp_per_frame;
     s->stride = (kp_per_frame + 31) / 32 * 32;
-    const size_t F = max_frames, P = max_frames - 1, st = s->stride, kp = kp_per_frame;
+    s->max_pairs = max_pairs;
+    s->n_list = max_frames - 1;
+    const size_t F = max_frames, P = max_pairs, st = s->stride, kp = kp_per_frame;
     s->chunk = (int)std::min<size_t>(SEQ_CHUNK, P);
     const size_t C = P;        // group-scoped buffers are allocated for every pair, so groups never alias
     int rc = 0;
@@ -214,6 +227,7 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
     A(d_desc, F * kp * 8);
     A(d_planes, F * kp * 8);
     A(d_counts, F);
+    A(d_fq, P); A(d_ft, P);
     A(d_mq, P * st); A(d_mt, P * st); A(d_md, P * st); A(d_nmatch, P);
     A(d_emask, P * st); A(d_pmask, P * st);
     A(d_E, P * 9); A(d_R, P * 9); A(d_t, P * 3); A(d_T, P * 16); A(d_T0, P * 16);
@@ -258,6 +272,9 @@ int epivo_seq_create(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per
         EPV_CUDA(ctx, cudaMemcpyAsync(s->d_counts, full.data(), full.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    rc = epivo_seq_set_pairs(s, 0, nullptr, nullptr);      // consecutive pairs (p, p + 1)
+    if (rc) { epivo_seq_destroy(s); return rc; }
+    s->pairs_set = false;
     EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = s;
     return EPIVO_OK;
@@ -297,6 +314,35 @@ int epivo_seq_upload(epivo_seq* s, int first_frame, int n_frames, const float* k
                                   cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(s->d_desc + (size_t)first_frame * kp * 8, descs, (size_t)n_frames * kp * 32,
                                   cudaMemcpyHostToDevice, ctx->stream));
+    s->frames_hi = std::max(s->frames_hi, first_frame + n_frames);
+    return EPIVO_OK;
+}
+
+int epivo_seq_set_pairs(epivo_seq* s, int n_pairs, const int32_t* fq, const int32_t* ft) {
+    if (!s) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    std::vector<int32_t> h;
+    if (n_pairs <= 0 || !fq || !ft) {                      // back to the consecutive pairs (p, p + 1)
+        n_pairs = s->max_frames - 1;
+        h.resize((size_t)n_pairs * 2);
+        for (int p = 0; p < n_pairs; ++p) { h[p] = p; h[(size_t)n_pairs + p] = p + 1; }
+        s->pairs_set = false;
+    } else {
+        if (n_pairs > s->max_pairs) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "%d pairs > capacity %d (epivo_seq_create_pairs)", n_pairs, s->max_pairs);
+        h.resize((size_t)n_pairs * 2);
+        for (int p = 0; p < n_pairs; ++p) {
+            if (fq[p] < 0 || fq[p] >= s->max_frames || ft[p] < 0 || ft[p] >= s->max_frames)
+                EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair %d = (%d,%d) outside [0,%d)", p, fq[p], ft[p], s->max_frames);
+            h[p] = fq[p];
+            h[(size_t)n_pairs + p] = ft[p];
+        }
+        s->pairs_set = true;
+    }
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    EPV_CUDA(ctx, cudaMemcpyAsync(s->d_fq, h.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(s->d_ft, h.data() + n_pairs, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s->n_list = n_pairs;
     return EPIVO_OK;
 }
 
@@ -435,8 +481,23 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
     mp.ev0 = s->evk[c][0];
     mp.ev1 = s->evk[c][1];
     mp.pad_smem = s->match_pad;
-    mp.counts = s->counts_set ? s->d_counts + p0 : nullptr;
-    rc = epv_match_launch(ctx, mp, true);
+    const bool general = s->counts_set || s->pairs_set;     // per-frame counts and / or an explicit pair list
+    bool prepass = true;
+    if (general) {
+        mp.desc = s->d_desc;                                // frames are addressed through fq / ft from the array base
+        mp.planes = s->d_planes;
+        mp.fq = s->d_fq + p0;
+        mp.ft = s->d_ft + p0;
+        mp.counts = s->d_counts;
+        if (s->pairs_set) {                                 // any frame may be referenced: convert every uploaded
+            prepass = (c == 0);                             // frame once per run, with the first group
+            mp.prepass_row0 = 0;
+            mp.total_rows = (int64_t)s->frames_hi * kp;
+        } else {
+            mp.prepass_row0 = (int64_t)p0 * kp;
+        }
+    }
+    rc = epv_match_launch(ctx, mp, prepass);
     if (rc) return rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][1], ctx->stream));
     FinalizePlan fp{};
@@ -468,7 +529,12 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
     fp.bx = -prm->K[2] * ax;
     fp.ay = ay;
     fp.by = -prm->K[5] * ay;
-    fp.counts = s->counts_set ? s->d_counts + p0 : nullptr;
+    if (general) {
+        fp.kps = s->d_kps;
+        fp.fq = s->d_fq + p0;
+        fp.ft = s->d_ft + p0;
+        fp.counts = s->d_counts;
+    }
     rc = epv_finalize_launch(ctx, fp);
     if (rc) return rc;
     return EPIVO_OK;
@@ -478,18 +544,22 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
 // the copy stream and every matcher group starts as soon as its frames have landed, so the
 // host->device transfer hides under the matcher; the geometry then runs once over all pairs.
 static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair, int n_pairs,
-                       const float* h_kps, const uint8_t* h_desc) {
+                       const float* h_kps, const uint8_t* h_desc, int n_frames_up) {
     epivo_ctx* ctx = s->ctx;
-    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
-        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range [%d,+%d) outside [0,%d)", first_pair, n_pairs, s->max_frames - 1);
+    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->n_list)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range [%d,+%d) outside [0,%d)", first_pair, n_pairs, s->n_list);
     if (prm->lm_points < 1 || prm->lm_points > 64) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "lm_points must be in [1,64]");
     if (prm->method != EPIVO_RANSAC && prm->method != EPIVO_LMEDS) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "method");
     if (prm->match_mode < 0 || prm->match_mode > 2) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "match_mode");
     if (prm->norm != EPIVO_NORM_HAMMING && prm->norm != EPIVO_NORM_HAMMING2) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "norm");
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t main_stream = ctx->stream;
-    const bool upload = h_kps != nullptr;
-    const bool overlap = s->overlap && !upload;
+    // an explicit pair list may reference any frame: host buffers are then uploaded whole before the first group
+    const bool upload_all = h_kps != nullptr && s->pairs_set;
+    const bool upload = h_kps != nullptr && !upload_all;
+    const bool overlap = s->overlap && !upload && !upload_all;
+    if (upload_all) s->frames_hi = std::max(s->frames_hi, n_frames_up);
+    if (s->pairs_set && s->frames_hi == 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair list set but no frames uploaded");
     // matcher groups / geometry groups (event slots: matcher [0, HALF), geometry [HALF, 2*HALF))
     constexpr int HALF = SEQ_MAX_CHUNKS / 2;
     // matcher groups.  Resident data: uniform groups.  Host buffers: the upload is cut into pieces of
@@ -535,6 +605,13 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
             EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], s->stream2));
         }
     }
+    if (upload_all) {
+        EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
+        EPV_CUDA(ctx, cudaMemcpyAsync(s->d_kps, h_kps, (size_t)n_frames_up * kp * 8, cudaMemcpyHostToDevice, s->stream2));
+        EPV_CUDA(ctx, cudaMemcpyAsync(s->d_desc, h_desc, (size_t)n_frames_up * kp * 32, cudaMemcpyHostToDevice, s->stream2));
+        EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[0], s->stream2));
+        EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_matched[0], 0));
+    }
     if (overlap) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
     for (int c = 0; c < n_m && !rc; ++c) {
         const int p0 = mg[c].first, np = mg[c].second;
@@ -568,7 +645,7 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
 
 int epivo_seq_run(epivo_seq* s, const epivo_pipeline_params* prm, int first_pair, int n_pairs) {
     if (!s || !prm) return EPIVO_ERR_INVALID;
-    return seq_execute(s, prm, first_pair, n_pairs, nullptr, nullptr);
+    return seq_execute(s, prm, first_pair, n_pairs, nullptr, nullptr, 0);
 }
 
 int epivo_seq_process(epivo_seq* s, const epivo_pipeline_params* prm, int n_frames, const float* kps,
@@ -577,15 +654,17 @@ int epivo_seq_process(epivo_seq* s, const epivo_pipeline_params* prm, int n_fram
     epivo_ctx* ctx = s->ctx;
     if (!kps || !descs || !out) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null buffer");
     if (n_frames < 2 || n_frames > s->max_frames) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_frames %d outside [2,%d]", n_frames, s->max_frames);
-    int rc = seq_execute(s, prm, 0, n_frames - 1, kps, descs);
+    // consecutive pairs: n_frames - 1 of them; explicit pair list (epivo_seq_set_pairs): the whole list
+    const int n_pairs = s->pairs_set ? s->n_list : n_frames - 1;
+    int rc = seq_execute(s, prm, 0, n_pairs, kps, descs, n_frames);
     if (rc) return rc;
-    return epivo_seq_download(s, out, 0, n_frames - 1);
+    return epivo_seq_download(s, out, 0, n_pairs);
 }
 
 int epivo_seq_download(epivo_seq* s, epivo_pair_result* out, int first_pair, int n_pairs) {
     if (!s || !out) return EPIVO_ERR_INVALID;
     epivo_ctx* ctx = s->ctx;
-    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
+    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->n_list)
         EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range");
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     // a pinned caller buffer takes the DMA directly; pageable memory goes through the pinned staging copy
@@ -604,8 +683,8 @@ int epivo_seq_cloud(epivo_seq* s, const double* scales, int first_pair, int n_pa
                     int64_t cap, int64_t* limits, int64_t* n_points) {
     if (!s) return EPIVO_ERR_INVALID;
     epivo_ctx* ctx = s->ctx;
-    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->max_frames - 1)
-        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range [%d,+%d) outside [0,%d)", first_pair, n_pairs, s->max_frames - 1);
+    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > s->n_list)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair range [%d,+%d) outside [0,%d)", first_pair, n_pairs, s->n_list);
     if (first_pair < s->last_first || first_pair + n_pairs > s->last_first + s->last_n_pairs)
         EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pairs [%d,+%d) were not part of the last run", first_pair, n_pairs);
     if (n_points) *n_points = 0;
@@ -687,7 +766,7 @@ int epivo_seq_stage_ms(epivo_seq* s, float* ms, int n) {
 int epivo_seq_get_matches(epivo_seq* s, int pair, int32_t* query_idx, int32_t* train_idx, int32_t* dist, int* n_out) {
     if (!s || !n_out) return EPIVO_ERR_INVALID;
     epivo_ctx* ctx = s->ctx;
-    if (pair < 0 || pair >= s->max_frames - 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair index");
+    if (pair < 0 || pair >= s->n_list) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair index");
     int32_t n = 0;
     const size_t o = (size_t)pair * s->stride;
     EPV_CUDA(ctx, cudaMemcpyAsync(&n, s->d_nmatch + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -703,7 +782,7 @@ int epivo_seq_get_matches(epivo_seq* s, int pair, int32_t* query_idx, int32_t* t
 int epivo_seq_get_masks(epivo_seq* s, int pair, uint8_t* e_mask, int* n_e, uint8_t* pose_mask, int* n_pose) {
     if (!s) return EPIVO_ERR_INVALID;
     epivo_ctx* ctx = s->ctx;
-    if (pair < 0 || pair >= s->max_frames - 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair index");
+    if (pair < 0 || pair >= s->n_list) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair index");
     int32_t nm = 0, ni = 0;
     const size_t o = (size_t)pair * s->stride;
     EPV_CUDA(ctx, cudaMemcpyAsync(&nm, s->d_nmatch + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));

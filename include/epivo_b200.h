@@ -160,6 +160,14 @@ int epivo_seq_upload(epivo_seq* seq, int first_frame, int n_frames, const float*
 /* Real detectors return a different number of keypoints per frame: counts[i] (<= kp_per_frame) keypoints of
  * frame slot first_frame + i are valid (the rest of the slot is ignored).  Default: every slot is full. */
 int epivo_seq_set_counts(epivo_seq* seq, int first_frame, int n_frames, const int32_t* counts);
+/* Explicit pair list.  kitti_ba.cpp:603-607 does not walk consecutive frames only: it matches
+ * (i + window[j].first, i + window[j].second) for every window offset j (e.g. (0,1), (0,2), (1,2), or the
+ * left/right frames of a stereo rig).  After this call pair p matches frame fq[p] (query, desc0 of
+ * kitti_ba.cpp:630) against frame ft[p] (train, desc1), and run / process / download / get_matches address
+ * pairs [0, n_pairs).  epivo_seq_create_pairs gives room for more pairs than max_frames - 1.
+ * n_pairs = 0 or NULL lists restore the default (p, p + 1).  epivo_seq_cloud's pose chain assumes consecutive pairs. */
+int epivo_seq_create_pairs(epivo_ctx* ctx, epivo_seq** out, int max_frames, int kp_per_frame, int max_pairs);
+int epivo_seq_set_pairs(epivo_seq* seq, int n_pairs, const int32_t* fq, const int32_t* ft);
 /* enqueue the pipeline for pairs [first_pair, first_pair + n_pairs) (async) */
 int epivo_seq_run(epivo_seq* seq, const epivo_pipeline_params* p, int first_pair, int n_pairs);
 /* The reference-facing call with HOST buffers: upload n_frames frames (kps n_frames x kp x 2 f32,

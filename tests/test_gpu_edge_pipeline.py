@@ -124,3 +124,58 @@ def test_variable_keypoint_counts_per_frame(ctx):
     with pytest.raises(api.EpivoError):
         pipe.set_counts(np.array([901], dtype=np.int32))
     pipe.close()
+
+
+def test_explicit_pair_list_window_walk(ctx):
+    """kitti_ba.cpp:603-607 matches (i + window[j].first, i + window[j].second) for every window offset, not only
+    consecutive frames: epivo_seq_set_pairs takes that list (more pairs than frames, repeated and reversed pairs,
+    per-frame keypoint counts at the same time)."""
+    seq = synth.make_sequence(n_frames=5, n=700, seed=synth.seed_for(3, 46))
+    counts = np.array([700, 655, 700, 512, 689], dtype=np.int32)
+    window = [(0, 1), (0, 2), (1, 2), (1, 0)]
+    fq, ft = [], []
+    for i in range(seq.n_frames):
+        for a, b in window:
+            if max(i + a, i + b) < seq.n_frames:
+                fq.append(i + a)
+                ft.append(i + b)
+    assert len(fq) > seq.n_frames - 1
+    prm = api.default_params(seq.K.astype(np.float32))
+    kps, descs = seq.kps.copy(), seq.descs.copy()
+    for f, c in enumerate(counts):
+        kps[f, c:] = -1e6
+        descs[f, c:] = descs[f, :1]
+    with pytest.raises(api.EpivoError):                       # capacity is fixed at creation
+        small = api.SequencePipeline(seq.n_frames, 700, ctx=ctx)
+        try:
+            small.set_pairs(fq, ft)
+        finally:
+            small.close()
+    pipe = api.SequencePipeline(seq.n_frames, 700, ctx=ctx, max_pairs=len(fq))
+    pipe.set_counts(counts)
+    pipe.set_pairs(fq, ft)
+    res = pipe.process(prm, kps, descs).copy()                # host-buffer path
+    assert res.shape[0] == len(fq)
+    for p, (a, b) in enumerate(zip(fq, ft)):
+        ca, cb = counts[a], counts[b]
+        o = OP.pair_pipeline(seq.kps[a][:ca], seq.descs[a][:ca], seq.kps[b][:cb], seq.descs[b][:cb], seq.K)
+        qi, ti, d = pipe.matches(p)
+        assert np.array_equal(qi, o["matches"][0]) and np.array_equal(ti, o["matches"][1]) and np.array_equal(d, o["matches"][2])
+        em, pm = pipe.masks(p)
+        assert np.array_equal(em, o["e_mask"]) and np.array_equal(pm, o["pose_mask"])
+        assert res[p]["n_matches"] == len(qi) and res[p]["ransac_iters"] == o["e_info"]["iters"]
+        assert np.abs(res[p]["T"] - o["T"]).max() < 1e-6
+    # resident path, a sub-range of the list, plain Hamming (no plane pre-pass): same pairs -> same matches
+    pipe.run(prm, 3, 5)
+    again = pipe.download(3, 5)
+    assert again.tobytes() == res[3:8].tobytes()
+    with pytest.raises(api.EpivoError):
+        pipe.set_pairs([0, 5], [1, 2])                        # frame index out of range
+    # back to consecutive pairs
+    pipe.set_pairs(None, None)
+    pipe.run(prm, 0, seq.n_frames - 1)
+    cons = pipe.download(0, seq.n_frames - 1)
+    for i in range(seq.n_frames - 1):
+        p = [k for k, (a, b) in enumerate(zip(fq, ft)) if (a, b) == (i, i + 1)][0]
+        assert cons[i].tobytes() == res[p].tobytes()
+    pipe.close()
