@@ -93,9 +93,21 @@ __device__ __forceinline__ float sampson_f32(const double* __restrict__ E, doubl
 //     num/den >  B (1 + 2^-50)    =>  RN64(num/den) >  B        => outlier
 // and the sign of B*den - num is exact in one FMA.  Only quotients within 2^-50 of B (or
 // den == 0 / NaN) take the division; num and den are the same un-fused values OpenCV computes.
+// high 32 bits of a double: for positive normal x, y:  hi(x) > hi(y)  =>  x > y,  and hi(y 2^e) = hi(y) + (e << 20)
+__host__ __device__ inline int samp_hi(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return (int)(b >> 32);
+#endif
+}
+
 struct SampThr {
     double B, C;     // C = B * 2^-50
     double Blo, Bhi, dmin;   // pre-filter of sampson_inlier_unit: B (1 -+ 2e-6); smallest trusted denominator
+    int eoff, hdmin;         // integer form of the pre-filter: see prefilter_decide()
     float thr32;
 };
 __host__ __device__ inline SampThr make_samp_thr(float thr32) {
@@ -128,6 +140,18 @@ __host__ __device__ inline SampThr make_samp_thr(float thr32) {
     t.Blo = mid * (1.0 - 2e-6);
     t.Bhi = mid * (1.0 + 2e-6);
     t.dmin = mid > 0.0 ? fmax(1e-8, 1e-13 / mid) : 1e300;     // invalid threshold: the pre-filter never decides
+    // integer pre-filter: 2^e = the smallest power of two >= 2.1e-6 B, as an offset on the high word of a double
+    {
+        int e = 0;
+        if (mid > 1e-200) {
+            const double m = frexp(mid * 2.1e-6, &e);          // mid * 2.1e-6 = m 2^e, 0.5 <= m < 1  =>  2^e > B 2.1e-6
+            (void)m;
+        } else {
+            t.dmin = 1e300;                                     // absurdly small threshold: exact path only
+        }
+        t.eoff = e * (1 << 20);
+        t.hdmin = samp_hi(t.dmin);
+    }
     return t;
 }
 
@@ -169,8 +193,25 @@ __device__ __noinline__ bool sampson_inlier_slow(const double* E, double a1, dou
 // the solver emits; every quantity of the test is homogeneous in the scale of E)
 // E: the model in registers; Emem: the same nine values in (shared / global) memory, read only by the
 // out-of-line fallback -- passing the register copy there would force it onto the stack.
+// Decision of the pre-filter from the fused num, den.  t = RN(num - B den); the point is decided when
+//     |t| > den 2^e  (2^e >= 2.1e-6 B: num is outside [B (1 - 2e-6) den, B (1 + 2e-6) den], the band the error
+//                     analysis above needs),   den > dmin,   and t, den are finite,
+// and all three are tested on the HIGH WORDS as integers: hi(|t|) > hi(den) + (e << 20) implies |t| > den 2^e
+// for normal numbers (den 2^e is normal because den > dmin >= 1e-13 / B), hi(den) > hi(dmin) implies
+// den > dmin, and hi(|t|) < 0x7ff00000 excludes inf / NaN in num or den.  The integer tests are slightly
+// stricter than the real-number ones (by at most 2^-20 relative), which only sends a few more points to the
+// exact path.  They issue on the integer ALU, which this FP64-bound loop leaves idle: 17 FP64 instructions per
+// (model, correspondence) instead of 21 (two threshold products and three FP64 compares before).
+__device__ __forceinline__ bool prefilter_decide(double num, double den, const SampThr& T, int hdmin, bool& in) {
+    const double t = fma(-den, T.B, num);
+    const int ht = __double2hiint(t), hd = __double2hiint(den);
+    const int at = ht & 0x7FFFFFFF;
+    in = ht < 0;
+    return at > hd + T.eoff && at < 0x7FF00000 && hd > hdmin;
+}
+
 __device__ __forceinline__ bool sampson_inlier_scaled(const double (&E)[9], const double* Emem, double a1, double b1,
-                                                      double a2, double b2, const SampThr& T, double dmin) {
+                                                      double a2, double b2, const SampThr& T, int hdmin) {
     const double ex0 = fma(E[0], a1, fma(E[1], b1, E[2]));
     const double ex1 = fma(E[3], a1, fma(E[4], b1, E[5]));
     const double ex2 = fma(E[6], a1, fma(E[7], b1, E[8]));
@@ -179,21 +220,20 @@ __device__ __forceinline__ bool sampson_inlier_scaled(const double (&E)[9], cons
     const double sx = fma(a2, ex0, fma(b2, ex1, ex2));
     const double den = fma(ex0, ex0, fma(ex1, ex1, fma(et0, et0, et1 * et1)));
     const double num = sx * sx;
-    // clear by a relative 2e-6 on either side, and far from degenerate (T.dmin folds den > 1e-8 and
-    // B den > 1e-13).  Branch-free: the three comparisons feed one (practically never taken) branch.
-    const bool in = num < den * T.Blo, out = num > den * T.Bhi;
-    if ((in || out) && den > dmin) return in;
+    // Branch-free: the integer comparisons feed one (practically never taken) branch.
+    bool in;
+    if (prefilter_decide(num, den, T, hdmin, in)) return in;
     return sampson_inlier_slow(Emem, a1, b1, a2, b2, T);
 }
 
 __device__ __forceinline__ bool sampson_inlier_unit(const double (&E)[9], const double* Emem, double a1, double b1,
                                                     double a2, double b2, const SampThr& T) {
-    return sampson_inlier_scaled(E, Emem, a1, b1, a2, b2, T, T.dmin);
+    return sampson_inlier_scaled(E, Emem, a1, b1, a2, b2, T, T.hdmin);
 }
 
 // Pre-filter alone: returns true if the fused evaluation decides the test (then `in` is the answer).
 __device__ __forceinline__ bool sampson_fast(const double (&E)[9], double a1, double b1, double a2, double b2,
-                                             const SampThr& T, double dmin, bool& in) {
+                                             const SampThr& T, int hdmin, bool& in) {
     const double ex0 = fma(E[0], a1, fma(E[1], b1, E[2]));
     const double ex1 = fma(E[3], a1, fma(E[4], b1, E[5]));
     const double ex2 = fma(E[6], a1, fma(E[7], b1, E[8]));
@@ -202,8 +242,7 @@ __device__ __forceinline__ bool sampson_fast(const double (&E)[9], double a1, do
     const double sx = fma(a2, ex0, fma(b2, ex1, ex2));
     const double den = fma(ex0, ex0, fma(ex1, ex1, fma(et0, et0, et1 * et1)));
     const double num = sx * sx;
-    in = num < den * T.Blo;
-    return (in || num > den * T.Bhi) && den > dmin;
+    return prefilter_decide(num, den, T, hdmin, in);
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -492,8 +531,8 @@ __device__ __forceinline__ void count_two(P X1, int stride, int n, int first, in
     for (int i = first; i < n; i += step) {
         const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
         bool in0, in1;
-        const bool d0 = sampson_fast(E0, a1, b1, a2, b2, T, T.dmin, in0);
-        const bool d1 = sampson_fast(E1, a1, b1, a2, b2, T, T.dmin, in1);
+        const bool d0 = sampson_fast(E0, a1, b1, a2, b2, T, T.hdmin, in0);
+        const bool d1 = sampson_fast(E1, a1, b1, a2, b2, T, T.hdmin, in1);
         c0 += (d0 && in0) ? 1 : 0;
         c1 += (d1 && in1) ? 1 : 0;
         undecided |= !(d0 && d1);
@@ -502,8 +541,8 @@ __device__ __forceinline__ void count_two(P X1, int stride, int n, int first, in
         for (int i = first; i < n; i += step) {
             const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
             bool in0, in1;
-            if (!sampson_fast(E0, a1, b1, a2, b2, T, T.dmin, in0)) c0 += sampson_inlier_slow(M0, a1, b1, a2, b2, T) ? 1 : 0;
-            if (!sampson_fast(E1, a1, b1, a2, b2, T, T.dmin, in1)) c1 += sampson_inlier_slow(M1, a1, b1, a2, b2, T) ? 1 : 0;
+            if (!sampson_fast(E0, a1, b1, a2, b2, T, T.hdmin, in0)) c0 += sampson_inlier_slow(M0, a1, b1, a2, b2, T) ? 1 : 0;
+            if (!sampson_fast(E1, a1, b1, a2, b2, T, T.hdmin, in1)) c1 += sampson_inlier_slow(M1, a1, b1, a2, b2, T) ? 1 : 0;
         }
     }
 }
@@ -517,7 +556,7 @@ __device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int
 #pragma unroll 2
     for (int i = first; i < n; i += step) {
         bool in;
-        const bool d = sampson_fast(E, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T, T.dmin, in);
+        const bool d = sampson_fast(E, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T, T.hdmin, in);
         c += (d && in) ? 1 : 0;
         undecided |= !d;
     }
@@ -525,7 +564,7 @@ __device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int
         for (int i = first; i < n; i += step) {
             const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
             bool in;
-            if (!sampson_fast(E, a1, b1, a2, b2, T, T.dmin, in)) c += sampson_inlier_slow(M, a1, b1, a2, b2, T) ? 1 : 0;
+            if (!sampson_fast(E, a1, b1, a2, b2, T, T.hdmin, in)) c += sampson_inlier_slow(M, a1, b1, a2, b2, T) ? 1 : 0;
         }
     }
     return c;
@@ -923,17 +962,23 @@ five_point_b2_kernel(const double* __restrict__ rec, int m, const uint32_t* __re
 // in shared memory (broadcast reads); votes are counted per warp with ballot + popc, per CTA
 // in shared memory and per model with one global atomicAdd per (CTA, model).
 constexpr int SC_THREADS = 256;
-#ifndef EPV_SC_PPT
-#define EPV_SC_PPT 4
-#endif
-constexpr int SC_PPT = EPV_SC_PPT;           // correspondences per thread, in registers
+// correspondences per thread, in registers: 4, 5 or 6 (template parameter), whichever wastes the fewest point
+// slots for the given n (more independent FP64 chains per thread hide more of the DFMA latency: 6 is preferred)
 constexpr int SC_MODELS = 128;               // models per CTA tile, at most
+#ifndef EPV_SC_KUNROLL
+#define EPV_SC_KUNROLL 1
+#endif
+constexpr int SC_KUNROLL = EPV_SC_KUNROLL;   // models in flight per loop iteration
 
-__global__ void __launch_bounds__(SC_THREADS)
+#ifndef EPV_SC_MINBLOCKS
+#define EPV_SC_MINBLOCKS 2
+#endif
+template <int SC_PPT>
+__global__ void __launch_bounds__(SC_THREADS, EPV_SC_MINBLOCKS)
 score_count_kernel(const double* __restrict__ E, int m, int mtile, const double* __restrict__ xn, int stride, int n,
                    float thr32, int32_t* __restrict__ counts) {
     __shared__ double s_E[SC_MODELS][9];
-    __shared__ double s_dmin[SC_MODELS];
+    __shared__ int s_hdmin[SC_MODELS];
     __shared__ int s_cnt[SC_MODELS];
     const int tid = threadIdx.x, lane = tid & 31;
     const int m0 = blockIdx.y * mtile;
@@ -946,7 +991,7 @@ score_count_kernel(const double* __restrict__ E, int m, int mtile, const double*
         double f2 = 0.0;
 #pragma unroll
         for (int c = 0; c < 9; ++c) f2 += s_E[k][c] * s_E[k][c];
-        s_dmin[k] = T.dmin * f2;             // NaN / inf scale: the pre-filter never decides
+        s_hdmin[k] = samp_hi(fabs(T.dmin * f2)) | (f2 > 0.0 ? 0 : 0x7FF00000);   // zero / NaN / inf scale: the pre-filter never decides
     }
     double a1[SC_PPT], b1[SC_PPT], a2[SC_PPT], b2[SC_PPT];
     bool valid[SC_PPT];
@@ -958,17 +1003,34 @@ score_count_kernel(const double* __restrict__ E, int m, int mtile, const double*
         a1[q] = xn[ii]; b1[q] = xn[stride + ii]; a2[q] = xn[2 * stride + ii]; b2[q] = xn[3 * stride + ii];
     }
     __syncthreads();
+    // Branch-free hot loop (as count_two): the SC_PPT correspondences of a thread are independent FP64 chains
+    // that the compiler interleaves only when no branch separates them (with one branch per point the first
+    // version exposed the full DFMA latency of every chain: 60 % of the FP64 pipe).  Points the pre-filter
+    // cannot decide are flagged in bit 16 of the vote word; a set flag anywhere in the warp -- practically
+    // never -- sends the whole warp through the exact test for that model.
+#pragma unroll SC_KUNROLL
     for (int k = 0; k < mm; ++k) {
         double e[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) e[c] = s_E[k][c];
-        const double dmin = s_dmin[k];
-        int c = 0;
+        const int dmin = s_hdmin[k];
+        int v = 0;
 #pragma unroll
-        for (int q = 0; q < SC_PPT; ++q)
-            c += (valid[q] && sampson_inlier_scaled(e, s_E[k], a1[q], b1[q], a2[q], b2[q], T, dmin)) ? 1 : 0;
-        c = warp_sum(c);
-        if (lane == 0 && c) atomicAdd(&s_cnt[k], c);
+        for (int q = 0; q < SC_PPT; ++q) {
+            bool in;
+            const bool d = sampson_fast(e, a1[q], b1[q], a2[q], b2[q], T, dmin, in);
+            v += (valid[q] && d && in) ? 1 : 0;
+            v |= (valid[q] && !d) ? (1 << 16) : 0;
+        }
+        v = warp_sum(v);                     // counts <= 32 SC_PPT in the low half, undecided lanes in the high half
+        if (v >> 16) {                       // warp-uniform
+            int c = 0;
+#pragma unroll
+            for (int q = 0; q < SC_PPT; ++q)
+                c += (valid[q] && sampson_inlier_scaled(e, s_E[k], a1[q], b1[q], a2[q], b2[q], T, dmin)) ? 1 : 0;
+            v = warp_sum(c);
+        }
+        if (lane == 0 && v) atomicAdd(&s_cnt[k], v);
     }
     __syncthreads();
     for (int k = tid; k < mm; k += SC_THREADS)
@@ -1173,11 +1235,21 @@ int epv_score_launch(epivo_ctx* ctx, const double* d_E, int m, const double* d_x
     if (m > 0 && n > 0) {
         // model tile: as large as possible (fewer re-loads of the correspondences) while the grid still
         // covers the GPU about four times
-        const int pblocks = (n + SC_THREADS * SC_PPT - 1) / (SC_THREADS * SC_PPT);
+        int ppt = 6, best_slots = 0;
+        for (int c = 6; c >= 4; --c) {           // fewest point slots; ties go to the larger count
+            const int slots = (n + SC_THREADS * c - 1) / (SC_THREADS * c) * c;
+            if (c == 6 || slots < best_slots) { ppt = c; best_slots = slots; }
+        }
+        const int pblocks = (n + SC_THREADS * ppt - 1) / (SC_THREADS * ppt);
         int mtile = SC_MODELS;
         while (mtile > 8 && (long long)pblocks * ((m + mtile - 1) / mtile) < 4LL * ctx->sm_count) mtile /= 2;
         dim3 grid(pblocks, (m + mtile - 1) / mtile);
-        score_count_kernel<<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, m, mtile, d_xn, stride, n, thr32, d_counts);
+        if (ppt == 6)
+            score_count_kernel<6><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, m, mtile, d_xn, stride, n, thr32, d_counts);
+        else if (ppt == 5)
+            score_count_kernel<5><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, m, mtile, d_xn, stride, n, thr32, d_counts);
+        else
+            score_count_kernel<4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, m, mtile, d_xn, stride, n, thr32, d_counts);
         EPV_LAUNCHED(ctx);
         if (d_medians) {
             score_median_kernel<<<(m * 32 + 255) / 256, 256, 0, ctx->stream>>>(d_E, m, d_xn, stride, n, d_errbuf,

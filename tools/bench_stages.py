@@ -57,15 +57,18 @@ if os.environ.get("CFG4", "grid") == "diag":
 for N, M, outl in GRID:
     p = synth.make_pair(synth.seed_for(4, N) + int(outl * 10), n=N, outlier_frac=outl)
     Kf = p.K.astype(np.float32)
-    x0, x1 = O.normalize_points(p.kp0, Kf), O.normalize_points(p.kp1, Kf)
+    # correspondences in row order: true partner for the inliers, a random frame-1 point for the outliers
+    c0 = p.kp0
+    c1 = np.ascontiguousarray(p.kp1[np.where(p.gt_match >= 0, p.gt_match, rng.integers(0, N, N))])
+    x0, x1 = O.normalize_points(c0, Kf), O.normalize_points(c1, Kf)
     # M samples of 5 distinct indices (argsort of uniform keys: distinct by construction)
     idx = np.argsort(rng.random((M, 64)), axis=1)[:, :5] * (N // 64) + rng.integers(0, N // 64, size=(M, 5))
     X1, X2 = x0[idx], x1[idx]
     dt = timed(lambda: api.fivePointRaw(X1, X2, ctx=ctx), reps=2)
     Es, nm = api.fivePointRaw(X1, X2, ctx=ctx)
     models = np.concatenate([Es[i, :nm[i]] for i in range(M)]).reshape(-1, 9)[: M]
-    dt2 = timed(lambda: api.scoreSampson(models, p.kp0, p.kp1, Kf, 1.0, ctx=ctx, medians=False), reps=2)
-    cnt = api.scoreSampson(models, p.kp0, p.kp1, Kf, 1.0, ctx=ctx, medians=False)[0]
+    dt2 = timed(lambda: api.scoreSampson(models, c0, c1, Kf, 1.0, ctx=ctx, medians=False), reps=2)
+    cnt = api.scoreSampson(models, c0, c1, Kf, 1.0, ctx=ctx, medians=False)[0]
     out[f"cfg4_N{N}_M{M}_out{int(outl * 100)}"] = {
         "k2_samples_per_s": M / dt, "k3_hyp_points_per_s": len(models) * N / dt2,
         "k3_gflops": len(models) * N * 34 / dt2 / 1e9, "models": int(nm.sum()), "best_inliers": int(np.max(cnt))}
