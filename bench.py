@@ -170,11 +170,31 @@ def run_reference(a):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line when
+    NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
+    saved original descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     a = parse()
+    quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
         return
@@ -348,7 +368,7 @@ def main():
                                           f"{R.cv2.__version__ if R.HAVE_CV2 else 'missing'} BFMatcher/findEssentialMat/"
                                           f"recoverPose + plain-C restatement of the reference LM; {cores} processes x 1 thread"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     pipe.close()
     ctx.close()
     if world > 1:

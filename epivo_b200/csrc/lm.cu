@@ -15,6 +15,9 @@
 // Reference quirks kept on purpose: the Jacobian's Huber branch switches on e'e <= delta
 // while res switches on e'e/2 > delta (sqrt(2) mismatch at delta = 1e-5); reverse reps
 // differentiate a LEFT perturbation of the zeta although the update is right-multiplied.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "stages.cuh"
 
@@ -773,6 +776,13 @@ int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
     LmArgs a;
     a.p = p;
     a.D = 6 * p.n_zeta;
+    if (const char* e = getenv("EPIVO_LM_SHAPE")) {                 // tuning override: "<threads>x<tile points>"
+        if (!strcmp(e, "512x128")) return lm_launch_shape<512, 128>(ctx, a);
+        if (!strcmp(e, "384x128")) return lm_launch_shape<384, 128>(ctx, a);
+        if (!strcmp(e, "256x128")) return lm_launch_shape<256, 128>(ctx, a);
+        if (!strcmp(e, "192x96")) return lm_launch_shape<192, 96>(ctx, a);
+        if (!strcmp(e, "128x64")) return lm_launch_shape<128, 64>(ctx, a);
+    }
     if (p.N <= 32) return lm_launch_shape<64, 32>(ctx, a);          // e.g. the shipped kitti_ba shape: 9 reps x 32 points
     if (p.N >= 96) return lm_launch_shape<192, 96>(ctx, a);         // e.g. cfg5: 20 reps x 250 points
     return lm_launch_shape<128, 64>(ctx, a);

@@ -8,7 +8,8 @@ from epivo_b200 import api, synth
 ctx = api.Context(0)
 REPS10 = [(i, i) for i in range(10)] + [(0, i) for i in range(10)]
 STEREO = [(0, 1), (1, 1), (0, 0), (0, 3), (1, 3), (0, 0), (2, 3), (3, 3), (2, 2)]
-for name, nz, reps, N, B in [("cfg5", 10, REPS10, 250, 504), ("stereo_ws3", 4, STEREO, 32, 2270)]:
+B5 = int(os.environ.get("B5", "504"))
+for name, nz, reps, N, B in [("cfg5", 10, REPS10, 250, B5), ("stereo_ws3", 4, STEREO, 32, max(1, B5 * 2270 // 504))]:
     data = [synth.gen_scene_sequence(500 + b, N, nz, reps) for b in range(32)]
     T0 = np.stack([data[b % 32][1] for b in range(B)])
     pr = np.stack([data[b % 32][2] for b in range(B)])
