@@ -273,8 +273,15 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     }
     __syncthreads();
 
+#ifdef EPV_LM_PROFILE
+    long long tp_[5] = {0, 0, 0, 0, 0}, tp0_ = clock64();
+#define LM_TICK(i) do { long long n_ = clock64(); tp_[i] += n_ - tp0_; tp0_ = n_; } while (0)
+#else
+#define LM_TICK(i) do { } while (0)
+#endif
     for (int iter = 0; iter < p.max_iters; ++iter) {
         if (tid == 0) s_iters = iter + 1;
+        LM_TICK(4);
         // ---- chain memo + inverses                                              [:328-335]
         for (int j = tid; j < nz; j += LM_THREADS) {
             Rt acc = sT[j];
@@ -293,6 +300,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
             sRep[j] = (z0 <= z1) ? sMem[z0 * nz + z1] : sInv[z1 * nz + z0];
         }
         __syncthreads();
+        LM_TICK(0);
         // ---- residuals, Jacobian tiles, H = J'J, b = J'r
         double rsq = 0.0;
         for (int j = 0; j < nr; ++j) {
@@ -403,6 +411,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                 __syncthreads();
             }
         }
+        LM_TICK(1);
         // symmetrise, damp, Frobenius norm, negate b                                [:403,473]
         for (int e = tid; e < D * D; e += LM_THREADS) {
             const int r = e / D, c = e % D;
@@ -487,6 +496,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
             if (nan || sqrt(nrm) < p.epsilon) s_stop = 1;                            // [:407-414]
         }
         __syncthreads();
+        LM_TICK(2);
         if (s_stop) break;
         // ---- candidate update T' = T exp(delta_k)                                  [:416-422]
         for (int k = tid; k < nz; k += LM_THREADS) {
@@ -538,8 +548,14 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
             for (int k = tid; k < nz; k += LM_THREADS) sT[k] = sTn[k];
         }
         __syncthreads();
+        LM_TICK(3);
     }
     __syncthreads();
+#ifdef EPV_LM_PROFILE
+    if (tid == 0 && prob == 0)
+        printf("lm_kernel<%d,%d> phases (clocks): memo %lld  jac+gram %lld  solve %lld  candidate %lld  other %lld\n", LM_THREADS,
+               LM_TP, tp_[0], tp_[1], tp_[2], tp_[3], tp_[4]);
+#endif
     for (int k = tid; k < nz; k += LM_THREADS) {
         for (int i = 0; i < 3; ++i) {
             for (int j = 0; j < 3; ++j) gT[k * 16 + i * 4 + j] = sT[k].R[i * 3 + j];
@@ -784,6 +800,9 @@ int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
         if (!strcmp(e, "128x64")) return lm_launch_shape<128, 64>(ctx, a);
     }
     if (p.N <= 32) return lm_launch_shape<64, 32>(ctx, a);          // e.g. the shipped kitti_ba shape: 9 reps x 32 points
+    // few large windows (a multi-GPU shard of cfg5: 63 windows per GPU): every CTA has an SM to itself, so the
+    // wider CTA wins (63 cfg5 windows: 11.3 ms against 14.0 ms); with several CTAs per SM the narrower one does
+    if (p.N >= 96 && p.B <= ctx->sm_count) return lm_launch_shape<384, 128>(ctx, a);
     if (p.N >= 96) return lm_launch_shape<192, 96>(ctx, a);         // e.g. cfg5: 20 reps x 250 points
     return lm_launch_shape<128, 64>(ctx, a);
 }
