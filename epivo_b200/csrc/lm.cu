@@ -18,8 +18,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "stages.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -228,13 +232,165 @@ struct LmArgs {
     size_t smem_doubles;
 };
 
-template <int LM_THREADS, int LM_TP>
+__device__ __forceinline__ double lm_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// Damped normal equations H delta = -b on the augmented D x (D + 1) matrix in shared memory: LU with partial
+// pivoting [:405] and back substitution by NW warps (one per SM sub-partition) that meet at a NAMED barrier, not at
+// the block barrier.  A pivot step on 60..96 unknowns is a few thousand multiply-adds behind a chain of dependent
+// latencies (pivot -> reciprocal -> row factor -> update -> next pivot); the block-wide version paid three block
+// barriers and a separate pivot search for it (3600 cycles per step).  Here
+//  * warp w updates the rows k + 1 + w, k + 1 + w + NW, ...; lane l owns columns k + 1 + l + 32 i (i < NC) and keeps
+//    the pivot row in registers; rows are updated RB at a time, every load of a batch issued before its first store
+//    (row by row the compiler must assume that a store aliases the next row's loads and serialises them);
+//  * lane 0 of a warp owns column k + 1, i.e. it produces that warp's candidates for the NEXT pivot: it keeps the
+//    first largest |value| as it goes (compared as integers: for non-negative doubles the bit patterns order like
+//    the values; NaN never wins, as in a sequential `>` search) and posts it; after the barrier every warp picks
+//    the winner of the NW posts itself (largest, then lowest row), so the separate search disappears;
+//  * two named barriers per step (after the row swap, after the update); warps outside the solve wait at the
+//    block barrier that follows.
+// Returns through sDelta; *stop is set on NaN / inf or |delta| < eps [:407-414].
+template <int NW>
+__device__ __forceinline__ void lm_solve_bar() {
+    if (NW > 1) asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    else __syncwarp();
+}
+
+template <int NC, int RB, int NW>
+__device__ __noinline__ void lm_warp_solve(double* sH, double* sDelta, int D, int tid, double epsilon, int* stop,
+                                           long long* sKey, int* sRow) {
+    const int lane = tid & 31, w = tid >> 5, W1 = D + 1;
+    // pivot of column 0: every warp searches the whole column itself (first row with the largest |value|)
+    double best = -1.0;
+    int pv = 0;
+    for (int r = lane; r < D; r += 32) {
+        const double v = fabs(sH[(size_t)r * W1]);
+        if (v > best) { best = v; pv = r; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const int op = __shfl_xor_sync(0xFFFFFFFFu, pv, o);
+        if (ob > best || (ob == best && op < pv)) { best = ob; pv = op; }
+    }
+    lm_solve_bar<NW>();                              // nobody swaps before everybody has searched
+    for (int k = 0; k < D; ++k) {
+        if (pv != k) {                               // row swap: one column per thread (D + 1 <= 32 NC <= 32 NW NC)
+            for (int c = k + tid; c <= D; c += 32 * NW) {
+                const double t = sH[(size_t)k * W1 + c];
+                sH[(size_t)k * W1 + c] = sH[(size_t)pv * W1 + c];
+                sH[(size_t)pv * W1 + c] = t;
+            }
+        }
+        lm_solve_bar<NW>();
+        const double* prw = sH + (size_t)k * W1;
+        const double ipiv = 1.0 / prw[k];
+        double prow[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = k + 1 + lane + 32 * i;
+            prow[i] = (c <= D) ? prw[c] : 0.0;
+        }
+        long long nkey = -1;                         // lane 0: bit pattern of the largest |value| of column k + 1 so far
+        int npv = D;
+        for (int r0 = k + 1 + w; r0 < D; r0 += RB * NW) {
+            double f[RB], v[RB][NC];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const double* row = sH + (size_t)min(r0 + j * NW, D - 1) * W1;     // clamped rows are loaded, never stored
+                f[j] = row[k];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int c = k + 1 + lane + 32 * i;
+                    v[j][i] = (c <= D) ? row[c] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                f[j] *= ipiv;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) v[j][i] -= f[j] * prow[i];
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const int r = r0 + j * NW;
+                if (r < D) {
+                    double* row = sH + (size_t)r * W1;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int c = k + 1 + lane + 32 * i;
+                        if (c <= D) row[c] = v[j][i];
+                    }
+                    long long key = __double_as_longlong(v[j][0]) & 0x7FFFFFFFFFFFFFFFLL;
+                    if (key > 0x7FF0000000000000LL) key = -1;          // NaN
+                    if (key > nkey) { nkey = key; npv = r; }           // rows ascend within a warp: first maximum
+                }
+            }
+        }
+        if (lane == 0) { sKey[w] = nkey; sRow[w] = npv; }
+        lm_solve_bar<NW>();
+        long long bk = sKey[0];
+        pv = sRow[0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) {
+            const long long kq = sKey[q];
+            const int rq = sRow[q];
+            if (kq > bk || (kq == bk && rq < pv)) { bk = kq; pv = rq; }
+        }
+        if (bk < 0) pv = k + 1;                       // nothing comparable (all NaN, or no rows left): keep the diagonal
+    }
+    if (w != 0) return;
+    // back substitution, column oriented, by warp 0: lane l keeps y_r of rows r = l + 32 i in registers; for
+    // c = D-1 .. 0 the owner forms delta_c = y_c / U_cc, broadcasts it, and every lane updates its rows above c
+    double y[NC], dgl[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int r = lane + 32 * i;
+        y[i] = (r < D) ? sH[(size_t)r * W1 + D] : 0.0;
+        dgl[i] = (r < D) ? sH[(size_t)r * W1 + r] : 1.0;
+    }
+    bool nan = false;
+    double nrm = 0.0;
+    for (int c = D - 1; c >= 0; --c) {
+        double yc = 0.0, dg = 1.0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if ((c >> 5) == i) { yc = y[i]; dg = dgl[i]; }
+        double col[NC];                              // column c above the diagonal: loaded while the division runs
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int r = lane + 32 * i;
+            col[i] = (r < c) ? sH[(size_t)r * W1 + c] : 0.0;
+        }
+        double dc = yc / dg;                         // every lane divides its own candidate; the owner's is taken
+        dc = __shfl_sync(0xFFFFFFFFu, dc, c & 31);
+        if (lane == 0) sDelta[c] = dc;
+        nan |= !(dc == dc) || isinf(dc);
+        nrm += dc * dc;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) y[i] -= col[i] * dc;
+    }
+    if (lane == 0 && (nan || sqrt(nrm) < epsilon)) *stop = 1;                      // [:407-414]
+}
+
+// CL > 1: a window is shared by a thread-block CLUSTER of CL CTAs (launched with a cluster dimension of CL).  Each
+// CTA builds the Jacobian / Gram tiles t with t % CL == rank into its own partial H | b; after one cluster barrier
+// every CTA sums the CL partials straight out of the peers' shared memory (DSMEM) in rank order, so all of them hold
+// the same H | b bit for bit and run the (cheap, latency-bound) damped solve redundantly -- no broadcast of delta is
+// needed and every CTA takes the same stop / accept decisions.  The candidate residual is split the same way.  Used
+// when the batch is too small to fill the GPU with one CTA per window (a multi-GPU shard of cfg5).
+template <int LM_THREADS, int LM_TP, int CL>
 __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     extern __shared__ __align__(16) double sm[];
     const LmPlan& p = a.p;
     const int nz = p.n_zeta, nr = p.n_rep, N = p.N, D = a.D;
-    const int tid = threadIdx.x, prob = blockIdx.x;
-    if (p.active && !p.active[prob]) return;
+    const int tid = threadIdx.x, prob = blockIdx.x / CL;
+    int crank = 0;
+    if (CL > 1) crank = (int)cg::this_cluster().block_rank();
+    if (p.active && !p.active[prob]) return;          // the whole cluster leaves together
     // shared layout
     Rt* sT = reinterpret_cast<Rt*>(sm);            // [nz] current
     Rt* sTn = sT + nz;                             // [nz] candidate
@@ -246,6 +402,11 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
     double* sJ = sH + (size_t)D * (D + 1);         // [LM_TP][JS] tile: J columns of the span + residual
     double* sDelta = sJ + (size_t)LM_TP * JS;      // [D]
     double* sRed = sDelta + D;                     // [LM_THREADS]
+    double* sHp = sRed + LM_THREADS;               // [D][D+1] this CTA's partial H | b (CL > 1 only)
+    double* sAcc = (CL > 1) ? sHp : sH;            // where the Gram blocks are accumulated
+    __shared__ double s_part[2];                   // this CTA's partial sums of squares (r0, candidate)
+    __shared__ long long s_key[4];                 // solver warps: next-pivot candidates
+    __shared__ int s_row[4];
     __shared__ double s_lambda, s_prevE, s_Hnorm, s_rnorm;
     __shared__ int s_stop, s_iters, s_piv;
     __shared__ Rt s_identity;
@@ -293,7 +454,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                 rt_inv(acc, sInv[j * nz + k]);
             }
         }
-        for (int i = tid; i < D * (D + 1); i += LM_THREADS) sH[i] = 0.0;
+        for (int i = tid; i < D * (D + 1); i += LM_THREADS) sAcc[i] = 0.0;
         __syncthreads();
         for (int j = tid; j < nr; j += LM_THREADS) {                                // [:338-348]
             const int z0 = p.reps[2 * j], z1 = p.reps[2 * j + 1];
@@ -303,6 +464,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
         LM_TICK(0);
         // ---- residuals, Jacobian tiles, H = J'J, b = J'r
         double rsq = 0.0;
+        int tile_id = 0;                            // running tile counter over all reps: tile t belongs to rank t % CL
         for (int j = 0; j < nr; ++j) {
             const int z0 = p.reps[2 * j], z1 = p.reps[2 * j + 1];
             const int lo = min(z0, z1), hi = max(z0, z1);
@@ -310,6 +472,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
             const bool fwd = z0 <= z1;
             const double wj = w[j];
             for (int base = 0; base < N; base += LM_TP) {
+                if (CL > 1 && (tile_id++ % CL) != crank) continue;
                 const int np = min(LM_TP, N - base);
                 // work item = (point, lane group g): the per-point part of Dr_Deps (everything that depends only on
                 // the rep's full transform) is computed once and reused for the zetas g, g + LM_G, ... of the span;
@@ -397,8 +560,8 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                                     const int u = min(r0, c0), v = max(r0, c0);      // mirror into the upper triangle
                                     if (v > W || u == W) continue;
                                     const int gr = 6 * lo + u;
-                                    if (v == W) sH[(size_t)gr * (D + 1) + D] += acc[i][j];
-                                    else sH[(size_t)gr * (D + 1) + 6 * lo + v] += acc[i][j];
+                                    if (v == W) sAcc[(size_t)gr * (D + 1) + D] += acc[i][j];
+                                    else sAcc[(size_t)gr * (D + 1) + 6 * lo + v] += acc[i][j];
                                 }
                             }
                         }
@@ -412,21 +575,49 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
             }
         }
         LM_TICK(1);
+        if (CL > 1) {                               // cluster reduction of the partial H | b and of |r0|^2
+            rsq = lm_warp_sum(rsq);
+            if ((tid & 31) == 0) sRed[tid >> 5] = rsq;
+            __syncthreads();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int i = 0; i < LM_THREADS / 32; ++i) s += sRed[i];
+                s_part[0] = s;
+            }
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();                         // every rank's partial sums are complete and visible
+            for (int e = tid; e < D * (D + 1); e += LM_THREADS) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < CL; ++r) s += cluster.map_shared_rank(sHp, r)[e];     // rank order: identical in every CTA
+                sH[e] = s;
+            }
+            if (tid == 0) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < CL; ++r) s += *cluster.map_shared_rank(&s_part[0], r);
+                s_rnorm = sqrt(s);
+            }
+            __syncthreads();
+        }
         // symmetrise, damp, Frobenius norm, negate b                                [:403,473]
         for (int e = tid; e < D * D; e += LM_THREADS) {
             const int r = e / D, c = e % D;
             if (c < r) sH[(size_t)r * (D + 1) + c] = sH[(size_t)c * (D + 1) + r];
         }
-        sRed[tid] = rsq;
+        if (CL == 1) {
+            rsq = lm_warp_sum(rsq);                  // per-warp partials: thread 0 adds LM_THREADS / 32 values, not LM_THREADS
+            if ((tid & 31) == 0) sRed[tid >> 5] = rsq;
+        }
         __syncthreads();
         const double lam = s_lambda;
         for (int r = tid; r < D; r += LM_THREADS) {
             sH[(size_t)r * (D + 1) + r] += lam * sH[(size_t)r * (D + 1) + r];
             sH[(size_t)r * (D + 1) + D] = -sH[(size_t)r * (D + 1) + D];
         }
-        if (tid == 0) {
+        if (CL == 1 && tid == 0) {
             double s = 0.0;
-            for (int i = 0; i < LM_THREADS; ++i) s += sRed[i];
+            for (int i = 0; i < LM_THREADS / 32; ++i) s += sRed[i];
             s_rnorm = sqrt(s);
         }
         __syncthreads();
@@ -437,63 +628,23 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
                 hs += v * v;
             }
             __syncthreads();
-            sRed[tid] = hs;
+            hs = lm_warp_sum(hs);
+            if ((tid & 31) == 0) sRed[tid >> 5] = hs;
             __syncthreads();
             if (tid == 0) {
                 double s = 0.0;
-                for (int i = 0; i < LM_THREADS; ++i) s += sRed[i];
+                for (int i = 0; i < LM_THREADS / 32; ++i) s += sRed[i];
                 s_Hnorm = sqrt(s);
             }
         }
         // ---- solve H delta = -b: LU with partial pivoting on the augmented matrix  [:405]
-        for (int k = 0; k < D; ++k) {
-            __syncthreads();
-            if (tid < 32) {                                  // pivot search by warp 0: first row with the largest |value|
-                double best = -1.0;
-                int pv = k;
-                for (int r = k + tid; r < D; r += 32) {
-                    const double v = fabs(sH[(size_t)r * (D + 1) + k]);
-                    if (v > best) { best = v; pv = r; }      // NaN never wins, as in the sequential search
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
-                    const int op = __shfl_xor_sync(0xFFFFFFFFu, pv, o);
-                    if (ob > best || (ob == best && op < pv)) { best = ob; pv = op; }
-                }
-                if (tid == 0) s_piv = pv;
-            }
-            __syncthreads();
-            const int pv = s_piv;
-            if (pv != k) {
-                for (int c = k + tid; c <= D; c += LM_THREADS) {
-                    const double t = sH[(size_t)k * (D + 1) + c];
-                    sH[(size_t)k * (D + 1) + c] = sH[(size_t)pv * (D + 1) + c];
-                    sH[(size_t)pv * (D + 1) + c] = t;
-                }
-                __syncthreads();
-            }
-            const double ipiv = 1.0 / sH[(size_t)k * (D + 1) + k];
-            // eliminate below: warp w takes rows k+1+w, k+1+w+4, ...; lanes take the columns k+1..D
-            for (int r = k + 1 + (tid >> 5); r < D; r += LM_THREADS / 32) {
-                const double f = sH[(size_t)r * (D + 1) + k] * ipiv;
-                for (int c = k + 1 + (tid & 31); c <= D; c += 32)
-                    sH[(size_t)r * (D + 1) + c] -= f * sH[(size_t)k * (D + 1) + c];
-            }
-        }
         __syncthreads();
-        if (tid == 0) {
-            bool nan = false;
-            double nrm = 0.0;
-            for (int r = D - 1; r >= 0; --r) {
-                double s = sH[(size_t)r * (D + 1) + D];
-                for (int c = r + 1; c < D; ++c) s -= sH[(size_t)r * (D + 1) + c] * sDelta[c];
-                const double v = s / sH[(size_t)r * (D + 1) + r];
-                sDelta[r] = v;
-                nan |= !(v == v) || isinf(v);
-                nrm += v * v;
+        {
+            constexpr int NW = LM_THREADS >= 128 ? 4 : LM_THREADS / 32;     // solver warps: one per SM sub-partition
+            if (tid < 32 * NW) {
+                if (D + 1 <= 64) lm_warp_solve<2, 4, NW>(sH, sDelta, D, tid, p.epsilon, &s_stop, s_key, s_row);
+                else lm_warp_solve<4, 4, NW>(sH, sDelta, D, tid, p.epsilon, &s_stop, s_key, s_row);
             }
-            if (nan || sqrt(nrm) < p.epsilon) s_stop = 1;                            // [:407-414]
         }
         __syncthreads();
         LM_TICK(2);
@@ -522,16 +673,30 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
         }
         __syncthreads();
         double csq = 0.0;                                                            // [:445-456]
-        for (int it = tid; it < nr * N; it += LM_THREADS) {
+        for (int it = crank * LM_THREADS + tid; it < nr * N; it += CL * LM_THREADS) {
             const int j = it / N;
             const double r = res_one(sRep[j], gpr + (size_t)it * 3, gp_r + (size_t)it * 3, hd);
             csq += r * r;
         }
-        sRed[tid] = csq;
+        csq = lm_warp_sum(csq);
+        if ((tid & 31) == 0) sRed[tid >> 5] = csq;
         __syncthreads();
+        if (CL > 1) {
+            if (tid == 0) {
+                double s = 0.0;
+                for (int i = 0; i < LM_THREADS / 32; ++i) s += sRed[i];
+                s_part[1] = s;
+            }
+            cg::this_cluster().sync();
+        }
         if (tid == 0) {
             double s = 0.0;
-            for (int i = 0; i < LM_THREADS; ++i) s += sRed[i];
+            if (CL > 1) {
+#pragma unroll
+                for (int r = 0; r < CL; ++r) s += *cg::this_cluster().map_shared_rank(&s_part[1], r);
+            } else {
+                for (int i = 0; i < LM_THREADS / 32; ++i) s += sRed[i];
+            }
             const double currE = sqrt(s);
             s_rnorm = currE;                                                         // r0 now holds the candidate residuals
             if (currE < s_prevE) {                                                   // [:457-467]
@@ -551,6 +716,10 @@ __global__ void __launch_bounds__(LM_THREADS) lm_kernel(LmArgs a) {
         LM_TICK(3);
     }
     __syncthreads();
+    if (CL > 1) {
+        cg::this_cluster().sync();                  // no CTA may exit while a peer can still read its shared memory
+        if (crank != 0) return;                     // rank 0 reports (every rank holds the same result)
+    }
 #ifdef EPV_LM_PROFILE
     if (tid == 0 && prob == 0)
         printf("lm_kernel<%d,%d> phases (clocks): memo %lld  jac+gram %lld  solve %lld  candidate %lld  other %lld\n", LM_THREADS,
@@ -758,20 +927,37 @@ __global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_ker
     }
 }
 
-size_t lm_smem_doubles(int nz, int nr, int D, int threads, int tp) {
+size_t lm_smem_doubles(int nz, int nr, int D, int threads, int tp, int cl) {
     size_t rt = sizeof(Rt) / sizeof(double);
-    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) + (size_t)tp * ((D + 1) | 1) + D + threads;
+    return rt * (2 * (size_t)nz + 2 * (size_t)nz * nz + nr) + (size_t)D * (D + 1) * (cl > 1 ? 2 : 1) +
+           (size_t)tp * ((D + 1) | 1) + D + threads;
 }
 
-template <int THREADS, int TP>
+template <int THREADS, int TP, int CL = 1>
 int lm_launch_shape(epivo_ctx* ctx, LmArgs& a) {
-    a.smem_doubles = lm_smem_doubles(a.p.n_zeta, a.p.n_rep, a.D, THREADS, TP);
+    a.smem_doubles = lm_smem_doubles(a.p.n_zeta, a.p.n_rep, a.D, THREADS, TP, CL);
     const size_t bytes = a.smem_doubles * sizeof(double);
     if (bytes > 220 * 1024)
         EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "LM problem needs %zu bytes of shared memory (n_zeta=%d, n_rep=%d)", bytes,
                  a.p.n_zeta, a.p.n_rep);
-    EPV_CUDA(ctx, cudaFuncSetAttribute(lm_kernel<THREADS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    lm_kernel<THREADS, TP><<<a.p.B, THREADS, bytes, ctx->stream>>>(a);
+    EPV_CUDA(ctx, cudaFuncSetAttribute(lm_kernel<THREADS, TP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (CL == 1) {
+        lm_kernel<THREADS, TP, CL><<<a.p.B, THREADS, bytes, ctx->stream>>>(a);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)a.p.B * CL);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = bytes;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        EPV_CUDA(ctx, cudaLaunchKernelEx(&cfg, lm_kernel<THREADS, TP, CL>, a));
+    }
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
 }
@@ -793,6 +979,10 @@ int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
     a.p = p;
     a.D = 6 * p.n_zeta;
     if (const char* e = getenv("EPIVO_LM_SHAPE")) {                 // tuning override: "<threads>x<tile points>"
+        if (!strcmp(e, "384x128x2")) return lm_launch_shape<384, 128, 2>(ctx, a);
+        if (!strcmp(e, "256x128x2")) return lm_launch_shape<256, 128, 2>(ctx, a);
+        if (!strcmp(e, "256x64x4")) return lm_launch_shape<256, 64, 4>(ctx, a);
+        if (!strcmp(e, "384x64x4")) return lm_launch_shape<384, 64, 4>(ctx, a);
         if (!strcmp(e, "512x128")) return lm_launch_shape<512, 128>(ctx, a);
         if (!strcmp(e, "384x128")) return lm_launch_shape<384, 128>(ctx, a);
         if (!strcmp(e, "256x128")) return lm_launch_shape<256, 128>(ctx, a);
@@ -802,6 +992,10 @@ int epv_lm_launch(epivo_ctx* ctx, const LmPlan& p) {
     if (p.N <= 32) return lm_launch_shape<64, 32>(ctx, a);          // e.g. the shipped kitti_ba shape: 9 reps x 32 points
     // few large windows (a multi-GPU shard of cfg5: 63 windows per GPU): every CTA has an SM to itself, so the
     // wider CTA wins (63 cfg5 windows: 11.3 ms against 14.0 ms); with several CTAs per SM the narrower one does
+    // and when even that leaves SMs idle, a window is shared by a cluster of 2 or 4 CTAs (63 windows: 6.65 ms on
+    // pairs of CTAs; 30 windows: 6.05 ms on clusters of four, 9.9 ms on single CTAs)
+    if (p.N >= 96 && p.B * 4 <= ctx->sm_count) return lm_launch_shape<384, 64, 4>(ctx, a);
+    if (p.N >= 96 && p.B * 2 <= ctx->sm_count) return lm_launch_shape<384, 128, 2>(ctx, a);
     if (p.N >= 96 && p.B <= ctx->sm_count) return lm_launch_shape<384, 128>(ctx, a);
     if (p.N >= 96) return lm_launch_shape<192, 96>(ctx, a);         // e.g. cfg5: 20 reps x 250 points
     return lm_launch_shape<128, 64>(ctx, a);

@@ -185,3 +185,30 @@ def test_lm_window_batch_sharded_like_8_gpus(ctx):
     for k, d in enumerate(data[a:b_]):
         To, lo = clib.levenberg_marquardt(3, 1e-8, reps, [1.0] * 6, 1e-2, d[1], d[2], d[3], huber_delta=1.0)
         assert its[k] == lo["iters"] and np.abs(Tb[k] - To).max() < 1e-6
+
+
+@pytest.mark.parametrize("shape", ["384x128x2", "256x128x2", "256x64x4", "384x64x4"])
+def test_lm_cfg5_window_on_a_cluster(ctx, shape, monkeypatch):
+    """Small batches share a window between the CTAs of a thread-block cluster (partial H | b summed over DSMEM):
+    same parity bar as the one-CTA kernel, against the plain-C restatement, both Huber settings, plus a batch
+    whose windows differ (every cluster must keep to its own window)."""
+    monkeypatch.setenv("EPIVO_LM_SHAPE", shape)
+    Ts, Tg, lg = _check_vs_c(ctx, 10, REPS10, 250, 51, 1.0, 30)
+    for k in range(10):
+        assert np.linalg.norm(Tg[k][:3, :3] - Ts[k][:3, :3]) < 1e-5
+    _check_vs_c(ctx, 10, REPS10, 250, 52, 1e-5, 30)
+    _check_vs_c(ctx, 10, REPS10, 97, 53, 1.0, 30)             # ragged last tile, tiles not a multiple of the cluster
+    from oracle import clib
+    B = 5
+    data = [synth.gen_scene_sequence(300 + b, 130, 10, REPS10) for b in range(B)]
+    Tb, res, its = api.Levenberg_Marquardt_batch(10, 1e-8, REPS10, [1.0] * 20, 1e-2, np.stack([d[1] for d in data]),
+                                                 np.stack([d[2] for d in data]), np.stack([d[3] for d in data]),
+                                                 huber_delta=1.0, ctx=ctx)
+    for k, d in enumerate(data):
+        To, lo = clib.levenberg_marquardt(10, 1e-8, REPS10, [1.0] * 20, 1e-2, d[1], d[2], d[3], huber_delta=1.0)
+        # (one of these windows is still descending after 30 iterations: its translation scale -- a gauge freedom of
+        # the reprojection error -- is pinned to ~2e-6 only, for the one-CTA kernel as well)
+        assert its[k] == lo["iters"] and np.abs(Tb[k] - To).max() < 1e-5
+        for z in range(10):
+            assert rot_angle(Tb[k][z][:3, :3], To[z][:3, :3]) < ROT_TOL
+        assert abs(res[k][1] - lo["r_norm"]) <= 1e-5 * max(lo["r_norm"], 1e-12) + 1e-15
