@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--norm", default="hamming2", choices=["hamming", "hamming2"])
     ap.add_argument("--cpu-pairs", type=int, default=128, help="bounded CPU-baseline sample (pairs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "ba_windows"],
+                    help="pairs = the headline metric (default); ba_windows = BASELINE.json config 5: the 504 "
+                         "kitti_ba windows of a sequence (n_zeta 10, 20 reps x 250) sharded over the GPUs (strong scaling)")
+    ap.add_argument("--windows", type=int, default=504)
     return ap.parse_args()
 
 
@@ -192,11 +196,85 @@ def emit(line):
     out.flush()
 
 
+def run_windows(a):
+    """BASELINE.json config 5 (not the headline line): the windows of one sequence, sharded over the ranks in
+    contiguous blocks (strong scaling: the total is fixed), one batched Levenberg_Marquardt launch per rank.
+    value = windows / max over ranks of the kernel time; e2e = the same through epivo_lm_rt_batch with pinned
+    host buffers (H2D of the reprojections + D2H of the refined chains inside the timed region)."""
+    import torch
+    import torch.distributed as dist
+    from epivo_b200 import api, shard, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nz, N = 10, 250
+    reps = [(i, i) for i in range(nz)] + [(0, i) for i in range(nz)]
+    lo, hi = shard.shard_range(a.windows, world, rank)
+    B = hi - lo
+    data = [synth.gen_scene_sequence(500 + (lo + b) % 64, N, nz, reps) for b in range(min(B, 64))]
+
+    def pinned(k):
+        t = torch.from_numpy(np.stack([data[b % len(data)][k] for b in range(B)])).pin_memory()
+        return t, t.numpy()
+    keep = [pinned(k) for k in (1, 2, 3)]
+    T0, pr, p_r = (x[1] for x in keep)
+    ctx = api.Context(local)
+    w = [1.0] * len(reps)
+
+    def step():
+        return api.Levenberg_Marquardt_batch(nz, 1e-8, reps, w, 1e-2, T0, pr, p_r, huber_delta=1.0, ctx=ctx)
+    for _ in range(max(a.warmup, 1)):
+        step()
+    clocks = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = ctx.launch_count
+    t0 = time.perf_counter()
+    k_ms = 0.0
+    for _ in range(a.steps):
+        T, res, its = step()
+        k_ms += ctx.last_kernel_ms()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    k_ms /= a.steps
+    launches = ctx.launch_count - n0
+    if world > 1:
+        t = torch.tensor([k_ms, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        k_ms, wall_ms = float(t[0].item()), float(t[1].item())
+        dist.barrier()
+    clk = clocks.stop()
+    line = {"metric": "kitti_ba windows/sec (windowed Rt LM, n_zeta 10, 20 reps x 250 correspondences, 30 iterations)",
+            "value": a.windows / (k_ms * 1e-3), "unit": "windows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": k_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE config 5: {a.windows} windows (sequence.hpp scenes), contiguous blocks per rank, "
+                                   f"{B} on rank {rank}", "parallelism": f"windows sharded, {world} x 1 GPU, no collective"},
+            "clocks": clk,
+            "e2e": {"value": a.windows / (wall_ms * 1e-3), "unit": "windows/s", "ms_per_step": wall_ms,
+                    "h2d_bytes_per_step": int(T0.nbytes + pr.nbytes + p_r.nbytes), "d2h_bytes_per_step": int(T0.nbytes + B * 28)},
+            "gpu_launches": int(launches), "mean_iters": float(its.mean())}
+    if rank == 0:
+        emit(line)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
+        return
+    if a.workload == "ba_windows":
+        run_windows(a)
         return
     import torch
     import torch.distributed as dist

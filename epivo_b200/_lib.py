@@ -71,6 +71,7 @@ SIGNATURES = {
     "epivo_seq_create": (_i, [_vp, C.POINTER(_vp), _i, _i]),
     "epivo_seq_destroy": (None, [_vp]),
     "epivo_seq_upload": (_i, [_vp, _i, _i, _vp, _vp]),
+    "epivo_last_kernel_ms": (_i, [_vp, _vp]),
     "epivo_seq_set_counts": (_i, [_vp, _i, _i, _vp]),
     "epivo_seq_create_pairs": (_i, [_vp, C.POINTER(_vp), _i, _i, _i]),
     "epivo_seq_set_pairs": (_i, [_vp, _i, _vp, _vp]),

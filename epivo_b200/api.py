@@ -69,6 +69,12 @@ class Context:
     def sync(self):
         self.check(self.lib.epivo_sync(self.h))
 
+    def last_kernel_ms(self) -> float:
+        """Device time of the kernels of the last Levenberg_Marquardt[_batch] call (no copies)."""
+        ms = C.c_float(0.0)
+        self.check(self.lib.epivo_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def microbench(self, which: int) -> float:
         v = C.c_double()
         self.check(self.lib.epivo_microbench(self.h, which, C.byref(v)))

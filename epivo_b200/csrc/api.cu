@@ -61,6 +61,8 @@ void epivo_destroy(epivo_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+    if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -68,6 +70,13 @@ void epivo_destroy(epivo_ctx* ctx) {
 const char* epivo_last_error(const epivo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void* epivo_stream(epivo_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t epivo_launch_count(const epivo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int epivo_last_kernel_ms(epivo_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return EPIVO_ERR_INVALID;
+    if (!ctx->ev_k0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "no timed call yet");
+    EPV_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+    return EPIVO_OK;
+}
 
 int epivo_sync(epivo_ctx* ctx) {
     if (!ctx) return EPIVO_ERR_INVALID;
@@ -459,8 +468,14 @@ int epivo_lm_rt_batch(epivo_ctx* ctx, int B, int n_zeta, double epsilon, const i
     lp.iters = d_it;
     lp.active = nullptr;
     lp.single_pair = (n_zeta == 1 && n_rep == 1 && reps[0] == 0 && reps[1] == 0) ? 1 : 0;
+    if (!ctx->ev_k0) {
+        EPV_CUDA(ctx, cudaEventCreate(&ctx->ev_k0));
+        EPV_CUDA(ctx, cudaEventCreate(&ctx->ev_k1));
+    }
+    EPV_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     rc = epv_lm_launch(ctx, lp);
     if (rc) return rc;
+    EPV_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(T0s, d_T, nT * 8, cudaMemcpyDeviceToHost, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)B * sizeof(epivo_lm_res), cudaMemcpyDeviceToHost, ctx->stream));
     if (iters_run) EPV_CUDA(ctx, cudaMemcpyAsync(iters_run, d_it, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -22,6 +22,8 @@ struct epivo_ctx {
     char* pin = nullptr;
     size_t pin_bytes = 0;
     size_t pin_used = 0;
+    // events around the kernels of the last stage-wise call that records them (epivo_last_kernel_ms)
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
 };
 
 #define EPV_FAIL(ctx, code, ...)                          \

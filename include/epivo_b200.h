@@ -49,6 +49,9 @@ void* epivo_stream(epivo_ctx* ctx);
 /* number of this library's kernels launched on the context so far */
 int64_t epivo_launch_count(const epivo_ctx* ctx);
 int epivo_sync(epivo_ctx* ctx);
+/* device time (CUDA events on the context stream) of the kernels of the last epivo_lm_rt / epivo_lm_rt_batch call,
+ * without its host<->device copies: what the benchmark reports next to the end-to-end time */
+int epivo_last_kernel_ms(epivo_ctx* ctx, float* ms);
 
 /* ---- M1: cv::BFMatcher(normType, crossCheck).match(desc0, desc1, matches) ------------
  * replaces kitti_ba.cpp:602,641.  q: nq x desc_bytes, t: nt x desc_bytes, row-major u8
