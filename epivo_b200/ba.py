@@ -134,3 +134,60 @@ def finish(opt_T, T0s, T_opt, lm, starts, nz, lo, step, stereo):
                 opt_T[w0 + k][:3, 3] /= scale
             optimized[w0 + k] = True
     return opt_T, np.asarray(lm), reverted
+
+
+def window_pairs(window, stride, num_frames):
+    """The (i0, i1) keys `match_kp` visits, in its order, without the repeats it skips (kitti_ba.cpp:603-615)."""
+    pairs, seen = [], set()
+    for i in range(0, num_frames, stride):
+        for a, b in window:
+            i0, i1 = i + a, i + b
+            if (i0, i1) in seen:
+                continue
+            if max(i0, i1) >= num_frames:
+                break
+            seen.add((i0, i1))
+            pairs.append((i0, i1))
+    return pairs
+
+
+def match_kp(kps, descs, window, stride, K, counts=None, ctx=None):
+    """`match_kp` (kitti_ba.cpp:583-755) for a whole drive in ONE pipeline pass: every window pair
+    (i + first, i + second) is matched (BFMatcher NORM_HAMMING2 cross-check, :602,641), filtered by
+    findEssentialMat(LMEDS, 0.99, 0.1) (:702) and recoverPose (:715), and the `reprojs` map the bundle
+    adjustment consumes is returned: p0 / p1 = matched pixels that are E-inliers (mask == 1) AND pass the
+    cheirality test (rec_mask == 255), R / t = recoverPose's; fewer than 8 matches -> identity and
+    (0.1, 0.1, -0.9) with no points (:741-744).
+
+    kps (F, kp, 2) f32, descs (F, kp, 32) u8, counts (F,) optional keypoints per frame.  The reference's
+    association thread does this pair by pair on the CPU while the BA thread polls the map; here the explicit
+    pair list (`epivo_seq_set_pairs`) makes it a single batch."""
+    kps = np.ascontiguousarray(kps, dtype=np.float32)
+    descs = np.ascontiguousarray(descs, dtype=np.uint8)
+    F, kp = kps.shape[0], kps.shape[1]
+    pairs = window_pairs(window, stride, F)
+    reprojs = {}
+    if not pairs:
+        return reprojs
+    pipe = api.SequencePipeline(F, kp, ctx=ctx, max_pairs=max(len(pairs), F - 1))
+    try:
+        if counts is not None:
+            pipe.set_counts(counts)
+        pipe.set_pairs([p[0] for p in pairs], [p[1] for p in pairs])
+        prm = api.default_params(np.asarray(K, dtype=np.float32), method=api.LMEDS, prob=0.99, threshold=0.1)
+        res = pipe.process(prm, kps, descs)
+        for p, (i0, i1) in enumerate(pairs):
+            r = Reproj(p0=np.zeros((0, 2), np.float32), p1=np.zeros((0, 2), np.float32), R=np.eye(3),
+                       t=np.array([0.1, 0.1, -0.9]))
+            if res[p]["n_matches"] >= 8:
+                qi, ti, _ = pipe.matches(p)
+                em, pm = pipe.masks(p)
+                keep = np.flatnonzero(em == 1)[pm == 255]
+                r.p0 = kps[i0][qi[keep]]
+                r.p1 = kps[i1][ti[keep]]
+                r.R = res[p]["R"].copy()
+                r.t = res[p]["t"].copy()
+            reprojs[(i0, i1)] = r
+    finally:
+        pipe.close()
+    return reprojs

@@ -73,3 +73,33 @@ def bundle_adjustment(reprojs, window, stride, num_frames, K, stereo=False, hube
         reverted.append(rev)
         starts.append(i)
     return np.array(opt_T), np.array(lms).reshape(-1, 3), np.array(reverted, dtype=bool), starts
+
+
+def match_kp(kps, descs, window, stride, K, counts=None):
+    """CPU restatement of `match_kp` (kitti_ba.cpp:583-755), pair by pair in the reference's order: cross-check
+    HAMMING2 matching (:602,641), >= 8 matches -> findEssentialMat(LMEDS, 0.99, 0.1) (:702), mask == 1
+    compaction (:705-710), recoverPose (:715), rec_mask == 255 compaction (:729-735); else identity and
+    (0.1, 0.1, -0.9) (:741-744).  Returns {(i0, i1): (p0, p1, R, t)}.  Checker only."""
+    from . import oracle as O
+    F = kps.shape[0]
+    out = {}
+    for i in range(0, F, stride):
+        for a, b in window:
+            i0, i1 = i + a, i + b
+            if (i0, i1) in out:
+                continue
+            if max(i0, i1) >= F:
+                break
+            n0 = kps.shape[1] if counts is None else int(counts[i0])
+            n1 = kps.shape[1] if counts is None else int(counts[i1])
+            qi, ti, _ = O.bf_match(descs[i0][:n0], descs[i1][:n1], O.NORM_HAMMING2, True)
+            c0, c1 = kps[i0][qi], kps[i1][ti]
+            R, t = np.eye(3), np.array([0.1, 0.1, -0.9])
+            p0 = p1 = np.zeros((0, 2), np.float32)
+            if len(qi) >= 8:
+                E, mask, _ = O.find_essential_mat(c0, c1, np.asarray(K, dtype=np.float32), O.LMEDS, 0.99, 0.1)
+                c0, c1 = c0[mask == 1], c1[mask == 1]
+                n_good, R, t, pmask = O.recover_pose(E, c0, c1, np.asarray(K, dtype=np.float32))
+                p0, p1 = c0[pmask == 255], c1[pmask == 255]
+            out[(i0, i1)] = (p0, p1, R, np.asarray(t).reshape(3))
+    return out

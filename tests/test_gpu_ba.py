@@ -79,3 +79,23 @@ def test_stereo_windows_ws3(ctx, delta):
 def test_no_window_fits(ctx):
     opt, lm, rev, starts = ba.bundle_adjustment({}, window_ws(3), 2, 2, synth.KITTI_K, ctx=ctx)
     assert starts == [] and opt.shape == (2, 4, 4)
+
+
+def test_match_kp_window_walk_on_gpu(ctx):
+    """`match_kp` (kitti_ba.cpp:583-755) as one pipeline pass over an explicit pair list: the reprojs map must hold
+    the reference's keys, bit-identical point sets (match indices, E mask == 1, rec_mask == 255) and the
+    recoverPose estimate within north_star's tolerances; then the map feeds the windowed BA as it does in main()."""
+    seq = synth.make_sequence(n_frames=7, n=800, seed=synth.seed_for(3, 91))
+    counts = np.array([800, 760, 800, 5, 800, 790, 800], dtype=np.int32)     # frame 3 has 5 keypoints: < 8 matches
+    window = window_ws(3)
+    got = ba.match_kp(seq.kps, seq.descs, window, 2, seq.K, counts=counts, ctx=ctx)
+    want = OBA.match_kp(seq.kps, seq.descs, window, 2, seq.K, counts=counts)
+    assert list(got.keys()) == list(want.keys()) == ba.window_pairs(window, 2, 7)
+    for key, (p0, p1, R, t) in want.items():
+        g = got[key]
+        assert np.array_equal(g.p0, p0) and np.array_equal(g.p1, p1), key
+        assert np.arccos(np.clip((np.trace(g.R.T @ R) - 1) / 2, -1, 1)) < 1e-4
+        assert np.arccos(np.clip(g.t @ t / (np.linalg.norm(g.t) * np.linalg.norm(t)), -1, 1)) < 1e-3
+    assert len(got[(2, 3)].p0) == 0 and np.array_equal(got[(2, 3)].t, [0.1, 0.1, -0.9])     # kitti_ba.cpp:741-744
+    opt, lm, rev, starts = ba.bundle_adjustment(got, window, 2, 7, seq.K, False, 1.0, ctx=ctx)
+    assert starts == [0, 2, 4] and np.isfinite(opt).all()

@@ -52,3 +52,19 @@ def test_stereo_window_expansion_and_reps():
     win = ba.expand_stereo_window([(0, 1), (0, 2), (1, 2)])
     assert win == [(0, 2), (1, 2), (0, 1), (0, 4), (1, 4), (0, 1), (2, 4), (3, 4), (2, 3)]
     assert ba.window_reps(win) == [(0, 1), (1, 1), (0, 0), (0, 3), (1, 3), (0, 0), (2, 3), (3, 3), (2, 2)]
+
+
+def test_window_pairs_order_and_oracle_match_kp():
+    """The keys match_kp visits (kitti_ba.cpp:603-615): window offsets per start frame, repeats skipped, the inner
+    loop broken at the first pair past the end; and the CPU restatement fills exactly those keys."""
+    from epivo_b200 import ba, synth
+    from oracle import ba as OBA
+    window = [(0, 1), (0, 2), (1, 2)]
+    assert ba.window_pairs(window, 2, 5) == [(0, 1), (0, 2), (1, 2), (2, 3), (2, 4), (3, 4)]
+    assert ba.window_pairs(window, 1, 4) == [(0, 1), (0, 2), (1, 2), (1, 3), (2, 3)]       # (3,4) breaks the inner loop
+    assert ba.window_pairs(window, 2, 1) == []
+    seq = synth.make_sequence(n_frames=3, n=300, seed=synth.seed_for(3, 90))
+    rp = OBA.match_kp(seq.kps, seq.descs, window, 2, seq.K)
+    assert list(rp.keys()) == ba.window_pairs(window, 2, 3)
+    p0, p1, R, t = rp[(0, 1)]
+    assert len(p0) == len(p1) > 50 and abs(np.linalg.det(R) - 1) < 1e-9 and abs(np.linalg.norm(t) - 1) < 1e-9
