@@ -569,10 +569,15 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     {
         const int mchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
         int wave = upload ? epv_match_pairs_per_wave(ctx, s->kp) : mchunk;
+        int max_pieces = 4;
+        if (upload) {                                   // tuning knobs (environment): first piece = wave / div, piece count
+            if (const char* e = getenv("EPIVO_UPLOAD_DIV")) wave = std::max(1, wave / std::max(1, atoi(e)));
+            if (const char* e = getenv("EPIVO_UPLOAD_PIECES")) max_pieces = std::max(1, atoi(e));
+        }
         int p0 = first_pair, left = n_pairs, waves = 1;
         while (left > 0) {
             int np = upload ? wave * waves : mchunk;
-            if (upload && ((int)mg.size() >= 3 || left - np < wave)) np = left;    // the fourth piece takes the rest
+            if (upload && ((int)mg.size() >= max_pieces - 1 || left - np < wave)) np = left;    // the last piece takes the rest
             np = std::min(np, left);
             mg.push_back(std::make_pair(p0, np));
             p0 += np;
