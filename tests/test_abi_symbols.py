@@ -32,3 +32,20 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.LmRes) == 24
     assert C.sizeof(_lib.PairResult) == (9 + 9 + 3 + 16 + 16 + 3) * 8 + 8 * 4
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (what a cgo / FFI binding would include)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    assert cc, "no C compiler"
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "epivo_b200.h"\n'
+                   "int main(void) { epivo_pipeline_params p; epivo_pair_result r; epivo_lm_res l; "
+                   "(void)p; (void)r; (void)l; return sizeof(epivo_pair_result) == %d ? 0 : 1; }\n"
+                   % ((9 + 9 + 3 + 16 + 16 + 3) * 8 + 8 * 4))
+    exe = tmp_path / "use_header"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0          # same struct size as the ctypes mirror
