@@ -520,6 +520,11 @@ __global__ void __launch_bounds__(SB2_THREADS, EPV_SB2_MINBLOCKS) solve_b2_kerne
 // points are staged there, so the loads compile to LDS rather than generic loads)
 // The hot loop is branch-free (pre-filter only); points it cannot decide -- practically none -- are
 // recounted with the exact test in a second loop that is normally skipped.
+#ifndef EPV_ES_UNROLL
+#define EPV_ES_UNROLL 3
+#endif
+constexpr int ES_UNROLL = EPV_ES_UNROLL;   // correspondences in flight per lane in the scoring loops
+
 template <class P>
 __device__ __forceinline__ void count_two(P X1, int stride, int n, int first, int step, const double* M0,
                                           const double* M1, const SampThr& T, int& c0, int& c1) {
@@ -527,7 +532,7 @@ __device__ __forceinline__ void count_two(P X1, int stride, int n, int first, in
 #pragma unroll
     for (int c = 0; c < 9; ++c) { E0[c] = M0[c]; E1[c] = M1[c]; }
     bool undecided = false;
-#pragma unroll 2
+#pragma unroll ES_UNROLL
     for (int i = first; i < n; i += step) {
         const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
         bool in0, in1;
@@ -553,7 +558,7 @@ __device__ __forceinline__ int count_one(P X1, int stride, int n, int first, int
     for (int c = 0; c < 9; ++c) E[c] = M[c];
     int c = 0;
     bool undecided = false;
-#pragma unroll 2
+#pragma unroll ES_UNROLL
     for (int i = first; i < n; i += step) {
         bool in;
         const bool d = sampson_fast(E, X1[i], X1[stride + i], X1[2 * stride + i], X1[3 * stride + i], T, T.hdmin, in);

@@ -36,6 +36,7 @@ struct epivo_seq {
     bool pairs_set = false;
     int max_pairs = 0, n_list = 0;   // capacity / pairs currently addressable
     int frames_hi = 0;               // frames [0, frames_hi) have been uploaded (plane pre-pass range in list mode)
+    int list_max = 0;                // largest frame index the pair list references
     // per pair, whole sequence
     int32_t *d_mq = nullptr, *d_mt = nullptr, *d_md = nullptr, *d_nmatch = nullptr;
     uint8_t *d_emask = nullptr, *d_pmask = nullptr;
@@ -330,12 +331,15 @@ int epivo_seq_set_pairs(epivo_seq* s, int n_pairs, const int32_t* fq, const int3
     } else {
         if (n_pairs > s->max_pairs) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "%d pairs > capacity %d (epivo_seq_create_pairs)", n_pairs, s->max_pairs);
         h.resize((size_t)n_pairs * 2);
+        int lmax = 0;
         for (int p = 0; p < n_pairs; ++p) {
             if (fq[p] < 0 || fq[p] >= s->max_frames || ft[p] < 0 || ft[p] >= s->max_frames)
                 EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair %d = (%d,%d) outside [0,%d)", p, fq[p], ft[p], s->max_frames);
             h[p] = fq[p];
             h[(size_t)n_pairs + p] = ft[p];
+            lmax = std::max(lmax, std::max(fq[p], ft[p]));
         }
+        s->list_max = lmax;                              // only once the whole list has been accepted
         s->pairs_set = true;
     }
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -660,6 +664,8 @@ int epivo_seq_process(epivo_seq* s, const epivo_pipeline_params* prm, int n_fram
     if (!kps || !descs || !out) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null buffer");
     if (n_frames < 2 || n_frames > s->max_frames) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_frames %d outside [2,%d]", n_frames, s->max_frames);
     // consecutive pairs: n_frames - 1 of them; explicit pair list (epivo_seq_set_pairs): the whole list
+    if (s->pairs_set && s->list_max >= n_frames)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "the pair list references frame %d but only %d frames are given", s->list_max, n_frames);
     const int n_pairs = s->pairs_set ? s->n_list : n_frames - 1;
     int rc = seq_execute(s, prm, 0, n_pairs, kps, descs, n_frames);
     if (rc) return rc;

@@ -171,6 +171,8 @@ def test_explicit_pair_list_window_walk(ctx):
     assert again.tobytes() == res[3:8].tobytes()
     with pytest.raises(api.EpivoError):
         pipe.set_pairs([0, 5], [1, 2])                        # frame index out of range
+    with pytest.raises(api.EpivoError):
+        pipe.process(prm, kps[:3], descs[:3])                 # the list references frames 3 and 4
     # back to consecutive pairs
     pipe.set_pairs(None, None)
     pipe.run(prm, 0, seq.n_frames - 1)
