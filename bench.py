@@ -441,6 +441,13 @@ def main():
         pool.run(range(min(n, cores)))
         v, res = pool.run(range(n))
         pool.close()
+        # SURVEY 8d's other arrangement: one process, OpenCV's own threads over all cores (16 pairs, ~2 s)
+        n1 = min(16, n)
+        v1 = R.single_process_rate(seq.kps[:n1 + 1], seq.descs[:n1 + 1], seq.K, n1, 8 if a.method == "ransac" else 4, 0.99,
+                                   a.thr, threads=cores, norm=7 if a.norm == "hamming2" else 6,
+                                   ratio=None if a.match == "crosscheck" else 0.8)
+        line["cpu_baseline_single_process"] = {"value": v1, "unit": UNIT, "cores": cores,
+                                               "sample": f"first {n1} pairs, one process, cv2.setNumThreads({cores})"}
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference" if R.HAVE_CV2 else "port",
                                 "sample": f"first {n} pairs of the same sequence; cv2 "
                                           f"{R.cv2.__version__ if R.HAVE_CV2 else 'missing'} BFMatcher/findEssentialMat/"

@@ -113,3 +113,22 @@ class CpuPool:
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+def single_process_rate(kps, descs, K, n_pairs, method=8, prob=0.99, thr=1.0, threads=None, norm=7, ratio=None):
+    """SURVEY 8d's second CPU arrangement: ONE process, OpenCV's own thread pool over `threads` cores
+    (cv2.setNumThreads), pairs one after the other.  -> pairs/s (one warm-up pair is not timed)."""
+    if not HAVE_CV2:
+        return None
+    threads = threads or (os.cpu_count() or 1)
+    Kf = np.asarray(K, dtype=np.float32)
+    clib.build()
+    cv2.setNumThreads(threads)
+    try:
+        pair_cv2(kps[0], descs[0], kps[1], descs[1], Kf, method, prob, thr, norm=norm, ratio=ratio)
+        t0 = time.perf_counter()
+        for i in range(n_pairs):
+            pair_cv2(kps[i], descs[i], kps[i + 1], descs[i + 1], Kf, method, prob, thr, norm=norm, ratio=ratio)
+        return n_pairs / (time.perf_counter() - t0)
+    finally:
+        cv2.setNumThreads(1)
