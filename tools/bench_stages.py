@@ -50,7 +50,14 @@ seq_rate("cfg2_euroc_ransac_0.3", euroc, 1500, threshold=0.3)
 
 # cfg4: fixed hypothesis sets -- the whole grid of BASELINE.json config 4 (N x M x outlier fraction)
 rng = np.random.default_rng(4)
-from oracle import oracle as O
+
+
+def knorm(p, K):
+    """K-normalised float64 coordinates of float32 pixels (inputs of the stand-alone 5-point solver)."""
+    p = np.asarray(p, dtype=np.float32).astype(np.float64)
+    return np.stack([(p[:, 0] - K[0, 2]) / K[0, 0], (p[:, 1] - K[1, 2]) / K[1, 1]], axis=1)
+
+
 GRID = [(N, M, outl) for N in (2000, 8000, 20000) for M in (4096, 16384, 65536) for outl in (0.3, 0.5, 0.7)]
 if os.environ.get("CFG4", "grid") == "diag":
     GRID = [(2000, 4096, 0.3), (8000, 16384, 0.5), (20000, 65536, 0.7)]
@@ -60,7 +67,7 @@ for N, M, outl in GRID:
     # correspondences in row order: true partner for the inliers, a random frame-1 point for the outliers
     c0 = p.kp0
     c1 = np.ascontiguousarray(p.kp1[np.where(p.gt_match >= 0, p.gt_match, rng.integers(0, N, N))])
-    x0, x1 = O.normalize_points(c0, Kf), O.normalize_points(c1, Kf)
+    x0, x1 = knorm(c0, p.K), knorm(c1, p.K)
     # M samples of 5 distinct indices (argsort of uniform keys: distinct by construction)
     idx = np.argsort(rng.random((M, 64)), axis=1)[:, :5] * (N // 64) + rng.integers(0, N // 64, size=(M, 5))
     X1, X2 = x0[idx], x1[idx]
