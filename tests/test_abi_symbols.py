@@ -49,3 +49,30 @@ def test_header_is_plain_c(tmp_path):
     subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
                     "-o", str(exe)], check=True)
     assert subprocess.run([str(exe)]).returncode == 0          # same struct size as the ctypes mirror
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under epivo_b200/ (nor the tuning tools) may import or execute it --
+    only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference arm do."""
+    import ast
+    offenders = []
+    for top in ("epivo_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if not f.endswith(".py"):
+                    continue
+                path = os.path.join(dirpath, f)
+                tree = ast.parse(open(path).read())
+                for node in ast.walk(tree):
+                    mods = []
+                    if isinstance(node, ast.Import):
+                        mods = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        mods = [node.module or ""]
+                    if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                        offenders.append(os.path.relpath(path, ROOT))
+    assert not offenders, offenders
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "epivo_b200", "csrc")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h")):
+                assert "oracle/" not in open(os.path.join(dirpath, f)).read(), f
