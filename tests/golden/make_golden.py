@@ -98,9 +98,34 @@ def golden_essential():
     np.savez_compressed(os.path.join(HERE, "essential.npz"), **out)
 
 
+def golden_callsites():
+    """The remaining findEssentialMat call shapes of the reference, which differ from the ones above in `prob`
+    (it drives RANSACUpdateNumIters): kitti_ba.cpp:232 RANSAC(0.95, 0.05), kitti_ba.cpp:1279-1285
+    RANSAC(0.999, 0.3), kitti_ba.cpp:702 LMEDS(0.99, 0.1), euroc_E.cpp:205-207 RANSAC(0.99, 0.3) on the EuRoC
+    camera.  Separate file, so that essential.npz stays byte-identical."""
+    out = {"cv2_version": cv2.__version__}
+    cases = [("kitti", synth.make_kitti_pair(11, n=500)), ("euroc", synth.make_euroc_pair(5, n=450))]
+    calls = [("ransac095_005", cv2.RANSAC, 0.95, 0.05), ("ransac0999_03", cv2.RANSAC, 0.999, 0.3),
+             ("lmeds_01", cv2.LMEDS, 0.99, 0.1), ("ransac099_03", cv2.RANSAC, 0.99, 0.3)]
+    for name, pr in cases:
+        p0, p1 = _matched_points(pr)
+        Kf = pr.K.astype(np.float32)
+        out[f"{name}_p0"], out[f"{name}_p1"], out[f"{name}_K"] = p0, p1, Kf
+        for cname, method, prob, thr in calls:
+            E, mask = cv2.findEssentialMat(p0, p1, Kf, method, prob, thr)
+            out[f"{name}_{cname}_E"] = E
+            out[f"{name}_{cname}_mask"] = mask.ravel()
+            out[f"{name}_{cname}_args"] = np.array([method, prob, thr], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "essential_callsites.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--callsites-only" in sys.argv:
+        golden_callsites()
+        sys.exit(0)
     golden_match()
     golden_essential()
+    golden_callsites()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

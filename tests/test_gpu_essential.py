@@ -190,3 +190,17 @@ def test_find_essential_large_n_matches_oracle(ctx):
         assert info["iters"] == io["iters"]
         assert np.array_equal(mask, mo)                    # bit-exact over > 13000 correspondences
         assert esame(E, Eo) < 1e-6                         # the winning minimal sample is conditioned ~1e8 here
+
+
+@pytest.mark.parametrize("case", ["kitti", "euroc"])
+@pytest.mark.parametrize("cname", ["ransac095_005", "ransac0999_03", "lmeds_01", "ransac099_03"])
+def test_other_reference_call_sites_vs_cv2(ctx, case, cname):
+    """kitti_ba.cpp:232 RANSAC(.95,.05), :1279 RANSAC(.999,.3), :702 LMEDS(.99,.1), euroc_E.cpp:205 RANSAC(.99,.3):
+    whole-call parity with cv2 (E up to sign, identical mask) for the `prob` values the main golden file lacks."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "essential_callsites.npz"))
+    method, prob, thr = g[f"{case}_{cname}_args"]
+    E, m, info = api.findEssentialMat(g[f"{case}_p0"], g[f"{case}_p1"], g[f"{case}_K"], int(method), float(prob), float(thr),
+                                      ctx=ctx, return_info=True)
+    assert E is not None and esame(E, g[f"{case}_{cname}_E"]) < E_TOL
+    assert np.array_equal(m, g[f"{case}_{cname}_mask"])

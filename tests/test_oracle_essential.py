@@ -82,3 +82,23 @@ def test_recover_pose_reproduces_cv2(golden_ess, case, cname):
     assert np.abs(t - golden_ess[f"{case}_{cname}_t"]).max() < 1e-9
     assert np.array_equal(mask, golden_ess[f"{case}_{cname}_pose_mask"])
     assert set(np.unique(mask)) <= {0, 255}
+
+
+CALLSITES = ["ransac095_005", "ransac0999_03", "lmeds_01", "ransac099_03"]
+
+
+def _callsites():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "essential_callsites.npz"))
+
+
+@pytest.mark.parametrize("case", ["kitti", "euroc"])
+@pytest.mark.parametrize("cname", [c for c in CALLSITES if c != "ransac095_005"])    # ~1000 iterations: too slow in numpy
+def test_other_call_sites_whole_call(case, cname):
+    """The reference's remaining findEssentialMat shapes (kitti_ba.cpp:702,1279; euroc_E.cpp:205): `prob` other
+    than 0.99 exercises RANSACUpdateNumIters; E and mask of cv2 must be reproduced by the restatement."""
+    g = _callsites()
+    method, prob, thr = g[f"{case}_{cname}_args"]
+    E, mask, info = O.find_essential_mat(g[f"{case}_p0"], g[f"{case}_p1"], g[f"{case}_K"], int(method), float(prob), float(thr))
+    assert esame(E, g[f"{case}_{cname}_E"]) < 1e-6
+    assert np.array_equal(mask, g[f"{case}_{cname}_mask"])
