@@ -15,7 +15,9 @@
 // `cv::` / unqualified calls with `epivo::` ones -- see INTEGRATION.md.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -181,6 +183,98 @@ double Levenberg_Marquardt(Context& ctx, const int n_zeta, const double epsilon,
     LM_res res;
     Levenberg_Marquardt(ctx, n_zeta, epsilon, reps, w, lambda0, T0s, pr, p_r, res);
     return res.r_norm;
+}
+
+// `struct reproj` (kitti_ba.cpp:167-175) with plain arrays for R (row-major) and t.
+template <typename Pt>
+struct Reproj {
+    std::vector<Pt> p0, p1;
+    double R[9], t[3];
+};
+
+// void match_kp(window, stride, num_frames, source_kp, img_fns, descs, cam, reprojs)   kitti_ba.cpp:583-755
+// for a whole drive in ONE device pass.  The reference walks (i + window[j].first, i + window[j].second) pair by
+// pair on the association thread (BFMatcher NORM_HAMMING2 cross-check :602,641; findEssentialMat(LMEDS, 0.99, 0.1)
+// :702; mask == 1 compaction :705-710; recoverPose :715; rec_mask == 255 compaction :729-735; fewer than 8
+// matches -> identity and (0.1, 0.1, -0.9), :741-744).  Here the walk becomes an explicit pair list
+// (epivo_seq_set_pairs) over the frames' keypoints / descriptors and the map is filled from the results.
+//   source_kp[f]  keypoints of frame f (any count per frame)
+//   descs[f]      source_kp[f].size() x 32 descriptor bytes, row-major (cv::Mat::data of the ORB descriptors)
+template <typename Pt>
+void match_kp(Context& ctx, const std::vector<std::pair<int, int> >& window, const int stride, const int num_frames,
+              const std::vector<std::vector<Pt> >& source_kp, const std::vector<const uint8_t*>& descs,
+              const double cam[9], std::map<std::pair<int, int>, Reproj<Pt> >& reprojs) {
+    if (stride <= 0) throw std::invalid_argument("stride must be positive");                       // :592 assert
+    if ((int)source_kp.size() < num_frames || (int)descs.size() < num_frames)
+        throw std::invalid_argument("source_kp / descs shorter than num_frames");
+    std::vector<std::pair<int, int> > pairs;                                                       // :603-615
+    for (int i = 0; i < num_frames; i += stride) {
+        for (size_t j = 0; j < window.size(); ++j) {
+            const std::pair<int, int> key(i + window[j].first, i + window[j].second);
+            if (reprojs.count(key)) continue;
+            bool seen = false;
+            for (size_t q = 0; q < pairs.size() && !seen; ++q) seen = pairs[q] == key;
+            if (seen) continue;
+            if (key.first >= num_frames || key.second >= num_frames) break;
+            pairs.push_back(key);
+        }
+    }
+    if (pairs.empty() || num_frames < 2) return;
+    size_t kp = 1;
+    for (int f = 0; f < num_frames; ++f) kp = source_kp[f].size() > kp ? source_kp[f].size() : kp;
+    std::vector<float> kps((size_t)num_frames * kp * 2, 0.f);
+    std::vector<uint8_t> dsc((size_t)num_frames * kp * 32, 0);
+    std::vector<int32_t> counts(num_frames), fq(pairs.size()), ft(pairs.size());
+    for (int f = 0; f < num_frames; ++f) {
+        counts[f] = (int32_t)source_kp[f].size();
+        for (size_t k = 0; k < source_kp[f].size(); ++k) {
+            kps[((size_t)f * kp + k) * 2] = source_kp[f][k].x;
+            kps[((size_t)f * kp + k) * 2 + 1] = source_kp[f][k].y;
+        }
+        if (counts[f]) std::copy(descs[f], descs[f] + (size_t)counts[f] * 32, dsc.begin() + (size_t)f * kp * 32);
+    }
+    for (size_t p = 0; p < pairs.size(); ++p) { fq[p] = pairs[p].first; ft[p] = pairs[p].second; }
+    epivo_seq* seq = nullptr;
+    const int max_pairs = (int)pairs.size() > num_frames - 1 ? (int)pairs.size() : num_frames - 1;
+    ctx.check(epivo_seq_create_pairs(ctx.get(), &seq, num_frames, (int)kp, max_pairs));
+    struct Guard { epivo_seq* s; ~Guard() { epivo_seq_destroy(s); } } guard = {seq};
+    ctx.check(epivo_seq_set_counts(seq, 0, num_frames, counts.data()));
+    ctx.check(epivo_seq_set_pairs(seq, (int)pairs.size(), fq.data(), ft.data()));
+    epivo_pipeline_params prm;
+    epivo_pipeline_params_default(&prm);
+    for (int i = 0; i < 9; ++i) prm.K[i] = cam[i];
+    prm.method = EPIVO_LMEDS;                                                                      // :702
+    prm.prob = 0.99;
+    prm.threshold = 0.1;
+    std::vector<epivo_pair_result> res(pairs.size());
+    ctx.check(epivo_seq_process(seq, &prm, num_frames, kps.data(), dsc.data(), res.data()));
+    std::vector<int32_t> qi(kp), ti(kp), di(kp);
+    std::vector<uint8_t> em(kp), pm(kp);
+    for (size_t p = 0; p < pairs.size(); ++p) {
+        Reproj<Pt> rep;
+        const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t0[3] = {0.1, 0.1, -0.9};                 // :741-744
+        std::copy(I, I + 9, rep.R);
+        std::copy(t0, t0 + 3, rep.t);
+        if (res[p].n_matches >= 8) {                                                               // :700
+            int nm = 0, ne = 0, np = 0;
+            ctx.check(epivo_seq_get_matches(seq, (int)p, qi.data(), ti.data(), di.data(), &nm));
+            ctx.check(epivo_seq_get_masks(seq, (int)p, em.data(), &ne, pm.data(), &np));
+            const std::vector<Pt>& k0 = source_kp[pairs[p].first];
+            const std::vector<Pt>& k1 = source_kp[pairs[p].second];
+            int c = 0;                                             // index into the compacted E-inlier list
+            for (int m = 0; m < nm; ++m) {
+                if (em[m] != 1) continue;                                                          // :705-710
+                if (c < np && pm[c] == 255) {                                                      // :729-735
+                    rep.p0.push_back(k0[qi[m]]);
+                    rep.p1.push_back(k1[ti[m]]);
+                }
+                ++c;
+            }
+            std::copy(res[p].R, res[p].R + 9, rep.R);
+            std::copy(res[p].t, res[p].t + 3, rep.t);
+        }
+        reprojs.insert(std::make_pair(pairs[p], rep));
+    }
 }
 
 }  // namespace epivo

@@ -83,6 +83,56 @@ int main() {
     epivo::BFMatcher(ctx, epivo::NORM_HAMMING2, true).match(d.data(), 64, d.data(), 64, 32, matches);
     if (matches.size() != 64) return 4;
     for (int i = 0; i < 64; ++i) if (matches[i].queryIdx != i || matches[i].trainIdx != i || matches[i].distance != 0.f) return 5;
+    // ---- match_kp (kitti_ba.cpp:583-755): three frames of one scene, window {(0,1),(0,2),(1,2)}; frame 2 sees fewer
+    //      landmarks and frame order is shuffled, so counts differ and matching is not the identity
+    {
+        const int L = 400, F = 3;
+        const double ang[F][3] = {{0, 0, 0}, {0.02, -0.01, 0.015}, {0.04, -0.02, 0.03}};
+        const double tt[F][3] = {{0, 0, 0}, {0.05, -0.02, -1.0}, {0.1, -0.04, -2.0}};
+        std::vector<std::vector<uint8_t> > ldesc(L, std::vector<uint8_t>(32));
+        std::vector<double> X(3 * L);
+        for (int i = 0; i < L; ++i) {
+            X[3 * i] = 30 * (urand() - 0.5); X[3 * i + 1] = 8 * (urand() - 0.5); X[3 * i + 2] = 12 + 40 * urand();
+            for (int b = 0; b < 32; ++b) ldesc[i][b] = (uint8_t)(rand() & 255);
+        }
+        std::vector<std::vector<Point2f> > kp(F);
+        std::vector<std::vector<uint8_t> > dsc(F);
+        std::vector<Mat> Rf;
+        for (int f = 0; f < F; ++f) {
+            Rf.push_back(rot_xyz(ang[f][0], ang[f][1], ang[f][2]));
+            const int nl = f == 2 ? L - 37 : L;
+            for (int q = 0; q < nl; ++q) {
+                const int i = (q * 7 + 3 * f) % nl;                       // a different order in every frame
+                double Y[3];
+                for (int a = 0; a < 3; ++a) Y[a] = Rf[f](a, 0) * X[3 * i] + Rf[f](a, 1) * X[3 * i + 1] + Rf[f](a, 2) * X[3 * i + 2] + tt[f][a];
+                Point2f pt = {(float)(cam[0] * Y[0] / Y[2] + cam[2]), (float)(cam[4] * Y[1] / Y[2] + cam[5])};
+                kp[f].push_back(pt);
+                dsc[f].insert(dsc[f].end(), ldesc[i].begin(), ldesc[i].end());
+            }
+        }
+        std::vector<const uint8_t*> dptr;
+        for (int f = 0; f < F; ++f) dptr.push_back(dsc[f].data());
+        std::vector<std::pair<int, int> > window;
+        window.push_back(std::make_pair(0, 1)); window.push_back(std::make_pair(0, 2)); window.push_back(std::make_pair(1, 2));
+        std::map<std::pair<int, int>, epivo::Reproj<Point2f> > reprojs;
+        epivo::match_kp(ctx, window, 2, F, kp, dptr, cam, reprojs);
+        if (reprojs.size() != 3) return 6;
+        for (std::map<std::pair<int, int>, epivo::Reproj<Point2f> >::iterator it = reprojs.begin(); it != reprojs.end(); ++it) {
+            const int a = it->first.first, b = it->first.second;
+            const epivo::Reproj<Point2f>& r = it->second;
+            // ground truth: x_b = Rb Ra^T x_a + ...
+            double dRm = 0;
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+                double g = 0;
+                for (int k = 0; k < 3; ++k) g += Rf[b](i, k) * Rf[a](j, k);
+                dRm += (r.R[i * 3 + j] - g) * (r.R[i * 3 + j] - g);
+            }
+            printf("match_kp (%d,%d): %zu points  |R-Rgt| %.3e  t (%.3f %.3f %.3f)\n", a, b, r.p0.size(), sqrt(dRm), r.t[0], r.t[1], r.t[2]);
+            if (r.p0.size() != r.p1.size() || r.p0.size() < 200 || sqrt(dRm) > 2e-3) return 7;
+        }
+        epivo::match_kp(ctx, window, 2, F, kp, dptr, cam, reprojs);     // every key is present: nothing to do (:609-611)
+        if (reprojs.size() != 3) return 8;
+    }
     printf("shims ok\n");
     return 0;
 }
