@@ -18,6 +18,7 @@
 #include <map>
 #include <stdexcept>
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <utility>
 #include <vector>
@@ -275,6 +276,114 @@ void match_kp(Context& ctx, const std::vector<std::pair<int, int> >& window, con
         }
         reprojs.insert(std::make_pair(pairs[p], rep));
     }
+}
+
+// int bundle_adjustment(reprojs, window, stride, num_frames, cam, opt_T)                    kitti_ba.cpp:757-905
+// The reference walks the windows one by one, polling the reprojs map with 20 ms sleeps (:793-797).  A window's
+// LM problem depends only on that window's reprojections -- its initial chain is rebuilt from reprojs[(j, j+1)]
+// every time (:856-859, `!optimized[j] || true`) -- so all windows are assembled first and solved by ONE
+// epivo_lm_rt_batch launch; only the sequential tail is replayed on the host as written: revert when
+// r_norm > 1e-2 (:889-891), divide the translations by the scale carried from the previous window (:853-855,
+// :898-901), later windows overwrite the overlap.  Every reprojection a window needs must already be in the map
+// (std::out_of_range otherwise: there is no association thread to wait for -- see match_kp above).
+//   M: a matrix type with M(rows, cols) and (i, j) access (Eigen::MatrixXd); opt_T must come in empty (:764).
+template <typename Pt, typename M>
+int bundle_adjustment(Context& ctx, const std::map<std::pair<int, int>, Reproj<Pt> >& reprojs,
+                      const std::vector<std::pair<int, int> >& window, const int stride, const int num_frames,
+                      const double cam[9], std::vector<M>& opt_T, std::vector<LM_res>* lm_out = nullptr,
+                      double huber_delta = 1e-5 /* jac_Rt_gen_.cpp:17 */) {
+    if (stride <= 0) throw std::invalid_argument("stride must be positive");                       // :763
+    if (!opt_T.empty()) throw std::invalid_argument("opt_T must be empty");                        // :764
+    if (window.empty()) throw std::invalid_argument("empty window");
+    for (int f = 0; f < num_frames; ++f) {                                                         // :767-770
+        M I(4, 4);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) I(i, j) = i == j ? 1.0 : 0.0;
+        opt_T.push_back(I);
+    }
+    if (lm_out) lm_out->clear();
+    // cam^-1 (:772-774), general 3x3 inverse
+    double Ki[9];
+    {
+        const double* k = cam;
+        const double det = k[0] * (k[4] * k[8] - k[5] * k[7]) - k[1] * (k[3] * k[8] - k[5] * k[6]) + k[2] * (k[3] * k[7] - k[4] * k[6]);
+        Ki[0] = (k[4] * k[8] - k[5] * k[7]) / det; Ki[1] = (k[2] * k[7] - k[1] * k[8]) / det; Ki[2] = (k[1] * k[5] - k[2] * k[4]) / det;
+        Ki[3] = (k[5] * k[6] - k[3] * k[8]) / det; Ki[4] = (k[0] * k[8] - k[2] * k[6]) / det; Ki[5] = (k[2] * k[3] - k[0] * k[5]) / det;
+        Ki[6] = (k[3] * k[7] - k[4] * k[6]) / det; Ki[7] = (k[1] * k[6] - k[0] * k[7]) / det; Ki[8] = (k[0] * k[4] - k[1] * k[3]) / det;
+    }
+    const int min_pt = 32, n_rep = (int)window.size();                                             // :777
+    int lo = window[0].first, hi = window[0].first;
+    std::vector<int32_t> reps(2 * (size_t)n_rep);
+    for (int j = 0; j < n_rep; ++j) {
+        const int a = window[j].first, b = window[j].second;
+        if (a == b) throw std::invalid_argument("window entry with first == second");              // :812 assert
+        lo = std::min(lo, std::min(a, b));
+        hi = std::max(hi, std::max(a, b));
+        reps[2 * j] = b > a ? a : a - 1;                                                           // :813-817
+        reps[2 * j + 1] = b > a ? b - 1 : b;
+    }
+    const int nz = hi - lo;                                                                        // w1 - w0 (:874)
+    std::vector<int> starts;                                                                       // :780-801
+    for (int i = 0; i < num_frames; i += stride) {
+        if (i + hi >= num_frames) break;
+        starts.push_back(i);
+    }
+    const int B = (int)starts.size();
+    if (B == 0) return 0;
+    std::vector<double> T0((size_t)B * nz * 16, 0.0), pr((size_t)B * n_rep * min_pt * 3, 1.0), p_r(pr.size(), 1.0),
+        w((size_t)B * n_rep, 0.0);
+    for (int b = 0; b < B; ++b) {
+        const int i = starts[b];
+        for (int j = 0; j < n_rep; ++j) {
+            const Reproj<Pt>& r = reprojs.at(std::make_pair(i + window[j].first, i + window[j].second));
+            if ((int)r.p0.size() < min_pt) continue;                // "Bad pts": weight 0, all-ones points (:819-824)
+            w[(size_t)b * n_rep + j] = 1.0;
+            for (int k = 0; k < min_pt; ++k) {                                                     // :838-845
+                const double u0 = r.p0[k].x, v0 = r.p0[k].y, u1 = r.p1[k].x, v1 = r.p1[k].y;
+                double* a = &pr[(((size_t)b * n_rep + j) * min_pt + k) * 3];
+                double* c = &p_r[(((size_t)b * n_rep + j) * min_pt + k) * 3];
+                for (int q = 0; q < 3; ++q) {
+                    a[q] = Ki[3 * q] * u0 + Ki[3 * q + 1] * v0 + Ki[3 * q + 2];
+                    c[q] = Ki[3 * q] * u1 + Ki[3 * q + 1] * v1 + Ki[3 * q + 2];
+                }
+            }
+        }
+        for (int k = 0; k < nz; ++k) {                                                             // :856-868
+            const Reproj<Pt>& r = reprojs.at(std::make_pair(i + lo + k, i + lo + k + 1));
+            double* T = &T0[((size_t)b * nz + k) * 16];
+            for (int q = 0; q < 3; ++q) {
+                for (int c = 0; c < 3; ++c) T[4 * q + c] = r.R[3 * q + c];
+                T[4 * q + 3] = r.t[q];
+            }
+            T[15] = 1.0;
+        }
+    }
+    std::vector<double> T(T0);
+    std::vector<epivo_lm_res> res(B);
+    std::vector<int32_t> iters(B);
+    ctx.check(epivo_lm_rt_batch(ctx.get(), B, nz, 1e-8, reps.data(), w.data(), n_rep, 1e-2, 30, huber_delta, T.data(),
+                                pr.data(), p_r.data(), min_pt, res.data(), iters.data()));        // :881
+    std::vector<bool> optimized(num_frames, false);
+    for (int b = 0; b < B; ++b) {                                                                  // :853-855, :889-903
+        const int w0 = starts[b] + lo;
+        double scale = 1.0;
+        if (optimized[w0]) {
+            const M& P = opt_T[w0];
+            scale = std::sqrt(P(0, 3) * P(0, 3) + P(1, 3) * P(1, 3) + P(2, 3) * P(2, 3));
+        }
+        const double* Ts = res[b].r_norm > 1e-2 ? &T0[(size_t)b * nz * 16] : &T[(size_t)b * nz * 16];
+        for (int k = 0; k < nz; ++k) {
+            M& O = opt_T[w0 + k];
+            for (int q = 0; q < 4; ++q) for (int c = 0; c < 4; ++c) O(q, c) = Ts[16 * k + 4 * q + c];
+            for (int q = 0; q < 3; ++q) O(q, 3) /= scale;
+            optimized[w0 + k] = true;
+        }
+        if (lm_out) {
+            LM_res l;
+            l.H_norm = res[b].H_norm; l.r_norm = res[b].r_norm; l.lambda = res[b].lambda;
+            lm_out->push_back(l);
+        }
+    }
+    return B;
 }
 
 }  // namespace epivo

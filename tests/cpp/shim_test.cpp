@@ -132,6 +132,23 @@ int main() {
         }
         epivo::match_kp(ctx, window, 2, F, kp, dptr, cam, reprojs);     // every key is present: nothing to do (:609-611)
         if (reprojs.size() != 3) return 8;
+        // ---- bundle_adjustment (kitti_ba.cpp:757-905) on that map: one window (frames 0..2), two poses
+        std::vector<Mat> opt_T;
+        std::vector<LM_res> lms;
+        const int nwin = epivo::bundle_adjustment(ctx, reprojs, window, 2, F, cam, opt_T, &lms, /*huber_delta=*/1.0);
+        if (nwin != 1 || opt_T.size() != (size_t)F || lms.size() != 1) return 9;
+        for (int k = 0; k < 2; ++k) {                      // opt_T[k] = refined pose of frame k -> k + 1
+            double dRm = 0;
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+                double g = 0;
+                for (int q = 0; q < 3; ++q) g += Rf[k + 1](i, q) * Rf[k](j, q);
+                dRm += (opt_T[k](i, j) - g) * (opt_T[k](i, j) - g);
+            }
+            printf("bundle_adjustment pose %d: |R-Rgt| %.3e  t (%.3f %.3f %.3f)  r_norm %.3e\n", k, sqrt(dRm), opt_T[k](0, 3),
+                   opt_T[k](1, 3), opt_T[k](2, 3), lms[0].r_norm);
+            if (!(sqrt(dRm) < 2e-3) || !(lms[0].r_norm == lms[0].r_norm)) return 10;
+        }
+        if (opt_T[2](0, 0) != 1.0 || opt_T[2](0, 3) != 0.0) return 11;       // frame 2 starts no window: identity (:767)
     }
     printf("shims ok\n");
     return 0;
