@@ -191,6 +191,11 @@ template <typename Pt>
 struct Reproj {
     std::vector<Pt> p0, p1;
     double R[9], t[3];
+    double w;                 // reprojection weight (kitti_ba.cpp:171-172): 0 freezes it (the stereo extrinsics)
+    Reproj() : w(1.0) {
+        for (int i = 0; i < 9; ++i) R[i] = i % 4 == 0 ? 1.0 : 0.0;
+        t[0] = t[1] = t[2] = 0.0;
+    }
 };
 
 // void match_kp(window, stride, num_frames, source_kp, img_fns, descs, cam, reprojs)   kitti_ba.cpp:583-755
@@ -287,15 +292,20 @@ void match_kp(Context& ctx, const std::vector<std::pair<int, int> >& window, con
 // :898-901), later windows overwrite the overlap.  Every reprojection a window needs must already be in the map
 // (std::out_of_range otherwise: there is no association thread to wait for -- see match_kp above).
 //   M: a matrix type with M(rows, cols) and (i, j) access (Eigen::MatrixXd); opt_T must come in empty (:764).
+namespace detail {
+// mono: nodes = frames, node_step 1, unit weights, scale carry; stereo: nodes 2f (left) / 2f + 1 (right), node_step 2,
+// the reprojections' own weights, no scale carry (kitti_ba.cpp:908-1068)
 template <typename Pt, typename M>
-int bundle_adjustment(Context& ctx, const std::map<std::pair<int, int>, Reproj<Pt> >& reprojs,
-                      const std::vector<std::pair<int, int> >& window, const int stride, const int num_frames,
-                      const double cam[9], std::vector<M>& opt_T, std::vector<LM_res>* lm_out = nullptr,
-                      double huber_delta = 1e-5 /* jac_Rt_gen_.cpp:17 */) {
+int windowed_ba(Context& ctx, const std::map<std::pair<int, int>, Reproj<Pt> >& reprojs,
+                const std::vector<std::pair<int, int> >& window, const int stride, const int num_frames,
+                const int node_step, const double cam[9], std::vector<M>& opt_T, std::vector<LM_res>* lm_out,
+                double huber_delta) {
+    const bool stereo = node_step == 2;
+    const int num_nodes = node_step * num_frames;
     if (stride <= 0) throw std::invalid_argument("stride must be positive");                       // :763
     if (!opt_T.empty()) throw std::invalid_argument("opt_T must be empty");                        // :764
     if (window.empty()) throw std::invalid_argument("empty window");
-    for (int f = 0; f < num_frames; ++f) {                                                         // :767-770
+    for (int f = 0; f < num_nodes; ++f) {                                                          // :767-770, :918-921
         M I(4, 4);
         for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) I(i, j) = i == j ? 1.0 : 0.0;
         opt_T.push_back(I);
@@ -324,7 +334,7 @@ int bundle_adjustment(Context& ctx, const std::map<std::pair<int, int>, Reproj<P
     const int nz = hi - lo;                                                                        // w1 - w0 (:874)
     std::vector<int> starts;                                                                       // :780-801
     for (int i = 0; i < num_frames; i += stride) {
-        if (i + hi >= num_frames) break;
+        if (node_step * i + hi >= num_nodes) break;
         starts.push_back(i);
     }
     const int B = (int)starts.size();
@@ -332,11 +342,11 @@ int bundle_adjustment(Context& ctx, const std::map<std::pair<int, int>, Reproj<P
     std::vector<double> T0((size_t)B * nz * 16, 0.0), pr((size_t)B * n_rep * min_pt * 3, 1.0), p_r(pr.size(), 1.0),
         w((size_t)B * n_rep, 0.0);
     for (int b = 0; b < B; ++b) {
-        const int i = starts[b];
+        const int i = node_step * starts[b];
         for (int j = 0; j < n_rep; ++j) {
             const Reproj<Pt>& r = reprojs.at(std::make_pair(i + window[j].first, i + window[j].second));
             if ((int)r.p0.size() < min_pt) continue;                // "Bad pts": weight 0, all-ones points (:819-824)
-            w[(size_t)b * n_rep + j] = 1.0;
+            w[(size_t)b * n_rep + j] = stereo ? r.w : 1.0;                                         // :832 / :996
             for (int k = 0; k < min_pt; ++k) {                                                     // :838-845
                 const double u0 = r.p0[k].x, v0 = r.p0[k].y, u1 = r.p1[k].x, v1 = r.p1[k].y;
                 double* a = &pr[(((size_t)b * n_rep + j) * min_pt + k) * 3];
@@ -362,11 +372,11 @@ int bundle_adjustment(Context& ctx, const std::map<std::pair<int, int>, Reproj<P
     std::vector<int32_t> iters(B);
     ctx.check(epivo_lm_rt_batch(ctx.get(), B, nz, 1e-8, reps.data(), w.data(), n_rep, 1e-2, 30, huber_delta, T.data(),
                                 pr.data(), p_r.data(), min_pt, res.data(), iters.data()));        // :881
-    std::vector<bool> optimized(num_frames, false);
+    std::vector<bool> optimized(num_nodes, false);
     for (int b = 0; b < B; ++b) {                                                                  // :853-855, :889-903
-        const int w0 = starts[b] + lo;
+        const int w0 = node_step * starts[b] + lo;
         double scale = 1.0;
-        if (optimized[w0]) {
+        if (!stereo && optimized[w0]) {
             const M& P = opt_T[w0];
             scale = std::sqrt(P(0, 3) * P(0, 3) + P(1, 3) * P(1, 3) + P(2, 3) * P(2, 3));
         }
@@ -384,6 +394,34 @@ int bundle_adjustment(Context& ctx, const std::map<std::pair<int, int>, Reproj<P
         }
     }
     return B;
+}
+}  // namespace detail
+
+template <typename Pt, typename M>
+int bundle_adjustment(Context& ctx, const std::map<std::pair<int, int>, Reproj<Pt> >& reprojs,
+                      const std::vector<std::pair<int, int> >& window, const int stride, const int num_frames,
+                      const double cam[9], std::vector<M>& opt_T, std::vector<LM_res>* lm_out = nullptr,
+                      double huber_delta = 1e-5 /* jac_Rt_gen_.cpp:17 */) {
+    return detail::windowed_ba(ctx, reprojs, window, stride, num_frames, 1, cam, opt_T, lm_out, huber_delta);
+}
+
+// int bundle_adjustment_stereo(reprojs, window, stride, num_frames, cam, opt_T)             kitti_ba.cpp:908-1068
+// -- the form the shipped main() runs (:1157).  Frame f becomes nodes 2f (left) and 2f + 1 (right); every window
+// entry (a, b) expands to (2a, 2b), (2a + 1, 2b), (2a, 2a + 1) (:934-941); the reprojections carry their own
+// weights (0 on left -> right: frozen extrinsics); opt_T gets 2 * num_frames entries; no scale carry.
+template <typename Pt, typename M>
+int bundle_adjustment_stereo(Context& ctx, const std::map<std::pair<int, int>, Reproj<Pt> >& reprojs,
+                             const std::vector<std::pair<int, int> >& window, const int stride, const int num_frames,
+                             const double cam[9], std::vector<M>& opt_T, std::vector<LM_res>* lm_out = nullptr,
+                             double huber_delta = 1e-5) {
+    std::vector<std::pair<int, int> > ws;
+    for (size_t i = 0; i < window.size(); ++i) {
+        const int a = window[i].first, b = window[i].second;
+        ws.push_back(std::make_pair(2 * a, 2 * b));
+        ws.push_back(std::make_pair(2 * a + 1, 2 * b));
+        ws.push_back(std::make_pair(2 * a, 2 * a + 1));
+    }
+    return detail::windowed_ba(ctx, reprojs, ws, stride, num_frames, 2, cam, opt_T, lm_out, huber_delta);
 }
 
 }  // namespace epivo

@@ -149,6 +149,52 @@ int main() {
             if (!(sqrt(dRm) < 2e-3) || !(lms[0].r_norm == lms[0].r_norm)) return 10;
         }
         if (opt_T[2](0, 0) != 1.0 || opt_T[2](0, 3) != 0.0) return 11;       // frame 2 starts no window: identity (:767)
+
+        // ---- bundle_adjustment_stereo (kitti_ba.cpp:908-1068, what main() runs): nodes 2f = left, 2f + 1 = right camera
+        //      (0.54 m to the side); the node pairs one window needs come from match_kp over the six node "frames"
+        std::vector<std::vector<Point2f> > nkp(2 * F);
+        std::vector<std::vector<uint8_t> > ndsc(2 * F);
+        for (int n = 0; n < 2 * F; ++n) {
+            const int f = n / 2;
+            for (int q = 0; q < L; ++q) {
+                const int i = (q * 11 + 5 * n) % L;
+                double Y[3];
+                for (int a = 0; a < 3; ++a) Y[a] = Rf[f](a, 0) * X[3 * i] + Rf[f](a, 1) * X[3 * i + 1] + Rf[f](a, 2) * X[3 * i + 2] + tt[f][a];
+                if (n & 1) Y[0] -= 0.54;
+                Point2f pt = {(float)(cam[0] * Y[0] / Y[2] + cam[2]), (float)(cam[4] * Y[1] / Y[2] + cam[5])};
+                nkp[n].push_back(pt);
+                ndsc[n].insert(ndsc[n].end(), ldesc[i].begin(), ldesc[i].end());
+            }
+        }
+        std::vector<const uint8_t*> nptr;
+        for (int n = 0; n < 2 * F; ++n) nptr.push_back(ndsc[n].data());
+        const int need[8][2] = {{0, 1}, {0, 2}, {1, 2}, {2, 3}, {0, 4}, {1, 4}, {2, 4}, {3, 4}};
+        std::vector<std::pair<int, int> > nodepairs;
+        for (int q = 0; q < 8; ++q) nodepairs.push_back(std::make_pair(need[q][0], need[q][1]));
+        std::map<std::pair<int, int>, epivo::Reproj<Point2f> > srep;
+        epivo::match_kp(ctx, nodepairs, 1000, 2 * F, nkp, nptr, cam, srep);
+        if (srep.size() != 8) return 12;
+        srep[std::make_pair(0, 1)].w = 0.0;                 // left -> right: the rig's extrinsics stay frozen (:171-172)
+        srep[std::make_pair(2, 3)].w = 0.0;
+        std::vector<Mat> sT;
+        std::vector<LM_res> slm;
+        const int swin = epivo::bundle_adjustment_stereo(ctx, srep, window, 2, F, cam, sT, &slm, /*huber_delta=*/1.0);
+        if (swin != 1 || sT.size() != (size_t)(2 * F) || slm.size() != 1) return 13;
+        // The pairwise translations recoverPose returns are unit vectors, so the chain the LM starts from is not
+        // metrically consistent (the rig baseline is 0.54 of a frame step): the LM trades scale against small
+        // rotations, exactly as it does inside the reference.  What is checked here is the plumbing: proper rigid
+        // transforms for the four poses of the window, identity for nodes outside it, a finite residual that was
+        // not reverted.  Numerical parity of this orchestration is pinned in tests/test_gpu_ba.py against oracle/ba.py.
+        for (int k = 0; k < 2 * F; ++k) {
+            const Mat& T = sT[k];
+            const double det = T(0, 0) * (T(1, 1) * T(2, 2) - T(1, 2) * T(2, 1)) - T(0, 1) * (T(1, 0) * T(2, 2) - T(1, 2) * T(2, 0)) +
+                               T(0, 2) * (T(1, 0) * T(2, 1) - T(1, 1) * T(2, 0));
+            printf("bundle_adjustment_stereo node %d: det R %.9f  t (%.3f %.3f %.3f)\n", k, det, T(0, 3), T(1, 3), T(2, 3));
+            if (!(fabs(det - 1.0) < 1e-6) || T(3, 3) != 1.0) return 14;
+            if (k >= 4 && (T(0, 0) != 1.0 || T(0, 3) != 0.0)) return 15;
+        }
+        printf("bundle_adjustment_stereo r_norm %.3e lambda %.3e\n", slm[0].r_norm, slm[0].lambda);
+        if (!(slm[0].r_norm < 1e-2)) return 16;
     }
     printf("shims ok\n");
     return 0;
