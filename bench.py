@@ -260,6 +260,14 @@ def run_windows(a):
             "e2e": {"value": a.windows / (wall_ms * 1e-3), "unit": "windows/s", "ms_per_step": wall_ms,
                     "h2d_bytes_per_step": int(T0.nbytes + pr.nbytes + p_r.nbytes), "d2h_bytes_per_step": int(T0.nbytes + B * 28)},
             "gpu_launches": int(launches), "mean_iters": float(its.mean())}
+    if world == 1 and not a.no_cpu_baseline:
+        from oracle import cpu_reference as R
+        cores = os.cpu_count() or 1
+        n = 2 * cores
+        v = R.windows_rate(data, nz, reps, n, cores=cores)
+        line["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} windows of the same shape; plain-C restatement of the reference LM "
+                                          f"(Eigen/Sophus original not buildable), {cores} processes x 1 thread"}
     if rank == 0:
         emit(line)
     ctx.close()

@@ -132,3 +132,32 @@ def single_process_rate(kps, descs, K, n_pairs, method=8, prob=0.99, thr=1.0, th
         return n_pairs / (time.perf_counter() - t0)
     finally:
         cv2.setNumThreads(1)
+
+
+_WIN = {}
+
+
+def _win_work(b):
+    nz, reps, data, delta = _WIN["args"]
+    Ts, T0, pr, p_r = data[b % len(data)]
+    clib.levenberg_marquardt(nz, 1e-8, reps, [1.0] * len(reps), 1e-2, T0, pr, p_r, huber_delta=delta, max_iters=30)
+    return b
+
+
+def windows_rate(data, nz, reps, n_windows, cores=None, huber_delta=1.0):
+    """kitti_ba windows (config 5) on the host cores: the plain-C restatement of the reference's Levenberg_Marquardt
+    (the Eigen / Sophus original cannot be built here), one window per process at a time.  -> windows/s."""
+    import multiprocessing as mp
+    cores = cores or (os.cpu_count() or 1)
+    clib.build()
+    clib.lib()
+    _WIN["args"] = (nz, reps, data, huber_delta)
+    pool = mp.get_context("fork").Pool(cores)
+    try:
+        pool.map(_win_work, range(cores), chunksize=1)          # warm-up: load the library in every worker
+        t0 = time.perf_counter()
+        pool.map(_win_work, range(n_windows), chunksize=1)
+        return n_windows / (time.perf_counter() - t0)
+    finally:
+        pool.close()
+        pool.join()
