@@ -97,7 +97,7 @@ __device__ __forceinline__ void se3_exp(const double* d, Rt& o) {
     for (int i = 0; i < 9; ++i) {
         const double I = (i % 4 == 0) ? 1.0 : 0.0;
         o.R[i] = I + a * Om[i] + b * Om2[i];
-        V[i] = I + b * Om[i] + c * Om2[i];
+        V[i] = (th < 1e-10) ? o.R[i] : I + b * Om[i] + c * Om2[i];    // Sophus: V = so3.matrix() below epsilon
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) o.t[i] = V[i * 3] * d[0] + V[i * 3 + 1] * d[1] + V[i * 3 + 2] * d[2];
@@ -252,7 +252,7 @@ __device__ __forceinline__ double lm_warp_sum(double v) {
 //    the winner of the NW posts itself (largest, then lowest row), so the separate search disappears;
 //  * two named barriers per step (after the row swap, after the update); warps outside the solve wait at the
 //    block barrier that follows.
-// Returns through sDelta; *stop is set on NaN / inf or |delta| < eps [:407-414].
+// Returns through sDelta; *stop is set on NaN or |delta| < eps [:407-414].
 template <int NW>
 __device__ __forceinline__ void lm_solve_bar() {
     if (NW > 1) asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
@@ -368,7 +368,7 @@ __device__ __noinline__ void lm_warp_solve(double* sH, double* sDelta, int D, in
         double dc = yc / dg;                         // every lane divides its own candidate; the owner's is taken
         dc = __shfl_sync(0xFFFFFFFFu, dc, c & 31);
         if (lane == 0) sDelta[c] = dc;
-        nan |= !(dc == dc) || isinf(dc);
+        nan |= !(dc == dc);                          // hasNaN(): NaN only, an inf passes (as in the reference)
         nrm += dc * dc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) y[i] -= col[i] * dc;
@@ -802,8 +802,9 @@ __global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_ker
             pb[k][c] = have[k] ? gp_r[i * 3 + c] : 1.0;
         }
     }
-    // squared norms are carried; the square roots are taken once at the end
-    double lambda = p.lambda0, prevE2 = 1e20, hs_out = 0.0, rsq_out = 0.0;
+    // the accept test compares NORMS as the reference does [:456-457]: on a converged plateau two sums of squares
+    // that differ by an ulp can have equal square roots, and `<` must then reject
+    double lambda = p.lambda0, prevE = 1e10, hs_out = 0.0, rsq_out = 0.0;
     int iters = 0;
     for (int iter = 0; iter < p.max_iters; ++iter) {
         if (__all_sync(0xFFFFFFFFu, done)) break;
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_ker
 #pragma unroll
             for (int c = r + 1; c < 6; ++c) s -= A[r][c] * d[c];
             d[r] = s * ip[r];
-            bad |= !(d[r] == d[r]) || isinf(d[r]);
+            bad |= !(d[r] == d[r]);                                                 // hasNaN(): NaN only
             dn += d[r] * d[r];
         }
         if (!done) { rsq_out = rsq; hs_out = hs; }
@@ -902,8 +903,9 @@ __global__ void __launch_bounds__(LMP_WARPS * 32, EPV_LMP_MINBLOCKS) lm_pair_ker
         csq = group_sum_d(csq);
         if (!done) {
             rsq_out = csq;                                                          // r0 now holds the candidate residuals
-            if (csq < prevE2) {                                                     // [:457-467] (|r| < prev_E, squared)
-                prevE2 = csq;
+            const double currE = sqrt(csq);
+            if (currE < prevE) {                                                    // [:457-467]
+                prevE = currE;
                 T = Tn;
                 lambda /= 2.0;
             } else {

@@ -29,9 +29,10 @@ def lib():
     global _lib
     if _lib is None:
         _lib = C.CDLL(build())
-        _lib.oracle_lm.restype = C.c_int
-        _lib.oracle_lm.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
-                                   C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_LmRes)]
+        _lib.oracle_lm_trace.restype = C.c_int
+        _lib.oracle_lm_trace.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                         C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_LmRes),
+                                         C.c_void_p]
     return _lib
 
 
@@ -42,7 +43,10 @@ def levenberg_marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r, hub
     pr = np.ascontiguousarray(pr, dtype=np.float64)
     p_r = np.ascontiguousarray(p_r, dtype=np.float64)
     res = _LmRes()
-    it = lib().oracle_lm(int(n_zeta), float(epsilon), reps.ctypes.data, w.ctypes.data, reps.shape[0], float(lambda0),
-                         int(max_iters), float(huber_delta), T.ctypes.data, pr.ctypes.data, p_r.ctypes.data,
-                         int(pr.shape[1]), C.byref(res))
-    return T.reshape(n_zeta, 4, 4), {"H_norm": res.H_norm, "r_norm": res.r_norm, "lambda": res.lambda_, "iters": it}
+    tr = np.full((int(max_iters), 2), np.nan)
+    it = lib().oracle_lm_trace(int(n_zeta), float(epsilon), reps.ctypes.data, w.ctypes.data, reps.shape[0],
+                               float(lambda0), int(max_iters), float(huber_delta), T.ctypes.data, pr.ctypes.data,
+                               p_r.ctypes.data, int(pr.shape[1]), C.byref(res), tr.ctypes.data)
+    trace = [(float(d), None if e != e else float(e)) for d, e in tr[:it]]
+    return T.reshape(n_zeta, 4, 4), {"H_norm": res.H_norm, "r_norm": res.r_norm, "lambda": res.lambda_, "iters": it,
+                                      "trace": trace}

@@ -147,15 +147,19 @@ static void se3_exp(const double* d, double* T) {
         for (int j = 0; j < 3; ++j) {
             double I = (i == j) ? 1.0 : 0.0;
             T[i * 4 + j] = I + a * Om[i * 3 + j] + b * Om2[i * 3 + j];
-            V[i * 3 + j] = I + b * Om[i * 3 + j] + c * Om2[i * 3 + j];
+            /* Sophus: V = so3.matrix() below epsilon = 1e-10 */
+            V[i * 3 + j] = (th < 1e-10) ? T[i * 4 + j] : I + b * Om[i * 3 + j] + c * Om2[i * 3 + j];
         }
     for (int i = 0; i < 3; ++i) T[i * 4 + 3] = V[i * 3] * d[0] + V[i * 3 + 1] * d[1] + V[i * 3 + 2] * d[2];
     T[15] = 1.0;
 }
 
-/* jac_Rt_gen_.cpp:287-478.  T0s (n_zeta x 16) is updated in place.  Returns iterations run. */
-int oracle_lm(int n_zeta, double epsilon, const int* reps, const double* wreps, int n_rep, double lambda0,
-              int max_iters, double hd, double* T0s, const double* pr, const double* p_r, int N, lm_res_t* out) {
+/* jac_Rt_gen_.cpp:287-478.  T0s (n_zeta x 16) is updated in place.  Returns iterations started.
+ * trace (optional, 2 x max_iters doubles): per started iteration |delta| and the candidate |r0| (NaN when the
+ * loop broke before computing it) -- the same two numbers oracle/_ref exposes of the reference's trajectory. */
+int oracle_lm_trace(int n_zeta, double epsilon, const int* reps, const double* wreps, int n_rep, double lambda0,
+                    int max_iters, double hd, double* T0s, const double* pr, const double* p_r, int N, lm_res_t* out,
+                    double* trace) {
     const int D = 6 * n_zeta, RN = n_rep * N;
     double* mem = (double*)calloc((size_t)n_zeta * n_zeta * 16, sizeof(double));
     double* r0 = (double*)calloc(RN, sizeof(double));
@@ -228,9 +232,10 @@ int oracle_lm(int n_zeta, double epsilon, const int* reps, const double* wreps, 
             double s = 0;
             for (int c = 0; c < D; ++c) s += Hi[(size_t)a * D + c] * b[c];
             delta[a] = -s;
-            if (!(delta[a] == delta[a]) || isinf(delta[a])) has_nan = 1;
+            if (!(delta[a] == delta[a])) has_nan = 1;                        /* hasNaN(): NaN only, inf passes */
             dn += delta[a] * delta[a];
         }
+        if (trace) { trace[2 * iter] = sqrt(dn); trace[2 * iter + 1] = NAN; }
         if (has_nan) break;                                                  /* :407-410 */
         if (sqrt(dn) < epsilon) break;                                       /* :412-414 */
         for (int j = 0; j < n_zeta; ++j) {                                   /* :416-422 */
@@ -248,6 +253,7 @@ int oracle_lm(int n_zeta, double epsilon, const int* reps, const double* wreps, 
         double cs = 0;
         for (int i = 0; i < RN; ++i) cs += r0[i] * r0[i];
         double currE = sqrt(cs);                                             /* :456-467 */
+        if (trace) trace[2 * iter + 1] = currE;
         if (currE < prevE) {
             prevE = currE;
             memcpy(T0s, Tn, sizeof(double) * (size_t)n_zeta * 16);
@@ -264,4 +270,9 @@ int oracle_lm(int n_zeta, double epsilon, const int* reps, const double* wreps, 
     out->lambda = lambda;
     free(mem); free(r0); free(J); free(H); free(Hi); free(b); free(delta); free(Tn); free(rr);
     return it;
+}
+
+int oracle_lm(int n_zeta, double epsilon, const int* reps, const double* wreps, int n_rep, double lambda0,
+              int max_iters, double hd, double* T0s, const double* pr, const double* p_r, int N, lm_res_t* out) {
+    return oracle_lm_trace(n_zeta, epsilon, reps, wreps, n_rep, lambda0, max_iters, hd, T0s, pr, p_r, N, out, 0);
 }

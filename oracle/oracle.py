@@ -643,7 +643,7 @@ def se3_exp(delta) -> np.ndarray:
     Om2 = Om @ Om
     if th < 1e-10:
         Rm = np.eye(3) + Om + 0.5 * Om2
-        V = np.eye(3) + 0.5 * Om + Om2 / 6.0
+        V = Rm                       # Sophus: `V = so3.matrix()` below epsilon = 1e-10 (pinned by oracle/_ref's stand-in)
     else:
         Rm = np.eye(3) + (math.sin(th) / th) * Om + ((1 - math.cos(th)) / th2) * Om2
         V = np.eye(3) + ((1 - math.cos(th)) / th2) * Om + ((th - math.sin(th)) / (th2 * th)) * Om2
@@ -666,6 +666,7 @@ def levenberg_marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r,
     H = np.zeros((D, D))
     r0 = np.zeros(n_rep * N)
     it_done = 0
+    trace = []                                                        # (|delta|, candidate |r0| or None) per iteration
     for _ in range(max_iters):                                        # :323
         it_done += 1
         r0 = np.zeros(n_rep * N)
@@ -687,6 +688,7 @@ def levenberg_marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r,
                 delta = -np.linalg.inv(H) @ b                         # :405
         except np.linalg.LinAlgError:
             delta = np.full(D, np.nan)
+        trace.append((float(np.linalg.norm(delta)), None))
         if np.isnan(delta).any():                                     # :407-410
             break
         if np.linalg.norm(delta) < epsilon:                           # :412-414
@@ -702,6 +704,7 @@ def levenberg_marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r,
                     T = np.linalg.inv(T0s_[k]) @ T
             r0[j * N:(j + 1) * N] = res(T[:3, :3], T[:3, 3], pr[j], p_r[j], huber_delta)
         curr_E = float(np.linalg.norm(r0))                            # :456
+        trace[-1] = (trace[-1][0], curr_E)
         if curr_E < prev_E:                                           # :457-467
             prev_E = curr_E
             T0s = T0s_
@@ -709,7 +712,7 @@ def levenberg_marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r,
         else:
             lam *= 5.0
     out = {"H_norm": float(np.linalg.norm(H)), "r_norm": float(np.linalg.norm(r0)),
-           "lambda": float(lam), "iters": it_done}                    # :473-475
+           "lambda": float(lam), "iters": it_done, "trace": trace}    # :473-475
     return np.stack(T0s), out
 
 
