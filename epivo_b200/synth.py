@@ -148,7 +148,7 @@ class Sequence:
 
 def make_sequence(n_frames: int = 4541, n: int = 2000, seed: int = seed_for(3, 0),
                   K: np.ndarray = KITTI_K, size=KITTI_SIZE, depth=(5.0, 60.0),
-                  px_sigma: float = 0.5, outlier_frac: float = 0.30) -> Sequence:
+                  px_sigma: float = 0.5, outlier_frac: float = 0.30, step=(0.6, 1.2)) -> Sequence:
     """KITTI seq-00-length synthetic run with a smooth random-walk trajectory.
 
     Frame f+1 re-observes ~70 % of frame f's landmarks (re-projected under the frame
@@ -172,7 +172,7 @@ def make_sequence(n_frames: int = 4541, n: int = 2000, seed: int = seed_for(3, 0
         w = 0.9 * w + rng.normal(0.0, 0.004, 3)          # smooth yaw/pitch/roll walk
         v = 0.95 * v + 0.05 * np.array([0.02, -0.01, 1.0]) + rng.normal(0.0, 0.01, 3)
         R = rodrigues(w)
-        t_pt = -v / np.linalg.norm(v) * rng.uniform(0.6, 1.2)
+        t_pt = -v / np.linalg.norm(v) * rng.uniform(step[0], step[1])
         X1 = _backproject(K, px, dep) @ R.T + t_pt
         ok = X1[:, 2] > 0.5
         p1 = np.full((n, 2), -1.0)

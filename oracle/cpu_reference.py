@@ -161,3 +161,57 @@ def windows_rate(data, nz, reps, n_windows, cores=None, huber_delta=1.0):
     finally:
         pool.close()
         pool.join()
+
+
+# ---- live-cv2 parity census (tests/test_gpu_cv2_census.py, bench.py `parity_vs_cv2`) -------------------------------
+# The reference's findEssentialMat call shapes (method, prob, threshold), by call site.
+CALL_SHAPES = {
+    "kitti.cpp:101": (8, 0.99, 1.0),          # RANSAC
+    "kitti_E.cpp:101": (4, 0.99, 0.01),       # LMEDS (threshold unused by LMedS)
+    "euroc_E.cpp:205": (8, 0.99, 0.3),        # RANSAC, EuRoC camera, 1500 keypoints
+    "kitti_ba.cpp:232": (8, 0.95, 0.05),
+    "kitti_ba.cpp:308": (8, 0.99, 0.05),
+    "kitti_ba.cpp:702": (4, 0.99, 0.1),
+}
+
+
+def _census_work(i):
+    kps, descs, Kf = _SEQ["kps"], _SEQ["descs"], _SEQ["K"]
+    norm, _ = _SEQ["match"]
+    ms = cv2.BFMatcher(norm, True).match(descs[i], descs[i + 1])
+    qi = np.fromiter((m.queryIdx for m in ms), dtype=np.int32, count=len(ms))
+    ti = np.fromiter((m.trainIdx for m in ms), dtype=np.int32, count=len(ms))
+    p0, p1 = kps[i][qi], kps[i + 1][ti]
+    out = {"pair": i, "qi": qi, "ti": ti, "shapes": {}}
+    for name in _SEQ["shapes"]:
+        method, prob, thr = CALL_SHAPES[name]
+        E, mask = cv2.findEssentialMat(p0, p1, Kf, method, prob, thr)
+        rec = {"E": None}
+        if E is not None and E.shape == (3, 3):
+            m = mask.ravel() == 1
+            n_good, R, t, rm = cv2.recoverPose(E, p0[m], p1[m], Kf)
+            rec = {"E": E, "e_mask": mask.ravel().astype(np.uint8), "n_good": int(n_good), "R": R, "t": t.ravel(),
+                   "pose_mask": rm.ravel().astype(np.uint8)}
+        out["shapes"][name] = rec
+    return out
+
+
+def census(kps, descs, K, shapes, norm=7, cores=None):
+    """cv2's matches, E, {0,1} mask, recoverPose count / R / t / {0,255} mask for every consecutive pair of the
+    sequence and every named call shape -- the live reference the GPU pipeline is compared with, pair-parallel."""
+    import multiprocessing as mp
+    assert HAVE_CV2
+    cores = cores or (os.cpu_count() or 1)
+    Kf = np.asarray(K, dtype=np.float32)
+    _SEQ["shapes"] = list(shapes)
+    pool = mp.get_context("fork").Pool(cores, initializer=_census_init, initargs=(kps, descs, Kf, norm, list(shapes)))
+    try:
+        return pool.map(_census_work, range(kps.shape[0] - 1), chunksize=1)
+    finally:
+        pool.close()
+        pool.join()
+
+
+def _census_init(kps, descs, Kf, norm, shapes):
+    _SEQ["kps"], _SEQ["descs"], _SEQ["K"], _SEQ["match"], _SEQ["shapes"] = kps, descs, Kf, (norm, None), shapes
+    cv2.setNumThreads(1)

@@ -1,0 +1,95 @@
+"""Whole-call parity census against LIVE cv2 at benchmark size: for every findEssentialMat call
+shape the reference's drivers use, >= 256 synthetic pairs at 2000 keypoints (1500 on the EuRoC camera) go through
+cv2 (BFMatcher -> findEssentialMat -> recoverPose, the calls the reference makes) and through the GPU pipeline;
+matches, the {0,1} essential mask and the {0,255} pose mask must be identical pair by pair, R / t within
+north_star's tolerances.  The census (counts of differing pairs per shape) is written to
+gpurun_out/cv2_census.json; DESIGN section 2 records it."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_PAIRS = int(os.environ.get("EPIVO_CENSUS_PAIRS", "256"))
+KITTI_SHAPES = ["kitti.cpp:101", "kitti_E.cpp:101", "kitti_ba.cpp:232", "kitti_ba.cpp:308", "kitti_ba.cpp:702"]
+
+
+def _rot_angle(a, b):
+    return float(np.arccos(np.clip((np.trace(a.T @ b) - 1) / 2, -1, 1)))
+
+
+def _run_census(seq, shapes, tag):
+    from epivo_b200 import api
+    from oracle import cpu_reference as R
+    ref = R.census(seq.kps, seq.descs, seq.K, shapes)
+    ctx = api.Context(0)
+    pipe = api.SequencePipeline(seq.n_frames, seq.kps.shape[1], ctx=ctx)
+    pipe.upload(seq.kps, seq.descs)
+    Kf = seq.K.astype(np.float32)
+    report = {}
+    try:
+        for name in shapes:
+            method, prob, thr = R.CALL_SHAPES[name]
+            prm = api.default_params(Kf, method=method, prob=prob, threshold=thr)
+            pipe.run(prm, 0, seq.n_pairs)
+            res = pipe.download(0, seq.n_pairs)
+            rep = {"pairs": seq.n_pairs, "matches_differ": [], "e_mask_differ": [], "pose_mask_differ": [],
+                   "n_good_differ": [], "max_rot_diff_rad": 0.0, "max_t_angle_rad": 0.0, "max_E_diff": 0.0}
+            for i in range(seq.n_pairs):
+                o = ref[i]["shapes"][name]
+                qi, ti, _ = pipe.matches(i)
+                if not (np.array_equal(qi, ref[i]["qi"]) and np.array_equal(ti, ref[i]["ti"])):
+                    rep["matches_differ"].append(i)
+                    continue
+                if o["E"] is None:
+                    continue
+                em, pm = pipe.masks(i)
+                if not np.array_equal(em, o["e_mask"]):
+                    rep["e_mask_differ"].append((i, int((em != o["e_mask"]).sum()) if em.shape == o["e_mask"].shape else -1))
+                    continue
+                Eg, Ec = res[i]["E"], o["E"]
+                Eg, Ec = Eg / np.linalg.norm(Eg), Ec / np.linalg.norm(Ec)
+                rep["max_E_diff"] = max(rep["max_E_diff"], float(min(np.abs(Eg - Ec).max(), np.abs(Eg + Ec).max())))
+                if not np.array_equal(pm, o["pose_mask"]):
+                    rep["pose_mask_differ"].append((i, int((pm != o["pose_mask"]).sum()) if pm.shape == o["pose_mask"].shape else -1))
+                    continue
+                if int(res[i]["n_good"]) != o["n_good"]:
+                    rep["n_good_differ"].append(i)
+                rep["max_rot_diff_rad"] = max(rep["max_rot_diff_rad"], _rot_angle(res[i]["R"], o["R"]))
+                tg, tc = res[i]["t"], o["t"]
+                c = float(tg @ tc / (np.linalg.norm(tg) * np.linalg.norm(tc)))
+                rep["max_t_angle_rad"] = max(rep["max_t_angle_rad"], float(np.arccos(np.clip(c, -1, 1))))
+            report[name] = rep
+    finally:
+        pipe.close()
+        ctx.close()
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = os.path.join("gpurun_out", "cv2_census.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old[tag] = report
+    json.dump(old, open(path, "w"), indent=1)
+    return report
+
+
+def _assert_clean(report):
+    for name, rep in report.items():
+        assert not rep["matches_differ"], (name, rep["matches_differ"][:5])
+        assert not rep["e_mask_differ"], (name, len(rep["e_mask_differ"]), rep["e_mask_differ"][:5])
+        assert not rep["pose_mask_differ"], (name, len(rep["pose_mask_differ"]), rep["pose_mask_differ"][:5])
+        assert not rep["n_good_differ"], (name, rep["n_good_differ"][:5])
+        assert rep["max_rot_diff_rad"] <= 1e-4 and rep["max_t_angle_rad"] <= 1e-3, (name, rep)
+
+
+def test_census_kitti_shape_2000kp_all_kitti_call_sites():
+    from epivo_b200 import synth
+    seq = synth.make_sequence(N_PAIRS + 1, 2000, seed=synth.seed_for(3, 0))
+    _assert_clean(_run_census(seq, KITTI_SHAPES, "kitti_2000kp"))
+
+
+def test_census_euroc_shape_1500kp():
+    from epivo_b200 import synth
+    seq = synth.make_sequence(N_PAIRS + 1, 1500, seed=synth.seed_for(2, 0), K=synth.EUROC_K, size=synth.EUROC_SIZE,
+                              depth=(1.0, 8.0), px_sigma=0.3, outlier_frac=0.25, step=(0.03, 0.07))
+    _assert_clean(_run_census(seq, ["euroc_E.cpp:205"], "euroc_1500kp"))
