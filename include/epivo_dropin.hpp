@@ -1,0 +1,105 @@
+// epivo_dropin.hpp -- the reference's call lines, VERBATIM, over libepivo_b200.
+//
+// include/epivo_shims.hpp exposes the path with an explicit epivo::Context and raw arrays.  This header
+// adds overloads with exactly the signatures the reference's drivers call, so that a driver switches by
+// adding ONE include after its own OpenCV / Eigen includes and touching no call site:
+//
+//   Mat ess = findEssentialMat(_cpt0, _cpt1_, cam, LMEDS, 0.99, 0.01, mask_ess);        kitti_E.cpp:98-104
+//   recoverPose(ess, cpt0, cpt1_, cam, rot, tr, rec_mask);                              kitti_E.cpp:120
+//   uncert = Levenberg_Marquardt(1, 1e-8, reps, 1e-2, T0s, pr, p_r);                    kitti_E.cpp:196
+//   Levenberg_Marquardt(nzeta, 1e-8, reps, wreps, 1e-2, T0s, pr, p_r, lm_res);          kitti_ba.cpp:881,1044
+//                        -- int Levenberg_Marquardt(const int, const double, const vector<pair<int,int>>&,
+//                           const vector<double>&, const double, vector<MatrixXd>&, vector<MatrixXd>&,
+//                           vector<MatrixXd>&, LM_res&)                                 jac_Rt_gen_.cpp:287-296
+//   BFMatcher matcher(NORM_HAMMING2, true);  matcher.match(desc0, desc1, matches);      kitti_ba.cpp:602,641
+//
+// How the unqualified calls reach these functions.  The drivers say `using namespace cv;` and call
+// `findEssentialMat(...)` unqualified.  The templates below live in the GLOBAL namespace and take the
+// caller's own types (std::vector<cv::Point2f>, cv::Mat, std::vector<uchar>) exactly, whereas
+// cv::findEssentialMat / cv::recoverPose take InputArray / OutputArray, which need a user-defined
+// conversion from every argument: overload resolution picks the exact match, i.e. the template, without
+// any edit.  A class cannot be overloaded that way, so for the matcher the driver writes
+// `epivo::BFMatcher` instead of `BFMatcher` (one token, kitti_ba.cpp:602).
+//
+// Context.  The calls carry no handle, so each host thread gets its own lazily created epivo::Context
+// (`thread_local`; device from $EPIVO_DEVICE, default 0) -- kitti_ba.cpp:1153-1163 calls the path from
+// two std::threads concurrently, and a context must not be shared between threads.
+//
+// Matrix types.  `MatT` is anything epivo::mat_traits knows: cv::Mat (specialisation below, compiled when
+// OpenCV's core header has been included first) or a type with M(rows, cols) / rows() / cols() / (i, j)
+// such as Eigen::MatrixXd.  Neither OpenCV nor Eigen exists in this image: tests/cpp/dropin_test.cpp
+// compiles the literal call lines above against stand-ins with the same member API.
+#pragma once
+#include <type_traits>
+
+#include "epivo_shims.hpp"
+
+namespace epivo {
+
+namespace detail {
+template <typename MatT>
+void cam_to_array(const MatT& cam, double K[9]) {
+    typedef mat_traits<MatT> MT;
+    if (MT::rows(cam) != 3 || MT::cols(cam) != 3) throw std::invalid_argument("cameraMatrix must be 3x3");
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) K[3 * i + j] = MT::get(cam, i, j);
+}
+}  // namespace detail
+
+}  // namespace epivo
+
+// ---- the reference's unqualified calls ---------------------------------------------------------------------------
+
+// Mat findEssentialMat(points1, points2, cameraMatrix, method, prob, threshold, mask)        kitti_E.cpp:98-104
+// Returns a 3x3 CV_64F-like matrix, or an empty (0x0) one where OpenCV returns an empty Mat; mask in {0,1}.
+template <typename Pt, typename MatT>
+MatT findEssentialMat(const std::vector<Pt>& points1, const std::vector<Pt>& points2, const MatT& cameraMatrix,
+                      int method, double prob, double threshold, std::vector<unsigned char>& mask) {
+    typedef epivo::mat_traits<MatT> MT;
+    double K[9], E[9];
+    epivo::detail::cam_to_array(cameraMatrix, K);
+    if (!epivo::findEssentialMat(epivo::default_context(), points1, points2, K, method, prob, threshold, E, mask))
+        return MT::create(0, 0);
+    MatT out = MT::create(3, 3);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) MT::set(out, i, j, E[3 * i + j]);
+    return out;
+}
+
+// int recoverPose(E, points1, points2, cameraMatrix, R, t, mask)                             kitti_E.cpp:120
+// R (3x3) and t (3x1) are created; mask in {0,255} (the drivers test == 255, kitti_E.cpp:177).
+template <typename Pt, typename MatT>
+int recoverPose(const MatT& E, const std::vector<Pt>& points1, const std::vector<Pt>& points2, const MatT& cameraMatrix,
+                MatT& R, MatT& t, std::vector<unsigned char>& mask) {
+    typedef epivo::mat_traits<MatT> MT;
+    if (MT::rows(E) != 3 || MT::cols(E) != 3) throw std::invalid_argument("E must be 3x3");
+    double K[9], e[9], r[9], tt[3];
+    epivo::detail::cam_to_array(cameraMatrix, K);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) e[3 * i + j] = MT::get(E, i, j);
+    const int good = epivo::recoverPose(epivo::default_context(), e, points1, points2, K, r, tt, mask);
+    R = MT::create(3, 3);
+    t = MT::create(3, 1);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) MT::set(R, i, j, r[3 * i + j]);
+        MT::set(t, i, 0, tt[i]);
+    }
+    return good;
+}
+
+// int Levenberg_Marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r, lm_res)       jac_Rt_gen_.cpp:287-296
+// The reference's huber_delta is a compile-time constant of that file (1e-5, :17) and so it is here.
+template <typename M>
+int Levenberg_Marquardt(const int n_zeta, const double epsilon, const std::vector<std::pair<int, int> >& reps,
+                        const std::vector<double>& wreps, const double lambda0, std::vector<M>& T0s, std::vector<M>& pr,
+                        std::vector<M>& p_r, LM_res& lm_res) {
+    return epivo::Levenberg_Marquardt(epivo::default_context(), n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r, lm_res);
+}
+
+// double Levenberg_Marquardt(n_zeta, epsilon, reps, lambda0, T0s, pr, p_r)                   kitti_E.cpp:196
+// The 7-argument call the reference makes but never defines; returns the residual norm (see epivo_shims.hpp).
+template <typename M>
+double Levenberg_Marquardt(const int n_zeta, const double epsilon, const std::vector<std::pair<int, int> >& reps,
+                           const double lambda0, std::vector<M>& T0s, std::vector<M>& pr, std::vector<M>& p_r) {
+    return epivo::Levenberg_Marquardt(epivo::default_context(), n_zeta, epsilon, reps, lambda0, T0s, pr, p_r);
+}

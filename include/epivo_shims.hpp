@@ -15,6 +15,7 @@
 // `cv::` / unqualified calls with `epivo::` ones -- see INTEGRATION.md.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <algorithm>
@@ -55,6 +56,45 @@ class Context {
     epivo_ctx* ctx_ = nullptr;
 };
 
+// One context per host thread, created on first use (device from $EPIVO_DEVICE, default 0): what the
+// handle-free overloads of include/epivo_dropin.hpp run on.  Throws if there is no CUDA device.
+inline Context& default_context() {
+    thread_local Context ctx([] {
+        const char* e = std::getenv("EPIVO_DEVICE");
+        return e ? std::atoi(e) : 0;
+    }());
+    return ctx;
+}
+
+// How to read / create a matrix of the caller's type.  Default: Eigen-like (rows(), cols(), (i, j), M(r, c)).
+template <typename MatT, typename Enable = void>
+struct mat_traits {
+    static int rows(const MatT& m) { return (int)m.rows(); }
+    static int cols(const MatT& m) { return (int)m.cols(); }
+    static bool empty(const MatT& m) { return m.rows() == 0 || m.cols() == 0; }
+    static double get(const MatT& m, int i, int j) { return (double)m(i, j); }
+    static MatT create(int r, int c) { return MatT(r, c); }          // double entries
+    static void set(MatT& m, int i, int j, double v) { m(i, j) = v; }
+    static const unsigned char* bytes(const MatT& m) { return reinterpret_cast<const unsigned char*>(m.data()); }
+};
+
+#ifdef OPENCV_CORE_MAT_HPP
+// cv::Mat: element type by depth (the reference's `cam` is CV_32F, kitti_E.cpp:38; E / R / t come back CV_64F,
+// as from OpenCV); public rows / cols / data members.
+template <>
+struct mat_traits<cv::Mat, void> {
+    static int rows(const cv::Mat& m) { return m.rows; }
+    static int cols(const cv::Mat& m) { return m.cols; }
+    static bool empty(const cv::Mat& m) { return m.empty(); }
+    static double get(const cv::Mat& m, int i, int j) {
+        return m.depth() == CV_32F ? (double)m.at<float>(i, j) : m.at<double>(i, j);
+    }
+    static cv::Mat create(int r, int c) { return cv::Mat(r, c, CV_64F); }
+    static void set(cv::Mat& m, int i, int j, double v) { m.at<double>(i, j) = v; }
+    static const unsigned char* bytes(const cv::Mat& m) { return m.data; }
+};
+#endif
+
 struct DMatch {               // cv::DMatch
     int queryIdx = -1, trainIdx = -1, imgIdx = 0;
     float distance = 0.f;
@@ -65,6 +105,9 @@ class BFMatcher {
   public:
     BFMatcher(Context& ctx, int normType = NORM_HAMMING2, bool crossCheck = false)
         : ctx_(ctx), norm_(normType), cross_(crossCheck) {}
+    // cv::BFMatcher's own constructor (kitti_ba.cpp:602): runs on the calling thread's default context
+    explicit BFMatcher(int normType = NORM_HAMMING2, bool crossCheck = false)
+        : ctx_(default_context()), norm_(normType), cross_(crossCheck) {}
     // desc0 / desc1: n x desc_bytes, row-major uint8 (cv::Mat::data of an ORB descriptor matrix)
     void match(const uint8_t* desc0, int n0, const uint8_t* desc1, int n1, int desc_bytes,
                std::vector<DMatch>& matches) const {
@@ -79,6 +122,26 @@ class BFMatcher {
             matches[i].trainIdx = t[i];
             matches[i].imgIdx = 0;
             matches[i].distance = (float)d[i];
+        }
+    }
+
+    // matcher.match(desc0, desc1, matches) on the descriptor MATRICES themselves (kitti_ba.cpp:641): MatT is a cv::Mat
+    // of CV_8U rows (or anything mat_traits can read bytes from), DM anything with cv::DMatch's four fields.
+    template <typename MatT, typename DM>
+    void match(const MatT& queryDescriptors, const MatT& trainDescriptors, std::vector<DM>& matches) const {
+        typedef mat_traits<MatT> MT;
+        if (!MT::empty(queryDescriptors) && !MT::empty(trainDescriptors) &&
+            MT::cols(queryDescriptors) != MT::cols(trainDescriptors))
+            throw std::invalid_argument("descriptor sizes differ");
+        std::vector<DMatch> m;
+        match(MT::bytes(queryDescriptors), MT::rows(queryDescriptors), MT::bytes(trainDescriptors),
+              MT::rows(trainDescriptors), MT::cols(queryDescriptors), m);
+        matches.resize(m.size());
+        for (size_t i = 0; i < m.size(); ++i) {
+            matches[i].queryIdx = m[i].queryIdx;
+            matches[i].trainIdx = m[i].trainIdx;
+            matches[i].imgIdx = m[i].imgIdx;
+            matches[i].distance = m[i].distance;
         }
     }
 

@@ -1,0 +1,223 @@
+// The reference's hot-path call lines, LITERALLY, compiled against include/epivo_dropin.hpp.
+//
+// OpenCV and Eigen are not in this image, so this file first defines stand-ins with the same member API the
+// drop-in touches -- a `cv` namespace (Mat with rows / cols / data / at<T>() / depth() / empty(), Mat_<T> with the
+// comma initialiser of kitti_E.cpp:38, Point2f, DMatch, the LMEDS / RANSAC / NORM_HAMMING2 / CV_32F / CV_64F
+// constants, cv2eigen) and the Eigen stand-in of oracle/ref_shim -- and then, like the drivers, says
+// `using namespace cv; using namespace std; using namespace Eigen;` and includes the drop-in header.  The lines
+// marked [verbatim] are the reference's call lines, character for character:
+//   kitti_E.cpp:38-40 (cam), :98-104 (findEssentialMat), :120 (recoverPose), :196 (7-argument LM),
+//   kitti_ba.cpp:602,641 (BFMatcher: class name qualified with epivo::, the one edit), :702, :715, :881 (9-argument LM).
+// Around them the loop body of kitti_E.cpp:96-201 is replayed on a synthetic pair.  Built by
+// tests/test_cpp_shims.py (compiles everywhere; runs on a GPU box).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include <Eigen/Dense>          // oracle/ref_shim stand-in
+
+#define OPENCV_CORE_MAT_HPP     // what <opencv2/core/mat.hpp> defines: enables the cv::Mat traits of the drop-in
+#define CV_8U 0
+#define CV_32F 5
+#define CV_64F 6
+typedef unsigned char uchar;
+namespace cv {
+enum { LMEDS = 4, RANSAC = 8, NORM_HAMMING = 6, NORM_HAMMING2 = 7 };
+struct Point2f { float x, y; Point2f() : x(0), y(0) {} Point2f(float a, float b) : x(a), y(b) {} };
+struct DMatch { int queryIdx, trainIdx, imgIdx; float distance; };
+class Mat {
+  public:
+    int rows, cols;
+    uchar* data;
+    Mat() : rows(0), cols(0), data(0), type_(CV_8U) {}
+    Mat(int r, int c, int type) : rows(r), cols(c), type_(type), buf_((size_t)r * c * esz(type), 0) { data = buf_.data(); }
+    Mat(const Mat& o) : rows(o.rows), cols(o.cols), type_(o.type_), buf_(o.buf_) { data = buf_.empty() ? 0 : buf_.data(); }
+    Mat& operator=(const Mat& o) { rows = o.rows; cols = o.cols; type_ = o.type_; buf_ = o.buf_; data = buf_.empty() ? 0 : buf_.data(); return *this; }
+    int depth() const { return type_; }
+    bool empty() const { return rows == 0 || cols == 0; }
+    template <typename T> T& at(int i, int j) { return reinterpret_cast<T*>(data)[(size_t)i * cols + j]; }
+    template <typename T> const T& at(int i, int j) const { return reinterpret_cast<const T*>(data)[(size_t)i * cols + j]; }
+  private:
+    static size_t esz(int t) { return t == CV_64F ? 8 : t == CV_32F ? 4 : 1; }
+    int type_;
+    std::vector<uchar> buf_;
+};
+template <typename T> struct MatCommaInit {
+    Mat m; int k;
+    MatCommaInit& operator,(double v) { m.at<T>(k / m.cols, k % m.cols) = (T)v; ++k; return *this; }
+    operator Mat() const { return m; }
+};
+template <typename T> class Mat_ {
+  public:
+    Mat_(int r, int c) : r_(r), c_(c) {}
+    MatCommaInit<T> operator<<(double v) const {
+        MatCommaInit<T> ci = {Mat(r_, c_, sizeof(T) == 4 ? CV_32F : CV_64F), 0};
+        ci, v;
+        return ci;
+    }
+  private:
+    int r_, c_;
+};
+inline void cv2eigen(const Mat& src, Eigen::MatrixXd& dst) {
+    dst = Eigen::MatrixXd(src.rows, src.cols);
+    for (int i = 0; i < src.rows; ++i) for (int j = 0; j < src.cols; ++j) dst(i, j) = src.at<double>(i, j);
+}
+}  // namespace cv
+
+#include "epivo_dropin.hpp"     // the ONE added include
+
+using namespace cv;
+using namespace std;
+using namespace Eigen;
+
+static double urand() { return (double)rand() / RAND_MAX; }
+
+int main() {
+    srand(11);
+    // [verbatim] kitti_E.cpp:38-40
+    Mat cam = (Mat_<float>(3,3) << 718.8560, 0.0, 607.1928,
+                                    0.0, 718.8560, 185.2157,
+                                    0.0, 0.0,      1.0);
+    MatrixXd cam_(3, 3);
+    cam_ << 718.8560, 0.0,      607.1928,
+            0.0,      718.8560, 185.2157,
+            0.0,      0.0,      1.0;
+    cam_ = cam_.inverse();
+
+    // a synthetic pair: 300 landmarks seen from two poses, 0.3 px noise, 20 % gross outliers
+    const double ang[3] = {0.012, -0.02, 0.008}, tgt[3] = {0.03, -0.02, -1.0};
+    MatrixXd Rx(3, 3), Ry(3, 3), Rz(3, 3);
+    Rx << 1, 0, 0, 0, cos(ang[0]), -sin(ang[0]), 0, sin(ang[0]), cos(ang[0]);
+    Ry << cos(ang[1]), 0, sin(ang[1]), 0, 1, 0, -sin(ang[1]), 0, cos(ang[1]);
+    Rz << cos(ang[2]), -sin(ang[2]), 0, sin(ang[2]), cos(ang[2]), 0, 0, 0, 1;
+    const MatrixXd Rgt = Rx * Ry * Rz;
+    vector<Point2f> _cpt0, _cpt1_;
+    for (int i = 0; i < 300; ++i) {
+        const double X[3] = {30 * (urand() - 0.5), 8 * (urand() - 0.5), 10 + 40 * urand()};
+        double Y[3];
+        for (int a = 0; a < 3; ++a) Y[a] = Rgt(a, 0) * X[0] + Rgt(a, 1) * X[1] + Rgt(a, 2) * X[2] + tgt[a];
+        Point2f a((float)(718.856 * X[0] / X[2] + 607.1928), (float)(718.856 * X[1] / X[2] + 185.2157));
+        Point2f b((float)(718.856 * Y[0] / Y[2] + 607.1928 + 0.6 * (urand() - 0.5)),
+                  (float)(718.856 * Y[1] / Y[2] + 185.2157 + 0.6 * (urand() - 0.5)));
+        if (i % 5 == 4) b = Point2f((float)(1241 * urand()), (float)(376 * urand()));
+        _cpt0.push_back(a);
+        _cpt1_.push_back(b);
+    }
+
+    vector<uchar> mask_ess;
+    // [verbatim] kitti_E.cpp:98-104
+    Mat ess = findEssentialMat(_cpt0,
+                               _cpt1_,
+                               cam,
+                               LMEDS,
+                               0.99,
+                               0.01,
+                               mask_ess);
+    if (ess.rows != 3 || ess.cols != 3 || ess.depth() != CV_64F || mask_ess.size() != _cpt0.size()) return 1;
+    vector<Point2f> cpt0, cpt1_;
+    for (int j = 0; j < (int)mask_ess.size(); j++) {
+        if ((int)mask_ess[j] != 0 && (int)mask_ess[j] != 1) return 2;          // {0,1}, as cv2 (:108 tests == 1)
+        if ((int)mask_ess[j] == 1) { cpt0.push_back(_cpt0[j]); cpt1_.push_back(_cpt1_[j]); }
+    }
+    Mat rot, tr;
+    vector<uchar> rec_mask;
+    // [verbatim] kitti_E.cpp:120
+    recoverPose(ess, cpt0, cpt1_, cam, rot, tr, rec_mask); // mask_ess
+    MatrixXd erot(3, 3), etr(3, 1);
+    cv2eigen(rot, erot);
+    cv2eigen(tr, etr);
+    int n255 = 0;
+    for (size_t j = 0; j < rec_mask.size(); ++j) {
+        if (rec_mask[j] != 0 && rec_mask[j] != 255) return 3;                  // {0,255} (:177 tests == 255)
+        n255 += rec_mask[j] == 255;
+    }
+    printf("findEssentialMat inliers %zu / %zu, recoverPose good %d, |R - Rgt| %.3e, trace %.6f\n", cpt0.size(),
+           _cpt0.size(), n255, (erot - Rgt).norm(), erot.trace());
+    if (cpt0.size() < 200 || n255 < 150 || (erot - Rgt).norm() > 5e-3 || rec_mask.size() != cpt0.size()) return 4;
+
+    vector<pair<int, int> > reps;
+    reps.push_back(make_pair(0, 0));
+    vector<MatrixXd> T0s;
+    MatrixXd T0_0 = MatrixXd::Identity(4, 4);
+    T0_0.block<3, 3>(0, 0) = erot;
+    T0_0.block<3, 1>(0, 3) = etr;
+    T0s.push_back(T0_0);
+    vector<MatrixXd> bT0s(T0s);
+    vector<MatrixXd> pr, p_r;
+    int N = 48;
+    MatrixXd pr_(N, 3), p_r_(N, 3);
+    for (int j = 0; j < N; j++) {                                              // kitti_E.cpp:173-186 (first N inliers)
+        MatrixXd a(3, 1), b(3, 1);
+        a << cpt0[j].x, cpt0[j].y, 1.0;
+        b << cpt1_[j].x, cpt1_[j].y, 1.0;
+        pr_.row(j) = (cam_ * a).transpose();
+        p_r_.row(j) = (cam_ * b).transpose();
+    }
+    pr.push_back(pr_);
+    p_r.push_back(p_r_);
+    double uncert;
+    // [verbatim] kitti_E.cpp:196
+    uncert = Levenberg_Marquardt(1, 1e-8, reps, 1e-2, T0s, pr, p_r);
+    printf("7-argument LM: uncert (r_norm) %.6e, |T - T0| %.3e\n", uncert, (T0s[0] - bT0s[0]).norm());
+    if (!(uncert == uncert) || !(uncert < 1e-3) || (T0s[0] - bT0s[0]).norm() == 0.0) return 5;
+
+    // kitti_ba.cpp:876-882: the 9-argument form on a two-zeta chain (frames 0 -> 1 -> 2, the second step = the first)
+    {
+        vector<pair<int, int> > reps;
+        vector<double> wreps;
+        reps.push_back(make_pair(0, 0)); wreps.push_back(1.0);
+        reps.push_back(make_pair(1, 1)); wreps.push_back(1.0);
+        vector<MatrixXd> T0s, pr, p_r;
+        T0s.push_back(bT0s[0]); T0s.push_back(bT0s[0]);
+        pr.push_back(pr_); pr.push_back(pr_);
+        p_r.push_back(p_r_); p_r.push_back(p_r_);
+        int nzeta = 2;
+        LM_res lm_res;
+        // [verbatim] kitti_ba.cpp:881
+            Levenberg_Marquardt(nzeta, 1e-8, reps, wreps, 1e-2, T0s, pr, p_r, lm_res);
+        printf("9-argument LM: H_norm %.3e r_norm %.6e lambda %.3e\n", lm_res.H_norm, lm_res.r_norm, lm_res.lambda);
+        if (!(lm_res.r_norm < 1e-3) || !(lm_res.H_norm > 0) || !(lm_res.lambda > 0)) return 6;
+        if (fabs(lm_res.r_norm - sqrt(2.0) * uncert) > 1e-6 * uncert + 1e-12) return 7;   // two copies of the same problem
+    }
+
+    // kitti_ba.cpp:602,641,702,715: descriptors -> matches -> E (LMEDS .99 .1) -> pose
+    {
+        Mat desc0(200, 32, CV_8U), desc1(200, 32, CV_8U);
+        for (int i = 0; i < 200 * 32; ++i) desc0.data[i] = (uchar)(rand() & 255);
+        for (int i = 0; i < 200; ++i) {                                       // frame 1 = frame 0 reversed, 8 % bits flipped
+            memcpy(desc1.data + (size_t)(199 - i) * 32, desc0.data + (size_t)i * 32, 32);
+            for (int b = 0; b < 20; ++b) desc1.data[(size_t)(199 - i) * 32 + (rand() % 32)] ^= (uchar)(1 << (rand() & 7));
+        }
+        // [verbatim, class name qualified] kitti_ba.cpp:602
+        epivo::BFMatcher matcher(NORM_HAMMING2, true); // , true
+        vector<DMatch> matches;
+        // [verbatim] kitti_ba.cpp:641
+            matcher.match(desc0, desc1, matches);
+        if (matches.size() != 200) return 8;
+        for (int i = 0; i < 200; ++i)
+            if (matches[i].queryIdx != i || matches[i].trainIdx != 199 - i || matches[i].imgIdx != 0 || matches[i].distance > 40.f) return 9;
+        vector<Point2f>& _cpt1 = _cpt1_;
+        vector<uchar> mask_ess;
+        vector<Point2f> cpt0, cpt1;
+        Mat rot, tr;
+        vector<uchar> rec_mask;
+            if(_cpt0.size() >= 8){
+                // [verbatim] kitti_ba.cpp:702
+                Mat ess = findEssentialMat(_cpt0, _cpt1, cam, LMEDS, 0.99, 0.1, mask_ess);
+                for(int k = 0; k < (int)mask_ess.size(); k++){
+                    if((int)mask_ess[k] == 1){
+                        cpt0.push_back(_cpt0[k]);
+                        cpt1.push_back(_cpt1[k]);
+                    }
+                }
+                // [verbatim] kitti_ba.cpp:715
+                recoverPose(ess, cpt0, cpt1, cam, rot, tr, rec_mask);
+            }
+        if (rot.rows != 3 || tr.rows != 3 || tr.cols != 1 || cpt0.size() < 200) return 10;
+    }
+    printf("dropin ok\n");
+    return 0;
+}
