@@ -15,8 +15,16 @@ is one pass of the whole hot path over that sequence:
 N > 1    : one process per GPU (torchrun); every rank processes its own 4540-pair sequence
            (weak scaling, no data-path collective); the per-pair poses are all-gathered with
            NCCL inside the e2e region; times are the max over ranks.
-`--impl reference`: the reference's CPU path (cv2 = the OpenCV calls the reference makes + the
-           plain-C restatement of its LM) on all host cores, bounded sample per step.
+`--impl reference`: the reference's CPU path on all host cores, bounded sample per step: the OpenCV calls the
+           reference makes (cv2) + the reference's OWN Levenberg_Marquardt (oracle/_ref: jac_Rt_gen_.cpp compiled
+           unmodified) when that library travelled with the snapshot, else the plain-C restatement.
+Extra objects on the default line (each outside the headline timed regions):
+  parity_vs_cv2   the cpu_baseline leg's cv2 results compared with the GPU results of the same pairs
+  configs         the reference's other call shapes on the full 4540-pair step (kitti_E LMedS, EuRoC camera at
+                  1500 kp, kitti_ba's RANSAC 0.05, ratio-mode matcher) and the 504 kitti_ba windows
+  pipe_fp64       FP64-pipe fraction of the RANSAC scoring kernel against the FMA rate measured in this run
+  strong_scaling  N > 1: BASELINE config 3 as written -- ONE sequence sharded by pair blocks over the ranks,
+                  poses gathered (NCCL) and chained on rank 0, checked against rank 0's single-GPU run
 """
 from __future__ import annotations
 
@@ -57,7 +65,19 @@ def parse():
                     help="pairs = the headline metric (default); ba_windows = BASELINE.json config 5: the 504 "
                          "kitti_ba windows of a sequence (n_zeta 10, 20 reps x 250) sharded over the GPUs (strong scaling)")
     ap.add_argument("--windows", type=int, default=504)
+    ap.add_argument("--huber", type=float, default=1.0,
+                    help="huber_delta of the ba_windows workload: 1.0 = the value the reference's demo tests with "
+                         "(test_jac_Rt_gen.cpp:16), 1e-5 = the value jac_Rt_gen_.cpp:17 ships")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra call-shape measurements (`configs`)")
     return ap.parse_args()
+
+
+def config_of(a, world):
+    """The `config` object: identical keys and values in both arms (the driver compares them)."""
+    P = a.frames - 1
+    return {"workload": workload_name(a), "pairs_per_gpu": P,
+            "l2": "inputs (%d MB/GPU) larger than L2" % round((a.frames * a.kp * 40) / 1e6),
+            "parallelism": f"pairs sharded, {world} x 1 GPU, no data-path collective"}
 
 
 def workload_name(a):
@@ -161,16 +181,13 @@ def run_reference(a):
     dt = time.perf_counter() - t0
     pool.close()
     value = a.steps * len(idx) / dt
-    kind = "reference" if R.HAVE_CV2 else "port"
-    sample = (f"{len(idx)} pairs per step of the same synthetic sequence; "
-              + ("cv2 %s BFMatcher/findEssentialMat/recoverPose (the OpenCV calls the reference makes) + plain-C "
-                 "restatement of its LM (Eigen/Sophus original not buildable)" % R.cv2.__version__ if R.HAVE_CV2
-                 else "numpy restatement (cv2 missing)")
+    kind = "reference" if (R.HAVE_CV2 and R.lm_kind() == "reference") else "port"
+    sample = (f"{len(idx)} pairs per step of the same synthetic sequence; " + R.describe()
               + f"; {cores} worker processes x 1 thread, pair-parallel")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8+f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(a), "pairs_per_step": len(idx)},
+            "config": config_of(a, max(a.gpus, 1)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -196,25 +213,16 @@ def emit(line):
     out.flush()
 
 
-def run_windows(a):
-    """BASELINE.json config 5 (not the headline line): the windows of one sequence, sharded over the ranks in
-    contiguous blocks (strong scaling: the total is fixed), one batched Levenberg_Marquardt launch per rank.
-    value = windows / max over ranks of the kernel time; e2e = the same through epivo_lm_rt_batch with pinned
-    host buffers (H2D of the reprojections + D2H of the refined chains inside the timed region)."""
+def windows_measure(a, ctx, world, rank, local, dist, steps, warmup, windows=None):
+    """BASELINE.json config 5: the windows of one sequence (n_zeta 10, reps {(i,i),(0,i)} x 250 correspondences,
+    test_jac_Rt_gen.cpp:282-297), sharded over the ranks in contiguous blocks (strong scaling: the total is fixed),
+    one batched Levenberg_Marquardt launch per rank.  -> dict(kernel ms, wall ms, launches, ...), max over ranks."""
     import torch
-    import torch.distributed as dist
     from epivo_b200 import api, shard, synth
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    windows = a.windows if windows is None else windows
     nz, N = 10, 250
     reps = [(i, i) for i in range(nz)] + [(0, i) for i in range(nz)]
-    lo, hi = shard.shard_range(a.windows, world, rank)
+    lo, hi = shard.shard_range(windows, world, rank)
     B = hi - lo
     data = [synth.gen_scene_sequence(500 + (lo + b) % 64, N, nz, reps) for b in range(min(B, 64))]
 
@@ -223,56 +231,212 @@ def run_windows(a):
         return t, t.numpy()
     keep = [pinned(k) for k in (1, 2, 3)]
     T0, pr, p_r = (x[1] for x in keep)
-    ctx = api.Context(local)
     w = [1.0] * len(reps)
 
     def step():
-        return api.Levenberg_Marquardt_batch(nz, 1e-8, reps, w, 1e-2, T0, pr, p_r, huber_delta=1.0, ctx=ctx)
-    for _ in range(max(a.warmup, 1)):
+        return api.Levenberg_Marquardt_batch(nz, 1e-8, reps, w, 1e-2, T0, pr, p_r, huber_delta=a.huber, ctx=ctx)
+    for _ in range(max(warmup, 1)):
         step()
-    clocks = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     n0 = ctx.launch_count
     t0 = time.perf_counter()
     k_ms = 0.0
-    for _ in range(a.steps):
+    for _ in range(steps):
         T, res, its = step()
         k_ms += ctx.last_kernel_ms()
     torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3 / a.steps
-    k_ms /= a.steps
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    k_ms /= steps
     launches = ctx.launch_count - n0
     if world > 1:
         t = torch.tensor([k_ms, wall_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         k_ms, wall_ms = float(t[0].item()), float(t[1].item())
         dist.barrier()
+    return {"windows": windows, "B": B, "k_ms": k_ms, "wall_ms": wall_ms, "launches": int(launches),
+            "mean_iters": float(its.mean()) if B else 0.0, "h2d": int(T0.nbytes + pr.nbytes + p_r.nbytes),
+            "d2h": int(T0.nbytes + B * 28), "data": data, "nz": nz, "reps": reps}
+
+
+def run_windows(a):
+    """`--workload ba_windows` (not the headline line): value = windows / max over ranks of the kernel time; e2e = the
+    same through epivo_lm_rt_batch with pinned host buffers (H2D of the reprojections + D2H of the refined chains)."""
+    import torch
+    import torch.distributed as dist
+    from epivo_b200 import api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = api.Context(local)
+    clocks = ClockSampler(local)
+    m = windows_measure(a, ctx, world, rank, local, dist, a.steps, a.warmup)
     clk = clocks.stop()
-    line = {"metric": "kitti_ba windows/sec (windowed Rt LM, n_zeta 10, 20 reps x 250 correspondences, 30 iterations)",
-            "value": a.windows / (k_ms * 1e-3), "unit": "windows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": k_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+    line = {"metric": "kitti_ba windows/sec (windowed Rt LM, n_zeta 10, 20 reps x 250 correspondences, 30 iterations, "
+                      "huber_delta %g)" % a.huber,
+            "value": a.windows / (m["k_ms"] * 1e-3), "unit": "windows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": m["k_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"BASELINE config 5: {a.windows} windows (sequence.hpp scenes), contiguous blocks per rank, "
-                                   f"{B} on rank {rank}", "parallelism": f"windows sharded, {world} x 1 GPU, no collective"},
+                                   f"{m['B']} on rank {rank}; huber_delta {a.huber:g} (jac_Rt_gen_.cpp:17 ships 1e-5, "
+                                   f"test_jac_Rt_gen.cpp:16 tests 1.0)",
+                       "parallelism": f"windows sharded, {world} x 1 GPU, no collective"},
             "clocks": clk,
-            "e2e": {"value": a.windows / (wall_ms * 1e-3), "unit": "windows/s", "ms_per_step": wall_ms,
-                    "h2d_bytes_per_step": int(T0.nbytes + pr.nbytes + p_r.nbytes), "d2h_bytes_per_step": int(T0.nbytes + B * 28)},
-            "gpu_launches": int(launches), "mean_iters": float(its.mean())}
+            "e2e": {"value": a.windows / (m["wall_ms"] * 1e-3), "unit": "windows/s", "ms_per_step": m["wall_ms"],
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+            "gpu_launches": m["launches"], "mean_iters": m["mean_iters"]}
     if world == 1 and not a.no_cpu_baseline:
-        from oracle import cpu_reference as R
-        cores = os.cpu_count() or 1
-        n = 2 * cores
-        v = R.windows_rate(data, nz, reps, n, cores=cores)
-        line["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
-                                "sample": f"{n} windows of the same shape; plain-C restatement of the reference LM "
-                                          f"(Eigen/Sophus original not buildable), {cores} processes x 1 thread"}
+        line["cpu_baseline"] = windows_cpu_baseline(a, m)
     if rank == 0:
         emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def windows_cpu_baseline(a, m):
+    from oracle import cpu_reference as R
+    cores = os.cpu_count() or 1
+    n = 2 * cores
+    v = R.windows_rate(m["data"], m["nz"], m["reps"], n, cores=cores, huber_delta=a.huber)
+    return {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
+            "sample": f"{n} windows of the same shape; plain-C restatement of the reference LM (pinned to the reference's "
+                      f"own build, tests/test_oracle_ref.py; that build -- g++ -O0 against a stand-in Eigen -- is ~100x "
+                      f"slower and would flatter the ratio), {cores} processes x 1 thread"}
+
+
+class PairsRunner:
+    """One resident sequence + pinned host copies; measures a parameter set both device-resident and end to end."""
+
+    def __init__(self, ctx, seq, local, world, dist):
+        import torch
+        from epivo_b200 import api
+        self.torch, self.api, self.ctx, self.seq, self.world, self.dist = torch, api, ctx, seq, world, dist
+        self.F, self.P, self.kp = seq.n_frames, seq.n_pairs, seq.kps.shape[1]
+        self.h_kps = torch.from_numpy(seq.kps).pin_memory()          # torch owns the pinned allocation;
+        self.h_desc = torch.from_numpy(seq.descs).pin_memory()       # numpy views go to the C ABI
+        self.kps_np, self.desc_np = self.h_kps.numpy(), self.h_desc.numpy()
+        self.pipe = api.SequencePipeline(self.F, self.kp, ctx=ctx)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+        self.h_res = torch.zeros(self.P * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self.results = self.h_res.numpy().view(api.RESULT_DTYPE)
+        self.pipe.upload(self.kps_np, self.desc_np)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def resident(self, prm, steps, warmup):
+        """EXACTLY `steps` steps with the inputs resident in HBM; CUDA events on the library's stream."""
+        torch, pipe, P = self.torch, self.pipe, self.P
+        for _ in range(warmup):
+            pipe.run(prm, 0, P)
+        self.ctx.sync()
+        launches0 = self.ctx.launch_count
+        stage_acc = np.zeros(16, dtype=np.float64)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            pipe.run(prm, 0, P)
+            stage_acc += pipe.stage_ms()      # syncs the stream (microseconds against a >= 17 ms step)
+        e1.record(self.stream)
+        self.barrier()
+        ms_step = self.max_over_ranks(e0.elapsed_time(e1) / steps)
+        return ms_step, stage_acc / steps, self.ctx.launch_count - launches0
+
+    def end_to_end(self, prm, steps, warmup=2, gather=True):
+        """The same through the public API with HOST buffers: H2D of the sequence (pipelined under the matcher),
+        run, D2H of the per-pair results, and -- N > 1 -- the NCCL all-gather of the poses, every step."""
+        torch, pipe, world = self.torch, self.pipe, self.world
+        for _ in range(warmup):
+            pipe.process(prm, self.kps_np, self.desc_np, self.results)
+        self.barrier()
+        t0 = time.perf_counter()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(self.stream)
+        for _ in range(steps):
+            pipe.process(prm, self.kps_np, self.desc_np, self.results)
+            if world > 1 and gather:          # the only collective: per-pair poses -> every rank (NCCL)
+                T = torch.from_numpy(np.ascontiguousarray(self.results["T"])).cuda(non_blocking=True)
+                gathered = torch.empty((world * T.shape[0],) + tuple(T.shape[1:]), dtype=T.dtype, device="cuda")
+                self.dist.all_gather_into_tensor(gathered, T)
+        e3.record(self.stream)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e2.elapsed_time(e3), wall * 1e3) / steps          # host-side staging counts too
+        return self.max_over_ranks(ms)
+
+    def close(self):
+        self.pipe.close()
+
+
+def rot_angle(a, b):
+    return float(np.arccos(np.clip((np.trace(a.T @ b) - 1) / 2, -1, 1)))
+
+
+def strong_scaling_leg(a, ctx, local, world, rank, dist, prm, runner0):
+    """BASELINE config 3 as written: ONE 4541-frame sequence (rank 0's), pairs sharded in contiguous blocks
+    (shard.shard_range, halo of one frame), every rank runs its block from host buffers, the per-pair poses are
+    all-gathered (NCCL) into sequence order and rank 0 chains them (kitti_E.cpp:218-228).  Checked against rank 0's
+    own single-GPU run of all pairs."""
+    import torch
+    from epivo_b200 import api, shard, synth
+    seq0 = runner0.seq if rank == 0 else synth.make_sequence(a.frames, a.kp, seed=synth.seed_for(3, 0))
+    P = seq0.n_pairs
+    lo, hi = shard.shard_range(P, world, rank)
+    f0, f1 = shard.frames_for(lo, hi)
+    nb = hi - lo
+    h_kps = torch.from_numpy(np.ascontiguousarray(seq0.kps[f0:f1])).pin_memory()
+    h_desc = torch.from_numpy(np.ascontiguousarray(seq0.descs[f0:f1])).pin_memory()
+    pipe = api.SequencePipeline(max(f1 - f0, 2), a.kp, ctx=ctx)
+    h_res = torch.zeros(max(nb, 1) * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    res = h_res.numpy().view(api.RESULT_DTYPE)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def step():
+        if nb > 0:
+            pipe.process(prm, h_kps.numpy(), h_desc.numpy(), res)
+        allT = shard.gather_poses(np.ascontiguousarray(res["T"][:nb]), P, world, rank, dist=dist, device="cuda")
+        return shard.chain_poses(allT) if rank == 0 else None, allT
+    for _ in range(2):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        poses, allT = step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out = {"pairs": P, "ms_per_step": ms, "value": P / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
+           "pairs_on_rank0": nb, "includes": "H2D of the rank's frames + run + D2H + NCCL all-gather of the poses + host chain "
+                                            "(rank 0), wall clock, max over ranks"}
+    if rank == 0:
+        single = runner0.pipe.process(prm, runner0.kps_np, runner0.desc_np, runner0.results)
+        Ts = np.array(single["T"])
+        out["equal_to_single_gpu"] = bool(np.array_equal(Ts, allT))
+        out["max_abs_diff_vs_single_gpu"] = float(np.abs(Ts - allT).max())
+        out["chain_max_abs_diff"] = float(np.nanmax(np.abs(poses - shard.chain_poses(Ts))))
+    pipe.close()
+    return out
 
 
 def main():
@@ -286,7 +450,7 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from epivo_b200 import api
+    from epivo_b200 import api, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -298,82 +462,28 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     seq = make_inputs(a, rank)
-    F, P, kp = seq.n_frames, seq.n_pairs, a.kp
-    # pinned host copies of the inputs (torch owns the pinned allocation; numpy views for the C ABI)
-    h_kps = torch.from_numpy(seq.kps).pin_memory()
-    h_desc = torch.from_numpy(seq.descs).pin_memory()
-    kps_np, desc_np = h_kps.numpy(), h_desc.numpy()
     ctx = api.Context(local)
-    pipe = api.SequencePipeline(F, kp, ctx=ctx)
+    run = PairsRunner(ctx, seq, local, world, dist)
+    P, kp = run.P, a.kp
     method = api.RANSAC if a.method == "ransac" else api.LMEDS
-    prm = api.default_params(seq.K.astype(np.float32), method=method, threshold=a.thr,
+    Kf = seq.K.astype(np.float32)
+    prm = api.default_params(Kf, method=method, threshold=a.thr,
                              match_mode=1 if a.match == "crosscheck" else 2, ratio=0.8,
                              norm=api.NORM_HAMMING2 if a.norm == "hamming2" else api.NORM_HAMMING)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-    # results land in pinned host memory too (the library DMAs straight into a pinned caller buffer)
-    h_res = torch.zeros(P * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    results = h_res.numpy().view(api.RESULT_DTYPE)
 
-    pipe.upload(kps_np, desc_np)
-    for _ in range(a.warmup):
-        pipe.run(prm, 0, P)
-    ctx.sync()
-
-    # ---------------- device-resident timed region: EXACTLY `steps` steps -----------------
-    launches0 = ctx.launch_count
+    # ---------------- headline: device-resident, then end to end with host buffers ------------------
     clocks = ClockSampler(local)
-    stage_acc = np.zeros(16, dtype=np.float64)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(a.steps):
-        pipe.run(prm, 0, P)
-        stage_acc += pipe.stage_ms()          # syncs the stream (microseconds against a ~100 ms step)
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0
-    ms_step = max_over_ranks(ms_total / a.steps)
+    ms_step, stages, launches = run.resident(prm, a.steps, a.warmup)
     value = world * P / (ms_step * 1e-3)
-
-    # ---------------- end to end through the public API with host buffers -----------------
-    for _ in range(2):
-        pipe.process(prm, kps_np, desc_np, results)
-    barrier()
-    gathered = None
-    t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    for _ in range(a.steps):
-        pipe.process(prm, kps_np, desc_np, results)   # H2D (pipelined under the matcher) + run + D2H + sync
-        if world > 1:                         # the only collective: per-pair poses -> every rank (NCCL)
-            T = torch.from_numpy(np.ascontiguousarray(results["T"])).cuda(non_blocking=True)
-            gathered = torch.empty((world * T.shape[0],) + tuple(T.shape[1:]), dtype=T.dtype, device="cuda")
-            dist.all_gather_into_tensor(gathered, T)
-    e3.record(stream)
-    barrier()
-    wall = time.perf_counter() - t0
-    ms_e2e = max(e2.elapsed_time(e3), wall * 1e3) / a.steps      # host-side staging counts too
-    ms_e2e = max_over_ranks(ms_e2e)
+    ms_e2e = run.end_to_end(prm, a.steps)
     e2e_value = world * P / (ms_e2e * 1e-3)
     clk = clocks.stop()
+    results = run.results.copy()
 
     # ---------------- roofline of the dominant kernel (the matcher) -------------------------
-    ms_match = stage_acc[7] / a.steps                        # tile kernel alone, summed over chunk launches
-    n_chunk_launches = int(round(stage_acc[8] / a.steps))
+    ms_match = stages[7]                                     # tile kernel alone, summed over chunk launches
+    n_chunk_launches = int(round(stages[8]))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -386,18 +496,22 @@ def main():
     achieved_gbs = bytes_per_pair * P / (ms_match * 1e-3) / 1e9
     popc_peak = ctx.microbench(0)                            # POPC.32 thread-ops/s, measured now on this GPU
     lop_peak = ctx.microbench(4)
+    fp64_peak = ctx.microbench(2)                            # FP64 FMA thread-ops/s
     # algorithmic POPC.32 per pair: nq*nt*(256/32) for plain Hamming; the Hamming2 bit-plane form
     # needs nq*nt*4 -- report against the instruction count the kernel actually needs (4)
     popc_per_pair = kp * kp * (4 if a.norm == "hamming2" else 8)
     achieved_popc = popc_per_pair * P / (ms_match * 1e-3)
-    # DRAM traffic of one matcher launch over the default workload, from the `ncu --set full` capture in
-    # profiles/r1_ncu_full_top_kernels.csv (dram__bytes_read.sum + dram__bytes_write.sum = 327.8 + 59.0 MB).
-    # It is BELOW the algorithmic bytes because consecutive pairs share a frame (train set of pair i =
-    # query set of pair i+1) and that frame is still in L2.  Only valid for the profiled shape.
-    traffic = 386.8e6 if (a.frames == 4541 and a.kp == 2000 and n_chunk_launches == 1 and a.norm == "hamming2"
-                          and a.match == "crosscheck") else None
+    # DRAM traffic of one matcher launch over the default workload: NOT measured in this run (it needs ncu); the figure
+    # is dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture named in traffic_source.  It is
+    # BELOW the algorithmic bytes because consecutive pairs share a frame (train set of pair i = query set of pair
+    # i+1) that is still in L2.  Only valid for the profiled shape.
+    default_shape = (a.frames == 4541 and a.kp == 2000 and n_chunk_launches == 1 and a.norm == "hamming2"
+                     and a.match == "crosscheck")
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": 386.8e6 if default_shape else None,
+                "traffic_source": "profiles/r1_ncu_full_top_kernels.csv (ncu --set full of this command, not measured live)"
+                                  if default_shape else None,
+                "peak_source": peak_src,
                 "kernel": "match_tile_kernel<8,%s%s>" % (a.norm.upper(), ",TOP2" if a.match == "ratio" else ""), "launches_per_step": n_chunk_launches,
                 "algorithmic_bytes_per_launch": bytes_per_pair * P / max(n_chunk_launches, 1),
                 "ms_per_step_in_kernel": ms_match,
@@ -415,20 +529,31 @@ def main():
                      (4, "Hamming2 on bit planes") if a.norm == "hamming2" else (8, "plain Hamming")),
                  "note": "frac = issued POPC.32 rate / POPC.32 peak measured in this run (epivo_microbench); the "
                          "algorithmic rate is higher because carry-save adders compress the words before counting; "
-                         "ncu (profiles/r1_ncu_full_top_kernels.csv): XU (POPC) pipe 88 %, ALU (LOP3) pipe 89 % of peak"}
+                         "ncu (profiles/): XU (POPC) pipe 88 %, ALU (LOP3) pipe 89 % of peak"}
+
+    def fp64_block(res, st):
+        """FP64 pipe of the RANSAC / LMedS scoring: (models scored) x (correspondences) Sampson tests at 17 FP64
+        instructions each (fused pre-filter path, DESIGN K3) over the time of the essential rounds (essential stage
+        minus sampling + minimal solver), against the FP64 FMA rate measured in this run."""
+        evals = float((res["n_models"].astype(np.float64) * res["n_matches"]).sum())
+        ms_rounds = max(st[3] - st[2], 1e-6)
+        ach = 17.0 * evals / (ms_rounds * 1e-3)
+        return {"kernel": "ess_round_kernel (+ bookkeeping inside the essential rounds)", "bound": "fp64 pipe",
+                "achieved": ach / 1e9, "peak": fp64_peak / 1e9, "unit": "G FP64 instr/s", "frac": ach / fp64_peak,
+                "model_x_point_tests_per_step": evals, "ms_per_step_in_rounds": ms_rounds,
+                "fp64_instr_per_test": 17}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32-popc+f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "pairs_per_gpu": P, "l2": "inputs (363 MB/GPU) larger than L2",
-                       "parallelism": f"pairs sharded, {world} x 1 GPU, no data-path collective",
-                       "host_affinity": (f"rank bound to {near_cpus} GPU-local cores (NVML)" if near_cpus else "unchanged")},
+            "config": config_of(a, world),
+            "host_affinity": (f"rank bound to {near_cpus} GPU-local cores (NVML)" if near_cpus else "unchanged"),
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(kps_np.nbytes + desc_np.nbytes),
-                    "d2h_bytes_per_step": int(results.nbytes), "ms_per_step": ms_e2e},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(run.kps_np.nbytes + run.desc_np.nbytes),
+                    "d2h_bytes_per_step": int(run.results.nbytes), "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
-            "roofline": roofline, "pipe": pipe_roof,
-            "stages_ms_per_step": {k: float(stage_acc[i] / a.steps) for i, k in
+            "roofline": roofline, "pipe": pipe_roof, "pipe_fp64": fp64_block(results, stages),
+            "stages_ms_per_step": {k: float(stages[i]) for i, k in
                                    enumerate(["total", "match", "presolve", "essential", "pose", "lm", "finish",
                                               "match_kernel"])},
             "quality": {"mean_matches": float(results["n_matches"].mean()),
@@ -437,8 +562,56 @@ def main():
                         "mean_ransac_iters": float(results["ransac_iters"].mean()),
                         "lm_ran_frac": float(results["lm_ran"].mean()),
                         "lm_reverted_frac": float(results["lm_reverted"].mean()),   # kitti_E.cpp:198-200 reverts when r_norm > 1e-9
-                        "median_rot_err_rad": float(np.median([np.arccos(np.clip((np.trace(results["R"][i].T @ seq.R[i]) - 1) / 2, -1, 1))
+                        "median_rot_err_rad": float(np.median([rot_angle(results["R"][i], seq.R[i])
                                                                for i in range(0, P, max(1, P // 256))]))}}
+    if world > 1:
+        e2e_lim = {"aggregate_h2d_GBps": world * (run.kps_np.nbytes + run.desc_np.nbytes) / (ms_e2e * 1e-3) / 1e9}
+        line["e2e"]["limiter"] = ("host->device input path: %d ranks x %.0f MB per step = %.0f GB/s aggregate through the host "
+                                  "(see profiles/r2_h2d_ceiling.json for the copy-only ceiling of this box class)"
+                                  % (world, (run.kps_np.nbytes + run.desc_np.nbytes) / 1e6, e2e_lim["aggregate_h2d_GBps"]))
+        line["e2e"].update(e2e_lim)
+
+    # ---------------- the reference's other call shapes, full step each (not the headline) ---------------
+    if not a.no_configs:
+        cfgs = {}
+
+        def shape(name, r, p, note, steps=3):
+            ms_r, st, _ = r.resident(p, steps, 1)
+            ms_e = r.end_to_end(p, 2, warmup=1, gather=False)
+            res = r.results
+            cfgs[name] = {"workload": note, "value": world * r.P / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r,
+                          "e2e": world * r.P / (ms_e * 1e-3), "e2e_ms_per_step": ms_e,
+                          "mean_ransac_iters": float(res["ransac_iters"].mean()), "mean_inliers": float(res["n_inliers"].mean()),
+                          "stages_ms": {"match": float(st[1]), "presolve": float(st[2]), "essential": float(st[3]),
+                                        "pose": float(st[4]), "lm": float(st[5])},
+                          "pipe_fp64": fp64_block(res.copy(), st)}
+        shape("kitti_E LMEDS(.99,.01)", run, api.default_params(Kf, method=api.LMEDS, prob=0.99, threshold=0.01),
+              "kitti_E.cpp:98-104 on the headline sequence")
+        shape("kitti_ba RANSAC(.99,.05)", run, api.default_params(Kf, method=api.RANSAC, prob=0.99, threshold=0.05),
+              "kitti_ba.cpp:308 (1000 iterations per pair) on the headline sequence", steps=2)
+        shape("ratio-mode matcher", run, api.default_params(Kf, method=method, threshold=a.thr, match_mode=2, ratio=0.8,
+                                                            norm=api.NORM_HAMMING),
+              "knnMatch(k=2) + Lowe ratio 0.8 on plain 256-bit Hamming (north_star's matcher mode), then the headline geometry")
+        seq_e = synth.make_sequence(a.frames, 1500, seed=synth.seed_for(2, rank), K=synth.EUROC_K, size=synth.EUROC_SIZE,
+                                    depth=(1.0, 8.0), px_sigma=0.3, outlier_frac=0.25, step=(0.03, 0.07))
+        run_e = PairsRunner(ctx, seq_e, local, world, dist)
+        shape("euroc_E RANSAC(.99,.3) 1500 kp", run_e,
+              api.default_params(synth.EUROC_K.astype(np.float32), method=api.RANSAC, prob=0.99, threshold=0.3,
+                                 fallback_t=(0.0, 0.0, 1.0)),
+              "euroc_E.cpp:202-208: EuRoC camera, 752x480, %d frames x 1500 kp" % a.frames)
+        run_e.close()
+        del run_e, seq_e
+        m = windows_measure(a, ctx, world, rank, local, dist, 3, 1)
+        cfgs["kitti_ba windows"] = {"workload": "BASELINE config 5: %d windows (n_zeta 10, 20 reps x 250), sharded over the ranks "
+                                                "(strong scaling), huber_delta %g" % (m["windows"], a.huber),
+                                    "value": m["windows"] / (m["k_ms"] * 1e-3), "unit": "windows/s", "ms_per_step": m["k_ms"],
+                                    "e2e": m["windows"] / (m["wall_ms"] * 1e-3), "e2e_ms_per_step": m["wall_ms"],
+                                    "mean_iters": m["mean_iters"], "windows_on_rank0": m["B"]}
+        line["configs"] = cfgs
+
+    # ---------------- N > 1: config 3 as written (one sequence sharded, gathered, chained) ---------------
+    if world > 1:
+        line["strong_scaling"] = strong_scaling_leg(a, ctx, local, world, rank, dist, prm, run)
 
     if world == 1 and rank == 0 and not a.no_cpu_baseline:
         from oracle import cpu_reference as R
@@ -449,6 +622,20 @@ def main():
         pool.run(range(min(n, cores)))
         v, res = pool.run(range(n))
         pool.close()
+        # live parity census: cv2's result for these pairs against the GPU's result for the same pairs
+        eq = {"n_matches": 0, "n_inliers": 0, "n_good": 0}
+        max_rot = 0.0
+        for (i, T, nm, ni, ng) in res:
+            g = results[i]
+            eq["n_matches"] += int(nm == g["n_matches"])
+            eq["n_inliers"] += int(ni == g["n_inliers"])
+            eq["n_good"] += int(ng == g["n_good"])
+            max_rot = max(max_rot, rot_angle(np.asarray(T)[:3, :3], g["T"][:3, :3]))
+        line["parity_vs_cv2"] = {"pairs": len(res), "n_matches_equal": eq["n_matches"], "n_inliers_equal": eq["n_inliers"],
+                                 "n_good_equal": eq["n_good"], "max_rot_diff_rad": max_rot,
+                                 "note": "whole-call comparison on the first pairs of the benchmark sequence; a differing pair "
+                                         "is one where cv2's own winning model violates the essential constraints (its "
+                                         "unrefined root on an ill-conditioned sample), see tests/test_gpu_cv2_census.py"}
         # SURVEY 8d's other arrangement: one process, OpenCV's own threads over all cores (16 pairs, ~2 s)
         n1 = min(16, n)
         v1 = R.single_process_rate(seq.kps[:n1 + 1], seq.descs[:n1 + 1], seq.K, n1, 8 if a.method == "ransac" else 4, 0.99,
@@ -456,13 +643,13 @@ def main():
                                    ratio=None if a.match == "crosscheck" else 0.8)
         line["cpu_baseline_single_process"] = {"value": v1, "unit": UNIT, "cores": cores,
                                                "sample": f"first {n1} pairs, one process, cv2.setNumThreads({cores})"}
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference" if R.HAVE_CV2 else "port",
-                                "sample": f"first {n} pairs of the same sequence; cv2 "
-                                          f"{R.cv2.__version__ if R.HAVE_CV2 else 'missing'} BFMatcher/findEssentialMat/"
-                                          f"recoverPose + plain-C restatement of the reference LM; {cores} processes x 1 thread"}
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores,
+                                "kind": "reference" if (R.HAVE_CV2 and R.lm_kind() == "reference") else "port",
+                                "sample": f"first {n} pairs of the same sequence; {R.describe()}; {cores} processes x 1 thread",
+                                "lm_ms_per_pair": R.lm_ms_per_pair()}
     if rank == 0:
         emit(line)
-    pipe.close()
+    run.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

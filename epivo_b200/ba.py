@@ -179,7 +179,8 @@ def match_kp(kps, descs, window, stride, K, counts=None, ctx=None):
         for p, (i0, i1) in enumerate(pairs):
             r = Reproj(p0=np.zeros((0, 2), np.float32), p1=np.zeros((0, 2), np.float32), R=np.eye(3),
                        t=np.array([0.1, 0.1, -0.9]))
-            if res[p]["n_matches"] >= 8:
+            # no model (findEssentialMat would return an empty Mat): keep the identity / (0.1, 0.1, -0.9) start
+            if res[p]["n_matches"] >= 8 and res[p]["n_inliers"] > 0:
                 qi, ti, _ = pipe.matches(p)
                 em, pm = pipe.masks(p)
                 keep = np.flatnonzero(em == 1)[pm == 255]

@@ -562,8 +562,11 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     const bool upload_all = h_kps != nullptr && s->pairs_set;
     const bool upload = h_kps != nullptr && !upload_all;
     const bool overlap = s->overlap && !upload && !upload_all;
-    if (upload_all) s->frames_hi = std::max(s->frames_hi, n_frames_up);
+    if (upload || upload_all) s->frames_hi = std::max(s->frames_hi, first_pair + n_frames_up);
     if (s->pairs_set && s->frames_hi == 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "pair list set but no frames uploaded");
+    if (s->pairs_set && s->list_max >= s->frames_hi)          // a slot never uploaded would be matched as garbage
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "the pair list references frame %d but only frames [0,%d) have been uploaded",
+                 s->list_max, s->frames_hi);
     // matcher groups / geometry groups (event slots: matcher [0, HALF), geometry [HALF, 2*HALF))
     constexpr int HALF = SEQ_MAX_CHUNKS / 2;
     // matcher groups.  Resident data: uniform groups.  Host buffers: the upload is cut into pieces of

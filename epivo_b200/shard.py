@@ -67,7 +67,8 @@ def chain_poses(T_pairs: np.ndarray, scales: np.ndarray | None = None) -> np.nda
         t = T_pairs[i][:3, 3]
         nt = np.linalg.norm(t)
         dT[:3, :3] = T_pairs[i][:3, :3]
-        dT[:3, 3] = (t / nt if nt > 0 else t) * scales[i]
+        with np.errstate(all="ignore"):       # |t| = 0 is not guarded: NaN from there on, as in the reference (:221)
+            dT[:3, 3] = t / nt * scales[i]    # and in the device chain (cloud.cu: scaled_dT)
         cT = cT @ np.linalg.inv(dT)
     out[n] = cT
     return out

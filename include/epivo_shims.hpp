@@ -324,7 +324,9 @@ void match_kp(Context& ctx, const std::vector<std::pair<int, int> >& window, con
         const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t0[3] = {0.1, 0.1, -0.9};                 // :741-744
         std::copy(I, I + 9, rep.R);
         std::copy(t0, t0 + 3, rep.t);
-        if (res[p].n_matches >= 8) {                                                               // :700
+        // (no model -- findEssentialMat would have returned an empty Mat, on which the reference's recoverPose
+        // throws -- keeps the identity / (0.1, 0.1, -0.9) start instead of the zeroed pose-stage outputs)
+        if (res[p].n_matches >= 8 && res[p].n_inliers > 0) {                                       // :700
             int nm = 0, ne = 0, np = 0;
             ctx.check(epivo_seq_get_matches(seq, (int)p, qi.data(), ti.data(), di.data(), &nm));
             ctx.check(epivo_seq_get_masks(seq, (int)p, em.data(), &ne, pm.data(), &np));

@@ -98,6 +98,9 @@ def match_kp(kps, descs, window, stride, K, counts=None):
             p0 = p1 = np.zeros((0, 2), np.float32)
             if len(qi) >= 8:
                 E, mask, _ = O.find_essential_mat(c0, c1, np.asarray(K, dtype=np.float32), O.LMEDS, 0.99, 0.1)
+                if E is None or np.asarray(E).shape != (3, 3):       # no model: the reference's recoverPose would throw
+                    out[(i0, i1)] = (p0, p1, R, t)
+                    continue
                 c0, c1 = c0[mask == 1], c1[mask == 1]
                 n_good, R, t, pmask = O.recover_pose(E, c0, c1, np.asarray(K, dtype=np.float32))
                 p0, p1 = c0[pmask == 255], c1[pmask == 255]

@@ -2,9 +2,11 @@
 
 The reference's per-pair path on host cores: the OpenCV calls the reference itself makes
 (through the cv2 wheel: BFMatcher.match, findEssentialMat, recoverPose -- kitti_ba.cpp:641,
-kitti_E.cpp:98-120) followed by the plain-C restatement of its Levenberg-Marquardt
-(oracle/lm_c.c; the Eigen/Sophus original cannot be built in this image).  If cv2 cannot be
-imported the numpy restatement (oracle.oracle) is timed instead and the JSON says so.
+kitti_E.cpp:98-120) followed by the reference's OWN Levenberg_Marquardt -- jac_Rt_gen_.cpp compiled
+unmodified into oracle/_ref/libref_lm.so (oracle/Makefile; built where /root/reference exists, the file
+travels to the GPU box).  Where that library is absent the plain-C restatement (oracle/lm_c.c) runs
+instead; if cv2 cannot be imported the numpy restatement (oracle.oracle) is timed.  The JSON line says
+which (`cpu_baseline.kind`, `.sample`).
 """
 from __future__ import annotations
 
@@ -22,8 +24,51 @@ except Exception:                                       # pragma: no cover
 
 from . import clib
 from . import oracle as O
+from . import reflib
 
 _SEQ = {}
+
+
+def lm_kind() -> str:
+    """"reference" when oracle/_ref/libref_lm.so (the reference's own LM) is loadable, else "port"."""
+    return "reference" if reflib.available() else "port"
+
+
+def describe() -> str:
+    if not HAVE_CV2:
+        return "numpy restatement (cv2 missing)"
+    lm = ("the reference's own Levenberg_Marquardt (jac_Rt_gen_.cpp compiled unmodified, oracle/_ref, g++ -O0 as its "
+          "functions without return statements require)" if lm_kind() == "reference"
+          else "plain-C restatement of its LM (oracle/_ref absent)")
+    return "cv2 %s BFMatcher/findEssentialMat/recoverPose (the OpenCV calls the reference makes) + %s" % (cv2.__version__, lm)
+
+
+def lm_ms_per_pair(n: int = 5) -> dict:
+    """Time of one kitti_E-shaped LM call (1 zeta, 48 points, 30 iterations) in the two CPU implementations, so that
+    a reader can see what the choice of LM build does to the baseline: the reference build is g++ -O0 (its functions
+    without return statements rule out optimisation) against a stand-in Eigen; the C port is -O2."""
+    from epivo_b200 import synth
+    Ts, T0s, pr, p_r = synth.gen_scene_sequence(9, 48, 1, [(0, 0)], noise_rot=1e-2, noise_tr=1e-2)
+    out = {}
+    impls = [("c_port", lambda: clib.levenberg_marquardt(1, 1e-8, [(0, 0)], [1.0], 1e-2, T0s, pr, p_r, 1e-5, 30))]
+    if lm_kind() == "reference":
+        impls.append(("reference_build", lambda: reflib.ref().levenberg_marquardt(1, 1e-8, [(0, 0)], [1.0], 1e-2, T0s, pr, p_r)))
+    for name, fn in impls:
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        out[name] = (time.perf_counter() - t0) / n * 1e3
+    return out
+
+
+def _lm(T, pr, p_r, huber_delta):
+    """kitti_E.cpp:196 -> (T_out (1,4,4), r_norm)"""
+    if lm_kind() == "reference" and huber_delta == 1e-5:
+        Tl, lm = reflib.ref().levenberg_marquardt(1, 1e-8, [(0, 0)], [1.0], 1e-2, T, pr, p_r)
+    else:
+        Tl, lm = clib.levenberg_marquardt(1, 1e-8, [(0, 0)], [1.0], 1e-2, T, pr, p_r, huber_delta, 30)
+    return Tl, lm["r_norm"]
 
 
 def pair_cv2(kp0, d0, kp1, d1, Kf, method=8, prob=0.99, thr=1.0, lm_points=48, huber_delta=1e-5,
@@ -60,8 +105,8 @@ def pair_cv2(kp0, d0, kp1, d1, Kf, method=8, prob=0.99, thr=1.0, lm_points=48, h
         x1 = O.normalize_points(c1[:N], Kf)
         pr = np.concatenate([x0, np.ones((N, 1))], axis=1)[None]
         p_r = np.concatenate([x1, np.ones((N, 1))], axis=1)[None]
-        Tl, lm = clib.levenberg_marquardt(1, 1e-8, [(0, 0)], [1.0], 1e-2, T[None], pr, p_r, huber_delta, 30)
-        if lm["r_norm"] <= 1e-9:
+        Tl, r_norm = _lm(T[None], pr, p_r, huber_delta)
+        if r_norm <= 1e-9:
             T = Tl[0]
     return T, len(p0), int(m.sum()), int(n_good)
 
@@ -78,6 +123,8 @@ def _init(kps, descs, Kf, method, prob, thr, norm=7, ratio=None):
     if HAVE_CV2:
         cv2.setNumThreads(1)                                # pair-parallel: one core per pair
     clib.lib()
+    if lm_kind() == "reference":
+        reflib.ref()
 
 
 def _work(i):

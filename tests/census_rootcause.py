@@ -1,5 +1,5 @@
 """Root-cause analysis of the pairs on which the whole-call census (tests/test_gpu_cv2_census.py) differs from cv2.
-TEST TOOLING (uses oracle/ and cv2); run in the build container:  python tools/census_rootcause.py 151:kitti.cpp:101 ...
+TEST TOOLING (uses oracle/ and cv2); run in the build container:  python tests/census_rootcause.py 151:kitti.cpp:101 ...
 
 For each pair: cv2's E / mask, the oracle's (== the GPU's, bit for bit on masks) E / mask, then
   * the Sampson error of every flipped point under both models against the f32 threshold, and
@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import cv2
 
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from epivo_b200 import synth  # noqa: E402
 from oracle import cpu_reference as R  # noqa: E402
 from oracle import oracle as O  # noqa: E402

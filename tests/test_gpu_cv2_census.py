@@ -7,7 +7,7 @@ north_star's tolerances.
 Known and accepted: on ~0.5 % of RANSAC calls cv2's WINNING model is an inaccurate root -- OpenCV's un-refined
 Nister solution on an ill-conditioned minimal sample violates the essential-matrix constraint
 2 E E' E - tr(E E') E = 0 by 1e-6 .. 1e-4 (1e-13 .. 1e-16 on every other pair; the GPU's and the oracle's roots
-satisfy it to 1e-16 with or without their Gauss-Newton polish, tools/census_rootcause.py).  Which way that root
+satisfy it to 1e-16 with or without their Gauss-Newton polish, tests/census_rootcause.py).  Which way that root
 errs depends on the null-space basis LAPACK's SVD hands OpenCV, so no independent implementation reproduces it;
 the mask then differs in the borderline points, or another model wins.  A differing pair is therefore accepted
 only if cv2's own E fails the constraint by more than 1e-8, and the rate is bounded.  The census is written to
