@@ -298,6 +298,8 @@ struct EssWork {
     uint32_t* items;         // [cap * 10] real roots of the round, compacted: slot << 4 | root index
     double* item_z;          // [cap * 10] the root itself
     int32_t* nitems;         // [ES_MAX_ROUNDS] roots per round
+    uint32_t* slow;          // [cap] hypotheses of the round whose root iteration was not settled by the fast path
+    int32_t* nslow;          // [ES_MAX_ROUNDS]
     size_t cap;              // n_pairs * ES_RMAX slots
 };
 
@@ -320,7 +322,10 @@ size_t ess_work_carve(EssWork* w, char* base, int n_pairs) {
     uint32_t* items = reinterpret_cast<uint32_t*>(take(cap * 10 * 4));
     double* item_z = reinterpret_cast<double*>(take(cap * 10 * 8));
     int32_t* nitems = reinterpret_cast<int32_t*>(take(ES_MAX_ROUNDS * 4));
+    uint32_t* slow = reinterpret_cast<uint32_t*>(take(cap * 4));
+    int32_t* nslow = reinterpret_cast<int32_t*>(take(ES_MAX_ROUNDS * 4));
     if (w) {
+        w->slow = slow; w->nslow = nslow;
         w->state = st; w->wl[0] = wl0; w->wl[1] = wl1; w->ctl = ctl; w->idx = idx; w->rec = rec;
         w->models = models; w->mflags = mf; w->items = items; w->item_z = item_z; w->nitems = nitems; w->cap = cap;
     }
@@ -354,7 +359,7 @@ __global__ void ess_init_kernel(EssArgs a) {
     if (pair == 0) {
         a.w.ctl[0] = a.n_pairs;
         for (int r = 1; r <= ES_MAX_ROUNDS; ++r) a.w.ctl[r] = 0;
-        for (int r = 0; r < ES_MAX_ROUNDS; ++r) a.w.nitems[r] = 0;
+        for (int r = 0; r < ES_MAX_ROUNDS; ++r) { a.w.nitems[r] = 0; a.w.nslow[r] = 0; }
     }
     if (pair >= a.n_pairs) return;
     const int n = a.n[pair];
@@ -469,6 +474,17 @@ __device__ __forceinline__ void append_roots(int count, const double (&zs)[10], 
     }
 }
 
+// warp-aggregated append of the lanes with `slow` set
+__device__ __forceinline__ void append_slow(bool slow, uint32_t slot, uint32_t* list, int32_t* total) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, slow);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(total, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (slow) list[base + __popc(m & ((1u << lane) - 1))] = slot;
+}
+
 __global__ void __launch_bounds__(SB1_THREADS, EPV_SB1_MINBLOCKS) solve_b1_kernel(EssArgs a, int round, int R) {
     const int count = a.w.ctl[round];
     const int32_t* wl = a.w.wl[round & 1];
@@ -485,10 +501,27 @@ __global__ void __launch_bounds__(SB1_THREADS, EPV_SB1_MINBLOCKS) solve_b1_kerne
         double zs[10];
         int nz = 0;
         if (valid) {
-            nz = fivept::stage_b1(a.w.rec + slot, a.w.cap, zs);
+            nz = fivept::stage_b1<false>(a.w.rec + slot, a.w.cap, zs);
             a.w.mflags[slot] = 0;
         }
-        append_roots(nz, zs, (uint32_t)slot, a.w.items, a.w.item_z, a.w.nitems + round);
+        append_slow(nz < 0, (uint32_t)slot, a.w.slow, a.w.nslow + round);
+        append_roots(max(nz, 0), zs, (uint32_t)slot, a.w.items, a.w.item_z, a.w.nitems + round);
+    }
+}
+
+// the hypotheses stage B1 could not settle, one lane each, with OpenCV's full 300 sweeps
+__global__ void __launch_bounds__(SB1_THREADS) solve_b1_slow_kernel(EssArgs a, int round) {
+    const int total = a.w.nslow[round];
+    for (int base = blockIdx.x * SB1_THREADS; base < total; base += gridDim.x * SB1_THREADS) {
+        const int i = base + threadIdx.x;
+        double zs[10];
+        int nz = 0;
+        uint32_t slot = 0;
+        if (i < total) {
+            slot = a.w.slow[i];
+            nz = fivept::stage_b1<true>(a.w.rec + slot, a.w.cap, zs);
+        }
+        append_roots(nz, zs, slot, a.w.items, a.w.item_z, a.w.nitems + round);
     }
 }
 
@@ -936,7 +969,8 @@ five_point_b1_kernel(const double* __restrict__ rec, int m, uint32_t* __restrict
         double zs[10];
         int nz = 0;
         if (i < m) {
-            nz = fivept::stage_b1(rec + i, (size_t)m, zs);
+            nz = fivept::stage_b1<false>(rec + i, (size_t)m, zs);
+            if (nz < 0) nz = fivept::stage_b1<true>(rec + i, (size_t)m, zs);     // stand-alone solver: slow path in place
             flags[i] = 0;
         }
         append_roots(nz, zs, (uint32_t)i, items, item_z, n_items);
@@ -1202,6 +1236,8 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
         solve_a_kernel<<<g_a, 32, SA_SMEM, ctx->stream>>>(a, r, R[r]);
         EPV_LAUNCHED(ctx);
         solve_b1_kernel<<<g_b1, SB1_THREADS, 0, ctx->stream>>>(a, r, R[r]);
+        EPV_LAUNCHED(ctx);
+        solve_b1_slow_kernel<<<full ? 2 * sms : sms, SB1_THREADS, 0, ctx->stream>>>(a, r);
         EPV_LAUNCHED(ctx);
         solve_b2_kernel<<<g_b2, SB2_THREADS, 0, ctx->stream>>>(a, r);
         EPV_LAUNCHED(ctx);

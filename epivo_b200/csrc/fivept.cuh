@@ -178,15 +178,19 @@ __device__ __forceinline__ void pmul(const double (&a)[NA + 1], const double (&b
 // fully unrolled.  Same start values and Gauss-Seidel sweep order as cv::solvePoly.
 // cv::solvePoly only stops when a sweep's update is exactly zero, which practically never
 // happens: it runs all 300 sweeps while the roots jitter at round-off level.  Stopping once
-// every update is below 1e-13 of the root leaves the roots equal to OpenCV's up to that jitter
-// (the solutions are refined on the constraints afterwards anyway).  Clustered roots never get
-// below their own noise floor (1e-12 .. 1e-9): once the update is small and no longer
-// shrinking by 10x per sweep (the quadratic phase is over), more sweeps only re-draw the
-// noise -- and would stall the whole warp.
+// every update is below 1e-13 of the root leaves the roots equal to OpenCV's up to that jitter.
+// Polynomials that do NOT get there quickly -- close root pairs converge linearly for a long time
+// before the quadratic phase sets in, clustered roots sit on a noise floor of 1e-12 .. 1e-9 -- are
+// not decided here: once the update is small and no longer shrinking by 10x per sweep the function
+// gives up and returns false, and the caller hands the hypothesis to the slow path (dk_sweeps_full:
+// all 300 sweeps, as OpenCV), so that one slow lane does not stall its warp for 300 sweeps and the
+// real / complex classification (|imag| <= 1e-10) is taken where OpenCV takes it.  (Round 1 treated
+// that early stop as final: on low-parallax EuRoC-shaped pairs it lost close pairs of real roots --
+// and with them, now and then, the winning model.)
 // The relative update of a sweep is tracked as a fraction (numerator, denominator) compared by
 // cross-multiplication, so a sweep costs one division per root, not two.
 template <int N>
-__device__ __forceinline__ void dk_sweeps(const double (&c)[11], double (&re)[10], double (&im)[10]) {
+__device__ __forceinline__ bool dk_sweeps(const double (&c)[11], double (&re)[10], double (&im)[10]) {
     {
         double pr = 1.0, pi = 0.0;
 #pragma unroll
@@ -226,23 +230,24 @@ __device__ __forceinline__ void dk_sweeps(const double (&c)[11], double (&re)[10
             if (q2 * mden > mnum * m || !(q2 == q2)) { mnum = q2; mden = m; }
         }
         const double maxrel2 = mnum / mden;
-        if (!(maxrel2 > 1e-26)) break;
-        if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) break;
+        if (!(maxrel2 > 1e-26)) return maxrel2 == maxrel2;   // converged (NaN: nothing more to do here either way)
+        if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) return false;   // slow: the full 300 sweeps decide
         prev2 = maxrel2;
     }
+    return true;                                             // 300 sweeps done: this is OpenCV's state
 }
 
-// Generic degree (the leading coefficients vanished): rare, kept out of line.
-__device__ __noinline__ void dk_sweeps_generic(const double (&c)[11], int n, double (&re)[10], double (&im)[10]) {
+// Generic degree, all sweeps: cv::solvePoly as written (stops only when a sweep changes nothing).  Used for the rare
+// polynomials whose leading coefficients vanished and for the slow path of dk_sweeps<N>; kept out of line.
+__device__ __noinline__ void dk_sweeps_full(const double (&c)[11], int n, double (&re)[10], double (&im)[10]) {
     double pr = 1.0, pi = 0.0;
     for (int i = 0; i < n; ++i) {
         re[i] = pr; im[i] = pi;
         const double t = pr - pi;
         pi = pr + pi; pr = t;
     }
-    double prev2 = 1e300;
     for (int iter = 0; iter < 300; ++iter) {
-        double maxrel2 = 0.0;
+        double maxdiff2 = 0.0;
         for (int i = 0; i < n; ++i) {
             const double xr = re[i], xi = im[i];
             double nr = c[n], ni = 0.0, dr = c[n], di = 0.0;
@@ -263,11 +268,9 @@ __device__ __noinline__ void dk_sweeps_generic(const double (&c)[11], int n, dou
             const double qr = (nr * dr + ni * di) * s;
             const double qi = (ni * dr - nr * di) * s;
             re[i] = xr - qr; im[i] = xi - qi;
-            maxrel2 = fmax(maxrel2, (qr * qr + qi * qi) / fmax(1.0, xr * xr + xi * xi));
+            maxdiff2 = fmax(maxdiff2, qr * qr + qi * qi);
         }
-        if (!(maxrel2 > 1e-26)) break;
-        if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) break;
-        prev2 = maxrel2;
+        if (!(maxdiff2 > 0.0)) break;                        // `if (maxDiff <= 0) break;`
     }
 }
 
@@ -465,7 +468,7 @@ __device__ __noinline__ void refine_essential(const double* e, int es, double (&
 
 // ---- stage B1: reduced rows -> degree-10 polynomial -> roots -----------------------------------
 // rec[k * rs]: the stage-A record.  zs[0..count): the real roots (|imag| <= 1e-10) in cv::solvePoly's
-// root order.  Returns their number (0 if stage A flagged a singular system).
+// root order.  Returns their number (0 if stage A flagged a singular system; -1: see the template parameter).
 // Row j of B(z) comes from reduced rows 4+2j ("e - z f"): the coefficient layout of the right block per
 // row is [xz^2 xz x | yz^2 yz y | z^3 z^2 z 1] (descending in z inside each group); entries (j,0),(j,1)
 // are cubic, (j,2) quartic, ascending powers.
@@ -492,6 +495,9 @@ __device__ __forceinline__ void build_B_row(const double* rec, size_t rs, int j,
     B[2][4] = -r2[6];
 }
 
+// SLOW = false: the fast path; returns -1 when the roots are not settled (the caller queues the hypothesis for a
+// SLOW = true pass, which runs OpenCV's full 300 sweeps).
+template <bool SLOW>
 __device__ __forceinline__ int stage_b1(const double* rec, size_t rs, double (&zs)[10]) {
     if (!(rec[36 * rs] == rec[36 * rs])) return 0;            // stage A flagged a singular system
     double B[3][3][5];
@@ -553,8 +559,8 @@ __device__ __forceinline__ int stage_b1(const double* rec, size_t rs, double (&z
     int n = 10;
     for (; n > 1; --n)
         if (fabs(c[n]) > 2.220446049250313e-16) break;      // DBL_EPSILON, as cv::solvePoly
-    if (n == 10) dk_sweeps<10>(c, re, im);
-    else dk_sweeps_generic(c, n, re, im);
+    if (SLOW || n != 10) dk_sweeps_full(c, n, re, im);
+    else if (!dk_sweeps<10>(c, re, im)) return -1;
     int count = 0;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {                           // unrolled: re/im stay in registers

@@ -16,8 +16,8 @@ class _LmRes(C.Structure):
 
 
 def build() -> str:
-    src = os.path.join(HERE, "lm_c.c")
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("lm_c.c", "poly_c.c")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", HERE, "-s"], check=True)
     return LIB
 
@@ -33,7 +33,18 @@ def lib():
         _lib.oracle_lm_trace.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
                                          C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_LmRes),
                                          C.c_void_p]
+        _lib.oracle_solve_poly.restype = C.c_int
+        _lib.oracle_solve_poly.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return _lib
+
+
+def solve_poly(coeffs_ascending, max_iters: int = 300) -> np.ndarray:
+    """cv::solvePoly(coeffs, roots, maxIters) restated (oracle/poly_c.c): complex roots in OpenCV's order."""
+    c = np.ascontiguousarray(coeffs_ascending, dtype=np.float64)
+    n0 = c.shape[0] - 1
+    out = np.zeros((n0, 2))
+    lib().oracle_solve_poly(c.ctypes.data, n0, int(max_iters), out.ctypes.data)
+    return out[:, 0] + 1j * out[:, 1]
 
 
 def levenberg_marquardt(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_r, huber_delta=1e-5, max_iters=30):

@@ -335,9 +335,8 @@ def five_point(x1: np.ndarray, x2: np.ndarray, refine: bool = True) -> np.ndarra
     real roots (|imag| <= 1e-10), (x, y) from the null vector of B(z), skip if its last
     entry is < 1e-10 in magnitude, E normalised to unit Frobenius norm; then, beyond OpenCV,
     each solution is refined on the constraints (refine_essential) unless refine=False.  The null-space
-    basis, and therefore the order of the solutions, depends on the SVD implementation;
-    OpenCV's comes from LAPACK and is not reproducible bit-for-bit, so solutions are compared
-    as a set.
+    basis depends on the SVD implementation (OpenCV's comes from LAPACK and is not reproducible
+    bit-for-bit); the solutions themselves do not, and they come out in cv::solvePoly's root order.
     """
     x1 = np.asarray(x1, dtype=np.float64)
     x2 = np.asarray(x2, dtype=np.float64)
@@ -366,10 +365,13 @@ def five_point(x1: np.ndarray, x2: np.ndarray, refine: bool = True) -> np.ndarra
     coeffs = np.zeros(11)
     c = det.coeffs
     coeffs[11 - len(c):] = c
-    nz = np.nonzero(np.abs(coeffs) > np.finfo(float).eps)[0]
-    if nz.size == 0:
+    if not (np.abs(coeffs) > np.finfo(float).eps).any():
         return np.zeros((0, 3, 3))
-    roots = np.roots(coeffs[nz[0]:])
+    # cv::solvePoly(coeffs, roots) with its default 300 Durand-Kerner sweeps, restated in C (oracle/poly_c.c):
+    # OpenCV's root ORDER fixes the order of a sample's models, and whether a close pair of real roots has
+    # settled below |imag| <= 1e-10 after exactly those sweeps fixes which models exist at all
+    from . import clib
+    roots = clib.solve_poly(coeffs[::-1], 300)
     sols = []
     for r in roots:
         if abs(r.imag) > 1e-10:
