@@ -179,16 +179,19 @@ __device__ __forceinline__ void pmul(const double (&a)[NA + 1], const double (&b
 // cv::solvePoly only stops when a sweep's update is exactly zero, which practically never
 // happens: it runs all 300 sweeps while the roots jitter at round-off level.  Stopping once
 // every update is below 1e-13 of the root leaves the roots equal to OpenCV's up to that jitter.
-// Polynomials that do NOT get there quickly -- close root pairs converge linearly for a long time
-// before the quadratic phase sets in, clustered roots sit on a noise floor of 1e-12 .. 1e-9 -- are
-// not decided here: once the update is small and no longer shrinking by 10x per sweep the function
-// gives up and returns false, and the caller hands the hypothesis to the slow path (dk_sweeps_full:
-// all 300 sweeps, as OpenCV), so that one slow lane does not stall its warp for 300 sweeps and the
-// real / complex classification (|imag| <= 1e-10) is taken where OpenCV takes it.  (Round 1 treated
-// that early stop as final: on low-parallax EuRoC-shaped pairs it lost close pairs of real roots --
-// and with them, now and then, the winning model.)
+// Some polynomials never get there: clustered roots sit on a noise floor of 1e-12 .. 1e-9, where the update
+// stops shrinking and merely fluctuates -- more sweeps only re-draw the noise, so the iteration ends there
+// (small update, not smaller than the sweep before).  Close pairs of real roots, on the other hand, converge
+// LINEARLY for dozens of sweeps before the quadratic phase sets in, their update shrinking a little every
+// sweep; these must be followed to the end, because whether the pair comes out real (|imag| <= 1e-10) decides
+// which models the sample contributes.  (Round 1 stopped as soon as the update shrank by less than 10x per
+// sweep: on low-parallax EuRoC-shaped pairs that lost close pairs of real roots and, now and then, the winning
+// model.)  A lane that is still shrinking after DK_FAST_SWEEPS sweeps returns false and the caller queues the
+// hypothesis for the slow pass (dk_sweeps_full: OpenCV's 300 sweeps), so that it does not stall its warp.
 // The relative update of a sweep is tracked as a fraction (numerator, denominator) compared by
 // cross-multiplication, so a sweep costs one division per root, not two.
+constexpr int DK_FAST_SWEEPS = 64;     // sweeps the one-lane-per-hypothesis fast path spends before handing over
+
 template <int N>
 __device__ __forceinline__ bool dk_sweeps(const double (&c)[11], double (&re)[10], double (&im)[10]) {
     {
@@ -230,11 +233,14 @@ __device__ __forceinline__ bool dk_sweeps(const double (&c)[11], double (&re)[10
             if (q2 * mden > mnum * m || !(q2 == q2)) { mnum = q2; mden = m; }
         }
         const double maxrel2 = mnum / mden;
-        if (!(maxrel2 > 1e-26)) return maxrel2 == maxrel2;   // converged (NaN: nothing more to do here either way)
-        if (maxrel2 < 1e-12 && maxrel2 > 1e-2 * prev2) return false;   // slow: the full 300 sweeps decide
+        if (!(maxrel2 > 1e-26)) return true;                 // converged (or NaN: nothing more to do either way)
+        // On the noise floor the update stops shrinking and fluctuates; while a close pair is still converging
+        // linearly it keeps shrinking, sweep after sweep.  So: small AND not smaller than last sweep's = floor.
+        if (maxrel2 < 1e-12 && !(maxrel2 < prev2)) return true;
         prev2 = maxrel2;
+        if (iter >= DK_FAST_SWEEPS) return false;            // still shrinking slowly: do not stall the warp
     }
-    return true;                                             // 300 sweeps done: this is OpenCV's state
+    return true;
 }
 
 // Generic degree, all sweeps: cv::solvePoly as written (stops only when a sweep changes nothing).  Used for the rare
@@ -317,6 +323,12 @@ __device__ __forceinline__ void mat3_mul_tn(const double* A, const double* B, do
         for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
 }
 
+constexpr int REFINE_ITERS = 10;
+// A refined model must satisfy the ten constraints to this (max-abs, unit Frobenius norm).  On a near-degenerate sample
+// the Gauss-Newton iteration can stall far from any solution (residual 1e-5 .. 1e-3): what it holds then is not an
+// essential matrix, and it is dropped -- OpenCV would carry its own, equally meaningless, un-refined root instead.
+constexpr double REFINE_ACCEPT = 1e-9;
+
 __device__ __forceinline__ double constraints10(const double* E, double* F) {
     double G[9], T[9];
     mat3_mul_nt(E, E, G);                      // E E'
@@ -331,7 +343,7 @@ __device__ __forceinline__ double constraints10(const double* E, double* F) {
 
 // e: the null-space basis, element i of basis matrix k at e[(k * 9 + i) * es] (es = element stride,
 // so the basis can stay in a thread-strided shared-memory block)
-__device__ __noinline__ void refine_essential(const double* e, int es, double (&E)[9]) {
+__device__ __noinline__ double refine_essential(const double* e, int es, double (&E)[9]) {
     double c[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -342,7 +354,7 @@ __device__ __noinline__ void refine_essential(const double* e, int es, double (&
     }
     {
         const double n2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3];
-        if (!(n2 > 0)) return;
+        if (!(n2 > 0)) return 1e300;
         const double in = rsqrt(n2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) c[k] *= in;
@@ -352,7 +364,7 @@ __device__ __noinline__ void refine_essential(const double* e, int es, double (&
     for (int i = 0; i < 9; ++i)
         Ec[i] = c[0] * e[i * es] + c[1] * e[(9 + i) * es] + c[2] * e[(18 + i) * es] + c[3] * e[(27 + i) * es];
     double fmaxv = constraints10(Ec, F);
-    for (int it = 0; it < 6; ++it) {
+    for (int it = 0; it < REFINE_ITERS; ++it) {
         // J column k = dF along basis matrix k
         double J[10][4];
         double G[9], EtE[9], cof[9];
@@ -464,6 +476,7 @@ __device__ __noinline__ void refine_essential(const double* e, int es, double (&
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) E[i] = Ec[i];
+    return fmaxv;
 }
 
 // ---- stage B1: reduced rows -> degree-10 polynomial -> roots -----------------------------------
@@ -576,7 +589,7 @@ __device__ __forceinline__ int stage_b1(const double* rec, size_t rs, double (&z
 // ---- stage B2: one real root -> one essential matrix ------------------------------------------
 // sh: this thread's scratch in shared memory for the null-space basis (36 doubles, element i at sh[i * ss]).
 // E: row-major, unit Frobenius norm, refined.  Returns false if OpenCV would skip this root (the null
-// vector of B(z) has a third component below 1e-10).
+// vector of B(z) has a third component below 1e-10) or the refinement did not reach a solution (REFINE_ACCEPT).
 __device__ __forceinline__ bool stage_b2(const double* rec, size_t rs, double z, double* sh, int ss, double (&E)[9]) {
     double Bz[3][3];
 #pragma unroll
@@ -603,8 +616,7 @@ __device__ __forceinline__ bool stage_b2(const double* rec, size_t rs, double z,
     const double inv = rsqrt(s);
 #pragma unroll
     for (int k = 0; k < 9; ++k) E[k] *= inv;
-    refine_essential(sh, ss, E);
-    return true;
+    return refine_essential(sh, ss, E) <= REFINE_ACCEPT;
 }
 
 }  // namespace fivept

@@ -290,7 +290,10 @@ def _essential_constraints_dir(E, D):
     return np.append(d.ravel(), float((cof * D).sum()))
 
 
-def refine_essential(E, EE, iters=6):
+REFINE_ACCEPT = 1e-9      # max-abs constraint residual a refined model must reach (unit Frobenius norm)
+
+
+def refine_essential(E, EE, iters=10):
     """Gauss-Newton refinement of one 5-point solution inside the 4-D null space.
 
     NOT part of OpenCV's runKernel.  Nister's elimination works in the chart "coefficient of
@@ -300,7 +303,9 @@ def refine_essential(E, EE, iters=6):
     degree-10 polynomial loses many digits, by an amount that differs from basis to basis.
     A few Newton steps on the constraints themselves, on the unit sphere of coefficients,
     make every implementation converge to the same exact solutions (quadratically: 2-5 steps).
-    A step is kept only if it lowers the constraint residual."""
+    A step is kept only if it lowers the constraint residual.  Returns (E, final max-abs residual): on a
+    near-degenerate sample the iteration can stall far from any solution (1e-5 .. 1e-3); the caller drops
+    such a "model" -- it is not an essential matrix."""
     B = EE.reshape(4, 3, 3)
     c = np.array([float((E * B[k]).sum()) for k in range(4)])
     c /= np.linalg.norm(c)
@@ -323,7 +328,7 @@ def refine_essential(E, EE, iters=6):
         c, Ecur, f = c2, E2, f2
         if np.linalg.norm(d) < 1e-14:
             break
-    return Ecur
+    return Ecur, float(np.abs(f).max())
 
 
 def five_point(x1: np.ndarray, x2: np.ndarray, refine: bool = True) -> np.ndarray:
@@ -384,7 +389,11 @@ def five_point(x1: np.ndarray, x2: np.ndarray, refine: bool = True) -> np.ndarra
         x, y = xy1[0] / xy1[2], xy1[1] / xy1[2]
         Ev = EE[0] * x + EE[1] * y + EE[2] * z + EE[3]
         Ev = (Ev / np.linalg.norm(Ev)).reshape(3, 3)
-        sols.append(refine_essential(Ev, EE) if refine else Ev)
+        if refine:
+            Ev, resid = refine_essential(Ev, EE)
+            if not resid <= REFINE_ACCEPT:
+                continue
+        sols.append(Ev)
     return np.array(sols).reshape(-1, 3, 3)
 
 
