@@ -12,6 +12,7 @@
 // sequential loop returns.
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -24,7 +25,7 @@ namespace {
 
 constexpr int ES_THREADS = 256;
 constexpr int ES_WARPS = ES_THREADS / 32;
-constexpr int ES_SUB = 16;           // samples per scoring sub-chunk, at most (<= 16: s_item packs sample << 4 | model)
+constexpr int ES_SUB = 32;           // samples per scoring sub-chunk, at most (one lane of warp 0 per sample in the replay)
 
 struct CvRng {   // cv::RNG: multiply-with-carry
     unsigned long long state;
@@ -279,6 +280,7 @@ __device__ float warp_select(const float* buf, int n, int k, int lane) {
 // =====================================================================================
 constexpr int ES_RMAX = 128;         // samples per pair per round, at most
 constexpr int ES_MAX_ROUNDS = 40;
+constexpr size_t ES_SLOW_CAP = 1 << 18;   // slow-pass slots per round (a few per cent of a round's hypotheses at most)
 
 struct RansacState {
     double best_score;
@@ -299,6 +301,7 @@ struct EssWork {
     double* item_z;          // [cap * 10] the root itself
     int32_t* nitems;         // [ES_MAX_ROUNDS] roots per round
     uint32_t* slow;          // [cap] hypotheses of the round whose root iteration was not settled by the fast path
+    double* slow_state;      // [DK_STATE][cap] their iterates (indexed by position in `slow`), SoA
     int32_t* nslow;          // [ES_MAX_ROUNDS]
     size_t cap;              // n_pairs * ES_RMAX slots
 };
@@ -323,9 +326,10 @@ size_t ess_work_carve(EssWork* w, char* base, int n_pairs) {
     double* item_z = reinterpret_cast<double*>(take(cap * 10 * 8));
     int32_t* nitems = reinterpret_cast<int32_t*>(take(ES_MAX_ROUNDS * 4));
     uint32_t* slow = reinterpret_cast<uint32_t*>(take(cap * 4));
+    double* slow_state = reinterpret_cast<double*>(take(ES_SLOW_CAP * fivept::DK_STATE * 8));
     int32_t* nslow = reinterpret_cast<int32_t*>(take(ES_MAX_ROUNDS * 4));
     if (w) {
-        w->slow = slow; w->nslow = nslow;
+        w->slow = slow; w->slow_state = slow_state; w->nslow = nslow;
         w->state = st; w->wl[0] = wl0; w->wl[1] = wl1; w->ctl = ctl; w->idx = idx; w->rec = rec;
         w->models = models; w->mflags = mf; w->items = items; w->item_z = item_z; w->nitems = nitems; w->cap = cap;
     }
@@ -474,15 +478,16 @@ __device__ __forceinline__ void append_roots(int count, const double (&zs)[10], 
     }
 }
 
-// warp-aggregated append of the lanes with `slow` set
-__device__ __forceinline__ void append_slow(bool slow, uint32_t slot, uint32_t* list, int32_t* total) {
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, slow);
-    if (!m) return;
+// warp-aggregated reservation of one slow-pass slot per lane that asks for one; -1 when the list is full
+__device__ __forceinline__ int reserve_slow(bool want, int32_t* total, int cap) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+    if (!m) return -1;
     const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
     int base = 0;
     if (lane == leader) base = atomicAdd(total, __popc(m));
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (slow) list[base + __popc(m & ((1u << lane) - 1))] = slot;
+    const int pos = base + __popc(m & ((1u << lane) - 1));
+    return (want && pos < cap) ? pos : -1;
 }
 
 __global__ void __launch_bounds__(SB1_THREADS, EPV_SB1_MINBLOCKS) solve_b1_kernel(EssArgs a, int round, int R) {
@@ -500,18 +505,29 @@ __global__ void __launch_bounds__(SB1_THREADS, EPV_SB1_MINBLOCKS) solve_b1_kerne
         }
         double zs[10];
         int nz = 0;
+        __shared__ double s_state[fivept::DK_STATE * SB1_THREADS];       // iterates of a lane that gives up
         if (valid) {
-            nz = fivept::stage_b1<false>(a.w.rec + slot, a.w.cap, zs);
+            nz = fivept::stage_b1<false>(a.w.rec + slot, a.w.cap, zs, s_state + threadIdx.x, SB1_THREADS);
             a.w.mflags[slot] = 0;
         }
-        append_slow(nz < 0, (uint32_t)slot, a.w.slow, a.w.nslow + round);
+        const int pos = reserve_slow(nz < 0, a.w.nslow + round, (int)ES_SLOW_CAP);
+        if (nz < 0) {
+            if (pos >= 0) {
+                a.w.slow[pos] = (uint32_t)slot;
+                for (int k = 0; k < fivept::DK_STATE; ++k) a.w.slow_state[(size_t)k * ES_SLOW_CAP + pos] = s_state[k * SB1_THREADS + threadIdx.x];
+            } else {
+                // list full (never seen: it holds 2^18 per round): finish in place, stalling only this warp
+                nz = fivept::stage_b1<true>(a.w.rec + slot, a.w.cap, zs, s_state + threadIdx.x, SB1_THREADS);
+            }
+        }
         append_roots(max(nz, 0), zs, (uint32_t)slot, a.w.items, a.w.item_z, a.w.nitems + round);
     }
 }
 
-// the hypotheses stage B1 could not settle, one lane each, with OpenCV's full 300 sweeps
+// the hypotheses stage B1 could not settle within DK_FAST_SWEEPS sweeps, one lane each, continued from the saved
+// iterates up to OpenCV's 300 sweeps (compacted: a warp here holds 32 slow hypotheses, not one among 31 finished)
 __global__ void __launch_bounds__(SB1_THREADS) solve_b1_slow_kernel(EssArgs a, int round) {
-    const int total = a.w.nslow[round];
+    const int total = min(a.w.nslow[round], (int)ES_SLOW_CAP);
     for (int base = blockIdx.x * SB1_THREADS; base < total; base += gridDim.x * SB1_THREADS) {
         const int i = base + threadIdx.x;
         double zs[10];
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(SB1_THREADS) solve_b1_slow_kernel(EssArgs a, i
         uint32_t slot = 0;
         if (i < total) {
             slot = a.w.slow[i];
-            nz = fivept::stage_b1<true>(a.w.rec + slot, a.w.cap, zs);
+            nz = fivept::stage_b1<true>(a.w.rec + slot, a.w.cap, zs, a.w.slow_state + i, ES_SLOW_CAP);
         }
         append_roots(nz, zs, slot, a.w.items, a.w.item_z, a.w.nitems + round);
     }
@@ -617,8 +633,9 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
     extern __shared__ __align__(16) double s_pts[];
     __shared__ double s_models[ES_SUB][10][9];    // models of the sub-chunk being scored
     __shared__ unsigned s_flags[ES_SUB];           // valid-model bit masks of the sub-chunk's samples
-    __shared__ unsigned char s_item[ES_SUB * 10];     // flattened (sample << 4 | model) list of the sub-chunk
+    __shared__ unsigned short s_item[ES_SUB * 10];    // flattened (sample << 4 | model) list of the sub-chunk
     __shared__ int s_nitems;
+    __shared__ int s_next;                         // next unclaimed pair of items (dynamic distribution over the warps)
     __shared__ float s_score[ES_SUB][10];         // LMedS: medians
     __shared__ int s_cnt[ES_SUB][10];             // RANSAC: inlier counts
     __shared__ double s_bestE[9];
@@ -670,13 +687,16 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
 
         // Sub-chunks: score, then replay.  RANSAC usually shrinks niters after the first few samples, so the
         // first two sub-chunks of a pair are 8 samples (samples at or beyond the current niters are never
-        // scored); after that 16 at a time, which balances the models better over the 8 warps.
+        // scored), the next 16; a pair that is still running after 32 samples is in for a long run and takes 32
+        // at a time (~140 models per barrier: the replay by warp 0 and the wait at the barrier are amortised).
         for (int sbase = 0, sub = 0; sbase < ch; sbase += sub) {
-            sub = (iter0 + sbase < 2 * ES_WARPS) ? ES_WARPS : ES_SUB;
+            const int done = iter0 + sbase;
+            sub = done < 2 * ES_WARPS ? ES_WARPS : (done < ES_SUB ? 2 * ES_WARPS : ES_SUB);
             const int r = min(sub, min(ch, s_niters - iter0) - sbase);          // samples scored now (>= 1)
             // stage the models of these samples and flatten them into a work list
             for (int i = tid; i < r * 90; i += ES_THREADS) (&s_models[0][0][0])[i] = gmodels[(size_t)sbase * 90 + i];
-            if (tid < ES_SUB * 10) (&s_cnt[0][0])[tid] = 0;
+            for (int i = tid; i < ES_SUB * 10; i += ES_THREADS) (&s_cnt[0][0])[i] = 0;
+            if (tid == ES_THREADS - 1) s_next = 0;
             if (warp == 0) {
                 const unsigned fl = lane < r ? gfl[sbase + lane] : 0u;
                 const int c = __popc(fl);
@@ -690,7 +710,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     s_flags[lane] = fl;
                     int pos = incl - c;
                     for (int j = 0; j < 10; ++j)
-                        if (fl >> j & 1u) s_item[pos++] = (unsigned char)(lane << 4 | j);
+                        if (fl >> j & 1u) s_item[pos++] = (unsigned short)(lane << 4 | j);
                 }
                 if (lane == ES_SUB - 1) s_nitems = incl;
             }
@@ -699,12 +719,17 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
             if (n != 5 && M > 0) {
                 if (!lmeds) {
                     if (M >= ES_WARPS) {
-                        // warp w scores items w, w + 8, ... two at a time: both models live in registers
-                        // and every correspondence (shared memory) is tested against both
-                        for (int j0 = warp; j0 < M; j0 += 2 * ES_WARPS) {
+                        // the warps claim items two at a time from a shared counter (models differ in nothing, but
+                        // a static split leaves the barrier waiting for the warp with the odd item): both models
+                        // live in registers and every correspondence (shared memory) is tested against both
+                        for (;;) {
+                            int j0 = 0;
+                            if (lane == 0) j0 = 2 * atomicAdd(&s_next, 1);
+                            j0 = __shfl_sync(0xFFFFFFFFu, j0, 0);
+                            if (j0 >= M) break;
                             const int code0 = s_item[j0];
-                            const bool two = j0 + ES_WARPS < M;
-                            const int code1 = two ? s_item[j0 + ES_WARPS] : code0;
+                            const bool two = j0 + 1 < M;
+                            const int code1 = two ? s_item[j0 + 1] : code0;
                             const double* M0 = s_models[code0 >> 4][code0 & 15];
                             const double* M1 = s_models[code1 >> 4][code1 & 15];
                             int c0 = 0, c1 = 0;
@@ -747,10 +772,14 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     const bool can_filter = have_best && bestf > 0.0f;
                     const SampThr thrL = make_samp_thr(can_filter ? __uint_as_float(__float_as_uint(bestf) - 1u) : 0.0f);
                     const int need = n / 2 + 1;                              // errors that must lie below the best
-                    for (int j0 = warp; j0 < M; j0 += 2 * ES_WARPS) {
+                    for (;;) {
+                        int j0 = 0;
+                        if (lane == 0) j0 = 2 * atomicAdd(&s_next, 1);
+                        j0 = __shfl_sync(0xFFFFFFFFu, j0, 0);
+                        if (j0 >= M) break;
                         const int code0 = s_item[j0];
-                        const bool two = j0 + ES_WARPS < M;
-                        const int code1 = two ? s_item[j0 + ES_WARPS] : code0;
+                        const bool two = j0 + 1 < M;
+                        const int code1 = two ? s_item[j0 + 1] : code0;
                         const double* M0 = s_models[code0 >> 4][code0 & 15];
                         const double* M1 = s_models[code1 >> 4][code1 & 15];
                         int c0 = need, c1 = need;                            // no best yet: every model needs its median
@@ -816,7 +845,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     int ni_before = __shfl_up_sync(0xFFFFFFFFu, ni_after, 1, ES_SUB);
                     if (q == 0) ni_before = ni_in;
                     const bool stop_here = live && !(iter0 + sbase + q < ni_before);
-                    const unsigned stops = __ballot_sync(0xFFFFFFFFu, stop_here) & ((1u << ES_SUB) - 1);
+                    const unsigned stops = __ballot_sync(0xFFFFFFFFu, stop_here);
                     const int qstop = stops ? __ffs(stops) - 1 : r;          // samples [0, qstop) are counted
                     const int B = __shfl_sync(0xFFFFFFFFu, pa, max(qstop - 1, 0));
                     const int ni_out = __shfl_sync(0xFFFFFFFFu, ni_after, max(qstop - 1, 0));
@@ -969,8 +998,19 @@ five_point_b1_kernel(const double* __restrict__ rec, int m, uint32_t* __restrict
         double zs[10];
         int nz = 0;
         if (i < m) {
-            nz = fivept::stage_b1<false>(rec + i, (size_t)m, zs);
-            if (nz < 0) nz = fivept::stage_b1<true>(rec + i, (size_t)m, zs);     // stand-alone solver: slow path in place
+#ifdef EPV_ESS_DEBUG
+            double dbg[31];
+            nz = fivept::stage_b1<false>(rec + i, (size_t)m, zs, nullptr, 1, dbg);
+            if (m == 1) {
+                printf("poly asc:");
+                for (int k = 0; k < 11; ++k) printf(" %.17g", dbg[k]);
+                printf("\nroots:");
+                for (int k = 0; k < 10; ++k) printf(" (%.12g, %.3e)", dbg[11 + k], dbg[21 + k]);
+                printf("\nreal roots kept: %d\n", nz);
+            }
+#else
+            nz = fivept::stage_b1<false>(rec + i, (size_t)m, zs);                // no state buffer: all sweeps in place
+#endif
             flags[i] = 0;
         }
         append_roots(nz, zs, (uint32_t)i, items, item_z, n_items);
@@ -1245,6 +1285,17 @@ int epv_essential_launch(epivo_ctx* ctx, const EssentialPlan& p) {
         ess_round_kernel<<<g_pairs, ES_THREADS, pts_smem, ctx->stream>>>(a, r, R[r], r == nr - 1 ? 1 : 0, pts_smem > 0);
         EPV_LAUNCHED(ctx);
     }
+#ifdef EPV_ESS_DEBUG
+    {   // debug build only: running pairs, real roots and slow-path hypotheses per round
+        int32_t ctl[ES_MAX_ROUNDS + 1], ni[ES_MAX_ROUNDS], ns[ES_MAX_ROUNDS];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(ctl, a.w.ctl, sizeof(ctl), cudaMemcpyDeviceToHost);
+        cudaMemcpy(ni, a.w.nitems, sizeof(ni), cudaMemcpyDeviceToHost);
+        cudaMemcpy(ns, a.w.nslow, sizeof(ns), cudaMemcpyDeviceToHost);
+        for (int r = 0; r < nr; ++r)
+            fprintf(stderr, "ess round %d: R %d pairs %d roots %d slow %d\n", r, R[r], ctl[r], ni[r], ns[r]);
+    }
+#endif
     return EPIVO_OK;
 }
 

@@ -187,14 +187,22 @@ __device__ __forceinline__ void pmul(const double (&a)[NA + 1], const double (&b
 // which models the sample contributes.  (Round 1 stopped as soon as the update shrank by less than 10x per
 // sweep: on low-parallax EuRoC-shaped pairs that lost close pairs of real roots and, now and then, the winning
 // model.)  A lane that is still shrinking after DK_FAST_SWEEPS sweeps returns false and the caller queues the
-// hypothesis for the slow pass (dk_sweeps_full: OpenCV's 300 sweeps), so that it does not stall its warp.
+// hypothesis for the slow pass (the same iteration, continued up to OpenCV's 300 sweeps), so that it does not
+// stall its warp.
 // The relative update of a sweep is tracked as a fraction (numerator, denominator) compared by
 // cross-multiplication, so a sweep costs one division per root, not two.
-constexpr int DK_FAST_SWEEPS = 64;     // sweeps the one-lane-per-hypothesis fast path spends before handing over
+#ifndef EPV_DK_FAST_SWEEPS
+#define EPV_DK_FAST_SWEEPS 32
+#endif
+constexpr int DK_FAST_SWEEPS = EPV_DK_FAST_SWEEPS;   // sweeps the fast path spends before handing a hypothesis over
+constexpr int DK_STATE = 21;                          // doubles saved for the slow pass: re[10], im[10], prev2
 
+// Sweeps [first, last) of the iteration; first == 0 sets the start values, otherwise re / im / prev2 continue a
+// previous call.  Returns true when the iteration is settled (converged, on the noise floor, or 300 sweeps done).
 template <int N>
-__device__ __forceinline__ bool dk_sweeps(const double (&c)[11], double (&re)[10], double (&im)[10]) {
-    {
+__device__ __forceinline__ bool dk_sweeps(const double (&c)[11], double (&re)[10], double (&im)[10], double& prev2,
+                                          int first, int last) {
+    if (first == 0) {
         double pr = 1.0, pi = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {                        // roots[i] = (1 + 1i)^i
@@ -202,10 +210,10 @@ __device__ __forceinline__ bool dk_sweeps(const double (&c)[11], double (&re)[10
             const double t = pr - pi;
             pi = pr + pi; pr = t;
         }
+        prev2 = 1e300;
     }
-    double prev2 = 1e300;
 #pragma unroll 1
-    for (int iter = 0; iter < 300; ++iter) {
+    for (int iter = first; iter < last; ++iter) {
         double mnum = 0.0, mden = 1.0;                       // max over roots of |update|^2 / max(1, |root|^2)
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -238,13 +246,12 @@ __device__ __forceinline__ bool dk_sweeps(const double (&c)[11], double (&re)[10
         // linearly it keeps shrinking, sweep after sweep.  So: small AND not smaller than last sweep's = floor.
         if (maxrel2 < 1e-12 && !(maxrel2 < prev2)) return true;
         prev2 = maxrel2;
-        if (iter >= DK_FAST_SWEEPS) return false;            // still shrinking slowly: do not stall the warp
     }
-    return true;
+    return last >= 300;                                      // false: still shrinking slowly -> the slow pass continues
 }
 
 // Generic degree, all sweeps: cv::solvePoly as written (stops only when a sweep changes nothing).  Used for the rare
-// polynomials whose leading coefficients vanished and for the slow path of dk_sweeps<N>; kept out of line.
+// polynomials whose leading coefficients vanished; kept out of line.
 __device__ __noinline__ void dk_sweeps_full(const double (&c)[11], int n, double (&re)[10], double (&im)[10]) {
     double pr = 1.0, pi = 0.0;
     for (int i = 0; i < n; ++i) {
@@ -509,9 +516,11 @@ __device__ __forceinline__ void build_B_row(const double* rec, size_t rs, int j,
 }
 
 // SLOW = false: the fast path; returns -1 when the roots are not settled (the caller queues the hypothesis for a
-// SLOW = true pass, which runs OpenCV's full 300 sweeps).
+// SLOW = true pass, which continues the iteration up to the 300 sweeps OpenCV runs).
+// state (DK_STATE doubles, stride ss): written by the fast path when it returns -1, read by the slow pass.
 template <bool SLOW>
-__device__ __forceinline__ int stage_b1(const double* rec, size_t rs, double (&zs)[10]) {
+__device__ __forceinline__ int stage_b1(const double* rec, size_t rs, double (&zs)[10], double* state = nullptr,
+                                        size_t ss = 1, double* dbg = nullptr) {
     if (!(rec[36 * rs] == rec[36 * rs])) return 0;            // stage A flagged a singular system
     double B[3][3][5];
 #pragma unroll
@@ -572,8 +581,28 @@ __device__ __forceinline__ int stage_b1(const double* rec, size_t rs, double (&z
     int n = 10;
     for (; n > 1; --n)
         if (fabs(c[n]) > 2.220446049250313e-16) break;      // DBL_EPSILON, as cv::solvePoly
-    if (SLOW || n != 10) dk_sweeps_full(c, n, re, im);
-    else if (!dk_sweeps<10>(c, re, im)) return -1;
+    if (n != 10) {
+        dk_sweeps_full(c, n, re, im);
+    } else if (!SLOW) {
+        double prev2;
+        if (!dk_sweeps<10>(c, re, im, prev2, 0, state ? DK_FAST_SWEEPS : 300)) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { state[i * ss] = re[i]; state[(10 + i) * ss] = im[i]; }
+            state[20 * ss] = prev2;
+            return -1;
+        }
+    } else {
+        double prev2 = state[20 * ss];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { re[i] = state[i * ss]; im[i] = state[(10 + i) * ss]; }
+        dk_sweeps<10>(c, re, im, prev2, DK_FAST_SWEEPS, 300);
+    }
+#ifdef EPV_ESS_DEBUG
+    if (dbg) {
+        for (int i = 0; i < 11; ++i) dbg[i] = c[i];
+        for (int i = 0; i < 10; ++i) { dbg[11 + i] = re[i]; dbg[21 + i] = im[i]; }
+    }
+#endif
     int count = 0;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {                           // unrolled: re/im stay in registers
