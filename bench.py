@@ -412,7 +412,7 @@ def strong_scaling_leg(a, ctx, local, world, rank, dist, prm, runner0):
         if nb > 0:
             pipe.process(prm, h_kps.numpy(), h_desc.numpy(), res)
         allT = shard.gather_poses(np.ascontiguousarray(res["T"][:nb]), P, world, rank, dist=dist, device="cuda")
-        return shard.chain_poses(allT) if rank == 0 else None, allT
+        return api.chain_poses(allT, ctx=ctx) if rank == 0 else None, allT      # device block scan (cloud.cu)
     for _ in range(2):
         step()
     dist.barrier()
@@ -434,7 +434,8 @@ def strong_scaling_leg(a, ctx, local, world, rank, dist, prm, runner0):
         Ts = np.array(single["T"])
         out["equal_to_single_gpu"] = bool(np.array_equal(Ts, allT))
         out["max_abs_diff_vs_single_gpu"] = float(np.abs(Ts - allT).max())
-        out["chain_max_abs_diff"] = float(np.nanmax(np.abs(poses - shard.chain_poses(Ts))))
+        out["chain_max_abs_diff"] = float(np.nanmax(np.abs(poses - api.chain_poses(Ts, ctx=ctx))))
+        out["chain_vs_host_restatement"] = float(np.nanmax(np.abs(poses - shard.chain_poses(Ts))))
     pipe.close()
     return out
 

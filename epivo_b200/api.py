@@ -282,6 +282,19 @@ def Levenberg_Marquardt_batch(n_zeta, epsilon, reps, wreps, lambda0, T0s, pr, p_
     return T.reshape(B, n_zeta, 4, 4), res, its
 
 
+def chain_poses(T_pairs, scales=None, ctx: Context | None = None) -> np.ndarray:
+    """kitti_E.cpp:218-228 on the device for poses that are already on the host (the all-gathered poses of a sharded
+    sequence): (n, 4, 4) refined pair transforms -> (n + 1, 4, 4) chained camera poses."""
+    ctx = ctx or default_context()
+    T = np.ascontiguousarray(T_pairs, dtype=np.float64).reshape(-1, 16)
+    n = T.shape[0]
+    sc = None if scales is None else np.ascontiguousarray(scales, dtype=np.float64)
+    assert sc is None or sc.shape == (n,)
+    poses = np.zeros((n + 1, 16), dtype=np.float64)
+    ctx.check(ctx.lib.epivo_chain_poses(ctx.h, _p(T), _p(sc) if sc is not None else None, n, _p(poses)))
+    return poses.reshape(n + 1, 4, 4)
+
+
 def default_params(K=None, **kw) -> PipelineParams:
     p = PipelineParams()
     _lib.load().epivo_pipeline_params_default(C.byref(p))

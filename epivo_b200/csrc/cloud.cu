@@ -50,32 +50,42 @@ __device__ __forceinline__ M34 m34_inv(const M34& a) {
 }
 
 // dT of pair i from its refined pose and the caller's scale (kitti_E.cpp:220-223)
-__device__ __forceinline__ M34 scaled_dT(const epivo_pair_result& r, double scale) {
+__device__ __forceinline__ M34 scaled_dT(const epivo_pair_result& r, double scale);
+__device__ __forceinline__ M34 scaled_dT(const double* T, double scale) {
     M34 d;
-    const double tx = r.T[3], ty = r.T[7], tz = r.T[11];
+    const double tx = T[3], ty = T[7], tz = T[11];
     const double nrm = sqrt(tx * tx + ty * ty + tz * tz);
     const double k = scale / nrm;                            // reference divides by the norm unguarded
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) d.m[i * 4 + j] = r.T[i * 4 + j];
+        for (int j = 0; j < 3; ++j) d.m[i * 4 + j] = T[i * 4 + j];
     }
     d.m[3] = tx * k; d.m[7] = ty * k; d.m[11] = tz * k;
     return d;
 }
 
+__device__ __forceinline__ M34 scaled_dT(const epivo_pair_result& r, double scale) { return scaled_dT(r.T, scale); }
+
 constexpr int CH_THREADS = 256;
 
+// where the refined 4x4 of pair i lives: inside the result records of a run, or in a plain n x 16 array (the poses
+// gathered from the ranks of a sharded sequence)
+struct PoseSrc {
+    const epivo_pair_result* res;
+    const double* T;
+    __device__ __forceinline__ const double* at(int i) const { return res ? res[i].T : T + (size_t)i * 16; }
+};
+
 // poses[i] = inv(dT_0) * ... * inv(dT_{i-1}), i = 0..n (n + 1 poses, poses[0] = I); one CTA
-__global__ void __launch_bounds__(CH_THREADS) chain_kernel(const epivo_pair_result* __restrict__ res,
-                                                           const double* __restrict__ scales, int n,
+__global__ void __launch_bounds__(CH_THREADS) chain_kernel(PoseSrc src, const double* __restrict__ scales, int n,
                                                            double* __restrict__ poses) {
     __shared__ M34 s_tot[CH_THREADS];
     const int tid = threadIdx.x;
     const int per = (n + CH_THREADS - 1) / CH_THREADS;
     const int lo = min(tid * per, n), hi = min(lo + per, n);
     M34 acc = m34_identity();
-    for (int i = lo; i < hi; ++i) acc = m34_mul(acc, m34_inv(scaled_dT(res[i], scales ? scales[i] : 1.0)));
+    for (int i = lo; i < hi; ++i) acc = m34_mul(acc, m34_inv(scaled_dT(src.at(i), scales ? scales[i] : 1.0)));
     s_tot[tid] = acc;
     __syncthreads();
     for (int o = 1; o < CH_THREADS; o <<= 1) {               // inclusive scan of the per-thread products
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(CH_THREADS) chain_kernel(const epivo_pair_resu
 #pragma unroll
         for (int k = 0; k < 12; ++k) out[k] = pre.m[k];
         out[12] = 0.0; out[13] = 0.0; out[14] = 0.0; out[15] = 1.0;
-        pre = m34_mul(pre, m34_inv(scaled_dT(res[i], scales ? scales[i] : 1.0)));
+        pre = m34_mul(pre, m34_inv(scaled_dT(src.at(i), scales ? scales[i] : 1.0)));
     }
     if (tid == CH_THREADS - 1) {                             // the pose after the last pair
         double* out = poses + (size_t)n * 16;
@@ -195,8 +205,33 @@ __global__ void __launch_bounds__(1024) limits_kernel(const int32_t* __restrict_
 }  // namespace
 
 int epv_chain_launch(epivo_ctx* ctx, const epivo_pair_result* d_res, const double* d_scales, int n, double* d_poses) {
-    chain_kernel<<<1, CH_THREADS, 0, ctx->stream>>>(d_res, d_scales, n, d_poses);
+    chain_kernel<<<1, CH_THREADS, 0, ctx->stream>>>(PoseSrc{d_res, nullptr}, d_scales, n, d_poses);
     EPV_LAUNCHED(ctx);
+    return EPIVO_OK;
+}
+
+// D1 for a sharded sequence: the per-pair poses gathered from all ranks (host, n x 16) -> the chained camera poses
+// (host, (n + 1) x 16), kitti_E.cpp:218-228.  Same kernel as epivo_seq_cloud's chain.
+extern "C" int epivo_chain_poses(epivo_ctx* ctx, const double* T_pairs, const double* scales, int n, double* poses) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (n < 0 || !poses || (n > 0 && !T_pairs)) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (n == 0) {
+        for (int i = 0; i < 16; ++i) poses[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        return EPIVO_OK;
+    }
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t np = (size_t)n;
+    int rc = epv_ws_reserve(ctx, epv_align(np * 128) + epv_align(np * 8) + epv_align((np + 1) * 128) + 4096);
+    if (rc) return rc;
+    double* d_T = epv_ws_take<double>(ctx, np * 16);
+    double* d_scales = scales ? epv_ws_take<double>(ctx, np) : nullptr;
+    double* d_poses = epv_ws_take<double>(ctx, (np + 1) * 16);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_T, T_pairs, np * 128, cudaMemcpyHostToDevice, ctx->stream));
+    if (scales) EPV_CUDA(ctx, cudaMemcpyAsync(d_scales, scales, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    chain_kernel<<<1, CH_THREADS, 0, ctx->stream>>>(PoseSrc{nullptr, d_T}, d_scales, n, d_poses);
+    EPV_LAUNCHED(ctx);
+    EPV_CUDA(ctx, cudaMemcpyAsync(poses, d_poses, (np + 1) * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EPIVO_OK;
 }
 

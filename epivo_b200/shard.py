@@ -59,18 +59,29 @@ def chain_poses(T_pairs: np.ndarray, scales: np.ndarray | None = None) -> np.nda
     all_T[i] is the pose BEFORE pair i is applied (kitti_E.cpp:227), so n+1 poses come back."""
     n = T_pairs.shape[0]
     scales = np.ones(n) if scales is None else np.asarray(scales, dtype=np.float64)
-    cT = np.eye(4)
     out = np.empty((n + 1, 4, 4))
-    for i in range(n):
-        out[i] = cT
-        dT = np.eye(4)
-        t = T_pairs[i][:3, 3]
-        nt = np.linalg.norm(t)
-        dT[:3, :3] = T_pairs[i][:3, :3]
-        with np.errstate(all="ignore"):       # |t| = 0 is not guarded: NaN from there on, as in the reference (:221)
-            dT[:3, 3] = t / nt * scales[i]    # and in the device chain (cloud.cu: scaled_dT)
-        cT = cT @ np.linalg.inv(dT)
-    out[n] = cT
+    out[0] = np.eye(4)
+    if n == 0:
+        return out
+    T_pairs = np.asarray(T_pairs, dtype=np.float64)
+    dT = np.tile(np.eye(4), (n, 1, 1))
+    dT[:, :3, :3] = T_pairs[:, :3, :3]
+    t = T_pairs[:, :3, 3]
+    with np.errstate(all="ignore"):           # |t| = 0 is not guarded: NaN from there on, as in the reference (:221)
+        dT[:, :3, 3] = t / np.linalg.norm(t, axis=1, keepdims=True) * scales[:, None]   # and in cloud.cu: scaled_dT
+        bad = ~np.isfinite(dT).all(axis=(1, 2))
+        dT[bad] = np.eye(4)                   # keep LAPACK away from NaN; the NaN is put back below
+        inv = np.linalg.inv(dT)               # the reference inverts the general 4x4 (:228)
+        inv[bad] = np.nan
+        # cT_i = inv_0 inv_1 ... inv_{i-1}: an inclusive scan of matrix products by doubling (4540 pairs: 13 batched
+        # products instead of a 4540-step Python loop; the matrix product is associative, so this differs from the
+        # sequential loop by rounding only -- as the device block scan of cloud.cu does)
+        acc = inv.copy()
+        o = 1
+        while o < n:
+            acc[o:] = acc[:-o] @ acc[o:]
+            o *= 2
+    out[1:] = acc
     return out
 
 

@@ -205,6 +205,12 @@ int epivo_seq_get_masks(epivo_seq* seq, int pair, uint8_t* e_mask, int* n_e, uin
 int epivo_seq_cloud(epivo_seq* seq, const double* scales, int first_pair, int n_pairs, double* poses,
                     double* points, int64_t cap, int64_t* limits, int64_t* n_points);
 
+/* D1 alone, for a sequence sharded over several GPUs: T_pairs = the refined 4x4 of every pair in sequence
+ * order (n x 16, host; what the ranks all-gather), scales = GT step lengths or NULL; poses = (n + 1) x 16 chained camera
+ * poses starting from identity, cT <- cT * dT^-1 with dT = [R | t/|t| * scale] (kitti_E.cpp:218-228), computed by the
+ * same device block scan as epivo_seq_cloud. */
+int epivo_chain_poses(epivo_ctx* ctx, const double* T_pairs, const double* scales, int n, double* poses);
+
 /* ---- pipe micro-benchmarks (roofline denominators MEASURED_PEAKS.json lacks) ----------
  * which: 0 POPC.32, 1 LOP3, 2 FP64 FMA, 3 FP32 FMA, 4 IADD3; result = thread-ops / s on the whole GPU */
 int epivo_microbench(epivo_ctx* ctx, int which, double* ops_per_sec);

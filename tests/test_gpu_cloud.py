@@ -62,3 +62,25 @@ def test_viewer_file_formats_roundtrip(run, tmp_path):
     assert np.array_equal(io.read_cloud(str(tmp_path / "pts.cld")), pts)
     assert np.array_equal(io.read_limits(str(tmp_path / "lims")), limits)
     assert np.array_equal(io.read_poses(str(tmp_path / "kitti.T")), poses[:-1])
+
+
+@pytest.mark.parametrize("with_scales", [False, True])
+def test_three_pose_chains_agree(run, ctx, with_scales):
+    """D1 has three implementations -- the chain inside epivo_seq_cloud (single GPU), epivo_chain_poses (the gathered
+    poses of a sharded sequence, same device block scan) and shard.chain_poses (host restatement): one rule in all
+    three, including the reference's unguarded t / |t| (kitti_E.cpp:221), which turns a zero translation into NaN
+    from that pair on."""
+    from epivo_b200 import shard
+    seq, pipe, res, inl0, inl1, Kf = run
+    scales = np.linspace(0.6, 1.4, seq.n_pairs) if with_scales else None
+    a, _, _ = pipe.cloud(scales, with_points=False)
+    b = api.chain_poses(res["T"], scales, ctx=ctx)
+    c = shard.chain_poses(res["T"], scales)
+    assert np.array_equal(a, b)                                   # same kernel, same inputs
+    assert np.abs(a - c).max() < 1e-10
+    T = np.array(res["T"])
+    T[2, :3, 3] = 0.0                                             # |t| = 0: not guarded, as in the reference
+    b0, c0 = api.chain_poses(T, scales, ctx=ctx), shard.chain_poses(T, scales)
+    for p in (b0, c0):
+        assert np.isfinite(p[:3]).all() and np.isnan(p[3:]).all(axis=(1, 2)).all()
+    assert api.chain_poses(np.zeros((0, 4, 4)), ctx=ctx).tolist() == [np.eye(4).tolist()]
