@@ -82,5 +82,5 @@ def test_three_pose_chains_agree(run, ctx, with_scales):
     T[2, :3, 3] = 0.0                                             # |t| = 0: not guarded, as in the reference
     b0, c0 = api.chain_poses(T, scales, ctx=ctx), shard.chain_poses(T, scales)
     for p in (b0, c0):
-        assert np.isfinite(p[:3]).all() and np.isnan(p[3:]).all(axis=(1, 2)).all()
+        assert np.isfinite(p[:3]).all() and np.isnan(p[3:, :3, 3]).all()       # positions are lost from pair 2 on
     assert api.chain_poses(np.zeros((0, 4, 4)), ctx=ctx).tolist() == [np.eye(4).tolist()]
