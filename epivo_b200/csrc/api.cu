@@ -1,4 +1,5 @@
 // C ABI: context management and the single-call entry points (host buffers in / out).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,6 +52,7 @@ int epivo_create(epivo_ctx** out, int device) {
         return EPIVO_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e = getenv("EPIVO_NVTX")) ctx->nvtx = e[0] == '1';
     *out = ctx;
     return EPIVO_OK;
 }

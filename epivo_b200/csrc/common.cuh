@@ -7,6 +7,16 @@
 
 #include "../../include/epivo_b200.h"
 
+// Stage ranges for profilers ("tracing"): header-only NVTX v3, active only when the context was created
+// with EPIVO_NVTX=1 in the environment -- otherwise one predictable branch per stage.
+#include <nvtx3/nvToolsExt.h>
+struct epivo_ctx;
+struct EpvRange {
+    bool on;
+    inline EpvRange(const epivo_ctx* ctx, const char* name);
+    ~EpvRange() { if (on) nvtxRangePop(); }
+};
+
 struct epivo_ctx {
     int device = 0;
     int sm_count = 148;
@@ -24,7 +34,10 @@ struct epivo_ctx {
     size_t pin_used = 0;
     // events around the kernels of the last stage-wise call that records them (epivo_last_kernel_ms)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    bool nvtx = false;             // EPIVO_NVTX=1 at epivo_create: NVTX ranges around the stages (nsys / ncu --nvtx)
 };
+
+inline EpvRange::EpvRange(const epivo_ctx* ctx, const char* name) : on(ctx && ctx->nvtx) { if (on) nvtxRangePushA(name); }
 
 #define EPV_FAIL(ctx, code, ...)                          \
     do {                                                  \

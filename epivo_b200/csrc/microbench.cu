@@ -62,6 +62,21 @@ __global__ void __launch_bounds__(512) pipe_kernel(uint32_t* out, uint32_t seed)
 #pragma unroll
         for (int k = 0; k < MB_ILP; ++k) s += x[k];
         if (s == 0.123f) out[tid] = 1;
+    } else if (WHICH == 5) {                 // FP64 tensor-core MMA m8n8k4 (DMMA): 256 FMA per warp instruction
+        double c[MB_ILP][2];
+#pragma unroll
+        for (int k = 0; k < MB_ILP; ++k) { c[k][0] = 1e-9 * (tid + k); c[k][1] = 1e-9 * k; }
+        const double a = 1.0 + 1e-12 * seed, b = 1e-3 + 1e-13 * tid;
+        for (int i = 0; i < MB_ITERS; ++i) {
+#pragma unroll
+            for (int k = 0; k < MB_ILP; ++k)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+        }
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < MB_ILP; ++k) s += c[k][0] + c[k][1];
+        if (s == 0.123) out[tid] = 1;
     } else {                                 // IADD3
         uint32_t x[MB_ILP];
 #pragma unroll
@@ -81,7 +96,7 @@ __global__ void __launch_bounds__(512) pipe_kernel(uint32_t* out, uint32_t seed)
 
 extern "C" int epivo_microbench(epivo_ctx* ctx, int which, double* ops_per_sec) {
     if (!ctx || !ops_per_sec) return EPIVO_ERR_INVALID;
-    if (which < 0 || which > 4) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "microbench id %d", which);
+    if (which < 0 || which > 5) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "microbench id %d", which);
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     const int threads = 512, blocks = ctx->sm_count * 4;
     int rc = epv_ws_reserve(ctx, (size_t)threads * blocks * 4);
@@ -98,6 +113,7 @@ extern "C" int epivo_microbench(epivo_ctx* ctx, int which, double* ops_per_sec) 
             case 1: pipe_kernel<1><<<blocks, threads, 0, ctx->stream>>>(out, 7u + rep); break;
             case 2: pipe_kernel<2><<<blocks, threads, 0, ctx->stream>>>(out, 7u + rep); break;
             case 3: pipe_kernel<3><<<blocks, threads, 0, ctx->stream>>>(out, 7u + rep); break;
+            case 5: pipe_kernel<5><<<blocks, threads, 0, ctx->stream>>>(out, 7u + rep); break;
             default: pipe_kernel<4><<<blocks, threads, 0, ctx->stream>>>(out, 7u + rep); break;
         }
         EPV_LAUNCHED(ctx);
@@ -109,7 +125,8 @@ extern "C" int epivo_microbench(epivo_ctx* ctx, int which, double* ops_per_sec) 
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    double ops = (double)threads * blocks * MB_ITERS * MB_ILP;
+    // which = 5: one warp instruction = 256 FMA = 8 per thread
+    double ops = (double)threads * blocks * MB_ITERS * MB_ILP * (which == 5 ? 8.0 : 1.0);
     *ops_per_sec = ops / (best * 1e-3);
     return EPIVO_OK;
 }

@@ -378,6 +378,7 @@ static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int 
     const size_t o = (size_t)p0;                 // group-scoped buffers are indexed by absolute pair
     int rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][2], ctx->stream));
+    EpvRange r_geo(ctx, "epivo: geometry (findEssentialMat + recoverPose + LM)");
     EssentialPlan ep{};
     ep.n_pairs = np;
     ep.stride = st;
@@ -400,7 +401,10 @@ static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int 
     ep.work = s->d_esswork;          // one group at a time uses it: groups are stream-ordered
     ep.work_bytes = s->esswork_bytes;
     ep.ev_presolved = s->evp[c];
-    rc = epv_essential_launch(ctx, ep);
+    {
+        EpvRange r(ctx, "epivo: findEssentialMat");
+        rc = epv_essential_launch(ctx, ep);
+    }
     if (rc) return rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][3], ctx->stream));
     PosePlan pp{};
@@ -416,7 +420,10 @@ static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int 
     pp.mask = s->d_pmask + o * st;
     pp.n_good = s->d_ngood + p0;
     pp.skip = s->d_status + p0;
-    rc = epv_pose_launch(ctx, pp);
+    {
+        EpvRange r(ctx, "epivo: recoverPose");
+        rc = epv_pose_launch(ctx, pp);
+    }
     if (rc) return rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][4], ctx->stream));
     lm_prep_kernel<<<np, 64, 0, ctx->stream>>>(np, st, *prm, s->d_R + o * 9, s->d_t + o * 3, s->d_status + p0,
@@ -442,7 +449,10 @@ static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int 
     lp.iters = s->d_lmiters + p0;
     lp.active = s->d_lmactive + p0;
     lp.single_pair = 1;
-    rc = epv_lm_launch(ctx, lp);
+    {
+        EpvRange r(ctx, "epivo: Levenberg_Marquardt");
+        rc = epv_lm_launch(ctx, lp);
+    }
     if (rc) return rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][5], ctx->stream));
     finish_kernel<<<(np + 127) / 128, 128, 0, ctx->stream>>>(
@@ -461,6 +471,7 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
     const size_t o = (size_t)p0;
     int rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][0], ctx->stream));
+    EpvRange r_match(ctx, "epivo: BFMatcher::match");
     MatchPlan mp{};
     mp.desc = s->d_desc + o * kp * 8;                     // group-local view: frames p0 .. p0+np
     mp.planes = s->d_planes + o * kp * 8;
@@ -558,6 +569,7 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     if (prm->norm != EPIVO_NORM_HAMMING && prm->norm != EPIVO_NORM_HAMMING2) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "norm");
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t main_stream = ctx->stream;
+    EpvRange r_seq(ctx, h_kps ? "epivo_seq_process" : "epivo_seq_run");
     // an explicit pair list may reference any frame: host buffers are then uploaded whole before the first group
     const bool upload_all = h_kps != nullptr && s->pairs_set;
     const bool upload = h_kps != nullptr && !upload_all;

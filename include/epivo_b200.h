@@ -212,7 +212,8 @@ int epivo_seq_cloud(epivo_seq* seq, const double* scales, int first_pair, int n_
 int epivo_chain_poses(epivo_ctx* ctx, const double* T_pairs, const double* scales, int n, double* poses);
 
 /* ---- pipe micro-benchmarks (roofline denominators MEASURED_PEAKS.json lacks) ----------
- * which: 0 POPC.32, 1 LOP3, 2 FP64 FMA, 3 FP32 FMA, 4 IADD3; result = thread-ops / s on the whole GPU */
+ * which: 0 POPC.32, 1 LOP3, 2 FP64 FMA, 3 FP32 FMA, 4 IADD3, 5 FP64 MMA m8n8k4 (in FMA);
+ * result = thread-ops / s on the whole GPU */
 int epivo_microbench(epivo_ctx* ctx, int which, double* ops_per_sec);
 
 #ifdef __cplusplus

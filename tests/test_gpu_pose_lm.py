@@ -212,3 +212,17 @@ def test_lm_cfg5_window_on_a_cluster(ctx, shape, monkeypatch):
         for z in range(10):
             assert rot_angle(Tb[k][z][:3, :3], To[z][:3, :3]) < ROT_TOL
         assert abs(res[k][1] - lo["r_norm"]) <= 1e-5 * max(lo["r_norm"], 1e-12) + 1e-15
+
+
+def test_lm_long_chain_uses_the_small_tile_shape(ctx):
+    """Chain length: the reference's bound is rep_max = 128 (jac_Rt_gen_.cpp:18); a window lives in shared memory here,
+    which fits up to n_zeta = 19 on the smallest tile shape (chosen automatically).  n_zeta = 18 against the C
+    restatement; n_zeta = 24 is refused with an error, never truncated."""
+    nz = 18
+    reps = [(i, i) for i in range(nz)] + [(0, i) for i in range(1, nz, 4)] + [(nz - 1, nz - 3)]
+    _check_vs_c(ctx, nz, reps, 24, 91, 1.0, 30)
+    nz = 24
+    reps = [(i, i) for i in range(nz)]
+    Ts, T0s, pr, p_r = synth.gen_scene_sequence(92, 8, nz, reps)
+    with pytest.raises(api.EpivoError):
+        api.Levenberg_Marquardt(nz, 1e-8, reps, [1.0] * nz, 1e-2, T0s, pr, p_r, ctx=ctx)
