@@ -197,6 +197,7 @@ static int match_common(epivo_ctx* ctx, const uint8_t* q, int nq, const uint8_t*
 int epivo_match_hamming(epivo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int desc_bytes,
                         int norm, int mode, float ratio, int32_t* query_idx, int32_t* train_idx, int32_t* dist,
                         int32_t* dist2, int* n_out) {
+    EpvRange nvtx_range(ctx, "epivo_match_hamming (BFMatcher::match)");
     return match_common(ctx, q, nq, t, nt, desc_bytes, norm, mode, ratio, query_idx, train_idx, dist, dist2,
                         n_out, nullptr, nullptr);
 }
@@ -217,6 +218,7 @@ int epivo_find_essential(epivo_ctx* ctx, const float* p0, const float* p1, int n
                          double prob, double threshold, int max_iters, const int32_t* samples, int m, double E[9],
                          uint8_t* mask, int* n_inliers, int* iters_run) {
     if (!ctx) return EPIVO_ERR_INVALID;
+    EpvRange nvtx_range(ctx, "epivo_find_essential (findEssentialMat)");
     if (n < 0 || (n > 0 && (!p0 || !p1)) || !K || !E) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
     if (method != EPIVO_RANSAC && method != EPIVO_LMEDS)
         EPV_FAIL(ctx, EPIVO_ERR_INVALID, "method %d is not RANSAC(8) / LMEDS(4)", method);
@@ -378,6 +380,7 @@ int epivo_recover_pose(epivo_ctx* ctx, const double E[9], const float* p0, const
                        double dist_thresh, const uint8_t* in_mask, double R[9], double t[3], uint8_t* mask,
                        int* n_good) {
     if (!ctx) return EPIVO_ERR_INVALID;
+    EpvRange nvtx_range(ctx, "epivo_recover_pose (recoverPose)");
     if (!E || !K || !R || !t || n < 0 || (n > 0 && (!p0 || !p1))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     const int stride = std::max(n, 1);
@@ -430,6 +433,7 @@ int epivo_lm_rt_batch(epivo_ctx* ctx, int B, int n_zeta, double epsilon, const i
                       int n_rep, double lambda0, int max_iters, double huber_delta, double* T0s, const double* pr,
                       const double* p_r, int N, epivo_lm_res* out, int32_t* iters_run) {
     if (!ctx) return EPIVO_ERR_INVALID;
+    EpvRange nvtx_range(ctx, "epivo_lm_rt_batch (Levenberg_Marquardt)");
     if (B < 0 || !reps || !wreps || !T0s || !pr || !p_r || !out) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
     if (n_zeta < 1 || n_rep < 1 || N < 1) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_zeta, n_rep and N must be >= 1");
     for (int j = 0; j < n_rep; ++j)                                  // sequence.hpp:118-122 asserts
