@@ -125,7 +125,9 @@ __device__ __forceinline__ uint32_t desc_dist(const uint32_t (&q)[WORDS], const 
     }
 }
 
-template <int WORDS, bool NORM2, bool TOP2, bool COUNTS>
+// RQ = query rows per thread: 8 (a CTA covers 1024 query rows) or 6 (768), whichever wastes fewer row slots for the
+// given set size -- 1500 EuRoC keypoints are two CTAs either way, but 2 x 768 instead of 2 x 1024 slots (mt_pick_rq).
+template <int WORDS, int RQ, bool NORM2, bool TOP2, bool COUNTS>
 __global__ void __launch_bounds__(MT_THREADS, WORDS <= 8 ? EPV_MT_MINBLOCKS : 1)   // 64-byte descriptors need the registers
 match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int64_t t0, int64_t ts, int nq,
                   int nt, uint32_t* __restrict__ rowkey, uint32_t* __restrict__ rowkey2,
@@ -139,7 +141,7 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
     const int pair = blockIdx.y;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int qbase = blockIdx.x * (MT_THREADS * MT_RQ);
+    const int qbase = blockIdx.x * (MT_THREADS * RQ);
     // GENERAL variant (template flag COUNTS): pair p matches frame fq[p] (query) against frame ft[p] (train) of a
     // frame array with qs rows per frame slot, of which counts[frame] are valid
     int64_t qrow0 = q0 + (int64_t)pair * qs, trow0 = t0 + (int64_t)pair * ts;
@@ -182,11 +184,11 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
 
     // query rows -> registers (rows past nq are clamped to the last valid row: a duplicate
     // produces the same keys as the genuine row, so it never changes a minimum)
-    uint32_t q[MT_RQ][WORDS];
-    uint32_t qidx[MT_RQ];
-    uint32_t best[MT_RQ], best2[MT_RQ];
+    uint32_t q[RQ][WORDS];
+    uint32_t qidx[RQ];
+    uint32_t best[RQ], best2[RQ];
 #pragma unroll
-    for (int r = 0; r < MT_RQ; ++r) {
+    for (int r = 0; r < RQ; ++r) {
         int qi = min(qbase + r * MT_THREADS + tid, nq - 1);
         qidx[r] = (uint32_t)qi;
         const uint4* src = reinterpret_cast<const uint4*>(qrows + (int64_t)qi * WORDS);
@@ -224,7 +226,7 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
             uint32_t cmin = 0xFFFFFFFFu;
             const uint32_t jj = jglob0 + jbase + j;
 #pragma unroll
-            for (int r = 0; r < MT_RQ; ++r) {
+            for (int r = 0; r < RQ; ++r) {
                 const uint32_t d = desc_dist<WORDS, NORM2>(q[r], t);
                 // keys as multiply-add so that they issue on the FMA pipe (IMAD), not the ALU
                 const uint32_t rk = d * (1u << EPV_KEY_SHIFT) + jj;
@@ -256,7 +258,7 @@ match_tile_kernel(const uint32_t* __restrict__ desc, int64_t q0, int64_t qs, int
     }
 
 #pragma unroll
-    for (int r = 0; r < MT_RQ; ++r) {
+    for (int r = 0; r < RQ; ++r) {
         int qi = qbase + r * MT_THREADS + tid;
         if (qi < nq) {
             rowkey[(int64_t)pair * stride + qi] = best[r];
@@ -351,20 +353,27 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(FinalizePlan fp) {
     if (tid == 0) fp.n_matches[pair] = s_base;
 }
 
-template <int WORDS>
+// query rows per thread for a set of nq descriptors: fewest row slots over the CTAs, ties to the larger block
+inline int mt_pick_rq(int nq, int words) {
+    if (words != 8) return MT_RQ;                       // the smaller block is instantiated for 32-byte descriptors only
+    auto slots = [nq](int rq) { return (nq + MT_THREADS * rq - 1) / (MT_THREADS * rq) * rq; };
+    return slots(6) < slots(MT_RQ) ? 6 : MT_RQ;
+}
+
+template <int WORDS, int RQ>
 int launch_words(epivo_ctx* ctx, const MatchPlan& mp, const uint32_t* src) {
     const int n_tiles = std::max(1, (mp.nt + MT_TILE - 1) / MT_TILE);
     const int tps = (n_tiles + mp.tsplits - 1) / mp.tsplits;
-    dim3 grid((mp.nq + MT_THREADS * MT_RQ - 1) / (MT_THREADS * MT_RQ), mp.n_pairs, (n_tiles + tps - 1) / tps);
+    dim3 grid((mp.nq + MT_THREADS * RQ - 1) / (MT_THREADS * RQ), mp.n_pairs, (n_tiles + tps - 1) / tps);
     const int64_t part = (int64_t)mp.n_pairs * mp.stride;
     dim3 block(MT_THREADS);
     const bool n2 = mp.norm == EPIVO_NORM_HAMMING2;
 #define EPV_MT(N2, T2, CN)                                                                                 \
     do {                                                                                                   \
         if (mp.pad_smem > 0)                                                                               \
-            cudaFuncSetAttribute(match_tile_kernel<WORDS, N2, T2, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            cudaFuncSetAttribute(match_tile_kernel<WORDS, RQ, N2, T2, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  mp.pad_smem);                                                             \
-        match_tile_kernel<WORDS, N2, T2, CN><<<grid, block, mp.pad_smem, ctx->stream>>>(                   \
+        match_tile_kernel<WORDS, RQ, N2, T2, CN><<<grid, block, mp.pad_smem, ctx->stream>>>(               \
             src, mp.q0, mp.qs, mp.t0, mp.ts, mp.nq, mp.nt, mp.rowkey, mp.rowkey2, mp.colkey, mp.stride, tps, part, \
             mp.fq, mp.ft, mp.counts);                                                                      \
     } while (0)
@@ -386,7 +395,8 @@ int launch_words(epivo_ctx* ctx, const MatchPlan& mp, const uint32_t* src) {
 }  // namespace
 
 int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt) {
-    const int64_t qblocks = (nq + MT_THREADS * MT_RQ - 1) / (MT_THREADS * MT_RQ);
+    const int rq = mt_pick_rq(nq, 8);
+    const int64_t qblocks = (nq + MT_THREADS * rq - 1) / (MT_THREADS * rq);
     const int n_tiles = (nt + MT_TILE - 1) / MT_TILE;
     if (n_tiles <= 1) return 1;
     const int64_t ctas = std::max<int64_t>(1, qblocks * n_pairs);
@@ -401,10 +411,11 @@ int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt) {
 // waves lose nothing to a partially filled last wave
 int epv_match_pairs_per_wave(const epivo_ctx* ctx, int nq) {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_tile_kernel<8, true, false, false>, MT_THREADS, 0) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_tile_kernel<8, MT_RQ, true, false, false>, MT_THREADS, 0) != cudaSuccess ||
         occ < 1)
         occ = 2;
-    const int qblocks = std::max(1, (nq + MT_THREADS * MT_RQ - 1) / (MT_THREADS * MT_RQ));
+    const int rq = mt_pick_rq(nq, 8);
+    const int qblocks = std::max(1, (nq + MT_THREADS * rq - 1) / (MT_THREADS * rq));
     return std::max(1, ctx->sm_count * occ / qblocks);
 }
 
@@ -435,9 +446,9 @@ int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass) {
     if (mp.ev0) EPV_CUDA(ctx, cudaEventRecord(mp.ev0, ctx->stream));
     int rc;
     switch (mp.words) {
-        case 4: rc = launch_words<4>(ctx, mp, src); break;
-        case 8: rc = launch_words<8>(ctx, mp, src); break;
-        default: rc = launch_words<16>(ctx, mp, src); break;
+        case 4: rc = launch_words<4, MT_RQ>(ctx, mp, src); break;
+        case 8: rc = mt_pick_rq(mp.nq, 8) == 6 ? launch_words<8, 6>(ctx, mp, src) : launch_words<8, MT_RQ>(ctx, mp, src); break;
+        default: rc = launch_words<16, MT_RQ>(ctx, mp, src); break;
     }
     if (rc) return rc;
     if (mp.ev1) EPV_CUDA(ctx, cudaEventRecord(mp.ev1, ctx->stream));

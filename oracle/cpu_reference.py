@@ -138,27 +138,34 @@ def _work(i):
     return i, T, nm, ni, ng
 
 
+# Worker processes are SPAWNED, not forked: the callers (bench.py after its GPU legs, the GPU census test) have a
+# live CUDA context and helper threads by then, and a fork()ed child of a multi-threaded process can deadlock on a
+# lock some other thread held at the time of the fork (seen once as a 20-minute hang of the census).
+_MP = "spawn"
+POOL_TIMEOUT_S = 900       # a pool whose workers cannot start would otherwise wait forever
+
+
 class CpuPool:
     """Pair-parallel CPU workers (how a CPU user would saturate the box): `cores` processes,
-    cv2.setNumThreads(1) each.  The sequence is inherited by fork, not pickled per task."""
+    cv2.setNumThreads(1) each.  The sequence is sent to every worker once (initializer), not per task."""
 
     def __init__(self, kps, descs, K, method=8, prob=0.99, thr=1.0, cores=None, norm=7, ratio=None):
         import multiprocessing as mp
         self.cores = cores or (os.cpu_count() or 1)
         clib.build()
         Kf = np.asarray(K, dtype=np.float32)
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_init,
+        self.pool = mp.get_context(_MP).Pool(self.cores, initializer=_init,
                                                 initargs=(kps, descs, Kf, method, prob, thr, norm, ratio))
 
     def run(self, pair_indices):
         """-> (pairs/s, results)"""
         t0 = time.perf_counter()
-        res = self.pool.map(_work, list(pair_indices), chunksize=1)
+        res = self.pool.map_async(_work, list(pair_indices), chunksize=1).get(timeout=POOL_TIMEOUT_S)
         dt = time.perf_counter() - t0
         return len(res) / dt, res
 
     def close(self):
-        self.pool.close()
+        self.pool.terminate()
         self.pool.join()
 
 
@@ -184,6 +191,11 @@ def single_process_rate(kps, descs, K, n_pairs, method=8, prob=0.99, thr=1.0, th
 _WIN = {}
 
 
+def _win_init(args):
+    _WIN["args"] = args
+    clib.lib()
+
+
 def _win_work(b):
     nz, reps, data, delta = _WIN["args"]
     Ts, T0, pr, p_r = data[b % len(data)]
@@ -198,12 +210,11 @@ def windows_rate(data, nz, reps, n_windows, cores=None, huber_delta=1.0):
     cores = cores or (os.cpu_count() or 1)
     clib.build()
     clib.lib()
-    _WIN["args"] = (nz, reps, data, huber_delta)
-    pool = mp.get_context("fork").Pool(cores)
+    pool = mp.get_context(_MP).Pool(cores, initializer=_win_init, initargs=((nz, reps, data, huber_delta),))
     try:
-        pool.map(_win_work, range(cores), chunksize=1)          # warm-up: load the library in every worker
+        pool.map_async(_win_work, range(cores), chunksize=1).get(timeout=POOL_TIMEOUT_S)   # warm-up: load the library
         t0 = time.perf_counter()
-        pool.map(_win_work, range(n_windows), chunksize=1)
+        pool.map_async(_win_work, range(n_windows), chunksize=1).get(timeout=POOL_TIMEOUT_S)
         return n_windows / (time.perf_counter() - t0)
     finally:
         pool.close()
@@ -251,9 +262,9 @@ def census(kps, descs, K, shapes, norm=7, cores=None):
     cores = cores or (os.cpu_count() or 1)
     Kf = np.asarray(K, dtype=np.float32)
     _SEQ["shapes"] = list(shapes)
-    pool = mp.get_context("fork").Pool(cores, initializer=_census_init, initargs=(kps, descs, Kf, norm, list(shapes)))
+    pool = mp.get_context(_MP).Pool(cores, initializer=_census_init, initargs=(kps, descs, Kf, norm, list(shapes)))
     try:
-        return pool.map(_census_work, range(kps.shape[0] - 1), chunksize=1)
+        return pool.map_async(_census_work, range(kps.shape[0] - 1), chunksize=1).get(timeout=POOL_TIMEOUT_S)
     finally:
         pool.close()
         pool.join()

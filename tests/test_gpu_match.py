@@ -92,3 +92,22 @@ def test_large_orb_setting_properties(ctx):
     a = set(zip(qi.tolist(), ti.tolist()))
     b = set(zip(ti2.tolist(), qi2.tolist()))
     assert a == b
+
+
+@pytest.mark.parametrize("norm", [api.NORM_HAMMING2, api.NORM_HAMMING])
+def test_large_orb_setting_exact_vs_live_cv2(ctx, norm):
+    """10000 x 10000 (ORB::create(10000), kitti_ba.cpp:128) against cv2.BFMatcher itself, run live: every
+    (queryIdx, trainIdx, distance) triple of the cross-check match, and the plain nearest neighbour with its ties
+    (a quarter of the train set are duplicates with a few bits cleared, so equal distances are common)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    n = 10000
+    q = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    t = synth.flip_bits(q, rng)[rng.permutation(n)]
+    t[: n // 4] = t[n // 4: n // 2] & np.uint8(0xFC)            # near-duplicates: ties in the row and column minima
+    for cross in (True, False):
+        qi, ti, d = api.BFMatcher(norm, cross, ctx=ctx).match(q, t)
+        ms = cv2.BFMatcher(norm, cross).match(q, t)
+        want = np.array([(m.queryIdx, m.trainIdx, int(m.distance)) for m in ms], dtype=np.int64).reshape(-1, 3)
+        got = np.stack([qi, ti, d], axis=1).astype(np.int64)
+        assert got.shape == want.shape and np.array_equal(got, want), (norm, cross, got.shape, want.shape)
