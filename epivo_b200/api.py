@@ -201,6 +201,18 @@ def fivePointRaw(x1, x2, ctx: Context | None = None):
     return E.reshape(m, 10, 3, 3), nm
 
 
+def eightPoint(x1, x2, ctx: Context | None = None):
+    """8-point hypotheses: m samples (m, 8, 2) of K-normalised points -> (E (m, 3, 3) unit Frobenius norm, ok (m,))."""
+    ctx = ctx or default_context()
+    x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(-1, 8, 2)
+    x2 = np.ascontiguousarray(x2, dtype=np.float64).reshape(-1, 8, 2)
+    m = x1.shape[0]
+    E = np.zeros((m, 9), dtype=np.float64)
+    ok = np.zeros(m, dtype=np.int32)
+    ctx.check(ctx.lib.epivo_eight_point(ctx.h, _p(x1), _p(x2), m, _p(E), _p(ok)))
+    return E.reshape(m, 3, 3), ok
+
+
 def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None,
                  medians: bool = True):
     """K3 alone: (counts (m,), medians (m,) f32, best index, mask of best (n,) {0,1}).

@@ -330,6 +330,27 @@ int epivo_five_point(epivo_ctx* ctx, const double* x1, const double* x2, int m, 
     return EPIVO_OK;
 }
 
+int epivo_eight_point(epivo_ctx* ctx, const double* x1, const double* x2, int m, double* E_out, int32_t* ok) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (m < 0 || (m > 0 && (!x1 || !x2 || !E_out || !ok))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (m == 0) return EPIVO_OK;
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = epv_ws_reserve(ctx, (size_t)m * (128 * 2 + 72 + 4) + 16384);
+    if (rc) return rc;
+    double* d_x1 = epv_ws_take<double>(ctx, (size_t)m * 16);
+    double* d_x2 = epv_ws_take<double>(ctx, (size_t)m * 16);
+    double* d_E = epv_ws_take<double>(ctx, (size_t)m * 9);
+    int32_t* d_ok = epv_ws_take<int32_t>(ctx, m);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_x1, x1, (size_t)m * 128, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_x2, x2, (size_t)m * 128, cudaMemcpyHostToDevice, ctx->stream));
+    rc = epv_eight_point_launch(ctx, d_x1, d_x2, m, d_E, d_ok);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaMemcpyAsync(E_out, d_E, (size_t)m * 72, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(ok, d_ok, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPIVO_OK;
+}
+
 int epivo_score_sampson(epivo_ctx* ctx, const double* E, int m, const float* p0, const float* p1, int n,
                         const double K[9], double threshold, int32_t* counts, float* medians, int* best,
                         uint8_t* best_mask) {

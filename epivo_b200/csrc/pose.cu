@@ -306,7 +306,109 @@ __global__ void __launch_bounds__(PS_THREADS, EPV_PS_MINBLOCKS) pose_kernel(Pose
     for (int i = tid; i < n; i += PS_THREADS) mask[i] = ((mask[i] >> k) & 1) ? 255 : 0;   // own writes only
 }
 
+// ---- 8-point hypotheses (north_star: "each warp solves one minimal 5-point (and 8-point) hypothesis") ----------------
+// The reference never calls an 8-point solver (every findEssentialMat call site runs OpenCV's 5-point estimator,
+// SURVEY section 0 M6), so this is the textbook algorithm, offered next to epivo_five_point for hypothesis generation
+// and scored by the same K3 (epivo_score_sampson):
+//   A (8 x 9), row = (x2 x1, x2 y1, x2, y2 x1, y2 y1, y2, x1, y1, 1) on K-normalised points  ->  null vector
+//   (Householder QR of A': the last column of Q)  ->  E0 (row-major)  ->  nearest essential matrix
+//   E = U diag(1, 1, 0) V' (V from the Jacobi eigen-decomposition of E0'E0, U = E0 V / s), unit Frobenius norm.
+// One LANE per hypothesis, everything in registers (a warp-per-hypothesis split would idle 24 of 32 lanes on
+// 8 x 9 work); ok = 0 when the eight points are degenerate (second singular value of E0 below 1e-12 of the first).
+__global__ void __launch_bounds__(128) eight_point_kernel(const double* __restrict__ x1, const double* __restrict__ x2,
+                                                          int m, double* __restrict__ E_out, int32_t* __restrict__ ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double A[9][8];                                  // A' : column c = row of correspondence c
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double a1 = x1[((size_t)i * 8 + c) * 2], b1 = x1[((size_t)i * 8 + c) * 2 + 1];
+        const double a2 = x2[((size_t)i * 8 + c) * 2], b2 = x2[((size_t)i * 8 + c) * 2 + 1];
+        A[0][c] = a2 * a1; A[1][c] = a2 * b1; A[2][c] = a2;
+        A[3][c] = b2 * a1; A[4][c] = b2 * b1; A[5][c] = b2;
+        A[6][c] = a1;      A[7][c] = b1;      A[8][c] = 1.0;
+    }
+    double beta[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {                    // Householder QR; v_k in A[k.., k]
+        double s = 0.0;
+#pragma unroll
+        for (int r = k; r < 9; ++r) s += A[r][k] * A[r][k];
+        const double nrm = sqrt(s);
+        const double alpha = A[k][k] > 0 ? -nrm : nrm;
+        const double v0 = A[k][k] - alpha;
+        const double vtv = s - A[k][k] * A[k][k] + v0 * v0;
+        beta[k] = vtv > 0 ? 2.0 / vtv : 0.0;
+        A[k][k] = v0;
+#pragma unroll
+        for (int c = k + 1; c < 8; ++c) {
+            double d = 0.0;
+#pragma unroll
+            for (int r = k; r < 9; ++r) d += A[r][k] * A[r][c];
+            d *= beta[k];
+#pragma unroll
+            for (int r = k; r < 9; ++r) A[r][c] -= d * A[r][k];
+        }
+    }
+    double e[9];                                     // Q e_8: the null vector
+#pragma unroll
+    for (int r = 0; r < 9; ++r) e[r] = (r == 8) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        double d = 0.0;
+#pragma unroll
+        for (int r = k; r < 9; ++r) d += A[r][k] * e[r];
+        d *= beta[k];
+#pragma unroll
+        for (int r = k; r < 9; ++r) e[r] -= d * A[r][k];
+    }
+    // nearest essential matrix
+    double M[3][3], V[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) M[a][b] = e[a] * e[b] + e[3 + a] * e[3 + b] + e[6 + a] * e[6 + b];   // E0'E0
+    jacobi_eig<3>(M, V);
+    int o0 = 0, o1 = 1, o2 = 2;                      // eigenvalues in descending order
+    if (M[o0][o0] < M[o1][o1]) { const int t = o0; o0 = o1; o1 = t; }
+    if (M[o1][o1] < M[o2][o2]) { const int t = o1; o1 = o2; o2 = t; }
+    if (M[o0][o0] < M[o1][o1]) { const int t = o0; o0 = o1; o1 = t; }
+    const double s0 = sqrt(fmax(M[o0][o0], 0.0)), s1 = sqrt(fmax(M[o1][o1], 0.0));
+    const bool good = s1 > 1e-12 * s0 && s0 > 0.0;
+    double E[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) E[q] = 0.0;
+    if (good) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const int col = which ? o1 : o0;
+            const double is = 1.0 / (which ? s1 : s0);
+            double v[3], u[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) v[a] = (col == 0) ? V[a][0] : (col == 1 ? V[a][1] : V[a][2]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) u[a] = (e[3 * a] * v[0] + e[3 * a + 1] * v[1] + e[3 * a + 2] * v[2]) * is;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) E[3 * a + b] += u[a] * v[b];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) E[q] *= 0.70710678118654752440;    // |U diag(1,1,0) V'|_F = sqrt(2)
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) E_out[(size_t)i * 9 + q] = E[q];
+    ok[i] = good ? 1 : 0;
+}
+
 }  // namespace
+
+int epv_eight_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_E, int32_t* d_ok) {
+    if (m <= 0) return EPIVO_OK;
+    eight_point_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(d_x1, d_x2, m, d_E, d_ok);
+    EPV_LAUNCHED(ctx);
+    return EPIVO_OK;
+}
 
 int epv_pose_launch(epivo_ctx* ctx, const PosePlan& p) {
     if (p.n_pairs <= 0) return EPIVO_OK;

@@ -48,6 +48,7 @@ struct PosePlan {
     const int32_t* skip;     // optional [pair]: nonzero status => pair skipped (outputs zeroed)
 };
 int epv_pose_launch(epivo_ctx* ctx, const PosePlan& p);
+int epv_eight_point_launch(epivo_ctx* ctx, const double* d_x1, const double* d_x2, int m, double* d_E, int32_t* d_ok);
 
 // ---- lm.cu ---------------------------------------------------------------------------
 struct LmPlan {

@@ -84,6 +84,12 @@ int epivo_find_essential(epivo_ctx* ctx, const float* p0, const float* p1, int n
 int epivo_five_point(epivo_ctx* ctx, const double* x1, const double* x2, int m,
                      double* E_out, int32_t* n_models);
 
+/* K2b: 8-point hypotheses (north_star names them; the reference has no call site -- every findEssentialMat call runs
+ * OpenCV's 5-point estimator).  m samples of 8 K-normalised correspondences (x1, x2: m x 8 x 2) -> one essential matrix
+ * each (m x 9, row-major, unit Frobenius norm: null vector of the 8 x 9 epipolar system projected onto the essential
+ * manifold, U diag(1,1,0) V'); ok[i] = 0 when the eight points are degenerate.  Score them with epivo_score_sampson. */
+int epivo_eight_point(epivo_ctx* ctx, const double* x1, const double* x2, int m, double* E_out, int32_t* ok);
+
 /* K3 alone: Sampson scoring of a fixed hypothesis set of m models (m x 9) against n
  * correspondences with OpenCV's exact inlier rule.  threshold in pixels (RANSAC rule);
  * counts: m inlier counts; medians: m LMedS medians (float32, may be NULL); best: index of

@@ -397,6 +397,21 @@ def five_point(x1: np.ndarray, x2: np.ndarray, refine: bool = True) -> np.ndarra
     return np.array(sols).reshape(-1, 3, 3)
 
 
+def eight_point(x1: np.ndarray, x2: np.ndarray) -> np.ndarray | None:
+    """Textbook 8-point on K-normalised points (no reference call site; north_star names it): null vector of the
+    8 x 9 epipolar system, projected onto the essential manifold U diag(1,1,0) V', unit Frobenius norm."""
+    x1 = np.asarray(x1, dtype=np.float64)
+    x2 = np.asarray(x2, dtype=np.float64)
+    Q = np.stack([x2[:, 0] * x1[:, 0], x2[:, 0] * x1[:, 1], x2[:, 0],
+                  x2[:, 1] * x1[:, 0], x2[:, 1] * x1[:, 1], x2[:, 1],
+                  x1[:, 0], x1[:, 1], np.ones(x1.shape[0])], axis=1)
+    E0 = np.linalg.svd(Q, full_matrices=True)[2][8].reshape(3, 3)
+    U, S, Vt = np.linalg.svd(E0)
+    if not S[1] > 1e-12 * S[0]:
+        return None
+    return U @ np.diag([1.0, 1.0, 0.0]) @ Vt / np.sqrt(2.0)
+
+
 def score_models(Es: np.ndarray, x1: np.ndarray, x2: np.ndarray, thresh: float | None):
     """K3 known-answer: per model the RANSAC inlier count (if thresh) and the LMedS median."""
     Es = np.asarray(Es, dtype=np.float64).reshape(-1, 3, 3)
