@@ -427,8 +427,8 @@ def strong_scaling_leg(a, ctx, local, world, rank, dist, prm, runner0):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     out = {"pairs": P, "ms_per_step": ms, "value": P / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
-           "pairs_on_rank0": nb, "includes": "H2D of the rank's frames + run + D2H + NCCL all-gather of the poses + host chain "
-                                            "(rank 0), wall clock, max over ranks"}
+           "pairs_on_rank0": nb, "includes": "H2D of the rank's frames + run + D2H + NCCL all-gather of the poses + pose chain on "
+                                            "rank 0's GPU (epivo_chain_poses), wall clock, max over ranks"}
     if rank == 0:
         single = runner0.pipe.process(prm, runner0.kps_np, runner0.desc_np, runner0.results)
         Ts = np.array(single["T"])
