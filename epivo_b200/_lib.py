@@ -85,6 +85,7 @@ SIGNATURES = {
     "epivo_seq_cloud": (_i, [_vp, _vp, _i, _i, _vp, _vp, C.c_int64, _vp, C.POINTER(C.c_int64)]),
     "epivo_chain_poses": (_i, [_vp, _vp, _vp, _i, _vp]),
     "epivo_eight_point": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "epivo_fast_detect": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "epivo_microbench": (_i, [_vp, _i, C.POINTER(_d)]),
 }
 

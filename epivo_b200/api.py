@@ -213,6 +213,35 @@ def eightPoint(x1, x2, ctx: Context | None = None):
     return E.reshape(m, 3, 3), ok
 
 
+def fastDetect(images, threshold: int = 10, nonmaxSuppression: bool = True, max_keypoints: int | None = None,
+               ctx: Context | None = None):
+    """cv2.FastFeatureDetector_create(threshold, nonmaxSuppression).detect for a batch of equally sized 8-bit
+    images (kitti_E.cpp:71-74: threshold 40; kitti_ba.cpp:98: the default 10).  images: (rows, cols) or
+    (n, rows, cols) uint8.  Returns a list of (pts (k, 2) float32 [x, y], response (k,) float32) per image, in
+    OpenCV's keypoint order; bit-exact with OpenCV.  max_keypoints bounds the per-image output buffer (default: a
+    quarter of the pixels, which no 8-bit image exceeds after suppression); a frame that exceeds it is re-run."""
+    ctx = ctx or default_context()
+    im = np.ascontiguousarray(images, dtype=np.uint8)
+    single = im.ndim == 2
+    if single:
+        im = im[None]
+    if im.ndim != 3:
+        raise ValueError("images must be (rows, cols) or (n, rows, cols) uint8")
+    n, rows, cols = im.shape
+    cap = int(max_keypoints) if max_keypoints is not None else max(1024, rows * cols // (4 if nonmaxSuppression else 1))
+    while True:
+        kps = np.zeros((n, cap, 2), dtype=np.float32)
+        resp = np.zeros((n, cap), dtype=np.float32)
+        counts = np.zeros(n, dtype=np.int32)
+        ctx.check(ctx.lib.epivo_fast_detect(ctx.h, _p(im), n, rows, cols, int(threshold), 1 if nonmaxSuppression else 0,
+                                            cap, _p(kps), _p(resp), _p(counts)))
+        if max_keypoints is not None or n == 0 or counts.max() <= cap:
+            break
+        cap = int(counts.max())
+    out = [(kps[i, :min(counts[i], cap)].copy(), resp[i, :min(counts[i], cap)].copy()) for i in range(n)]
+    return out[0] if single else out
+
+
 def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None,
                  medians: bool = True):
     """K3 alone: (counts (m,), medians (m,) f32, best index, mask of best (n,) {0,1}).

@@ -351,6 +351,39 @@ int epivo_eight_point(epivo_ctx* ctx, const double* x1, const double* x2, int m,
     return EPIVO_OK;
 }
 
+int epivo_fast_detect(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, int threshold,
+                      int nonmax, int max_kp, float* kps, float* response, int32_t* counts) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (n_images < 0 || rows < 0 || cols < 0 || max_kp < 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "negative size");
+    // outside [0, 255] OpenCV's own code paths disagree with each other (its vector path truncates the threshold to
+    // 8 bits, its scalar tail does not), so there is no reference result to reproduce
+    if (threshold < 0 || threshold > 255) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "threshold %d outside [0, 255]", threshold);
+    if (n_images > 0 && (!images || !counts || (max_kp > 0 && !kps))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (n_images == 0) return EPIVO_OK;
+    if (rows < 7 || cols < 7) {                  // no pixel has a full circle: OpenCV returns no keypoints
+        for (int i = 0; i < n_images; ++i) counts[i] = 0;
+        return EPIVO_OK;
+    }
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)n_images * rows * cols;
+    const size_t nk = (size_t)n_images * max_kp;
+    int rc = epv_ws_reserve(ctx, npx + epv_fast_work_bytes(n_images, rows, cols) + nk * 12 + (size_t)n_images * 4 + 4096);
+    if (rc) return rc;
+    uint8_t* d_img = epv_ws_take<uint8_t>(ctx, npx);
+    uint8_t* d_work = epv_ws_take<uint8_t>(ctx, epv_fast_work_bytes(n_images, rows, cols));
+    float* d_kps = epv_ws_take<float>(ctx, nk * 2 + 2);
+    float* d_resp = response ? epv_ws_take<float>(ctx, nk + 1) : nullptr;
+    int32_t* d_counts = epv_ws_take<int32_t>(ctx, n_images);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_img, images, npx, cudaMemcpyHostToDevice, ctx->stream));
+    rc = epv_fast_launch(ctx, d_img, n_images, rows, cols, threshold, nonmax, max_kp, d_kps, d_resp, d_counts, d_work);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)n_images * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nk) EPV_CUDA(ctx, cudaMemcpyAsync(kps, d_kps, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nk && response) EPV_CUDA(ctx, cudaMemcpyAsync(response, d_resp, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPIVO_OK;
+}
+
 int epivo_score_sampson(epivo_ctx* ctx, const double* E, int m, const float* p0, const float* p1, int n,
                         const double K[9], double threshold, int32_t* counts, float* medians, int* best,
                         uint8_t* best_mask) {

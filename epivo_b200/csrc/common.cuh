@@ -112,6 +112,7 @@ struct MatchPlan {
     int64_t prepass_row0 = 0;  // first row of desc / planes the HAMMING2 plane pre-pass converts (total_rows rows)
 };
 int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass);
+int epv_planes_launch(epivo_ctx* ctx, const uint32_t* desc, uint32_t* planes, int64_t rows, int words, cudaStream_t st);
 int epv_match_splits(const epivo_ctx* ctx, int n_pairs, int nq, int nt);   // train splits that fill the GPU
 int epv_match_pairs_per_wave(const epivo_ctx* ctx, int nq);                // pairs per full wave of matcher CTAs
 

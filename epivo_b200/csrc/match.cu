@@ -455,6 +455,16 @@ int epv_match_launch(epivo_ctx* ctx, const MatchPlan& mp, bool run_prepass) {
     return EPIVO_OK;
 }
 
+// The NORM_HAMMING2 plane pre-pass alone, on a stream of the caller's choice (the host-buffer path converts every
+// upload piece on the copy stream, right behind its cudaMemcpyAsync).
+int epv_planes_launch(epivo_ctx* ctx, const uint32_t* desc, uint32_t* planes, int64_t rows, int words, cudaStream_t st) {
+    if (rows <= 0) return EPIVO_OK;
+    const int64_t n = rows * (words / 2);
+    desc_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(desc, planes, rows, words);
+    EPV_LAUNCHED(ctx);
+    return EPIVO_OK;
+}
+
 int epv_finalize_launch(epivo_ctx* ctx, const FinalizePlan& fp) {
     if (fp.n_pairs <= 0) return EPIVO_OK;
     match_finalize_kernel<<<fp.n_pairs, 256, 0, ctx->stream>>>(fp);

@@ -60,6 +60,7 @@ struct epivo_seq {
     cudaEvent_t evp[SEQ_MAX_CHUNKS] = {};        // after sample + presolve
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaStream_t stream2 = nullptr;          // geometry stream (FP64 kernels) -- overlaps the integer-bound matcher
+    cudaStream_t stream3 = nullptr;          // host-buffer path: every other matcher piece (see seq_execute)
     cudaEvent_t ev_matched[SEQ_MAX_CHUNKS] = {};
     cudaEvent_t ev_geo_done = nullptr;
     int overlap = 0;   // measured on B200: co-running the matcher and the FP64 kernels gains nothing
@@ -260,6 +261,7 @@ int epivo_seq_create_pairs(epivo_ctx* ctx, epivo_seq** out, int max_frames, int 
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);       // hi = numerically lowest = highest priority
         ev_ok = ev_ok && cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ev_ok = ev_ok && cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking) == cudaSuccess;
     }
     if (rc || !ev_ok) {
         epivo_seq_destroy(s);
@@ -299,6 +301,7 @@ void epivo_seq_destroy(epivo_seq* s) {
         if (s->ev_matched[c]) cudaEventDestroy(s->ev_matched[c]);
     if (s->ev_geo_done) cudaEventDestroy(s->ev_geo_done);
     if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
+    if (s->stream3) { cudaStreamSynchronize(s->stream3); cudaStreamDestroy(s->stream3); }
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
     delete s;
@@ -465,7 +468,7 @@ static int seq_run_geometry(epivo_seq* s, const epivo_pipeline_params* prm, int 
 }
 
 // matcher + finalize of one group on the context stream
-static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, int p0, int np) {
+static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, int p0, int np, bool planes_ready = false) {
     epivo_ctx* ctx = s->ctx;
     const int kp = s->kp, st = s->stride;
     const size_t o = (size_t)p0;
@@ -512,6 +515,7 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
             mp.prepass_row0 = (int64_t)p0 * kp;
         }
     }
+    if (planes_ready) prepass = false;                      // converted on the copy stream, piece by piece
     rc = epv_match_launch(ctx, mp, prepass);
     if (rc) return rc;
     EPV_CUDA(ctx, cudaEventRecord(s->ev[c][1], ctx->stream));
@@ -581,17 +585,25 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
                  s->list_max, s->frames_hi);
     // matcher groups / geometry groups (event slots: matcher [0, HALF), geometry [HALF, 2*HALF))
     constexpr int HALF = SEQ_MAX_CHUNKS / 2;
-    // matcher groups.  Resident data: uniform groups.  Host buffers: the upload is cut into pieces of
-    // 1, 2, 4 ... waves of matcher CTAs (the PCIe copy is ~2x faster than the matcher consumes frames,
-    // so a small first piece starts the matcher early and the growing pieces never starve it).
+    // matcher groups.  Resident data: uniform groups.  Host buffers: the upload is cut into pieces of one wave of
+    // matcher CTAs each, every matcher launch waiting only for its own frames (and the launches alternate between
+    // two streams, see below, so a piece boundary costs nothing).  Small pieces are what matters when the copy is
+    // slower than the matcher: alone on a box the PCIe copy delivers frames 2x faster than the matcher consumes
+    // them (55 GB/s against 26 GB/s) and any schedule hides it, but with eight ranks pulling at once a rank gets
+    // 23 GB/s (profiles/r2_h2d_ceiling_8gpu.json), the matcher runs behind the copy, and the step ends one piece
+    // of matching after the last byte lands (round 1's 1, 2, 4, rest schedule left 2468 pairs = 7.5 ms there).
     std::vector<std::pair<int, int> > mg;     // (first pair, pairs)
     {
         const int mchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
         int wave = upload ? epv_match_pairs_per_wave(ctx, s->kp) : mchunk;
-        int max_pieces = 4;
-        if (upload) {                                   // tuning knobs (environment): first piece = wave / div, piece count
+        int max_pieces = HALF, cap_waves = 1;
+        if (upload) {                                   // tuning knobs (environment): first piece = wave / div, piece count, cap
             if (const char* e = getenv("EPIVO_UPLOAD_DIV")) wave = std::max(1, wave / std::max(1, atoi(e)));
-            if (const char* e = getenv("EPIVO_UPLOAD_PIECES")) max_pieces = std::max(1, atoi(e));
+            if (const char* e = getenv("EPIVO_UPLOAD_PIECES")) max_pieces = std::min(HALF, std::max(1, atoi(e)));
+            if (const char* e = getenv("EPIVO_UPLOAD_CAP")) cap_waves = std::max(1, atoi(e));
+            // never more pieces than event slots: widen the cap for very long sequences
+            while ((n_pairs + (int64_t)wave * cap_waves - 1) / ((int64_t)wave * cap_waves) + 2 > max_pieces && cap_waves < (1 << 20))
+                cap_waves *= 2;
         }
         int p0 = first_pair, left = n_pairs, waves = 1;
         while (left > 0) {
@@ -601,7 +613,7 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
             mg.push_back(std::make_pair(p0, np));
             p0 += np;
             left -= np;
-            waves *= 2;
+            waves = std::min(2 * waves, cap_waves);
         }
     }
     const int gchunk = overlap ? SEQ_CHUNK_OVERLAP : SEQ_CHUNK;
@@ -614,9 +626,13 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, main_stream));
     int rc = EPIVO_OK;
     const size_t kp = s->kp;
+    const bool planes_on_copy = upload && prm->norm == EPIVO_NORM_HAMMING2;
     if (upload) {
-        // all pieces are queued on the copy stream at once; they run back to back at PCIe rate
+        // all pieces are queued on the copy stream at once; they run back to back at PCIe rate.  HAMMING2: the bit
+        // planes of a piece's frames are made right behind its copy, on the copy stream, so that a matcher launch
+        // depends on nothing but its own event (no pre-pass in front of it, no frame converted twice).
         EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
+        EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream3, s->ev_begin, 0));
         for (int c = 0; c < n_m; ++c) {
             const int p0 = mg[c].first, np = mg[c].second;
             const int f0 = (c == 0) ? p0 : p0 + 1;                  // frame p0 came with the previous piece
@@ -626,6 +642,11 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
                                           cudaMemcpyHostToDevice, s->stream2));
             EPV_CUDA(ctx, cudaMemcpyAsync(s->d_desc + (size_t)f0 * kp * 8, h_desc + ho * kp * 32, (size_t)nf * kp * 32,
                                           cudaMemcpyHostToDevice, s->stream2));
+            if (planes_on_copy) {
+                rc = epv_planes_launch(ctx, s->d_desc + (size_t)f0 * kp * 8, s->d_planes + (size_t)f0 * kp * 8,
+                                       (int64_t)nf * kp, 8, s->stream2);
+                if (rc) return rc;
+            }
             EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], s->stream2));
         }
     }
@@ -639,8 +660,17 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     if (overlap) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
     for (int c = 0; c < n_m && !rc; ++c) {
         const int p0 = mg[c].first, np = mg[c].second;
-        if (upload) EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_matched[c], 0));
-        rc = seq_run_match(s, prm, c, p0, np);
+        cudaStream_t piece_stream = main_stream;
+        if (upload) {
+            // the matcher pieces alternate between two streams: piece c+1 (its frames have landed) fills the SMs
+            // that the draining CTAs of piece c free up, and its finalize / key-fill kernels run beside piece c+1's
+            // tiles -- on one stream every piece boundary cost ~0.1 ms of drained GPU
+            piece_stream = (c & 1) ? s->stream3 : main_stream;
+            EPV_CUDA(ctx, cudaStreamWaitEvent(piece_stream, s->ev_matched[c], 0));
+        }
+        ctx->stream = piece_stream;
+        rc = seq_run_match(s, prm, c, p0, np, planes_on_copy);
+        ctx->stream = main_stream;
         if (rc) break;
         if (overlap) {      // optional two-stream compute: geometry of group c under the matcher of c+1
             EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], main_stream));
@@ -649,6 +679,10 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
             rc = seq_run_geometry(s, prm, HALF + c, p0, np);
             ctx->stream = main_stream;
         }
+    }
+    if (upload && n_m > 1 && !rc) {     // the odd pieces join the context stream before the geometry
+        EPV_CUDA(ctx, cudaEventRecord(s->ev_geo_done, s->stream3));
+        EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_geo_done, 0));
     }
     ctx->stream = main_stream;
     if (rc) return rc;

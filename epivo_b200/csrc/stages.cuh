@@ -73,3 +73,8 @@ int epv_chain_launch(epivo_ctx* ctx, const epivo_pair_result* d_res, const doubl
 int epv_cloud_launch(epivo_ctx* ctx, int n_pairs, int stride, const epivo_pair_result* d_res, const double* d_scales,
                      const double* d_poses, const double* d_xin, const int32_t* d_ninl, int32_t* d_counts,
                      int64_t* d_limits, double* d_points, int64_t cap, int pass);
+
+// ---- frontend.cu (N4: FAST-9/16 detector, kitti_E.cpp:71-74) ---------------------------------
+size_t epv_fast_work_bytes(int n_images, int rows, int cols);
+int epv_fast_launch(epivo_ctx* ctx, const uint8_t* d_img, int n_images, int rows, int cols, int threshold, int nonmax,
+                    int max_kp, float* d_kps, float* d_resp, int32_t* d_counts, void* work);

@@ -90,6 +90,17 @@ int epivo_five_point(epivo_ctx* ctx, const double* x1, const double* x2, int m,
  * manifold, U diag(1,1,0) V'); ok[i] = 0 when the eight points are degenerate.  Score them with epivo_score_sampson. */
 int epivo_eight_point(epivo_ctx* ctx, const double* x1, const double* x2, int m, double* E_out, int32_t* ok);
 
+/* N4 front end, detector: cv::FastFeatureDetector (FAST-9/16) for a batch of n_images 8-bit images of rows x cols
+ * (dense, row-major, one after another) -- replaces FastFeatureDetector::create(40)->detect(src, kp0, Mat()) at
+ * kitti_E.cpp:71-74 and kitti_ba.cpp:49,62 (threshold 40) and create() at kitti_ba.cpp:98,117-118 (threshold 10).
+ * nonmax != 0: OpenCV's 3x3 non-maximum suppression on cornerScore.  kps: n_images x max_kp x 2 floats (x, y) in
+ * OpenCV's order (row by row, left to right); response: n_images x max_kp floats (the score; 0 without suppression)
+ * or NULL; counts[i] = corners FOUND in image i -- when it exceeds max_kp only the first max_kp are stored.
+ * Coordinates, order and response are bit-exact with OpenCV.  threshold must lie in [0, 255] (beyond that OpenCV's
+ * vector and scalar code paths give different answers). */
+int epivo_fast_detect(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, int threshold,
+                      int nonmax, int max_kp, float* kps, float* response, int32_t* counts);
+
 /* K3 alone: Sampson scoring of a fixed hypothesis set of m models (m x 9) against n
  * correspondences with OpenCV's exact inlier rule.  threshold in pixels (RANSAC rule);
  * counts: m inlier counts; medians: m LMedS medians (float32, may be NULL); best: index of
