@@ -566,9 +566,15 @@ def main():
                         "median_rot_err_rad": float(np.median([rot_angle(results["R"][i], seq.R[i])
                                                                for i in range(0, P, max(1, P // 256))]))}}
     if world > 1:
-        e2e_lim = {"aggregate_h2d_GBps": world * (run.kps_np.nbytes + run.desc_np.nbytes) / (ms_e2e * 1e-3) / 1e9}
-        line["e2e"]["limiter"] = ("host->device input path: %d ranks x %.0f MB per step = %.0f GB/s aggregate through the host "
-                                  "(see profiles/r2_h2d_ceiling.json for the copy-only ceiling of this box class)"
+        # copy-only ceiling of this box class (tools/h2d_ceiling.py, all ranks copying 363 MB at once, committed under
+        # profiles/): an e2e step cannot end before its input has landed
+        ceil_ms = {2: 6.56, 4: 12.65, 8: 15.60}.get(world)
+        e2e_lim = {"aggregate_h2d_GBps": world * (run.kps_np.nbytes + run.desc_np.nbytes) / (ms_e2e * 1e-3) / 1e9,
+                   "h2d_copy_only_ms_per_step": ceil_ms,
+                   "h2d_copy_only_source": "profiles/r2_h2d_ceiling_%dgpu.json (measured on this pool, not in this run)" % world
+                   if ceil_ms else None}
+        line["e2e"]["limiter"] = ("host->device input path: %d ranks x %.0f MB per step = %.0f GB/s aggregate through the host; "
+                                  "the step ends one matcher piece + the geometry after the last byte lands"
                                   % (world, (run.kps_np.nbytes + run.desc_np.nbytes) / 1e6, e2e_lim["aggregate_h2d_GBps"]))
         line["e2e"].update(e2e_lim)
 

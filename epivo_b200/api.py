@@ -242,6 +242,41 @@ def fastDetect(images, threshold: int = 10, nonmaxSuppression: bool = True, max_
     return out[0] if single else out
 
 
+def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, maxLevel: int = 3, maxCount: int = 30, epsilon: float = 0.01,
+                         minEigThreshold: float = 1e-4, ctx: Context | None = None):
+    """cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, None) with the 21 x 21 window (kitti_E.cpp:79-84):
+    (nextPts (n, 2) float32, status (n,) uint8)."""
+    seq = np.stack([np.ascontiguousarray(prevImg, dtype=np.uint8), np.ascontiguousarray(nextImg, dtype=np.uint8)])
+    nxt, st = trackSequenceLK(seq, [prevPts], maxLevel, maxCount, epsilon, minEigThreshold, ctx=ctx)
+    return nxt[0], st[0]
+
+
+def trackSequenceLK(images, points, maxLevel: int = 3, maxCount: int = 30, epsilon: float = 0.01,
+                    minEigThreshold: float = 1e-4, ctx: Context | None = None):
+    """The LK step of the kitti_E loop for a whole sequence in one call: images (n, rows, cols) uint8, points = one
+    (k_i, 2) float32 array per pair i (the detector's output on frame i); returns (list of nextPts, list of status),
+    pair i tracked from frame i into frame i + 1.  The pyramid of every frame is built once."""
+    ctx = ctx or default_context()
+    im = np.ascontiguousarray(images, dtype=np.uint8)
+    if im.ndim != 3 or im.shape[0] < 2:
+        raise ValueError("images must be (n >= 2, rows, cols) uint8")
+    n, rows, cols = im.shape
+    if len(points) != n - 1:
+        raise ValueError("one point set per consecutive pair")
+    pl = [np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 2) for p in points]
+    cap = max(1, max(len(p) for p in pl))
+    pts = np.zeros((n - 1, cap, 2), dtype=np.float32)
+    counts = np.zeros(n - 1, dtype=np.int32)
+    for i, p in enumerate(pl):
+        pts[i, :len(p)] = p
+        counts[i] = len(p)
+    nxt = np.zeros_like(pts)
+    st = np.zeros((n - 1, cap), dtype=np.uint8)
+    ctx.check(ctx.lib.epivo_lk_track(ctx.h, _p(im), n, rows, cols, _p(pts), _p(counts), cap, int(maxLevel), int(maxCount),
+                                     float(epsilon), float(minEigThreshold), _p(nxt), _p(st)))
+    return [nxt[i, :counts[i]].copy() for i in range(n - 1)], [st[i, :counts[i]].copy() for i in range(n - 1)]
+
+
 def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None,
                  medians: bool = True):
     """K3 alone: (counts (m,), medians (m,) f32, best index, mask of best (n,) {0,1}).

@@ -384,6 +384,45 @@ int epivo_fast_detect(epivo_ctx* ctx, const uint8_t* images, int n_images, int r
     return EPIVO_OK;
 }
 
+int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows, int cols, const float* pts,
+                   const int32_t* counts, int max_pts, int max_level, int max_count, double epsilon,
+                   double min_eig_threshold, float* next_pts, uint8_t* status) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (n_frames < 0 || rows < 0 || cols < 0 || max_pts < 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "negative size");
+    if (n_frames < 2 || max_pts == 0) return EPIVO_OK;
+    if (!images || !pts || !counts || !next_pts || !status) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (max_level < 0 || max_level > 7) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "max_level %d outside [0, 7]", max_level);
+    // lkpyramid.cpp clamps the criteria the same way
+    max_count = std::min(std::max(max_count, 0), 100);
+    epsilon = std::min(std::max(epsilon, 0.0), 10.0);
+    const int n_pairs = n_frames - 1;
+    for (int i = 0; i < n_pairs; ++i)
+        if (counts[i] < 0 || counts[i] > max_pts) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "counts[%d] = %d outside [0, %d]", i, counts[i], max_pts);
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)n_frames * rows * cols, np = (size_t)n_pairs * max_pts;
+    const size_t wb = epv_lk_work_bytes(n_frames, rows, cols, max_level);
+    int rc = epv_ws_reserve(ctx, npx + wb + np * 17 + (size_t)n_pairs * 4 + 8192);
+    if (rc) return rc;
+    uint8_t* d_img = epv_ws_take<uint8_t>(ctx, npx);
+    uint8_t* d_work = epv_ws_take<uint8_t>(ctx, wb);
+    float* d_pts = epv_ws_take<float>(ctx, np * 2);
+    float* d_next = epv_ws_take<float>(ctx, np * 2);
+    int32_t* d_counts = epv_ws_take<int32_t>(ctx, n_pairs);
+    uint8_t* d_status = epv_ws_take<uint8_t>(ctx, np);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_img, images, npx, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_pts, pts, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_counts, counts, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemsetAsync(d_next, 0, np * 8, ctx->stream));
+    EPV_CUDA(ctx, cudaMemsetAsync(d_status, 0, np, ctx->stream));
+    rc = epv_lk_launch(ctx, d_img, n_frames, rows, cols, d_pts, d_counts, max_pts, max_level, max_count, epsilon,
+                       min_eig_threshold, d_next, d_status, d_work);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaMemcpyAsync(next_pts, d_next, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(status, d_status, np, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPIVO_OK;
+}
+
 int epivo_score_sampson(epivo_ctx* ctx, const double* E, int m, const float* p0, const float* p1, int n,
                         const double K[9], double threshold, int32_t* counts, float* medians, int* best,
                         uint8_t* best_mask) {

@@ -191,3 +191,267 @@ int epv_fast_launch(epivo_ctx* ctx, const uint8_t* d_img, int n_images, int rows
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
 }
+
+// =================================================================================================================
+// N4 front end, tracker part: cv::calcOpticalFlowPyrLK with the defaults the reference uses
+//     calcOpticalFlowPyrLK(src, tgt, pt0, pt1_, status, err);     kitti_E.cpp:79-84, kitti_ba.cpp:203-208,281-286
+// (winSize 21 x 21, maxLevel 3, criteria COUNT+EPS (30, 0.01), flags 0, minEigThreshold 1e-4), OpenCV
+// video/src/lkpyramid.cpp restated: buildOpticalFlowPyramid (pyrDown, BORDER_REFLECT_101), calcSharrDeriv, and
+// LKTrackerInvoker level by level.  The integer parts -- pyramid, Scharr derivatives, the 14-bit fixed-point
+// bilinear windows -- are exact; the 2 x 2 normal equations are summed in exact integers and rounded once to float
+// (OpenCV accumulates them in float32 lanes; the sums of these integer products are almost always exactly
+// representable, so the two agree bit for bit on most points and to ~1e-4 px otherwise); everything after that is
+// OpenCV's float32 arithmetic spelled with round-to-nearest intrinsics (no FMA contraction).
+namespace {
+
+constexpr int LK_WIN = 21, LK_AREA = LK_WIN * LK_WIN, LK_PPL = (LK_AREA + 31) / 32;   // 14 window pixels per lane
+constexpr int LK_MAX_LEVELS = 8;
+
+struct LkGeom {
+    int levels;                         // pyramid levels actually built (maxLevel + 1 or fewer)
+    int rows[LK_MAX_LEVELS], cols[LK_MAX_LEVELS];
+    int64_t off[LK_MAX_LEVELS];         // element offset of each level inside a frame's pyramid
+    int64_t frame_stride;               // elements per frame pyramid
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    i = abs(i);
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+
+// cv::pyrDown, 8-bit: [1 4 6 4 1] x [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8; one thread per output pixel
+__global__ void __launch_bounds__(256) pyr_down_kernel(uint8_t* __restrict__ pyr, LkGeom g, int level) {
+    const int rows = g.rows[level - 1], cols = g.cols[level - 1], orow = g.rows[level], ocol = g.cols[level];
+    const uint8_t* src = pyr + (size_t)blockIdx.y * g.frame_stride + g.off[level - 1];
+    uint8_t* dst = pyr + (size_t)blockIdx.y * g.frame_stride + g.off[level];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= orow * ocol) return;
+    const int oy = i / ocol, ox = i % ocol;
+    const int w[5] = {1, 4, 6, 4, 1};
+    int sum = 0;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+        const uint8_t* r = src + (size_t)reflect101(2 * oy + dy - 2, rows) * cols;
+        int h = 0;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) h += w[dx] * r[reflect101(2 * ox + dx - 2, cols)];
+        sum += w[dy] * h;
+    }
+    dst[i] = (uint8_t)((sum + 128) >> 8);
+}
+
+// calcSharrDeriv: (dI/dx, dI/dy) as short2, 3-10-3 Scharr, BORDER_REFLECT_101; one thread per pixel
+__global__ void __launch_bounds__(256) scharr_kernel(const uint8_t* __restrict__ pyr, short2* __restrict__ dpyr, LkGeom g,
+                                                     int level) {
+    const int rows = g.rows[level], cols = g.cols[level];
+    const uint8_t* src = pyr + (size_t)blockIdx.y * g.frame_stride + g.off[level];
+    short2* dst = dpyr + (size_t)blockIdx.y * g.frame_stride + g.off[level];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int y = i / cols, x = i % cols;
+    const uint8_t* r0 = src + (size_t)reflect101(y - 1, rows) * cols;
+    const uint8_t* r1 = src + (size_t)y * cols;
+    const uint8_t* r2 = src + (size_t)reflect101(y + 1, rows) * cols;
+    const int xm = reflect101(x - 1, cols), xp = reflect101(x + 1, cols);
+    const int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10, t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
+    const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
+    dst[i] = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
+    const float s = 16384.0f;                                                   // 1 << W_BITS
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), s));   // cvRound: half to even
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), s));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), s));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+// one warp per point: all pyramid levels, all iterations
+__global__ void __launch_bounds__(128) lk_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ dpyr, LkGeom g,
+                                                 const float* __restrict__ pts, const int32_t* __restrict__ counts,
+                                                 int max_pts, int max_count, double eps2, float min_eig,
+                                                 float* __restrict__ next_pts, uint8_t* __restrict__ status) {
+    const int pair = blockIdx.y, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (p >= counts[pair]) return;
+    const float px = pts[((size_t)pair * max_pts + p) * 2], py = pts[((size_t)pair * max_pts + p) * 2 + 1];
+    const float half = (LK_WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float nx = 0.f, ny = 0.f;            // nextPts[ptidx]
+    bool ok = true;
+    short Iw[LK_PPL], Ix[LK_PPL], Iy[LK_PPL];
+    for (int level = g.levels - 1; level >= 0; --level) {
+        const int rows = g.rows[level], cols = g.cols[level];
+        const uint8_t* I = pyr + (size_t)pair * g.frame_stride + g.off[level];
+        const uint8_t* J = pyr + (size_t)(pair + 1) * g.frame_stride + g.off[level];
+        const short2* dI = dpyr + (size_t)pair * g.frame_stride + g.off[level];
+        const float sc = 1.f / (float)(1 << level);
+        float ppx = __fmul_rn(px, sc), ppy = __fmul_rn(py, sc);
+        if (level == g.levels - 1) { nx = ppx; ny = ppy; } else { nx = __fmul_rn(nx, 2.f); ny = __fmul_rn(ny, 2.f); }
+        ppx = __fsub_rn(ppx, half);
+        ppy = __fsub_rn(ppy, half);
+        const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
+        if (ipx < -LK_WIN || ipx >= cols || ipy < -LK_WIN || ipy >= rows) {
+            if (level == 0) ok = false;
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
+        long long s11 = 0, s12 = 0, s22 = 0;
+#pragma unroll
+        for (int k = 0; k < LK_PPL; ++k) {
+            const int idx = lane + 32 * k;
+            Iw[k] = Ix[k] = Iy[k] = 0;
+            if (idx < LK_AREA) {
+                const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
+                const int y0 = ipy + wy, x0 = ipx + wx;
+                const int ry0 = reflect101(y0, rows), ry1 = reflect101(y0 + 1, rows);
+                const int rx0 = reflect101(x0, cols), rx1 = reflect101(x0 + 1, cols);
+                const int iv = I[(size_t)ry0 * cols + rx0] * w00 + I[(size_t)ry0 * cols + rx1] * w01 +
+                               I[(size_t)ry1 * cols + rx0] * w10 + I[(size_t)ry1 * cols + rx1] * w11;
+                // the derivative image has a zero border (BORDER_CONSTANT), the pyramid a reflected one
+                const bool yin0 = y0 >= 0 && y0 < rows, yin1 = y0 + 1 >= 0 && y0 + 1 < rows;
+                const bool xin0 = x0 >= 0 && x0 < cols, xin1 = x0 + 1 >= 0 && x0 + 1 < cols;
+                const short2 z = make_short2(0, 0);
+                const short2 d00 = (yin0 && xin0) ? dI[(size_t)y0 * cols + x0] : z;
+                const short2 d01 = (yin0 && xin1) ? dI[(size_t)y0 * cols + x0 + 1] : z;
+                const short2 d10 = (yin1 && xin0) ? dI[(size_t)(y0 + 1) * cols + x0] : z;
+                const short2 d11 = (yin1 && xin1) ? dI[(size_t)(y0 + 1) * cols + x0 + 1] : z;
+                const int ixv = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
+                const int iyv = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
+                Iw[k] = (short)((iv + (1 << 8)) >> 9);                        // CV_DESCALE(., W_BITS1 - 5)
+                Ix[k] = (short)ixv;
+                Iy[k] = (short)iyv;
+                s11 += (long long)(ixv * ixv);
+                s12 += (long long)(ixv * iyv);
+                s22 += (long long)(iyv * iyv);
+            }
+        }
+        s11 = warp_sum_ll(s11);
+        s12 = warp_sum_ll(s12);
+        s22 = warp_sum_ll(s22);
+        const float A11 = __fmul_rn(__ll2float_rn(s11), FLT_SCALE), A12 = __fmul_rn(__ll2float_rn(s12), FLT_SCALE),
+                    A22 = __fmul_rn(__ll2float_rn(s22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float root = __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), root), (float)(2 * LK_WIN * LK_WIN));
+        if (minEig < min_eig || D < 1.1920929e-07f) {                        // FLT_EPSILON
+            if (level == 0) ok = false;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        float tx = __fsub_rn(nx, half), ty = __fsub_rn(ny, half);             // nextPt -= halfWin
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < max_count; ++j) {
+            const int inx = (int)floorf(tx), iny = (int)floorf(ty);
+            if (inx < -LK_WIN || inx >= cols || iny < -LK_WIN || iny >= rows) {
+                if (level == 0) ok = false;
+                break;
+            }
+            lk_weights(__fsub_rn(tx, (float)inx), __fsub_rn(ty, (float)iny), w00, w01, w10, w11);
+            long long b1 = 0, b2 = 0;
+#pragma unroll
+            for (int k = 0; k < LK_PPL; ++k) {
+                const int idx = lane + 32 * k;
+                if (idx < LK_AREA) {
+                    const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
+                    const int ry0 = reflect101(iny + wy, rows), ry1 = reflect101(iny + wy + 1, rows);
+                    const int rx0 = reflect101(inx + wx, cols), rx1 = reflect101(inx + wx + 1, cols);
+                    const int jv = J[(size_t)ry0 * cols + rx0] * w00 + J[(size_t)ry0 * cols + rx1] * w01 +
+                                   J[(size_t)ry1 * cols + rx0] * w10 + J[(size_t)ry1 * cols + rx1] * w11;
+                    const int diff = ((jv + (1 << 8)) >> 9) - Iw[k];
+                    b1 += (long long)(diff * Ix[k]);
+                    b2 += (long long)(diff * Iy[k]);
+                }
+            }
+            b1 = warp_sum_ll(b1);
+            b2 = warp_sum_ll(b2);
+            const float fb1 = __fmul_rn(__ll2float_rn(b1), FLT_SCALE), fb2 = __fmul_rn(__ll2float_rn(b2), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
+            tx = __fadd_rn(tx, dx);
+            ty = __fadd_rn(ty, dy);
+            nx = __fadd_rn(tx, half);
+            ny = __fadd_rn(ty, half);
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) break;
+            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                nx = __fsub_rn(nx, __fmul_rn(dx, 0.5f));
+                ny = __fsub_rn(ny, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx;
+            pdy = dy;
+        }
+    }
+    if (lane == 0) {
+        next_pts[((size_t)pair * max_pts + p) * 2] = nx;
+        next_pts[((size_t)pair * max_pts + p) * 2 + 1] = ny;
+        status[(size_t)pair * max_pts + p] = ok ? 1 : 0;
+    }
+}
+
+LkGeom lk_geometry(int rows, int cols, int max_level) {
+    LkGeom g{};
+    int64_t off = 0;
+    int r = rows, c = cols;
+    for (int l = 0; l <= max_level && l < LK_MAX_LEVELS; ++l) {
+        if (l > 0) {                                     // buildOpticalFlowPyramid: stop when a side would not exceed the window
+            const int nr = (r + 1) / 2, nc = (c + 1) / 2;
+            if (nc <= LK_WIN || nr <= LK_WIN) break;
+            r = nr;
+            c = nc;
+        }
+        g.rows[l] = r;
+        g.cols[l] = c;
+        g.off[l] = off;
+        off += ((int64_t)r * c + 63) & ~(int64_t)63;
+        g.levels = l + 1;
+    }
+    g.frame_stride = off;
+    return g;
+}
+
+}  // namespace
+
+// bytes of device scratch for n_frames frames: 8-bit pyramids + short2 derivative pyramids
+size_t epv_lk_work_bytes(int n_frames, int rows, int cols, int max_level) {
+    const LkGeom g = lk_geometry(rows, cols, max_level);
+    return (size_t)n_frames * g.frame_stride * (1 + 4) + 1024;
+}
+
+// d_images: [n_frames][rows][cols]; pair i tracks d_pts[i][0..counts[i]) from frame i into frame i + 1
+int epv_lk_launch(epivo_ctx* ctx, const uint8_t* d_images, int n_frames, int rows, int cols, const float* d_pts,
+                  const int32_t* d_counts, int max_pts, int max_level, int max_count, double epsilon, double min_eig,
+                  float* d_next, uint8_t* d_status, void* work) {
+    if (n_frames < 2 || max_pts <= 0) return EPIVO_OK;
+    if (rows <= LK_WIN || cols <= LK_WIN)
+        EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "image %d x %d not larger than the %d x %d window", cols, rows, LK_WIN, LK_WIN);
+    if (n_frames > 65535) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "more than 65535 frames per call");
+    const LkGeom g = lk_geometry(rows, cols, max_level);
+    uint8_t* pyr = (uint8_t*)work;
+    short2* dpyr = (short2*)(pyr + (((size_t)n_frames * g.frame_stride + 255) & ~(size_t)255));
+    // level 0 = the frames themselves (one strided copy), then level by level
+    EPV_CUDA(ctx, cudaMemcpy2DAsync(pyr, (size_t)g.frame_stride, d_images, (size_t)rows * cols, (size_t)rows * cols, n_frames,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int l = 1; l < g.levels; ++l) {
+        const int n = g.rows[l] * g.cols[l];
+        pyr_down_kernel<<<dim3((n + 255) / 256, n_frames), 256, 0, ctx->stream>>>(pyr, g, l);
+        EPV_LAUNCHED(ctx);
+    }
+    for (int l = 0; l < g.levels; ++l) {                 // derivatives of the PREVIOUS image of every pair: frames 0 .. n-2
+        const int n = g.rows[l] * g.cols[l];
+        scharr_kernel<<<dim3((n + 255) / 256, n_frames - 1), 256, 0, ctx->stream>>>(pyr, dpyr, g, l);
+        EPV_LAUNCHED(ctx);
+    }
+    lk_kernel<<<dim3((max_pts + 3) / 4, n_frames - 1), 128, 0, ctx->stream>>>(pyr, dpyr, g, d_pts, d_counts, max_pts, max_count,
+                                                                            epsilon * epsilon, (float)min_eig, d_next, d_status);
+    EPV_LAUNCHED(ctx);
+    return EPIVO_OK;
+}

@@ -78,3 +78,7 @@ int epv_cloud_launch(epivo_ctx* ctx, int n_pairs, int stride, const epivo_pair_r
 size_t epv_fast_work_bytes(int n_images, int rows, int cols);
 int epv_fast_launch(epivo_ctx* ctx, const uint8_t* d_img, int n_images, int rows, int cols, int threshold, int nonmax,
                     int max_kp, float* d_kps, float* d_resp, int32_t* d_counts, void* work);
+size_t epv_lk_work_bytes(int n_frames, int rows, int cols, int max_level);
+int epv_lk_launch(epivo_ctx* ctx, const uint8_t* d_images, int n_frames, int rows, int cols, const float* d_pts,
+                  const int32_t* d_counts, int max_pts, int max_level, int max_count, double epsilon, double min_eig,
+                  float* d_next, uint8_t* d_status, void* work);

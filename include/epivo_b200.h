@@ -101,6 +101,18 @@ int epivo_eight_point(epivo_ctx* ctx, const double* x1, const double* x2, int m,
 int epivo_fast_detect(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, int threshold,
                       int nonmax, int max_kp, float* kps, float* response, int32_t* counts);
 
+/* N4 front end, tracker: cv::calcOpticalFlowPyrLK with a 21 x 21 window (the default the reference uses) over a
+ * sequence of n_frames 8-bit images of rows x cols: pair i (0 <= i < n_frames - 1) tracks its counts[i] points
+ * pts[i][0..counts[i]) (n_frames-1 x max_pts x 2 floats, x y) from frame i into frame i + 1 -- replaces
+ * calcOpticalFlowPyrLK(src, tgt, pt0, pt1_, status, err) at kitti_E.cpp:79-84 and kitti_ba.cpp:203-208,281-286.
+ * The reference's defaults are max_level 3, max_count 30, epsilon 0.01, min_eig_threshold 1e-4 (flags 0, no initial
+ * flow).  next_pts: n_frames-1 x max_pts x 2; status: n_frames-1 x max_pts bytes {0,1}; entries beyond counts[i] are
+ * not written.  Pyramid, derivatives and the fixed-point windows are exact; positions agree with OpenCV to 1e-3 px
+ * except where a stopping test of the iteration falls on the other side. */
+int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows, int cols, const float* pts,
+                   const int32_t* counts, int max_pts, int max_level, int max_count, double epsilon,
+                   double min_eig_threshold, float* next_pts, uint8_t* status);
+
 /* K3 alone: Sampson scoring of a fixed hypothesis set of m models (m x 9) against n
  * correspondences with OpenCV's exact inlier rule.  threshold in pixels (RANSAC rule);
  * counts: m inlier counts; medians: m LMedS medians (float32, may be NULL); best: index of

@@ -12,6 +12,9 @@
 //                           const vector<double>&, const double, vector<MatrixXd>&, vector<MatrixXd>&,
 //                           vector<MatrixXd>&, LM_res&)                                 jac_Rt_gen_.cpp:287-296
 //   BFMatcher matcher(NORM_HAMMING2, true);  matcher.match(desc0, desc1, matches);      kitti_ba.cpp:602,641
+//   Ptr<FastFeatureDetector> detector = FastFeatureDetector::create(40);                kitti_E.cpp:70
+//   detector->detect(src, kp0, Mat());                                                  kitti_E.cpp:73
+//   calcOpticalFlowPyrLK(src, tgt, pt0, pt1_, status, err);                             kitti_E.cpp:79-84
 //
 // How the unqualified calls reach these functions.  The drivers say `using namespace cv;` and call
 // `findEssentialMat(...)` unqualified.  The templates below live in the GLOBAL namespace and take the
@@ -19,7 +22,8 @@
 // cv::findEssentialMat / cv::recoverPose take InputArray / OutputArray, which need a user-defined
 // conversion from every argument: overload resolution picks the exact match, i.e. the template, without
 // any edit.  A class cannot be overloaded that way, so for the matcher the driver writes
-// `epivo::BFMatcher` instead of `BFMatcher` (one token, kitti_ba.cpp:602).
+// `epivo::BFMatcher` instead of `BFMatcher` (one token, kitti_ba.cpp:602), and for the detector
+// `epivo::FastFeatureDetector` in the declaration and the create() call (kitti_E.cpp:70).
 //
 // Context.  The calls carry no handle, so each host thread gets its own lazily created epivo::Context
 // (`thread_local`; device from $EPIVO_DEVICE, default 0) -- kitti_ba.cpp:1153-1163 calls the path from
@@ -30,6 +34,7 @@
 // such as Eigen::MatrixXd.  Neither OpenCV nor Eigen exists in this image: tests/cpp/dropin_test.cpp
 // compiles the literal call lines above against stand-ins with the same member API.
 #pragma once
+#include <memory>
 #include <type_traits>
 
 #include "epivo_shims.hpp"
@@ -102,4 +107,82 @@ template <typename M>
 double Levenberg_Marquardt(const int n_zeta, const double epsilon, const std::vector<std::pair<int, int> >& reps,
                            const double lambda0, std::vector<M>& T0s, std::vector<M>& pr, std::vector<M>& p_r) {
     return epivo::Levenberg_Marquardt(epivo::default_context(), n_zeta, epsilon, reps, lambda0, T0s, pr, p_r);
+}
+
+// ---- N4 front end: detector and tracker --------------------------------------------------------------------------
+namespace epivo {
+
+// cv::FastFeatureDetector (TYPE_9_16).  `Ptr<epivo::FastFeatureDetector> detector = epivo::FastFeatureDetector::create(40);`
+// then `detector->detect(src, kp0, Mat());` unchanged (kitti_E.cpp:70-73, kitti_ba.cpp:49-62,98-118).  create() returns a
+// std::shared_ptr, which cv::Ptr is constructible from.  KP is the caller's cv::KeyPoint: pt, size (7), angle (-1),
+// response (the corner score), octave (0), class_id (-1) are set as OpenCV sets them.
+class FastFeatureDetector {
+  public:
+    static std::shared_ptr<FastFeatureDetector> create(int threshold = 10, bool nonmaxSuppression = true) {
+        return std::shared_ptr<FastFeatureDetector>(new FastFeatureDetector(threshold, nonmaxSuppression));
+    }
+    // image: 8-bit single channel, rows x cols, contiguous (a freshly imread grey image is); the mask must be empty
+    template <typename MatT, typename KP>
+    void detect(const MatT& image, std::vector<KP>& keypoints, const MatT& mask = MatT()) const {
+        typedef mat_traits<MatT> MT;
+        if (!MT::empty(mask)) throw std::invalid_argument("FastFeatureDetector::detect: masks are not supported");
+        keypoints.clear();
+        if (MT::empty(image)) return;
+        Context& ctx = default_context();
+        const int rows = MT::rows(image), cols = MT::cols(image);
+        int cap = std::max(1024, rows * cols / 16);
+        std::vector<float> xy, resp;
+        int32_t found = 0;
+        for (;;) {                              // a frame with more corners than the buffer holds is run again
+            xy.assign(2 * (size_t)cap, 0.f);
+            resp.assign((size_t)cap, 0.f);
+            ctx.check(epivo_fast_detect(ctx.get(), MT::bytes(image), 1, rows, cols, threshold_, nonmax_ ? 1 : 0, cap,
+                                        xy.data(), resp.data(), &found));
+            if (found <= cap) break;
+            cap = found;
+        }
+        keypoints.resize((size_t)found);
+        for (int i = 0; i < found; ++i) {
+            KP& k = keypoints[(size_t)i];
+            k.pt.x = xy[2 * (size_t)i];
+            k.pt.y = xy[2 * (size_t)i + 1];
+            k.size = 7.f;
+            k.angle = -1.f;
+            k.response = resp[(size_t)i];
+            k.octave = 0;
+            k.class_id = -1;
+        }
+    }
+
+  private:
+    FastFeatureDetector(int t, bool n) : threshold_(t), nonmax_(n) {}
+    int threshold_;
+    bool nonmax_;
+};
+
+}  // namespace epivo
+
+// void calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status, err)                   kitti_E.cpp:79-84
+// with OpenCV's defaults (21 x 21 window, 3 pyramid levels above the image, 30 iterations / 0.01).  status in {0,1}.
+// err is sized and zeroed, not computed: no reference driver reads it.
+template <typename MatT, typename Pt>
+void calcOpticalFlowPyrLK(const MatT& prevImg, const MatT& nextImg, const std::vector<Pt>& prevPts, std::vector<Pt>& nextPts,
+                          std::vector<unsigned char>& status, std::vector<float>& err) {
+    typedef epivo::mat_traits<MatT> MT;
+    if (MT::rows(prevImg) != MT::rows(nextImg) || MT::cols(prevImg) != MT::cols(nextImg))
+        throw std::invalid_argument("calcOpticalFlowPyrLK: image sizes differ");
+    const int n = (int)prevPts.size(), rows = MT::rows(prevImg), cols = MT::cols(prevImg);
+    nextPts.assign((size_t)n, Pt());
+    status.assign((size_t)n, 0);
+    err.assign((size_t)n, 0.f);
+    if (n == 0) return;
+    epivo::Context& ctx = epivo::default_context();
+    std::vector<unsigned char> frames(2 * (size_t)rows * cols);
+    std::copy(MT::bytes(prevImg), MT::bytes(prevImg) + (size_t)rows * cols, frames.begin());
+    std::copy(MT::bytes(nextImg), MT::bytes(nextImg) + (size_t)rows * cols, frames.begin() + (size_t)rows * cols);
+    std::vector<float> p = epivo::detail::flatten(prevPts), q(2 * (size_t)n);
+    const int32_t count = n;
+    ctx.check(epivo_lk_track(ctx.get(), frames.data(), 2, rows, cols, p.data(), &count, n, 3, 30, 0.01, 1e-4, q.data(),
+                             status.data()));
+    for (int i = 0; i < n; ++i) { nextPts[(size_t)i].x = q[2 * (size_t)i]; nextPts[(size_t)i].y = q[2 * (size_t)i + 1]; }
 }

@@ -79,3 +79,170 @@ def fast_detect(img: np.ndarray, threshold: int = 10, nonmax: bool = True):
     pts = np.stack([xs, ys], axis=1).astype(np.float32).reshape(-1, 2)
     resp = (score[ys, xs] if nonmax else np.zeros(len(xs))).astype(np.float32)
     return pts, resp
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# calcOpticalFlowPyrLK (OpenCV video/src/lkpyramid.cpp), as the reference calls it with all defaults
+#     calcOpticalFlowPyrLK(src, tgt, pt0, pt1_, status, err);          kitti_E.cpp:79-84, kitti_ba.cpp:203-208,281-286
+# i.e. winSize 21 x 21, maxLevel 3, criteria (COUNT + EPS, 30, 0.01), flags 0, minEigThreshold 1e-4.
+# Integer parts (pyramid, Scharr derivatives, the fixed-point bilinear patches) are exact; the float parts follow
+# OpenCV's float32 formulas, but its 2 x 2 system is accumulated in float32 in the lane order of its SSE code, which
+# this restatement (sums in exact integers, then one rounding) does not imitate: results agree with cv2 to ~1e-3 px,
+# except where a stopping test falls on the other side (tests/test_oracle_lk.py states the tolerances).
+
+def _reflect101(i, n):
+    i = np.abs(i)
+    return np.where(i >= n, 2 * (n - 1) - i, i)
+
+
+def pyr_down(img: np.ndarray) -> np.ndarray:
+    """cv::pyrDown for 8-bit images: separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8, size (n + 1) / 2."""
+    img = np.asarray(img, dtype=np.uint8)
+    rows, cols = img.shape
+    orow, ocol = (rows + 1) // 2, (cols + 1) // 2
+    w = np.array([1, 4, 6, 4, 1], dtype=np.int64)
+    xi = _reflect101(2 * np.arange(ocol)[:, None] + np.arange(-2, 3)[None, :], cols)       # (ocol, 5)
+    yi = _reflect101(2 * np.arange(orow)[:, None] + np.arange(-2, 3)[None, :], rows)
+    h = (img.astype(np.int64)[:, xi] * w).sum(axis=2)                                       # (rows, ocol)
+    v = (h[yi, :] * w[None, :, None]).sum(axis=1)                                           # (orow, ocol)
+    return ((v + 128) >> 8).astype(np.uint8)
+
+
+def scharr_deriv(img: np.ndarray) -> np.ndarray:
+    """calcSharrDeriv: (rows, cols, 2) int16 [dI/dx, dI/dy], 3-10-3 Scharr, BORDER_REFLECT_101."""
+    img = np.asarray(img, dtype=np.uint8).astype(np.int32)
+    rows, cols = img.shape
+    ym, yp = _reflect101(np.arange(rows) - 1, rows), _reflect101(np.arange(rows) + 1, rows)
+    t0 = (img[ym] + img[yp]) * 3 + img * 10
+    t1 = img[yp] - img[ym]
+    xm, xp = _reflect101(np.arange(cols) - 1, cols), _reflect101(np.arange(cols) + 1, cols)
+    dx = t0[:, xp] - t0[:, xm]
+    dy = (t1[:, xp] + t1[:, xm]) * 3 + t1 * 10
+    return np.stack([dx, dy], axis=2).astype(np.int16)
+
+
+def build_pyramid(img: np.ndarray, win: int = 21, max_level: int = 3):
+    """buildOpticalFlowPyramid: levels while both sides stay larger than the window."""
+    pyr = [np.asarray(img, dtype=np.uint8)]
+    for _ in range(max_level):
+        rows, cols = pyr[-1].shape
+        if (cols + 1) // 2 <= win or (rows + 1) // 2 <= win:
+            break
+        pyr.append(pyr_down(pyr[-1]))
+    return pyr
+
+
+def _descale(x, n):
+    return (x + (1 << (n - 1))) >> n
+
+
+def _weights(a, b):
+    f = np.float32
+    iw00 = np.rint((f(1) - a) * (f(1) - b) * f(1 << 14)).astype(np.int64)
+    iw01 = np.rint(a * (f(1) - b) * f(1 << 14)).astype(np.int64)
+    iw10 = np.rint((f(1) - a) * b * f(1 << 14)).astype(np.int64)
+    return iw00, iw01, iw10, (1 << 14) - iw00 - iw01 - iw10
+
+
+def _patch(img, ix, iy, wts, win, shift, zero_outside):
+    """Bilinear fixed-point window of every point: (P, win, win) int64.  img (rows, cols) integer; outside the image
+    BORDER_REFLECT_101 (the pyramid's border) or 0 (the derivative's BORDER_CONSTANT)."""
+    rows, cols = img.shape
+    ys = iy[:, None] + np.arange(win + 1)[None, :]
+    xs = ix[:, None] + np.arange(win + 1)[None, :]
+    if zero_outside:
+        oky = (ys >= 0) & (ys < rows)
+        okx = (xs >= 0) & (xs < cols)
+        g = img[np.clip(ys, 0, rows - 1)[:, :, None], np.clip(xs, 0, cols - 1)[:, None, :]].astype(np.int64)
+        g = g * (oky[:, :, None] & okx[:, None, :])
+    else:
+        g = img[_reflect101(ys, rows)[:, :, None], _reflect101(xs, cols)[:, None, :]].astype(np.int64)
+    iw00, iw01, iw10, iw11 = (w[:, None, None] for w in wts)
+    v = g[:, :-1, :-1] * iw00 + g[:, :-1, 1:] * iw01 + g[:, 1:, :-1] * iw10 + g[:, 1:, 1:] * iw11
+    return _descale(v, shift)
+
+
+def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray, win: int = 21, max_level: int = 3,
+                             max_count: int = 30, epsilon: float = 0.01, min_eig_threshold: float = 1e-4,
+                             exact_sums: bool = True):
+    """(next_pts (P, 2) float32, status (P,) uint8) of cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None) with the
+    reference's defaults.  Follows LKTrackerInvoker::operator() level by level; all point arithmetic in float32."""
+    f = np.float32
+    pts = np.asarray(pts, dtype=np.float32).reshape(-1, 2)
+    P = len(pts)
+    pp, pn = build_pyramid(prev, win, max_level), build_pyramid(nxt, win, max_level)
+    L = min(len(pp), len(pn)) - 1
+    status = np.ones(P, dtype=np.uint8)
+    nextp = np.zeros((P, 2), dtype=np.float32)
+    half = f((win - 1) * 0.5)
+    eps2 = f(epsilon) * f(epsilon)          # criteria.epsilon *= criteria.epsilon (a double in OpenCV; compared with a double dot)
+    eps2 = float(epsilon) * float(epsilon)
+    FLT_SCALE = f(1.0 / (1 << 20))
+    for level in range(L, -1, -1):
+        I, J = pp[level], pn[level]
+        rows, cols = I.shape
+        dI = scharr_deriv(I)
+        prevPt = pts * f(1.0 / (1 << level))
+        nextPt = prevPt.copy() if level == L else nextp * f(2)
+        nextp = nextPt.copy()
+        prevPt = prevPt - half
+        ip = np.floor(prevPt).astype(np.int64)
+        oob = (ip[:, 0] < -win) | (ip[:, 0] >= cols) | (ip[:, 1] < -win) | (ip[:, 1] >= rows)
+        if level == 0:
+            status[oob] = 0
+        act = ~oob
+        if not act.any():
+            continue
+        idx = np.nonzero(act)[0]
+        a = prevPt[idx, 0] - ip[idx, 0].astype(f)
+        b = prevPt[idx, 1] - ip[idx, 1].astype(f)
+        wts = _weights(a, b)
+        Iw = _patch(I, ip[idx, 0], ip[idx, 1], wts, win, 14 - 5, False)
+        Ix = _patch(dI[:, :, 0], ip[idx, 0], ip[idx, 1], wts, win, 14, True)
+        Iy = _patch(dI[:, :, 1], ip[idx, 0], ip[idx, 1], wts, win, 14, True)
+        A11 = (Ix * Ix).sum(axis=(1, 2)).astype(f) * FLT_SCALE
+        A12 = (Ix * Iy).sum(axis=(1, 2)).astype(f) * FLT_SCALE
+        A22 = (Iy * Iy).sum(axis=(1, 2)).astype(f) * FLT_SCALE
+        D = A11 * A22 - A12 * A12
+        minEig = (A22 + A11 - np.sqrt((A11 - A22) * (A11 - A22) + f(4) * A12 * A12)) / f(2 * win * win)
+        bad = (minEig < f(min_eig_threshold)) | (D < f(np.finfo(np.float32).eps))
+        if level == 0:
+            status[idx[bad]] = 0
+        keep = ~bad
+        idx, Iw, Ix, Iy = idx[keep], Iw[keep], Ix[keep], Iy[keep]
+        A11, A12, A22, D = A11[keep], A12[keep], A22[keep], D[keep]
+        with np.errstate(divide="ignore"):
+            D = f(1) / D
+        npt = nextPt[idx] - half
+        prevDelta = np.zeros((len(idx), 2), dtype=f)
+        live = np.ones(len(idx), dtype=bool)
+        for j in range(max_count):
+            if not live.any():
+                break
+            li = np.nonzero(live)[0]
+            inp = np.floor(npt[li]).astype(np.int64)
+            out = (inp[:, 0] < -win) | (inp[:, 0] >= cols) | (inp[:, 1] < -win) | (inp[:, 1] >= rows)
+            if level == 0:
+                status[idx[li[out]]] = 0
+            live[li[out]] = False
+            li, inp = li[~out], inp[~out]
+            if len(li) == 0:
+                break
+            a = npt[li, 0] - inp[:, 0].astype(f)
+            b = npt[li, 1] - inp[:, 1].astype(f)
+            Jw = _patch(J, inp[:, 0], inp[:, 1], _weights(a, b), win, 14 - 5, False)
+            diff = Jw - Iw[li]
+            b1 = (diff * Ix[li]).sum(axis=(1, 2)).astype(f) * FLT_SCALE
+            b2 = (diff * Iy[li]).sum(axis=(1, 2)).astype(f) * FLT_SCALE
+            delta = np.stack([(A12[li] * b2 - A22[li] * b1) * D[li], (A12[li] * b1 - A11[li] * b2) * D[li]], axis=1).astype(f)
+            npt[li] = npt[li] + delta
+            nextp[idx[li]] = npt[li] + half
+            dd = delta[:, 0].astype(np.float64) ** 2 + delta[:, 1].astype(np.float64) ** 2
+            conv = dd <= eps2
+            osc = np.zeros(len(li), dtype=bool)
+            if j > 0:
+                osc = (~conv) & (np.abs(delta[:, 0] + prevDelta[li, 0]) < 0.01) & (np.abs(delta[:, 1] + prevDelta[li, 1]) < 0.01)
+                nextp[idx[li[osc]]] = nextp[idx[li[osc]]] - delta[osc] * f(0.5)
+            live[li[conv | osc]] = False
+            prevDelta[li] = delta
+    return nextp, status

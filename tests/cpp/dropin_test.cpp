@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -28,6 +29,11 @@ namespace cv {
 enum { LMEDS = 4, RANSAC = 8, NORM_HAMMING = 6, NORM_HAMMING2 = 7 };
 struct Point2f { float x, y; Point2f() : x(0), y(0) {} Point2f(float a, float b) : x(a), y(b) {} };
 struct DMatch { int queryIdx, trainIdx, imgIdx; float distance; };
+struct KeyPoint {
+    Point2f pt; float size, angle, response; int octave, class_id;
+    static void convert(const std::vector<KeyPoint>& k, std::vector<Point2f>& p) { p.clear(); for (size_t i = 0; i < k.size(); ++i) p.push_back(k[i].pt); }
+};
+template <typename T> struct Ptr : std::shared_ptr<T> { Ptr() {} Ptr(const std::shared_ptr<T>& o) : std::shared_ptr<T>(o) {} };
 class Mat {
   public:
     int rows, cols;
@@ -217,6 +223,44 @@ int main() {
                 recoverPose(ess, cpt0, cpt1, cam, rot, tr, rec_mask);
             }
         if (rot.rows != 3 || tr.rows != 3 || tr.cols != 1 || cpt0.size() < 200) return 10;
+    }
+    // kitti_E.cpp:66-95: detector and tracker on a synthetic image pair (smooth texture shifted by (2, -1) pixels)
+    {
+        const int rows = 120, cols = 200;
+        Mat big(rows + 8, cols + 8, CV_8U);
+        for (int y = 0; y < big.rows; ++y)
+            for (int x = 0; x < big.cols; ++x)
+                big.at<uchar>(y, x) = (uchar)(127.5 + 60 * sin(0.31 * x) * cos(0.27 * y) + 50 * sin(0.11 * x * y * 0.05) + 10 * ((x * 7 + y * 13) % 5));
+        Mat src(rows, cols, CV_8U), tgt(rows, cols, CV_8U);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) { src.at<uchar>(y, x) = big.at<uchar>(y + 4, x + 4); tgt.at<uchar>(y, x) = big.at<uchar>(y + 5, x + 2); }
+        vector<KeyPoint> kp0, kp_; // kp1,
+        // [verbatim, class name qualified] kitti_E.cpp:70
+        Ptr<epivo::FastFeatureDetector> detector = epivo::FastFeatureDetector::create(40);
+        // [verbatim] kitti_E.cpp:73
+        detector->detect(src, kp0, Mat());
+        vector<Point2f> pt0, pt1_;
+        // [verbatim] kitti_E.cpp:77
+        cv::KeyPoint::convert(kp0, pt0);
+        vector<uchar> status;
+        vector<float> err;
+        // [verbatim] kitti_E.cpp:79-84
+        calcOpticalFlowPyrLK(src,
+                             tgt,
+                             pt0,
+                             pt1_,
+                             status,
+                             err);
+        int tracked = 0, close = 0;
+        for (size_t j = 0; j < status.size(); j++) {
+            if ((int)status[j] == 1) {                                         // kitti_E.cpp:88
+                ++tracked;
+                close += fabs(pt1_[j].x - pt0[j].x - 2.0) < 0.3 && fabs(pt1_[j].y - pt0[j].y + 1.0) < 0.3;
+            }
+        }
+        printf("FAST(40): %zu corners, LK tracked %d, %d within 0.3 px of the true shift\n", kp0.size(), tracked, close);
+        if (kp0.size() < 20 || pt1_.size() != pt0.size() || tracked < (int)kp0.size() * 8 / 10 || close < tracked * 8 / 10) return 11;
+        if (kp0[0].size != 7.f || kp0[0].angle != -1.f || kp0[0].response < 40.f) return 12;
     }
     printf("dropin ok\n");
     return 0;
