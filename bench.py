@@ -385,6 +385,33 @@ class PairsRunner:
         self.pipe.close()
 
 
+def front_end_measure(ctx, frames=32):
+    """N4: FastFeatureDetector(40) on every frame and calcOpticalFlowPyrLK into the next one (kitti_E.cpp:70-84) for a
+    KITTI-sized synthetic sequence, through the host API (the frames are uploaded inside the timed region)."""
+    from epivo_b200 import api
+    rng = np.random.default_rng(12)
+    tex = rng.integers(0, 256, (376 + 64, 1241 + 64)).astype(np.float32)
+    for _ in range(2):                                    # smooth texture: two 3 x 3 box filters
+        tex = sum(np.roll(np.roll(tex, dy, 0), dx, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)) / 9.0
+    tex = ((tex - tex.min()) / (tex.max() - tex.min()) * 255).astype(np.uint8)
+    seq = np.stack([tex[32 + (k % 5):32 + (k % 5) + 376, 32 + 2 * (k % 7):32 + 2 * (k % 7) + 1241] for k in range(frames)])
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        det = api.fastDetect(seq[:-1], 40, True, max_keypoints=16384, ctx=ctx)
+        t1 = time.perf_counter()
+        nxt, st = api.trackSequenceLK(seq, [d[0] for d in det], ctx=ctx)
+        t2 = time.perf_counter()
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1)
+    n = frames - 1
+    return {"workload": "kitti_E.cpp:70-84 on %d synthetic 1241x376 frames: FAST-9/16 threshold 40 with suppression, then "
+                        "21x21 pyramidal LK (3 levels, 30 iterations) of every corner into the next frame" % frames,
+            "value": n / best[0], "unit": "frames/s", "fast_ms_per_frame": best[1] * 1e3 / n, "lk_ms_per_pair": best[2] * 1e3 / n,
+            "mean_corners": float(np.mean([len(d[0]) for d in det])), "tracked_frac": float(np.mean([s.mean() for s in st])),
+            "includes": "host->device upload of the frames and device->host of the points, wall clock"}
+
+
 def rot_angle(a, b):
     return float(np.arccos(np.clip((np.trace(a.T @ b) - 1) / 2, -1, 1)))
 
@@ -614,6 +641,7 @@ def main():
                                     "value": m["windows"] / (m["k_ms"] * 1e-3), "unit": "windows/s", "ms_per_step": m["k_ms"],
                                     "e2e": m["windows"] / (m["wall_ms"] * 1e-3), "e2e_ms_per_step": m["wall_ms"],
                                     "mean_iters": m["mean_iters"], "windows_on_rank0": m["B"]}
+        cfgs["kitti_E front end FAST(40) + LK"] = front_end_measure(ctx)
         line["configs"] = cfgs
 
     # ---------------- N > 1: config 3 as written (one sequence sharded, gathered, chained) ---------------

@@ -466,9 +466,11 @@ class SequencePipeline:
         self.ctx.check(self.ctx.lib.epivo_seq_download(self.h, _p(out), int(first_pair), int(n_pairs)))
         return out
 
-    def set_overlap(self, on: bool):
-        """Two-stream pipelining of matcher and geometry across pair groups (default off)."""
-        self.ctx.check(self.ctx.lib.epivo_seq_set_overlap(self.h, 1 if on else 0))
+    def set_overlap(self, on):
+        """Scheduling of the geometry relative to the matcher (epivo_seq_set_overlap): False / 0 = default (adaptive for
+        host buffers), True / 1 = two-stream pipelining across pair groups for resident data, 2 / 3 = always / never
+        run the geometry between the matcher pieces of the host-buffer path.  Results do not depend on it."""
+        self.ctx.check(self.ctx.lib.epivo_seq_set_overlap(self.h, int(on)))
 
     def stage_ms(self):
         ms = np.zeros(16, dtype=np.float32)

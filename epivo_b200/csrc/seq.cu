@@ -61,6 +61,12 @@ struct epivo_seq {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaStream_t stream2 = nullptr;          // geometry stream (FP64 kernels) -- overlaps the integer-bound matcher
     cudaStream_t stream3 = nullptr;          // host-buffer path: every other matcher piece (see seq_execute)
+    cudaStream_t stream4 = nullptr;          // host-buffer path, copy-bound regime: geometry of the groups already matched
+    cudaEvent_t ev_piece[SEQ_MAX_CHUNKS] = {};   // matcher piece c (tiles + finalize) complete
+    cudaEvent_t ev_cp1 = nullptr;            // timing: last upload piece landed
+    int geo_mode = 0;                        // 0 adaptive, 2 always interleave, 3 never (epivo_seq_set_overlap)
+    int copy_bound = 0;                      // verdict of the previous host-buffer call (adaptive mode)
+    int last_upload_pieces = 0;              // > 0: the previous call was a host-buffer call with that many pieces
     cudaEvent_t ev_matched[SEQ_MAX_CHUNKS] = {};
     cudaEvent_t ev_geo_done = nullptr;
     int overlap = 0;   // measured on B200: co-running the matcher and the FP64 kernels gains nothing
@@ -262,6 +268,10 @@ int epivo_seq_create_pairs(epivo_ctx* ctx, epivo_seq** out, int max_frames, int 
         cudaDeviceGetStreamPriorityRange(&lo, &hi);       // hi = numerically lowest = highest priority
         ev_ok = ev_ok && cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
         ev_ok = ev_ok && cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking) == cudaSuccess;
+        ev_ok = ev_ok && cudaStreamCreateWithFlags(&s->stream4, cudaStreamNonBlocking) == cudaSuccess;
+        ev_ok = ev_ok && cudaEventCreate(&s->ev_cp1) == cudaSuccess;
+        for (int c = 0; c < SEQ_MAX_CHUNKS && ev_ok; ++c)
+            ev_ok &= cudaEventCreateWithFlags(&s->ev_piece[c], cudaEventDisableTiming) == cudaSuccess;
     }
     if (rc || !ev_ok) {
         epivo_seq_destroy(s);
@@ -302,6 +312,10 @@ void epivo_seq_destroy(epivo_seq* s) {
     if (s->ev_geo_done) cudaEventDestroy(s->ev_geo_done);
     if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
     if (s->stream3) { cudaStreamSynchronize(s->stream3); cudaStreamDestroy(s->stream3); }
+    if (s->stream4) { cudaStreamSynchronize(s->stream4); cudaStreamDestroy(s->stream4); }
+    if (s->ev_cp1) cudaEventDestroy(s->ev_cp1);
+    for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
+        if (s->ev_piece[c]) cudaEventDestroy(s->ev_piece[c]);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
     delete s;
@@ -370,7 +384,8 @@ int epivo_seq_set_counts(epivo_seq* s, int first_frame, int n_frames, const int3
 
 int epivo_seq_set_overlap(epivo_seq* s, int overlap) {
     if (!s) return EPIVO_ERR_INVALID;
-    s->overlap = overlap ? 1 : 0;
+    s->overlap = overlap == 1 ? 1 : 0;
+    s->geo_mode = (overlap == 2 || overlap == 3) ? overlap : 0;
     return EPIVO_OK;
 }
 
@@ -623,6 +638,22 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     s->last_ggroups = n_g;
     s->last_n_pairs = n_pairs;
     s->last_first = first_pair;
+    // Host-buffer path, regime of the PREVIOUS call (same object, so normally the same machine state): the input was
+    // the limiter when the last matcher piece could start only once its own frames had landed, i.e. right at the end
+    // of the copy; when the matcher is the limiter that piece starts milliseconds after the copy has finished.
+    if (upload && s->last_upload_pieces > 1 && s->geo_mode == 0) {
+        float t_copy = 0.f, t_last = 0.f;
+        if (cudaEventElapsedTime(&t_copy, s->ev_begin, s->ev_cp1) == cudaSuccess &&
+            cudaEventElapsedTime(&t_last, s->ev_begin, s->evk[s->last_upload_pieces - 1][0]) == cudaSuccess)
+            s->copy_bound = (t_last - t_copy) < 0.1f * t_copy ? 1 : 0;
+        else
+            (void)cudaGetLastError();
+    }
+    // copy-bound: the GPU idles between the matcher pieces, so the geometry of the pairs already matched runs in
+    // those gaps (four groups, own stream) instead of after the last piece; matcher-bound: geometry after the
+    // matcher, as for resident data (co-running them was measured slower: the matcher holds every SM)
+    const bool interleave = upload && n_m >= 8 && (s->geo_mode == 2 || (s->geo_mode == 0 && s->copy_bound));
+    s->last_upload_pieces = upload ? n_m : 0;
     EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, main_stream));
     int rc = EPIVO_OK;
     const size_t kp = s->kp;
@@ -649,6 +680,8 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
             }
             EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], s->stream2));
         }
+        EPV_CUDA(ctx, cudaEventRecord(s->ev_cp1, s->stream2));
+        if (interleave) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream4, s->ev_begin, 0));
     }
     if (upload_all) {
         EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
@@ -658,6 +691,7 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
         EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_matched[0], 0));
     }
     if (overlap) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
+    int n_geo = 0;                       // geometry groups already issued (interleaved mode)
     for (int c = 0; c < n_m && !rc; ++c) {
         const int p0 = mg[c].first, np = mg[c].second;
         cudaStream_t piece_stream = main_stream;
@@ -672,6 +706,21 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
         rc = seq_run_match(s, prm, c, p0, np, planes_on_copy);
         ctx->stream = main_stream;
         if (rc) break;
+        if (interleave) {
+            EPV_CUDA(ctx, cudaEventRecord(s->ev_piece[c], piece_stream));
+            const int per = (n_m + 3) / 4;                          // pieces per geometry group
+            if ((c + 1) % per == 0 || c == n_m - 1) {
+                const int c0 = (c / per) * per;                     // the group's first piece
+                const int gp0 = mg[c0].first, gnp = p0 + np - gp0;
+                EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream4, s->ev_piece[c], 0));
+                if (c > 0) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream4, s->ev_piece[c - 1], 0));   // the other stream's last piece
+                ctx->stream = s->stream4;
+                rc = seq_run_geometry(s, prm, HALF + n_geo, gp0, gnp);
+                ctx->stream = main_stream;
+                if (rc) break;
+                ++n_geo;
+            }
+        }
         if (overlap) {      // optional two-stream compute: geometry of group c under the matcher of c+1
             EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], main_stream));
             EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_matched[c], 0));
@@ -686,7 +735,11 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     }
     ctx->stream = main_stream;
     if (rc) return rc;
-    if (overlap) {          // later work on the context stream (download) is ordered after the geometry
+    if (interleave) {       // every group's geometry is already queued on stream4: join it
+        s->last_ggroups = n_geo;
+        EPV_CUDA(ctx, cudaEventRecord(s->ev_geo_done, s->stream4));
+        EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_geo_done, 0));
+    } else if (overlap) {   // later work on the context stream (download) is ordered after the geometry
         EPV_CUDA(ctx, cudaEventRecord(s->ev_geo_done, s->stream2));
         EPV_CUDA(ctx, cudaStreamWaitEvent(main_stream, s->ev_geo_done, 0));
     } else {
