@@ -369,8 +369,11 @@ class PairsRunner:
         t0 = time.perf_counter()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record(self.stream)
+        t_proc = 0.0
         for _ in range(steps):
+            tp = time.perf_counter()
             pipe.process(prm, self.kps_np, self.desc_np, self.results)
+            t_proc += time.perf_counter() - tp
             if world > 1 and gather:          # the only collective: per-pair poses -> every rank (NCCL)
                 T = torch.from_numpy(np.ascontiguousarray(self.results["T"])).cuda(non_blocking=True)
                 gathered = torch.empty((world * T.shape[0],) + tuple(T.shape[1:]), dtype=T.dtype, device="cuda")
@@ -379,6 +382,12 @@ class PairsRunner:
         self.barrier()
         wall = time.perf_counter() - t0
         ms = max(e2.elapsed_time(e3), wall * 1e3) / steps          # host-side staging counts too
+        self.process_ms_per_rank = None                            # this rank's own epivo_seq_process time, all ranks
+        if world > 1:
+            t = torch.tensor([t_proc * 1e3 / steps], device="cuda", dtype=torch.float64)
+            allt = [torch.empty_like(t) for _ in range(world)]
+            self.dist.all_gather(allt, t)
+            self.process_ms_per_rank = [round(float(x.item()), 3) for x in allt]
         return self.max_over_ranks(ms)
 
     def close(self):
@@ -604,6 +613,7 @@ def main():
                                   "the step ends one matcher piece + the geometry after the last byte lands"
                                   % (world, (run.kps_np.nbytes + run.desc_np.nbytes) / 1e6, e2e_lim["aggregate_h2d_GBps"]))
         line["e2e"].update(e2e_lim)
+        line["e2e"]["process_ms_per_rank"] = run.process_ms_per_rank     # the slowest rank sets the step (one gather per step)
 
     # ---------------- the reference's other call shapes, full step each (not the headline) ---------------
     if not a.no_configs:

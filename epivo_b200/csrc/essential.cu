@@ -767,14 +767,36 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     // the few models that pass (and everything before a first best exists) pay for the
                     // exact median: errors to scratch, bitwise radix select.
                     float* buf = a.errbuf + ((int64_t)pair * ES_WARPS + warp) * a.stride;
-                    const bool have_best = s_best_score < 1e300;
-                    const float bestf = (float)s_best_score;                 // exact: medians are floats
+                    bool have_best = s_best_score < 1e300;
+                    float bestf = (float)s_best_score;                       // exact: medians are floats
+                    int first = 0;                                           // items [0, first) already have their medians
+                    if (!have_best) {
+                        // No best yet (the pair's first sub-chunk).  The first ES_WARPS models get their exact medians,
+                        // one warp each; the smallest of them is an upper bound of the best median BEFORE every later
+                        // model of the sub-chunk, so those go through the same count filter as in the later sub-chunks
+                        // instead of paying for ~34 exact medians (40 % of the LMedS scoring time before).
+                        first = min(M, ES_WARPS);
+                        if (warp < first) {
+                            const int code = s_item[warp];
+                            const double* E = s_models[code >> 4][code & 15];
+                            for (int i = lane; i < n; i += 32) buf[i] = sampson_f32(E, X1[i], Y1[i], X2[i], Y2[i]);
+                            __syncwarp();
+                            const float med = warp_select(buf, n, n / 2, lane);
+                            __syncwarp();
+                            if (lane == 0) s_score[code >> 4][code & 15] = med;
+                        }
+                        __syncthreads();                                     // CTA-uniform branch (shared state only)
+                        float t = 3.0e38f;
+                        for (int j = 0; j < first; ++j) t = fminf(t, s_score[s_item[j] >> 4][s_item[j] & 15]);
+                        bestf = t;
+                        have_best = true;
+                    }
                     const bool can_filter = have_best && bestf > 0.0f;
                     const SampThr thrL = make_samp_thr(can_filter ? __uint_as_float(__float_as_uint(bestf) - 1u) : 0.0f);
                     const int need = n / 2 + 1;                              // errors that must lie below the best
                     for (;;) {
                         int j0 = 0;
-                        if (lane == 0) j0 = 2 * atomicAdd(&s_next, 1);
+                        if (lane == 0) j0 = first + 2 * atomicAdd(&s_next, 1);
                         j0 = __shfl_sync(0xFFFFFFFFu, j0, 0);
                         if (j0 >= M) break;
                         const int code0 = s_item[j0];

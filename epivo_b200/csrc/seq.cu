@@ -268,7 +268,9 @@ int epivo_seq_create_pairs(epivo_ctx* ctx, epivo_seq** out, int max_frames, int 
         cudaDeviceGetStreamPriorityRange(&lo, &hi);       // hi = numerically lowest = highest priority
         ev_ok = ev_ok && cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
         ev_ok = ev_ok && cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking) == cudaSuccess;
-        ev_ok = ev_ok && cudaStreamCreateWithFlags(&s->stream4, cudaStreamNonBlocking) == cudaSuccess;
+        // highest priority: a geometry kernel is a chain of ~70 short dependent launches; behind a resident wave of
+        // 0.9 ms matcher CTAs each of them would wait for a free slot at normal priority
+        ev_ok = ev_ok && cudaStreamCreateWithPriority(&s->stream4, cudaStreamNonBlocking, hi) == cudaSuccess;
         ev_ok = ev_ok && cudaEventCreate(&s->ev_cp1) == cudaSuccess;
         for (int c = 0; c < SEQ_MAX_CHUNKS && ev_ok; ++c)
             ev_ok &= cudaEventCreateWithFlags(&s->ev_piece[c], cudaEventDisableTiming) == cudaSuccess;
@@ -574,6 +576,18 @@ static int seq_run_match(epivo_seq* s, const epivo_pipeline_params* prm, int c, 
     return EPIVO_OK;
 }
 
+// Tuning aid (EPIVO_UPLOAD_DELAY_US): a sleeping kernel on the copy stream behind every upload piece, to reproduce on
+// one GPU the input rate a rank sees when eight ranks share the host's copy path.
+__device__ __forceinline__ unsigned long long epv_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void upload_delay_kernel(unsigned us) {
+    const unsigned long long t0 = epv_globaltimer_ns();
+    while (epv_globaltimer_ns() - t0 < (unsigned long long)us * 1000ull) __nanosleep(2000);
+}
+
 // Common executor.  With host buffers (h_kps/h_desc != NULL) the frames are uploaded in pieces on
 // the copy stream and every matcher group starts as soon as its frames have landed, so the
 // host->device transfer hides under the matcher; the geometry then runs once over all pairs.
@@ -652,7 +666,12 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     // copy-bound: the GPU idles between the matcher pieces, so the geometry of the pairs already matched runs in
     // those gaps (four groups, own stream) instead of after the last piece; matcher-bound: geometry after the
     // matcher, as for resident data (co-running them was measured slower: the matcher holds every SM)
-    const bool interleave = upload && n_m >= 8 && (s->geo_mode == 2 || (s->geo_mode == 0 && s->copy_bound));
+    int geo_mode = s->geo_mode;
+    if (const char* e = getenv("EPIVO_GEO_MODE")) geo_mode = atoi(e);      // tuning / experiments: 0 adaptive, 2 always, 3 never
+    const bool interleave = upload && n_m >= 8 && (geo_mode == 2 || (geo_mode == 0 && s->copy_bound));
+    if (upload && getenv("EPIVO_DEBUG_SCHED"))
+        fprintf(stderr, "[epivo dev %d] host-buffer call: %d pieces, copy_bound %d, interleave %d\n", ctx->device, n_m,
+                s->copy_bound, (int)interleave);
     s->last_upload_pieces = upload ? n_m : 0;
     EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, main_stream));
     int rc = EPIVO_OK;
@@ -664,6 +683,8 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
         // depends on nothing but its own event (no pre-pass in front of it, no frame converted twice).
         EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream2, s->ev_begin, 0));
         EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream3, s->ev_begin, 0));
+        const char* de = getenv("EPIVO_UPLOAD_DELAY_US");
+        const int delay_us = de ? atoi(de) : 0;
         for (int c = 0; c < n_m; ++c) {
             const int p0 = mg[c].first, np = mg[c].second;
             const int f0 = (c == 0) ? p0 : p0 + 1;                  // frame p0 came with the previous piece
@@ -678,6 +699,7 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
                                        (int64_t)nf * kp, 8, s->stream2);
                 if (rc) return rc;
             }
+            if (delay_us > 0) upload_delay_kernel<<<1, 1, 0, s->stream2>>>((unsigned)delay_us);
             EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], s->stream2));
         }
         EPV_CUDA(ctx, cudaEventRecord(s->ev_cp1, s->stream2));
