@@ -467,9 +467,9 @@ class SequencePipeline:
         return out
 
     def set_overlap(self, on):
-        """Scheduling of the geometry relative to the matcher (epivo_seq_set_overlap): False / 0 = default (adaptive for
-        host buffers), True / 1 = two-stream pipelining across pair groups for resident data, 2 / 3 = always / never
-        run the geometry between the matcher pieces of the host-buffer path.  Results do not depend on it."""
+        """Scheduling of the geometry relative to the matcher (epivo_seq_set_overlap): False / 0 = default (after the
+        matcher), True / 1 = two-stream pipelining across pair groups for resident data, 2 = the geometry between the
+        matcher pieces of the host-buffer path.  Results do not depend on it; both options measured slower."""
         self.ctx.check(self.ctx.lib.epivo_seq_set_overlap(self.h, int(on)))
 
     def stage_ms(self):

@@ -63,10 +63,7 @@ struct epivo_seq {
     cudaStream_t stream3 = nullptr;          // host-buffer path: every other matcher piece (see seq_execute)
     cudaStream_t stream4 = nullptr;          // host-buffer path, copy-bound regime: geometry of the groups already matched
     cudaEvent_t ev_piece[SEQ_MAX_CHUNKS] = {};   // matcher piece c (tiles + finalize) complete
-    cudaEvent_t ev_cp1 = nullptr;            // timing: last upload piece landed
-    int geo_mode = 0;                        // 0 adaptive, 2 always interleave, 3 never (epivo_seq_set_overlap)
-    int copy_bound = 0;                      // verdict of the previous host-buffer call (adaptive mode)
-    int last_upload_pieces = 0;              // > 0: the previous call was a host-buffer call with that many pieces
+    int geo_mode = 0;                        // 2: geometry between the matcher pieces of the host-buffer path (epivo_seq_set_overlap)
     cudaEvent_t ev_matched[SEQ_MAX_CHUNKS] = {};
     cudaEvent_t ev_geo_done = nullptr;
     int overlap = 0;   // measured on B200: co-running the matcher and the FP64 kernels gains nothing
@@ -271,7 +268,6 @@ int epivo_seq_create_pairs(epivo_ctx* ctx, epivo_seq** out, int max_frames, int 
         // highest priority: a geometry kernel is a chain of ~70 short dependent launches; behind a resident wave of
         // 0.9 ms matcher CTAs each of them would wait for a free slot at normal priority
         ev_ok = ev_ok && cudaStreamCreateWithPriority(&s->stream4, cudaStreamNonBlocking, hi) == cudaSuccess;
-        ev_ok = ev_ok && cudaEventCreate(&s->ev_cp1) == cudaSuccess;
         for (int c = 0; c < SEQ_MAX_CHUNKS && ev_ok; ++c)
             ev_ok &= cudaEventCreateWithFlags(&s->ev_piece[c], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -315,7 +311,6 @@ void epivo_seq_destroy(epivo_seq* s) {
     if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
     if (s->stream3) { cudaStreamSynchronize(s->stream3); cudaStreamDestroy(s->stream3); }
     if (s->stream4) { cudaStreamSynchronize(s->stream4); cudaStreamDestroy(s->stream4); }
-    if (s->ev_cp1) cudaEventDestroy(s->ev_cp1);
     for (int c = 0; c < SEQ_MAX_CHUNKS; ++c)
         if (s->ev_piece[c]) cudaEventDestroy(s->ev_piece[c]);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -387,7 +382,7 @@ int epivo_seq_set_counts(epivo_seq* s, int first_frame, int n_frames, const int3
 int epivo_seq_set_overlap(epivo_seq* s, int overlap) {
     if (!s) return EPIVO_ERR_INVALID;
     s->overlap = overlap == 1 ? 1 : 0;
-    s->geo_mode = (overlap == 2 || overlap == 3) ? overlap : 0;
+    s->geo_mode = overlap == 2 ? 2 : 0;
     return EPIVO_OK;
 }
 
@@ -652,27 +647,18 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
     s->last_ggroups = n_g;
     s->last_n_pairs = n_pairs;
     s->last_first = first_pair;
-    // Host-buffer path, regime of the PREVIOUS call (same object, so normally the same machine state): the input was
-    // the limiter when the last matcher piece could start only once its own frames had landed, i.e. right at the end
-    // of the copy; when the matcher is the limiter that piece starts milliseconds after the copy has finished.
-    if (upload && s->last_upload_pieces > 1 && s->geo_mode == 0) {
-        float t_copy = 0.f, t_last = 0.f;
-        if (cudaEventElapsedTime(&t_copy, s->ev_begin, s->ev_cp1) == cudaSuccess &&
-            cudaEventElapsedTime(&t_last, s->ev_begin, s->evk[s->last_upload_pieces - 1][0]) == cudaSuccess)
-            s->copy_bound = (t_last - t_copy) < 0.1f * t_copy ? 1 : 0;
-        else
-            (void)cudaGetLastError();
-    }
-    // copy-bound: the GPU idles between the matcher pieces, so the geometry of the pairs already matched runs in
-    // those gaps (four groups, own stream) instead of after the last piece; matcher-bound: geometry after the
-    // matcher, as for resident data (co-running them was measured slower: the matcher holds every SM)
+    // Host-buffer path: the geometry of the pairs already matched CAN run between the matcher pieces (four groups, own
+    // high-priority stream: epivo_seq_set_overlap(seq, 2)), which looks attractive when the copy is the limiter and
+    // the GPU idles between pieces.  Measured, it loses in every regime -- 17.2 -> 18.9 ms per step with the copy at
+    // full rate, 22.4 -> 23.1 ms with the copy throttled to the rate of an 8-rank run (EPIVO_UPLOAD_DELAY_US), and
+    // 19.7 -> 20.8 ms on 8 GPUs: a geometry group is a chain of ~70 short dependent launches whose CTAs take slots
+    // and issue cycles from the matcher wave that has just become ready, and the matcher then falls behind the copy.
+    // So the default stays: geometry after the last matcher piece.
     int geo_mode = s->geo_mode;
-    if (const char* e = getenv("EPIVO_GEO_MODE")) geo_mode = atoi(e);      // tuning / experiments: 0 adaptive, 2 always, 3 never
-    const bool interleave = upload && n_m >= 8 && (geo_mode == 2 || (geo_mode == 0 && s->copy_bound));
+    if (const char* e = getenv("EPIVO_GEO_MODE")) geo_mode = atoi(e);      // tuning / experiments: 2 = interleave
+    const bool interleave = upload && n_m >= 8 && geo_mode == 2;
     if (upload && getenv("EPIVO_DEBUG_SCHED"))
-        fprintf(stderr, "[epivo dev %d] host-buffer call: %d pieces, copy_bound %d, interleave %d\n", ctx->device, n_m,
-                s->copy_bound, (int)interleave);
-    s->last_upload_pieces = upload ? n_m : 0;
+        fprintf(stderr, "[epivo dev %d] host-buffer call: %d pieces, interleave %d\n", ctx->device, n_m, (int)interleave);
     EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, main_stream));
     int rc = EPIVO_OK;
     const size_t kp = s->kp;
@@ -702,7 +688,6 @@ static int seq_execute(epivo_seq* s, const epivo_pipeline_params* prm, int first
             if (delay_us > 0) upload_delay_kernel<<<1, 1, 0, s->stream2>>>((unsigned)delay_us);
             EPV_CUDA(ctx, cudaEventRecord(s->ev_matched[c], s->stream2));
         }
-        EPV_CUDA(ctx, cudaEventRecord(s->ev_cp1, s->stream2));
         if (interleave) EPV_CUDA(ctx, cudaStreamWaitEvent(s->stream4, s->ev_begin, 0));
     }
     if (upload_all) {

@@ -210,13 +210,13 @@ int epivo_seq_process(epivo_seq* seq, const epivo_pipeline_params* p, int n_fram
 /* device -> host copy of the results of the last run and stream sync */
 int epivo_seq_download(epivo_seq* seq, epivo_pair_result* out, int first_pair, int n_pairs);
 /* Scheduling of the geometry (findEssentialMat + recoverPose + LM) relative to the matcher; results do not depend on it.
- *   0 (default)  resident data (epivo_seq_run): geometry after the matcher.  Host buffers (epivo_seq_process): adaptive --
- *                when the previous call on this object was limited by the host->device copy (the last matcher piece
- *                had to wait for its frames), the geometry of the pairs already matched runs in the gaps between the
- *                matcher pieces, in four groups on its own stream; otherwise after the matcher.
- *   1            resident data: groups of pairs pipelined over two streams, the integer-bound matcher of group g+1 under
- *                the FP64-bound geometry of group g (measured on B200: not faster, the two contend for issue slots).
- *   2 / 3        host buffers: always / never interleave (what the adaptive rule chooses between). */
+ *   0 (default)  geometry after the matcher, on the context stream.
+ *   1            resident data (epivo_seq_run): groups of pairs pipelined over two streams, the integer-bound matcher of
+ *                group g+1 under the FP64-bound geometry of group g.
+ *   2            host buffers (epivo_seq_process): the geometry of the pairs already matched runs between the matcher
+ *                pieces, in four groups on its own stream.
+ * Both alternatives were measured slower than the default on B200 in every regime tried (the geometry kernels take
+ * issue slots and registers from the matcher, which holds every SM); they are kept as options, not chosen. */
 int epivo_seq_set_overlap(epivo_seq* seq, int overlap);
 /* per-stage device time of the last run (CUDA events on the context stream), ms:
  * [0] total [1] match [2] presolve (part of 3) [3] essential [4] pose [5] lm [6] finish [7] matcher tile kernel alone

@@ -102,9 +102,8 @@ def test_process_host_buffers_equals_upload_run_download(ctx):
 
 
 def test_process_geometry_interleaved_or_not_identical(ctx, monkeypatch):
-    """Host-buffer path: many small upload pieces, the geometry forced between the matcher pieces (mode 2, what the
-    adaptive rule picks when the copy is the limiter), forced after them (3), and adaptive (0) over repeated calls --
-    every run must give the bytes of upload + run + download."""
+    """Host-buffer path: many small upload pieces, the geometry between the matcher pieces (mode 2) or after them
+    (default) over repeated calls -- every run must give the bytes of upload + run + download."""
     monkeypatch.setenv("EPIVO_UPLOAD_DIV", "8")          # 74-pair pieces: 17 of them for 1200 pairs
     s = synth.make_sequence(n_frames=1201, n=256, seed=synth.seed_for(3, 5))
     prm = api.default_params(s.K.astype(np.float32))
@@ -114,14 +113,14 @@ def test_process_geometry_interleaved_or_not_identical(ctx, monkeypatch):
     ref = ref_pipe.download(0, s.n_pairs).tobytes()
     ref_pipe.close()
     pipe = api.SequencePipeline(s.n_frames, 256, ctx=ctx)
-    for mode in (2, 3, 0, 0, 2):
+    for mode in (2, 0, 0, 2):
         pipe.set_overlap(mode)
         assert pipe.process(prm, s.kps, s.descs).tobytes() == ref, mode
     assert pipe.stage_ms()[0] > 0
     # LMedS, ratio matcher and plain Hamming (no plane pre-pass on the copy stream) through the interleaved form
     for kw in (dict(method=api.LMEDS, threshold=0.01), dict(norm=api.NORM_HAMMING, match_mode=api.MATCH_RATIO)):
         p2 = api.default_params(s.K.astype(np.float32), **kw)
-        pipe.set_overlap(3)
+        pipe.set_overlap(0)
         a = pipe.process(p2, s.kps, s.descs).tobytes()
         pipe.set_overlap(2)
         assert pipe.process(p2, s.kps, s.descs).tobytes() == a, kw
