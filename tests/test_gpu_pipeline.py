@@ -105,6 +105,7 @@ def test_process_geometry_interleaved_or_not_identical(ctx, monkeypatch):
     """Host-buffer path: many small upload pieces, the geometry between the matcher pieces (mode 2) or after them
     (default) over repeated calls -- every run must give the bytes of upload + run + download."""
     monkeypatch.setenv("EPIVO_UPLOAD_DIV", "8")          # 74-pair pieces: 17 of them for 1200 pairs
+    monkeypatch.setenv("EPIVO_UPLOAD_CAP", "1")
     s = synth.make_sequence(n_frames=1201, n=256, seed=synth.seed_for(3, 5))
     prm = api.default_params(s.K.astype(np.float32))
     ref_pipe = api.SequencePipeline(s.n_frames, 256, ctx=ctx)
