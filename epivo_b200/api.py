@@ -277,6 +277,25 @@ def trackSequenceLK(images, points, maxLevel: int = 3, maxCount: int = 30, epsil
     return [nxt[i, :counts[i]].copy() for i in range(n - 1)], [st[i, :counts[i]].copy() for i in range(n - 1)]
 
 
+def remap(images, map1, map2, borderValue: int = 0, ctx: Context | None = None):
+    """cv2.remap(src, map1, map2, cv2.INTER_LINEAR) (BORDER_CONSTANT) with fixed-point maps -- map1 (h, w, 2) int16,
+    map2 (h, w) uint16, as cv2.initUndistortRectifyMap(..., m1type=cv2.CV_16SC2) / convertMaps make them
+    (euroc_E.cpp:105-113, 169-174) -- for one (rows, cols) image or a batch (n, rows, cols).  Bit-exact with OpenCV."""
+    ctx = ctx or default_context()
+    im = np.ascontiguousarray(images, dtype=np.uint8)
+    single = im.ndim == 2
+    if single:
+        im = im[None]
+    m1 = np.ascontiguousarray(map1, dtype=np.int16)
+    m2 = np.ascontiguousarray(map2, dtype=np.uint16)
+    if im.ndim != 3 or m1.ndim != 3 or m1.shape[2] != 2 or m2.shape != m1.shape[:2]:
+        raise ValueError("images (n, rows, cols) uint8, map1 (h, w, 2) int16, map2 (h, w) uint16")
+    n, rows, cols = im.shape
+    out = np.zeros((n,) + m2.shape, dtype=np.uint8)
+    ctx.check(ctx.lib.epivo_remap(ctx.h, _p(im), n, rows, cols, _p(m1), _p(m2), m2.shape[0], m2.shape[1], int(borderValue), _p(out)))
+    return out[0] if single else out
+
+
 def scoreSampson(Es, points1, points2, cameraMatrix, threshold: float, ctx: Context | None = None,
                  medians: bool = True):
     """K3 alone: (counts (m,), medians (m,) f32, best index, mask of best (n,) {0,1}).

@@ -423,6 +423,32 @@ int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows
     return EPIVO_OK;
 }
 
+int epivo_remap(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, const int16_t* map_xy,
+                const uint16_t* map_frac, int drows, int dcols, int border_value, uint8_t* out) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (n_images < 0 || rows < 0 || cols < 0 || drows < 0 || dcols < 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "negative size");
+    if (n_images == 0 || drows == 0 || dcols == 0) return EPIVO_OK;
+    if (!images || !map_xy || !map_frac || !out) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (rows == 0 || cols == 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "empty source image");
+    if (border_value < 0 || border_value > 255) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "border value outside [0, 255]");
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nsrc = (size_t)n_images * rows * cols, nmap = (size_t)drows * dcols, ndst = (size_t)n_images * nmap;
+    int rc = epv_ws_reserve(ctx, nsrc + nmap * 6 + ndst + 4096);
+    if (rc) return rc;
+    uint8_t* d_img = epv_ws_take<uint8_t>(ctx, nsrc);
+    int16_t* d_xy = epv_ws_take<int16_t>(ctx, nmap * 2);
+    uint16_t* d_fr = epv_ws_take<uint16_t>(ctx, nmap);
+    uint8_t* d_out = epv_ws_take<uint8_t>(ctx, ndst);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_img, images, nsrc, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_xy, map_xy, nmap * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_fr, map_frac, nmap * 2, cudaMemcpyHostToDevice, ctx->stream));
+    rc = epv_remap_launch(ctx, d_img, n_images, rows, cols, d_xy, d_fr, drows, dcols, border_value, d_out);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaMemcpyAsync(out, d_out, ndst, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPIVO_OK;
+}
+
 int epivo_score_sampson(epivo_ctx* ctx, const double* E, int m, const float* p0, const float* p1, int n,
                         const double K[9], double threshold, int32_t* counts, float* medians, int* best,
                         uint8_t* best_mask) {

@@ -84,3 +84,43 @@ def euroc_gt_scales(body_poses: np.ndarray, T_DC: np.ndarray) -> np.ndarray:
     """`dT = ((pT T_DC)^-1 (T T_DC))^-1`, scale = |dT.t| (euroc_E.cpp:300-301): camera-frame step lengths."""
     cam = np.asarray(body_poses) @ np.asarray(T_DC, dtype=np.float64)
     return gt_scales(cam)
+
+
+# EuRoC cam0 calibration as euroc_E.cpp:88-104 hard-codes it (sensor.yaml intrinsics + the stereo rectification it uses)
+EUROC_CAM0_K = np.array([[458.654, 0.0, 367.215], [0.0, 457.296, 248.375], [0.0, 0.0, 1.0]])
+EUROC_CAM0_DIST = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05])
+EUROC_CAM0_RECT = np.array([[0.999966347530033, -0.001422739138722922, 0.008079580483432283],
+                            [0.001365741834644127, 0.9999741760894847, 0.007055629199258132],
+                            [-0.008089410156878961, -0.007044357138835809, 0.9999424675829176]])
+EUROC_CAM0_PROJ = np.array([[435.2046959714599, 0.0, 367.4517211914062, 0.0],
+                            [0.0, 435.2046959714599, 252.2008514404297, 0.0],
+                            [0.0, 0.0, 1.0, 0.0]])
+
+
+def undistort_rectify_maps(K, dist, R, P, size):
+    """The fixed-point maps `initUndistortRectifyMap(cam, dist, rect, proj, Size(w, h), map1.type(), map1, map2)` makes
+    once before the frame loop (euroc_E.cpp:105-113; m1type 0 selects CV_16SC2 + CV_16UC1): (map_xy (h, w, 2) int16,
+    map_frac (h, w) uint16), the input of `api.remap` / `epivo_remap`.  Radial-tangential model k1 k2 p1 p2 [k3]."""
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    d = np.zeros(5)
+    dv = np.ravel(np.asarray(dist, dtype=np.float64))
+    if len(dv) > 5:
+        raise ValueError("only k1 k2 p1 p2 [k3] are supported")
+    d[:len(dv)] = dv
+    k1, k2, p1, p2, k3 = d
+    R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
+    P = np.asarray(P, dtype=np.float64)
+    iR = np.linalg.inv(P[:3, :3] @ R)                       # destination pixel -> rectified ray
+    w, h = size
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    W = iR[2, 0] * u + iR[2, 1] * v + iR[2, 2]
+    x = (iR[0, 0] * u + iR[0, 1] * v + iR[0, 2]) / W
+    y = (iR[1, 0] * u + iR[1, 1] * v + iR[1, 2]) / W
+    x2, y2, xy2 = x * x, y * y, 2 * x * y
+    r2 = x2 + y2
+    kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
+    mu = K[0, 0] * (x * kr + p1 * xy2 + p2 * (r2 + 2 * x2)) + K[0, 2]          # distorted source position
+    mv = K[1, 1] * (y * kr + p1 * (r2 + 2 * y2) + p2 * xy2) + K[1, 2]
+    iu, iv = np.rint(mu * 32).astype(np.int64), np.rint(mv * 32).astype(np.int64)   # 1/32-pixel fixed point
+    xy = np.stack([np.clip(iu >> 5, -32768, 32767), np.clip(iv >> 5, -32768, 32767)], axis=2).astype(np.int16)
+    return xy, ((iv & 31) * 32 + (iu & 31)).astype(np.uint16)

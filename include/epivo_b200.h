@@ -113,6 +113,14 @@ int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows
                    const int32_t* counts, int max_pts, int max_level, int max_count, double epsilon,
                    double min_eig_threshold, float* next_pts, uint8_t* status);
 
+/* N4 front end, undistortion: cv::remap(src, dst, map1, map2, INTER_LINEAR) (BORDER_CONSTANT) for a batch of n_images
+ * 8-bit images of rows x cols with the FIXED-POINT maps of initUndistortRectifyMap / convertMaps -- map_xy: drows x
+ * dcols x 2 int16 (CV_16SC2: integer source x, y), map_frac: drows x dcols uint16 (CV_16UC1: (fy << 5) | fx, fractions
+ * in 1/32 pixel) -- as the EuRoC driver builds them once (euroc_E.cpp:105-113) and applies them to every frame
+ * (:169-174).  out: n_images x drows x dcols.  Bit-exact with OpenCV. */
+int epivo_remap(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, const int16_t* map_xy,
+                const uint16_t* map_frac, int drows, int dcols, int border_value, uint8_t* out);
+
 /* K3 alone: Sampson scoring of a fixed hypothesis set of m models (m x 9) against n
  * correspondences with OpenCV's exact inlier rule.  threshold in pixels (RANSAC rule);
  * counts: m inlier counts; medians: m LMedS medians (float32, may be NULL); best: index of

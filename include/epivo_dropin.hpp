@@ -15,6 +15,7 @@
 //   Ptr<FastFeatureDetector> detector = FastFeatureDetector::create(40);                kitti_E.cpp:70
 //   detector->detect(src, kp0, Mat());                                                  kitti_E.cpp:73
 //   calcOpticalFlowPyrLK(src, tgt, pt0, pt1_, status, err);                             kitti_E.cpp:79-84
+//   remap(src, src_, map1, map2, INTER_LINEAR);                                         euroc_E.cpp:170
 //
 // How the unqualified calls reach these functions.  The drivers say `using namespace cv;` and call
 // `findEssentialMat(...)` unqualified.  The templates below live in the GLOBAL namespace and take the
@@ -185,4 +186,22 @@ void calcOpticalFlowPyrLK(const MatT& prevImg, const MatT& nextImg, const std::v
     ctx.check(epivo_lk_track(ctx.get(), frames.data(), 2, rows, cols, p.data(), &count, n, 3, 30, 0.01, 1e-4, q.data(),
                              status.data()));
     for (int i = 0; i < n; ++i) { nextPts[(size_t)i].x = q[2 * (size_t)i]; nextPts[(size_t)i].y = q[2 * (size_t)i + 1]; }
+}
+
+// void remap(src, dst, map1, map2, INTER_LINEAR)                                               euroc_E.cpp:170,174
+// with the fixed-point maps initUndistortRectifyMap(..., map1.type() == 0 -> CV_16SC2, ...) produced at :105-113 (map1:
+// rows x cols x 2 int16, map2: rows x cols uint16); BORDER_CONSTANT 0, as the call's defaults.  dst is created (8-bit,
+// the size of the maps).  Only interpolation == INTER_LINEAR (1) is provided.
+template <typename MatT>
+void remap(const MatT& src, MatT& dst, const MatT& map1, const MatT& map2, int interpolation) {
+    typedef epivo::mat_traits<MatT> MT;
+    if (interpolation != 1) throw std::invalid_argument("remap: only INTER_LINEAR is provided");
+    const int drows = MT::rows(map1), dcols = MT::cols(map1);
+    if (MT::rows(map2) != drows || MT::cols(map2) != dcols) throw std::invalid_argument("remap: map sizes differ");
+    dst = MT::create_u8(drows, dcols);
+    if (drows == 0 || dcols == 0) return;
+    epivo::Context& ctx = epivo::default_context();
+    ctx.check(epivo_remap(ctx.get(), MT::bytes(src), 1, MT::rows(src), MT::cols(src),
+                          reinterpret_cast<const int16_t*>(MT::bytes(map1)), reinterpret_cast<const uint16_t*>(MT::bytes(map2)),
+                          drows, dcols, 0, MT::bytes_mut(dst)));
 }

@@ -92,6 +92,8 @@ struct mat_traits<cv::Mat, void> {
     static cv::Mat create(int r, int c) { return cv::Mat(r, c, CV_64F); }
     static void set(cv::Mat& m, int i, int j, double v) { m.at<double>(i, j) = v; }
     static const unsigned char* bytes(const cv::Mat& m) { return m.data; }
+    static cv::Mat create_u8(int r, int c) { return cv::Mat(r, c, CV_8U); }      // the output image of remap
+    static unsigned char* bytes_mut(cv::Mat& m) { return m.data; }
 };
 #endif
 

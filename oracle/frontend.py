@@ -246,3 +246,63 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
             live[li[conv | osc]] = False
             prevDelta[li] = delta
     return nextp, status
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# cv::remap with the fixed-point maps of initUndistortRectifyMap (OpenCV imgproc: imgwarp.cpp remapBilinear,
+# undistort.dispatch.cpp), as the EuRoC driver uses them:
+#     initUndistortRectifyMap(cam, dist, rect, proj, Size(w, h), map1.type(), map1, map2);     euroc_E.cpp:105-113
+#     remap(src, src_, map1, map2, INTER_LINEAR);                                              euroc_E.cpp:169-174
+# (`map1.type()` of the still-empty Mat is 0, which selects CV_16SC2 + CV_16UC1).
+
+def remap_bilinear_fixed(img: np.ndarray, map_xy: np.ndarray, map_frac: np.ndarray, border: int = 0) -> np.ndarray:
+    """cv2.remap(img, map_xy, map_frac, INTER_LINEAR), BORDER_CONSTANT: integer position + 5 + 5 fraction bits,
+    weights {(32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx fy} * 32, (sum + 2^14) >> 15; source pixels outside the image
+    are the border value."""
+    img = np.asarray(img, dtype=np.uint8)
+    rows, cols = img.shape
+    sx = map_xy[:, :, 0].astype(np.int64)
+    sy = map_xy[:, :, 1].astype(np.int64)
+    f = map_frac.astype(np.int64) & 1023
+    fx, fy = f & 31, f >> 5
+    pad = np.full((rows + 2, cols + 2), border, dtype=np.int64)          # one border ring: everything further out is constant too
+    pad[1:-1, 1:-1] = img
+
+    def px(y, x):
+        return pad[np.clip(y + 1, 0, rows + 1), np.clip(x + 1, 0, cols + 1)]
+    v = (px(sy, sx) * (32 - fx) * (32 - fy) + px(sy, sx + 1) * fx * (32 - fy) + px(sy + 1, sx) * (32 - fx) * fy +
+         px(sy + 1, sx + 1) * fx * fy) * 32
+    return np.clip((v + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def init_undistort_rectify_map(K, dist, R, P, size):
+    """initUndistortRectifyMap(K, dist, R, P, (w, h), CV_16SC2): (map_xy (h, w, 2) int16, map_frac (h, w) uint16) for the
+    radial-tangential model k1 k2 p1 p2 [k3] (what the EuRoC calibration has).  Evaluated directly in float64; OpenCV
+    walks every row incrementally (x += ir[0] ...), so a position that falls on a 1/32-pixel rounding boundary can come
+    out one step apart (tests/test_oracle_remap.py: at most a handful of pixels per 752 x 480 map)."""
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    d = np.zeros(5)
+    d[:len(np.ravel(dist))] = np.ravel(dist)[:5]
+    k1, k2, p1, p2, k3 = d
+    R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
+    P = np.asarray(P, dtype=np.float64)
+    iR = np.linalg.inv(P[:3, :3] @ R)
+    w, h = size
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    X = iR[0, 0] * u + iR[0, 1] * v + iR[0, 2]
+    Y = iR[1, 0] * u + iR[1, 1] * v + iR[1, 2]
+    W = iR[2, 0] * u + iR[2, 1] * v + iR[2, 2]
+    x, y = X / W, Y / W
+    x2, y2 = x * x, y * y
+    r2 = x2 + y2
+    _2xy = 2 * x * y
+    kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2)
+    yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy
+    mu = K[0, 0] * xd + K[0, 2]
+    mv = K[1, 1] * yd + K[1, 2]
+    iu = np.rint(mu * 32).astype(np.int64)                  # saturate_cast<int>(u * INTER_TAB_SIZE)
+    iv = np.rint(mv * 32).astype(np.int64)
+    xy = np.stack([np.clip(iu >> 5, -32768, 32767), np.clip(iv >> 5, -32768, 32767)], axis=2).astype(np.int16)
+    frac = ((iv & 31) * 32 + (iu & 31)).astype(np.uint16)
+    return xy, frac

@@ -24,6 +24,9 @@
 #define CV_8U 0
 #define CV_32F 5
 #define CV_64F 6
+#define CV_16SC2 11       /* CV_MAKETYPE(CV_16S, 2) */
+#define CV_16UC1 2
+#define INTER_LINEAR 1
 typedef unsigned char uchar;
 namespace cv {
 enum { LMEDS = 4, RANSAC = 8, NORM_HAMMING = 6, NORM_HAMMING2 = 7 };
@@ -47,7 +50,7 @@ class Mat {
     template <typename T> T& at(int i, int j) { return reinterpret_cast<T*>(data)[(size_t)i * cols + j]; }
     template <typename T> const T& at(int i, int j) const { return reinterpret_cast<const T*>(data)[(size_t)i * cols + j]; }
   private:
-    static size_t esz(int t) { return t == CV_64F ? 8 : t == CV_32F ? 4 : 1; }
+    static size_t esz(int t) { return t == CV_64F ? 8 : t == CV_32F || t == CV_16SC2 ? 4 : t == CV_16UC1 ? 2 : 1; }
     int type_;
     std::vector<uchar> buf_;
 };
@@ -257,6 +260,22 @@ int main() {
                 ++tracked;
                 close += fabs(pt1_[j].x - pt0[j].x - 2.0) < 0.3 && fabs(pt1_[j].y - pt0[j].y + 1.0) < 0.3;
             }
+        }
+        // euroc_E.cpp:169-174: undistortion remap with fixed-point maps (here: a half-pixel shift to the right and down)
+        Mat map1(rows, cols, CV_16SC2), map2(rows, cols, CV_16UC1), src_;
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                reinterpret_cast<short*>(map1.data)[2 * ((size_t)y * cols + x)] = (short)x;
+                reinterpret_cast<short*>(map1.data)[2 * ((size_t)y * cols + x) + 1] = (short)y;
+                reinterpret_cast<unsigned short*>(map2.data)[(size_t)y * cols + x] = (unsigned short)(16 * 32 + 16);
+            }
+        // [verbatim] euroc_E.cpp:170
+        remap(src, src_, map1, map2, INTER_LINEAR);
+        if (src_.rows != rows || src_.cols != cols) return 13;
+        {
+            const int y = 50, x = 70;            // mean of the 2 x 2 neighbourhood, rounded half up
+            const int want = (src.at<uchar>(y, x) + src.at<uchar>(y, x + 1) + src.at<uchar>(y + 1, x) + src.at<uchar>(y + 1, x + 1) + 2) >> 2;
+            if (src_.at<uchar>(y, x) != want || src_.at<uchar>(rows - 1, cols - 1) != ((src.at<uchar>(rows - 1, cols - 1) + 2) >> 2)) return 14;
         }
         printf("FAST(40): %zu corners, LK tracked %d, %d within 0.3 px of the true shift\n", kp0.size(), tracked, close);
         if (kp0.size() < 20 || pt1_.size() != pt0.size() || tracked < (int)kp0.size() * 8 / 10 || close < tracked * 8 / 10) return 11;
