@@ -243,16 +243,16 @@ def fastDetect(images, threshold: int = 10, nonmaxSuppression: bool = True, max_
 
 
 def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, maxLevel: int = 3, maxCount: int = 30, epsilon: float = 0.01,
-                         minEigThreshold: float = 1e-4, ctx: Context | None = None):
+                         minEigThreshold: float = 1e-4, ctx: Context | None = None, returnErr: bool = False):
     """cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, None) with the 21 x 21 window (kitti_E.cpp:79-84):
-    (nextPts (n, 2) float32, status (n,) uint8)."""
+    (nextPts (n, 2) float32, status (n,) uint8 [, err (n,) float32 with returnErr])."""
     seq = np.stack([np.ascontiguousarray(prevImg, dtype=np.uint8), np.ascontiguousarray(nextImg, dtype=np.uint8)])
-    nxt, st = trackSequenceLK(seq, [prevPts], maxLevel, maxCount, epsilon, minEigThreshold, ctx=ctx)
-    return nxt[0], st[0]
+    out = trackSequenceLK(seq, [prevPts], maxLevel, maxCount, epsilon, minEigThreshold, ctx=ctx, returnErr=returnErr)
+    return tuple(o[0] for o in out)
 
 
 def trackSequenceLK(images, points, maxLevel: int = 3, maxCount: int = 30, epsilon: float = 0.01,
-                    minEigThreshold: float = 1e-4, ctx: Context | None = None):
+                    minEigThreshold: float = 1e-4, ctx: Context | None = None, returnErr: bool = False):
     """The LK step of the kitti_E loop for a whole sequence in one call: images (n, rows, cols) uint8, points = one
     (k_i, 2) float32 array per pair i (the detector's output on frame i); returns (list of nextPts, list of status),
     pair i tracked from frame i into frame i + 1.  The pyramid of every frame is built once."""
@@ -272,9 +272,13 @@ def trackSequenceLK(images, points, maxLevel: int = 3, maxCount: int = 30, epsil
         counts[i] = len(p)
     nxt = np.zeros_like(pts)
     st = np.zeros((n - 1, cap), dtype=np.uint8)
+    err = np.zeros((n - 1, cap), dtype=np.float32)          # always passed, as cv2 and the reference do (see the header)
     ctx.check(ctx.lib.epivo_lk_track(ctx.h, _p(im), n, rows, cols, _p(pts), _p(counts), cap, int(maxLevel), int(maxCount),
-                                     float(epsilon), float(minEigThreshold), _p(nxt), _p(st)))
-    return [nxt[i, :counts[i]].copy() for i in range(n - 1)], [st[i, :counts[i]].copy() for i in range(n - 1)]
+                                     float(epsilon), float(minEigThreshold), _p(nxt), _p(st), _p(err)))
+    out = ([nxt[i, :counts[i]].copy() for i in range(n - 1)], [st[i, :counts[i]].copy() for i in range(n - 1)])
+    if returnErr:
+        out += ([err[i, :counts[i]].copy() for i in range(n - 1)],)
+    return out
 
 
 def remap(images, map1, map2, borderValue: int = 0, ctx: Context | None = None):

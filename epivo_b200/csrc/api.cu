@@ -386,7 +386,7 @@ int epivo_fast_detect(epivo_ctx* ctx, const uint8_t* images, int n_images, int r
 
 int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows, int cols, const float* pts,
                    const int32_t* counts, int max_pts, int max_level, int max_count, double epsilon,
-                   double min_eig_threshold, float* next_pts, uint8_t* status) {
+                   double min_eig_threshold, float* next_pts, uint8_t* status, float* err) {
     if (!ctx) return EPIVO_ERR_INVALID;
     if (n_frames < 0 || rows < 0 || cols < 0 || max_pts < 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "negative size");
     if (n_frames < 2 || max_pts == 0) return EPIVO_OK;
@@ -401,7 +401,7 @@ int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows
     EPV_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t npx = (size_t)n_frames * rows * cols, np = (size_t)n_pairs * max_pts;
     const size_t wb = epv_lk_work_bytes(n_frames, rows, cols, max_level);
-    int rc = epv_ws_reserve(ctx, npx + wb + np * 17 + (size_t)n_pairs * 4 + 8192);
+    int rc = epv_ws_reserve(ctx, npx + wb + np * 21 + (size_t)n_pairs * 4 + 8192);
     if (rc) return rc;
     uint8_t* d_img = epv_ws_take<uint8_t>(ctx, npx);
     uint8_t* d_work = epv_ws_take<uint8_t>(ctx, wb);
@@ -409,16 +409,19 @@ int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows
     float* d_next = epv_ws_take<float>(ctx, np * 2);
     int32_t* d_counts = epv_ws_take<int32_t>(ctx, n_pairs);
     uint8_t* d_status = epv_ws_take<uint8_t>(ctx, np);
+    float* d_err = err ? epv_ws_take<float>(ctx, np) : nullptr;
+    if (d_err) EPV_CUDA(ctx, cudaMemsetAsync(d_err, 0, np * 4, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(d_img, images, npx, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(d_pts, pts, np * 8, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(d_counts, counts, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
     EPV_CUDA(ctx, cudaMemsetAsync(d_next, 0, np * 8, ctx->stream));
     EPV_CUDA(ctx, cudaMemsetAsync(d_status, 0, np, ctx->stream));
     rc = epv_lk_launch(ctx, d_img, n_frames, rows, cols, d_pts, d_counts, max_pts, max_level, max_count, epsilon,
-                       min_eig_threshold, d_next, d_status, d_work);
+                       min_eig_threshold, d_next, d_status, d_err, d_work);
     if (rc) return rc;
     EPV_CUDA(ctx, cudaMemcpyAsync(next_pts, d_next, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
     EPV_CUDA(ctx, cudaMemcpyAsync(status, d_status, np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (err) EPV_CUDA(ctx, cudaMemcpyAsync(err, d_err, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
     EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EPIVO_OK;
 }

@@ -276,7 +276,8 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 __global__ void __launch_bounds__(128) lk_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ dpyr, LkGeom g,
                                                  const float* __restrict__ pts, const int32_t* __restrict__ counts,
                                                  int max_pts, int max_count, double eps2, float min_eig,
-                                                 float* __restrict__ next_pts, uint8_t* __restrict__ status) {
+                                                 float* __restrict__ next_pts, uint8_t* __restrict__ status,
+                                                 float* __restrict__ err) {
     const int pair = blockIdx.y, lane = threadIdx.x & 31;
     const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (p >= counts[pair]) return;
@@ -389,6 +390,33 @@ __global__ void __launch_bounds__(128) lk_kernel(const uint8_t* __restrict__ pyr
             pdx = dx;
             pdy = dy;
         }
+        if (level == 0 && ok && err != nullptr) {
+            // lkpyramid.cpp, after the iterations, when the caller passes `err` (every reference call site does): the
+            // mean absolute window difference at the FINAL position -- which the loop did not range-check after its
+            // last update: outside [-win, size) the status is cleared
+            const float ex = __fsub_rn(nx, half), ey = __fsub_rn(ny, half);
+            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            if (iex < -LK_WIN || iex >= cols || iey < -LK_WIN || iey >= rows) {
+                ok = false;
+            } else {
+                lk_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
+                int sad = 0;
+#pragma unroll
+                for (int k = 0; k < LK_PPL; ++k) {
+                    const int idx = lane + 32 * k;
+                    if (idx < LK_AREA) {
+                        const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
+                        const int ry0 = reflect101(iey + wy, rows), ry1 = reflect101(iey + wy + 1, rows);
+                        const int rx0 = reflect101(iex + wx, cols), rx1 = reflect101(iex + wx + 1, cols);
+                        const int jv = J[(size_t)ry0 * cols + rx0] * w00 + J[(size_t)ry0 * cols + rx1] * w01 +
+                                       J[(size_t)ry1 * cols + rx0] * w10 + J[(size_t)ry1 * cols + rx1] * w11;
+                        sad += abs(((jv + (1 << 8)) >> 9) - Iw[k]);
+                    }
+                }
+                sad = __reduce_add_sync(0xFFFFFFFFu, sad);          // < 2^24: the float sum OpenCV forms is exact, in any order
+                if (lane == 0) err[(size_t)pair * max_pts + p] = __fdiv_rn((float)sad, (float)(32 * LK_AREA));
+            }
+        }
     }
     if (lane == 0) {
         next_pts[((size_t)pair * max_pts + p) * 2] = nx;
@@ -429,7 +457,7 @@ size_t epv_lk_work_bytes(int n_frames, int rows, int cols, int max_level) {
 // d_images: [n_frames][rows][cols]; pair i tracks d_pts[i][0..counts[i]) from frame i into frame i + 1
 int epv_lk_launch(epivo_ctx* ctx, const uint8_t* d_images, int n_frames, int rows, int cols, const float* d_pts,
                   const int32_t* d_counts, int max_pts, int max_level, int max_count, double epsilon, double min_eig,
-                  float* d_next, uint8_t* d_status, void* work) {
+                  float* d_next, uint8_t* d_status, float* d_err, void* work) {
     if (n_frames < 2 || max_pts <= 0) return EPIVO_OK;
     if (rows <= LK_WIN || cols <= LK_WIN)
         EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "image %d x %d not larger than the %d x %d window", cols, rows, LK_WIN, LK_WIN);
@@ -451,7 +479,7 @@ int epv_lk_launch(epivo_ctx* ctx, const uint8_t* d_images, int n_frames, int row
         EPV_LAUNCHED(ctx);
     }
     lk_kernel<<<dim3((max_pts + 3) / 4, n_frames - 1), 128, 0, ctx->stream>>>(pyr, dpyr, g, d_pts, d_counts, max_pts, max_count,
-                                                                            epsilon * epsilon, (float)min_eig, d_next, d_status);
+                                                                            epsilon * epsilon, (float)min_eig, d_next, d_status, d_err);
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
 }

@@ -81,6 +81,6 @@ int epv_fast_launch(epivo_ctx* ctx, const uint8_t* d_img, int n_images, int rows
 size_t epv_lk_work_bytes(int n_frames, int rows, int cols, int max_level);
 int epv_lk_launch(epivo_ctx* ctx, const uint8_t* d_images, int n_frames, int rows, int cols, const float* d_pts,
                   const int32_t* d_counts, int max_pts, int max_level, int max_count, double epsilon, double min_eig,
-                  float* d_next, uint8_t* d_status, void* work);
+                  float* d_next, uint8_t* d_status, float* d_err /* nullable */, void* work);
 int epv_remap_launch(epivo_ctx* ctx, const uint8_t* d_img, int n_images, int rows, int cols, const int16_t* d_map_xy,
                      const uint16_t* d_map_frac, int drows, int dcols, int border, uint8_t* d_out);

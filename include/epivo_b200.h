@@ -106,12 +106,15 @@ int epivo_fast_detect(epivo_ctx* ctx, const uint8_t* images, int n_images, int r
  * pts[i][0..counts[i]) (n_frames-1 x max_pts x 2 floats, x y) from frame i into frame i + 1 -- replaces
  * calcOpticalFlowPyrLK(src, tgt, pt0, pt1_, status, err) at kitti_E.cpp:79-84 and kitti_ba.cpp:203-208,281-286.
  * The reference's defaults are max_level 3, max_count 30, epsilon 0.01, min_eig_threshold 1e-4 (flags 0, no initial
- * flow).  next_pts: n_frames-1 x max_pts x 2; status: n_frames-1 x max_pts bytes {0,1}; entries beyond counts[i] are
- * not written.  Pyramid, derivatives and the fixed-point windows are exact; positions agree with OpenCV to 1e-3 px
- * except where a stopping test of the iteration falls on the other side. */
+ * flow).  next_pts: n_frames-1 x max_pts x 2; status: n_frames-1 x max_pts bytes {0,1}; err: n_frames-1 x max_pts floats
+ * (OpenCV's `err`: mean absolute window difference at the final position, 0 where the track is lost) or NULL -- as in
+ * OpenCV, passing `err` also clears the status of a point whose final position left the image; every reference call
+ * site passes it.  Entries beyond counts[i] are not written.  Pyramid, derivatives and the fixed-point windows are
+ * exact; positions agree with OpenCV to 1e-3 px except where a stopping test of the iteration falls on the other side
+ * (see DESIGN.md). */
 int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows, int cols, const float* pts,
                    const int32_t* counts, int max_pts, int max_level, int max_count, double epsilon,
-                   double min_eig_threshold, float* next_pts, uint8_t* status);
+                   double min_eig_threshold, float* next_pts, uint8_t* status, float* err);
 
 /* N4 front end, undistortion: cv::remap(src, dst, map1, map2, INTER_LINEAR) (BORDER_CONSTANT) for a batch of n_images
  * 8-bit images of rows x cols with the FIXED-POINT maps of initUndistortRectifyMap / convertMaps -- map_xy: drows x

@@ -165,7 +165,7 @@ class FastFeatureDetector {
 
 // void calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status, err)                   kitti_E.cpp:79-84
 // with OpenCV's defaults (21 x 21 window, 3 pyramid levels above the image, 30 iterations / 0.01).  status in {0,1}.
-// err is sized and zeroed, not computed: no reference driver reads it.
+// err: OpenCV's window error (mean absolute difference at the final position), 0 for lost tracks.
 template <typename MatT, typename Pt>
 void calcOpticalFlowPyrLK(const MatT& prevImg, const MatT& nextImg, const std::vector<Pt>& prevPts, std::vector<Pt>& nextPts,
                           std::vector<unsigned char>& status, std::vector<float>& err) {
@@ -184,7 +184,7 @@ void calcOpticalFlowPyrLK(const MatT& prevImg, const MatT& nextImg, const std::v
     std::vector<float> p = epivo::detail::flatten(prevPts), q(2 * (size_t)n);
     const int32_t count = n;
     ctx.check(epivo_lk_track(ctx.get(), frames.data(), 2, rows, cols, p.data(), &count, n, 3, 30, 0.01, 1e-4, q.data(),
-                             status.data()));
+                             status.data(), err.data()));
     for (int i = 0; i < n; ++i) { nextPts[(size_t)i].x = q[2 * (size_t)i]; nextPts[(size_t)i].y = q[2 * (size_t)i + 1]; }
 }
 

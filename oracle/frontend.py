@@ -164,15 +164,19 @@ def _patch(img, ix, iy, wts, win, shift, zero_outside):
 
 def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray, win: int = 21, max_level: int = 3,
                              max_count: int = 30, epsilon: float = 0.01, min_eig_threshold: float = 1e-4,
-                             exact_sums: bool = True):
-    """(next_pts (P, 2) float32, status (P,) uint8) of cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None) with the
-    reference's defaults.  Follows LKTrackerInvoker::operator() level by level; all point arithmetic in float32."""
+                             with_err: bool = True, return_err: bool = False):
+    """(next_pts (P, 2) float32, status (P,) uint8 [, err (P,) float32]) of cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None)
+    with the reference's defaults.  Follows LKTrackerInvoker::operator() level by level; all point arithmetic in
+    float32.  with_err: the caller passes an `err` output (every reference call site and cv2 do): OpenCV then measures
+    the window difference at the final position and clears the status if that position is out of range (the iteration
+    loop itself does not re-check the position its last update produced)."""
     f = np.float32
     pts = np.asarray(pts, dtype=np.float32).reshape(-1, 2)
     P = len(pts)
     pp, pn = build_pyramid(prev, win, max_level), build_pyramid(nxt, win, max_level)
     L = min(len(pp), len(pn)) - 1
     status = np.ones(P, dtype=np.uint8)
+    errv = np.zeros(P, dtype=np.float32)
     nextp = np.zeros((P, 2), dtype=np.float32)
     half = f((win - 1) * 0.5)
     eps2 = f(epsilon) * f(epsilon)          # criteria.epsilon *= criteria.epsilon (a double in OpenCV; compared with a double dot)
@@ -245,6 +249,22 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
                 nextp[idx[li[osc]]] = nextp[idx[li[osc]]] - delta[osc] * f(0.5)
             live[li[conv | osc]] = False
             prevDelta[li] = delta
+        if level == 0 and with_err:
+            # err: mean absolute window difference at the final nextPt - halfWin (same floor / fixed-point weights as an
+            # iteration); a final position outside [-win, size) clears the status
+            ok = np.nonzero(status[idx] == 1)[0]
+            np_ = nextp[idx[ok]] - half
+            ir = np.floor(np_).astype(np.int64)
+            out = (ir[:, 0] < -win) | (ir[:, 0] >= cols) | (ir[:, 1] < -win) | (ir[:, 1] >= rows)
+            status[idx[ok[out]]] = 0
+            ok, np_, ir = ok[~out], np_[~out], ir[~out]
+            if len(ok):
+                aa = np_[:, 0] - ir[:, 0].astype(f)
+                bb = np_[:, 1] - ir[:, 1].astype(f)
+                Jw = _patch(J, ir[:, 0], ir[:, 1], _weights(aa, bb), win, 14 - 5, False)
+                errv[idx[ok]] = np.abs(Jw - Iw[ok]).sum(axis=(1, 2)).astype(f) * f(1.0 / (32 * win * win))
+    if return_err:
+        return nextp, status, errv
     return nextp, status
 
 

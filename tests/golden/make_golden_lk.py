@@ -33,9 +33,10 @@ def main():
         rng = np.random.default_rng(len(pts))
         extra = np.stack([rng.uniform(0, a.shape[1] - 1, 40), rng.uniform(0, a.shape[0] - 1, 40)], axis=1).astype(np.float32)
         pts = np.concatenate([pts, extra])                    # sub-pixel points anywhere, borders included
-        nxt, st, _ = cv2.calcOpticalFlowPyrLK(a, b, pts, None)
+        nxt, st, err = cv2.calcOpticalFlowPyrLK(a, b, pts, None)
         res["prev_" + name], res["next_" + name], res["pts_" + name] = a, b, pts
         res["out_" + name], res["status_" + name] = nxt.reshape(-1, 2), st.ravel()
+        res["err_" + name] = np.where(st.ravel() == 1, err.ravel(), 0).astype(np.float32)     # cv2 leaves err of lost tracks undefined
         print(name, a.shape, len(pts), "tracked", int(st.sum()))
     res["cv2_version"] = np.array(cv2.__version__)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lk.npz"), **res)

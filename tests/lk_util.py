@@ -9,6 +9,15 @@ within 0.25 px."""
 import numpy as np
 
 
+def check_err(err, st, ref_err, ref_st, what=""):
+    """OpenCV's `err` (mean absolute window difference at the final position, a sum of integers scaled once): where both
+    track a point it follows the position, so it agrees to the same 1e-3 relative to the 0..255 grey range."""
+    both = (np.asarray(st).ravel() == 1) & (np.asarray(ref_st).ravel() == 1)
+    if both.any():
+        d = np.abs(np.asarray(err).ravel()[both] - np.asarray(ref_err).ravel()[both])
+        assert (d <= 1e-3).mean() >= 0.99 and d.max() <= 0.5, (what, float(d.max()))
+
+
 def check_lk(nxt, st, ref_nxt, ref_st, what=""):
     nxt, ref_nxt = np.asarray(nxt).reshape(-1, 2), np.asarray(ref_nxt).reshape(-1, 2)
     st, ref_st = np.asarray(st).ravel(), np.asarray(ref_st).ravel()

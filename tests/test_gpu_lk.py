@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from epivo_b200 import api
-from lk_util import check_lk
+from lk_util import check_err, check_lk
 from oracle import frontend as OF
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "lk.npz"))
@@ -17,13 +17,17 @@ NAMES = sorted(k[5:] for k in GOLD.files if k.startswith("prev_"))
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
 def test_gpu_lk_matches_cv2_golden(ctx, name):
-    nxt, st = api.calcOpticalFlowPyrLK(GOLD["prev_" + name], GOLD["next_" + name], GOLD["pts_" + name], ctx=ctx)
+    nxt, st, err = api.calcOpticalFlowPyrLK(GOLD["prev_" + name], GOLD["next_" + name], GOLD["pts_" + name], ctx=ctx,
+                                            returnErr=True)
     check_lk(nxt, st, GOLD["out_" + name], GOLD["status_" + name], name)
+    check_err(err, st, GOLD["err_" + name], GOLD["status_" + name], name)
     # against the restatement (exact integer sums on both sides): the same points, to float rounding of the update
-    o_nxt, o_st = OF.calc_optical_flow_pyr_lk(GOLD["prev_" + name], GOLD["next_" + name], GOLD["pts_" + name])
+    o_nxt, o_st, o_err = OF.calc_optical_flow_pyr_lk(GOLD["prev_" + name], GOLD["next_" + name], GOLD["pts_" + name],
+                                                     return_err=True)
     assert np.array_equal(st, o_st)
     both = st == 1
     assert np.abs(nxt[both] - o_nxt[both]).max() <= 1e-4
+    assert np.abs(err[both] - o_err[both]).max() <= 1e-3 and (err[~both] == 0).all()
 
 
 @pytest.mark.gpu

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import frontend as OF
-from lk_util import check_lk
+from lk_util import check_err, check_lk
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "lk.npz"))
 NAMES = sorted(k[5:] for k in GOLD.files if k.startswith("prev_"))
@@ -14,8 +14,9 @@ NAMES = sorted(k[5:] for k in GOLD.files if k.startswith("prev_"))
 
 @pytest.mark.parametrize("name", NAMES)
 def test_oracle_lk_matches_cv2_golden(name):
-    nxt, st = OF.calc_optical_flow_pyr_lk(GOLD["prev_" + name], GOLD["next_" + name], GOLD["pts_" + name])
+    nxt, st, err = OF.calc_optical_flow_pyr_lk(GOLD["prev_" + name], GOLD["next_" + name], GOLD["pts_" + name], return_err=True)
     check_lk(nxt, st, GOLD["out_" + name], GOLD["status_" + name], name)
+    check_err(err, st, GOLD["err_" + name], GOLD["status_" + name], name)
 
 
 def test_oracle_pyramid_and_derivatives_exact():
