@@ -482,6 +482,29 @@ class SequencePipeline:
         self.ctx.check(self.ctx.lib.epivo_seq_process(self.h, C.byref(params), F, _p(kps), _p(descs), _p(out)))
         return out
 
+    def process_points(self, params: PipelineParams, points0, points1, out=None):
+        """The geometry for correspondences the caller already has (the LK tracks of kitti_E.cpp:86-95) instead of
+        descriptor matches: points0[i], points1[i] are the (k_i, 2) float32 pixel positions of pair i in its two frames.
+        findEssentialMat -> recoverPose -> fallbacks -> LM for every pair; returns the per-pair results."""
+        n = len(points0)
+        assert len(points1) == n and n <= self.n_pairs
+        pl0 = [np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 2) for p in points0]
+        pl1 = [np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 2) for p in points1]
+        cap = max(1, max((len(p) for p in pl0), default=1))
+        p0 = np.zeros((n, cap, 2), dtype=np.float32)
+        p1 = np.zeros((n, cap, 2), dtype=np.float32)
+        counts = np.zeros(n, dtype=np.int32)
+        for i in range(n):
+            assert len(pl0[i]) == len(pl1[i])
+            counts[i] = len(pl0[i])
+            p0[i, :counts[i]] = pl0[i]
+            p1[i, :counts[i]] = pl1[i]
+        if out is None:
+            out = np.zeros(n, dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and out.shape[0] >= n
+        self.ctx.check(self.ctx.lib.epivo_seq_process_points(self.h, C.byref(params), n, _p(p0), _p(p1), _p(counts), cap, _p(out)))
+        return out
+
     def download(self, first_pair: int, n_pairs: int, out=None):
         if out is None:
             out = np.zeros(n_pairs, dtype=RESULT_DTYPE)

@@ -140,6 +140,28 @@ __global__ void lm_prep_kernel(int n_pairs, int stride, epivo_pipeline_params pr
     }
 }
 
+// correspondences supplied by the caller (LK tracks, kitti_E.cpp:86-95) instead of descriptor matches: the same
+// pixel -> K-normalised float64 step the matcher's finalize kernel ends with, for a batch of pairs
+__global__ void __launch_bounds__(256) points_in_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                        const int32_t* __restrict__ counts, int max_pts, int stride,
+                                                        double ax, double bx, double ay, double by,
+                                                        double* __restrict__ xn, int32_t* __restrict__ nmatch,
+                                                        int32_t* __restrict__ mq, int32_t* __restrict__ mt) {
+    const int pair = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const int n = min(max(counts[pair], 0), max_pts);
+    if (i == 0) nmatch[pair] = n;
+    if (i >= n) return;
+    const float2 a = reinterpret_cast<const float2*>(p0)[(size_t)pair * max_pts + i];
+    const float2 b = reinterpret_cast<const float2*>(p1)[(size_t)pair * max_pts + i];
+    double* x = xn + (size_t)pair * 4 * stride;
+    x[i] = __fma_rn((double)a.x, ax, bx);
+    x[stride + i] = __fma_rn((double)a.y, ay, by);
+    x[2 * stride + i] = __fma_rn((double)b.x, ax, bx);
+    x[3 * stride + i] = __fma_rn((double)b.y, ay, by);
+    mq[(size_t)pair * stride + i] = i;           // epivo_seq_get_matches then reports the identity association
+    mt[(size_t)pair * stride + i] = i;
+}
+
 __global__ void finish_kernel(int n_pairs, epivo_pipeline_params prm, const double* __restrict__ E,
                               const double* __restrict__ R, const double* __restrict__ t,
                               const double* __restrict__ T0, double* __restrict__ T,
@@ -782,6 +804,52 @@ int epivo_seq_process(epivo_seq* s, const epivo_pipeline_params* prm, int n_fram
     const int n_pairs = s->pairs_set ? s->n_list : n_frames - 1;
     int rc = seq_execute(s, prm, 0, n_pairs, kps, descs, n_frames);
     if (rc) return rc;
+    return epivo_seq_download(s, out, 0, n_pairs);
+}
+
+int epivo_seq_process_points(epivo_seq* s, const epivo_pipeline_params* prm, int n_pairs, const float* p0, const float* p1,
+                             const int32_t* counts, int max_pts, epivo_pair_result* out) {
+    if (!s || !prm) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (n_pairs < 0 || n_pairs > s->n_list) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "n_pairs %d outside [0,%d]", n_pairs, s->n_list);
+    if (n_pairs == 0) return EPIVO_OK;
+    if (!p0 || !p1 || !counts || !out) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null buffer");
+    if (max_pts < 1 || max_pts > s->kp) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "max_pts %d outside [1,%d]", max_pts, s->kp);
+    if (prm->lm_points < 1 || prm->lm_points > 64) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "lm_points must be in [1,64]");
+    if (prm->method != EPIVO_RANSAC && prm->method != EPIVO_LMEDS) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "method");
+    for (int i = 0; i < n_pairs; ++i)
+        if (counts[i] < 0 || counts[i] > max_pts) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "counts[%d] = %d outside [0,%d]", i, counts[i], max_pts);
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    EpvRange r_seq(ctx, "epivo_seq_process_points");
+    const size_t np = (size_t)n_pairs * max_pts;
+    int rc = epv_ws_reserve(ctx, np * 16 + (size_t)n_pairs * 4 + 4096);
+    if (rc) return rc;
+    float* d_p0 = epv_ws_take<float>(ctx, np * 2);
+    float* d_p1 = epv_ws_take<float>(ctx, np * 2);
+    int32_t* d_cnt = epv_ws_take<int32_t>(ctx, n_pairs);
+    cudaStream_t st = ctx->stream;
+    EPV_CUDA(ctx, cudaEventRecord(s->ev_begin, st));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_p0, p0, np * 8, cudaMemcpyHostToDevice, st));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_p1, p1, np * 8, cudaMemcpyHostToDevice, st));
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_cnt, counts, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+    const double ax = 1.0 / prm->K[0], ay = 1.0 / prm->K[4];
+    points_in_kernel<<<dim3((max_pts + 255) / 256, n_pairs), 256, 0, st>>>(d_p0, d_p1, d_cnt, max_pts, s->stride, ax,
+                                                                            -prm->K[2] * ax, ay, -prm->K[5] * ay, s->d_xn,
+                                                                            s->d_nmatch, s->d_mq, s->d_mt);
+    EPV_LAUNCHED(ctx);
+    constexpr int HALF = SEQ_MAX_CHUNKS / 2;
+    const int n_g = (n_pairs + SEQ_CHUNK - 1) / SEQ_CHUNK;
+    if (n_g > HALF) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "too many pair groups");
+    s->last_mgroups = 0;
+    s->last_ggroups = n_g;
+    s->last_n_pairs = n_pairs;
+    s->last_first = 0;
+    for (int c = 0; c < n_g; ++c) {
+        const int g0 = c * SEQ_CHUNK, gn = std::min(SEQ_CHUNK, n_pairs - g0);
+        rc = seq_run_geometry(s, prm, HALF + c, g0, gn);
+        if (rc) return rc;
+    }
+    EPV_CUDA(ctx, cudaEventRecord(s->ev_end, st));
     return epivo_seq_download(s, out, 0, n_pairs);
 }
 

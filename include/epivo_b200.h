@@ -218,6 +218,13 @@ int epivo_seq_run(epivo_seq* seq, const epivo_pipeline_params* p, int first_pair
  * and synchronise.  The upload is pipelined under the matcher on a second (copy) stream. */
 int epivo_seq_process(epivo_seq* seq, const epivo_pipeline_params* p, int n_frames, const float* kps,
                       const uint8_t* descs, epivo_pair_result* out);
+/* The same geometry for correspondences the caller already has -- the LK tracks with status 1 of kitti_E.cpp:86-95,
+ * euroc_E.cpp:190-196 -- instead of descriptor matches: pair i has counts[i] point pairs p0[i][k] -> p1[i][k]
+ * (n_pairs x max_pts x 2 floats each, pixels; max_pts <= kp_per_frame of the sequence object).  Runs
+ * findEssentialMat -> recoverPose -> fallbacks -> LM for pairs [0, n_pairs) and returns the results (n_matches =
+ * counts[i]); epivo_seq_get_masks / epivo_seq_cloud work on them as after epivo_seq_process. */
+int epivo_seq_process_points(epivo_seq* seq, const epivo_pipeline_params* p, int n_pairs, const float* p0, const float* p1,
+                             const int32_t* counts, int max_pts, epivo_pair_result* out);
 /* device -> host copy of the results of the last run and stream sync */
 int epivo_seq_download(epivo_seq* seq, epivo_pair_result* out, int first_pair, int n_pairs);
 /* Scheduling of the geometry (findEssentialMat + recoverPose + LM) relative to the matcher; results do not depend on it.

@@ -11,10 +11,21 @@ def pair_pipeline(kp0, desc0, kp1, desc1, K, method=O.RANSAC, prob=0.99, thr=1.0
                   norm=O.NORM_HAMMING2, cross_check=True, dist_thresh=50.0, min_trace=2.7,
                   fallback_t=(0.1, 0.1, -0.9), min_t_norm=1e-5, lm_points=48, lambda0=1e-2, eps=1e-8,
                   lm_iters=30, huber_delta=1e-5, lm_revert=1e-9):
-    out = {}
     qi, ti, d = O.bf_match(desc0, desc1, norm, cross_check)                 # kitti_ba.cpp:641
+    out = points_pipeline(kp0[qi], kp1[ti], K, method, prob, thr, max_iters, dist_thresh, min_trace, fallback_t,   # kitti_ba.cpp:684-693
+                          min_t_norm, lm_points, lambda0, eps, lm_iters, huber_delta, lm_revert)
     out["matches"] = (qi, ti, d)
-    p0, p1 = kp0[qi], kp1[ti]                                               # kitti_ba.cpp:684-693
+    return out
+
+
+def points_pipeline(p0, p1, K, method=O.RANSAC, prob=0.99, thr=1.0, max_iters=1000, dist_thresh=50.0, min_trace=2.7,
+                    fallback_t=(0.1, 0.1, -0.9), min_t_norm=1e-5, lm_points=48, lambda0=1e-2, eps=1e-8,
+                    lm_iters=30, huber_delta=1e-5, lm_revert=1e-9):
+    """The loop body after the association, kitti_E.cpp:96-201, for correspondences p0 -> p1 (pixels): whatever made
+    them -- descriptor matches (kitti_ba.cpp:684-693) or LK tracks with status 1 (kitti_E.cpp:86-95)."""
+    out = {}
+    p0 = np.asarray(p0, dtype=np.float32).reshape(-1, 2)
+    p1 = np.asarray(p1, dtype=np.float32).reshape(-1, 2)
     Kf = np.asarray(K, dtype=np.float32)
     E, mask, info = O.find_essential_mat(p0, p1, Kf, method, prob, thr, max_iters)   # kitti_E.cpp:98
     out["E"], out["e_mask"], out["e_info"] = E, mask, info
