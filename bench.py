@@ -326,6 +326,11 @@ class PairsRunner:
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
         self.h_res = torch.zeros(self.P * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
         self.results = self.h_res.numpy().view(api.RESULT_DTYPE)
+        if world > 1:                                                # staging of the pose gather: allocated once
+            self.T_pin = torch.zeros((self.P, 4, 4), dtype=torch.float64).pin_memory()
+            self.T_pin_np = self.T_pin.numpy()
+            self.T_dev = torch.empty((self.P, 4, 4), dtype=torch.float64, device="cuda")
+            self.T_all = torch.empty((world * self.P, 4, 4), dtype=torch.float64, device="cuda")
         self.pipe.upload(self.kps_np, self.desc_np)
 
     def barrier(self):
@@ -375,9 +380,9 @@ class PairsRunner:
             pipe.process(prm, self.kps_np, self.desc_np, self.results)
             t_proc += time.perf_counter() - tp
             if world > 1 and gather:          # the only collective: per-pair poses -> every rank (NCCL)
-                T = torch.from_numpy(np.ascontiguousarray(self.results["T"])).cuda(non_blocking=True)
-                gathered = torch.empty((world * T.shape[0],) + tuple(T.shape[1:]), dtype=T.dtype, device="cuda")
-                self.dist.all_gather_into_tensor(gathered, T)
+                np.copyto(self.T_pin_np, self.results["T"])                  # results are pinned: strided field -> pinned 4x4s
+                self.T_dev.copy_(self.T_pin, non_blocking=True)
+                self.dist.all_gather_into_tensor(self.T_all, self.T_dev)
         e3.record(self.stream)
         self.barrier()
         wall = time.perf_counter() - t0
