@@ -258,10 +258,12 @@ __global__ void __launch_bounds__(256) scharr_kernel(const uint8_t* __restrict__
     dst[i] = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
 }
 
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
+// warp total of per-lane 32-bit partial sums (the total needs up to 37 bits): two REDUX on the halves instead of a
+// five-step 64-bit shuffle chain -- the reduction sits on the dependent path of every LK iteration
+__device__ __forceinline__ long long warp_sum_i32(int v) {
+    const int hi = __reduce_add_sync(0xFFFFFFFFu, v >> 16);              // |v >> 16| <= 2^15 per lane
+    const int lo = __reduce_add_sync(0xFFFFFFFFu, v & 0xFFFF);           // < 2^16 per lane
+    return ((long long)hi << 16) + lo;
 }
 
 __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
@@ -273,7 +275,10 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 }
 
 // one warp per point: all pyramid levels, all iterations
-__global__ void __launch_bounds__(128) lk_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ dpyr, LkGeom g,
+#ifndef EPV_LK_MINBLOCKS
+#define EPV_LK_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ dpyr, LkGeom g,
                                                  const float* __restrict__ pts, const int32_t* __restrict__ counts,
                                                  int max_pts, int max_count, double eps2, float min_eig,
                                                  float* __restrict__ next_pts, uint8_t* __restrict__ status,
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(128) lk_kernel(const uint8_t* __restrict__ pyr
         }
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
-        long long s11 = 0, s12 = 0, s22 = 0;
+        int s11 = 0, s12 = 0, s22 = 0;                      // per lane: 14 x 4080^2 < 2^31
 #pragma unroll
         for (int k = 0; k < LK_PPL; ++k) {
             const int idx = lane + 32 * k;
@@ -329,16 +334,14 @@ __global__ void __launch_bounds__(128) lk_kernel(const uint8_t* __restrict__ pyr
                 Iw[k] = (short)((iv + (1 << 8)) >> 9);                        // CV_DESCALE(., W_BITS1 - 5)
                 Ix[k] = (short)ixv;
                 Iy[k] = (short)iyv;
-                s11 += (long long)(ixv * ixv);
-                s12 += (long long)(ixv * iyv);
-                s22 += (long long)(iyv * iyv);
+                s11 += ixv * ixv;
+                s12 += ixv * iyv;
+                s22 += iyv * iyv;
             }
         }
-        s11 = warp_sum_ll(s11);
-        s12 = warp_sum_ll(s12);
-        s22 = warp_sum_ll(s22);
-        const float A11 = __fmul_rn(__ll2float_rn(s11), FLT_SCALE), A12 = __fmul_rn(__ll2float_rn(s12), FLT_SCALE),
-                    A22 = __fmul_rn(__ll2float_rn(s22), FLT_SCALE);
+        const float A11 = __fmul_rn(__ll2float_rn(warp_sum_i32(s11)), FLT_SCALE),
+                    A12 = __fmul_rn(__ll2float_rn(warp_sum_i32(s12)), FLT_SCALE),
+                    A22 = __fmul_rn(__ll2float_rn(warp_sum_i32(s22)), FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dA = __fsub_rn(A11, A22);
         const float root = __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)));
@@ -357,23 +360,40 @@ __global__ void __launch_bounds__(128) lk_kernel(const uint8_t* __restrict__ pyr
                 break;
             }
             lk_weights(__fsub_rn(tx, (float)inx), __fsub_rn(ty, (float)iny), w00, w01, w10, w11);
-            long long b1 = 0, b2 = 0;
+            // per lane |diff * I'| <= 8160 * 4080 over 14 pixels fits 32 bits; the warp total needs 64
+            int s1 = 0, s2 = 0;
+            if (inx >= 0 && iny >= 0 && inx + LK_WIN < cols && iny + LK_WIN < rows) {
+                // the whole 22 x 22 footprint lies inside the image (the common case, warp-uniform): no border arithmetic
+                const uint8_t* Jb = J + (size_t)iny * cols + inx;
 #pragma unroll
-            for (int k = 0; k < LK_PPL; ++k) {
-                const int idx = lane + 32 * k;
-                if (idx < LK_AREA) {
-                    const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
-                    const int ry0 = reflect101(iny + wy, rows), ry1 = reflect101(iny + wy + 1, rows);
-                    const int rx0 = reflect101(inx + wx, cols), rx1 = reflect101(inx + wx + 1, cols);
-                    const int jv = J[(size_t)ry0 * cols + rx0] * w00 + J[(size_t)ry0 * cols + rx1] * w01 +
-                                   J[(size_t)ry1 * cols + rx0] * w10 + J[(size_t)ry1 * cols + rx1] * w11;
-                    const int diff = ((jv + (1 << 8)) >> 9) - Iw[k];
-                    b1 += (long long)(diff * Ix[k]);
-                    b2 += (long long)(diff * Iy[k]);
+                for (int k = 0; k < LK_PPL; ++k) {
+                    const int idx = lane + 32 * k;
+                    if (idx < LK_AREA) {
+                        const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
+                        const uint8_t* q = Jb + wy * cols + wx;
+                        const int jv = q[0] * w00 + q[1] * w01 + q[cols] * w10 + q[cols + 1] * w11;
+                        const int diff = ((jv + (1 << 8)) >> 9) - Iw[k];
+                        s1 += diff * Ix[k];
+                        s2 += diff * Iy[k];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < LK_PPL; ++k) {
+                    const int idx = lane + 32 * k;
+                    if (idx < LK_AREA) {
+                        const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
+                        const int ry0 = reflect101(iny + wy, rows), ry1 = reflect101(iny + wy + 1, rows);
+                        const int rx0 = reflect101(inx + wx, cols), rx1 = reflect101(inx + wx + 1, cols);
+                        const int jv = J[(size_t)ry0 * cols + rx0] * w00 + J[(size_t)ry0 * cols + rx1] * w01 +
+                                       J[(size_t)ry1 * cols + rx0] * w10 + J[(size_t)ry1 * cols + rx1] * w11;
+                        const int diff = ((jv + (1 << 8)) >> 9) - Iw[k];
+                        s1 += diff * Ix[k];
+                        s2 += diff * Iy[k];
+                    }
                 }
             }
-            b1 = warp_sum_ll(b1);
-            b2 = warp_sum_ll(b2);
+            const long long b1 = warp_sum_i32(s1), b2 = warp_sum_i32(s2);
             const float fb1 = __fmul_rn(__ll2float_rn(b1), FLT_SCALE), fb2 = __fmul_rn(__ll2float_rn(b2), FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
