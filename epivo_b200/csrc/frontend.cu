@@ -274,6 +274,85 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
     w11 = 16384 - w00 - w01 - w10;
 }
 
+// The 21 x 21 window is cut into 63 row segments of 7 pixels (3 per row); a lane owns segments `lane` and `lane + 32`.
+// The bilinear samples of a segment share their source pixels -- 2 x 8 loads for 7 samples instead of 4 per sample --
+// and the row / column border arithmetic is done once per segment.
+constexpr int LK_SEG = 7, LK_NSEG = LK_AREA / LK_SEG;        // 63
+
+template <bool INTERIOR>
+__device__ __forceinline__ void lk_row8(const uint8_t* __restrict__ img, int rows, int cols, int y, int x0, int (&v)[8]) {
+    if (INTERIOR) {
+        const uint8_t* r = img + (size_t)y * cols + x0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r[i];
+    } else {                                                 // the pyramid's border: BORDER_REFLECT_101
+        const uint8_t* r = img + (size_t)reflect101(y, rows) * cols;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r[reflect101(x0 + i, cols)];
+    }
+}
+template <bool INTERIOR>
+__device__ __forceinline__ void lk_drow8(const short2* __restrict__ d, int rows, int cols, int y, int x0, short2 (&v)[8]) {
+    if (INTERIOR) {
+        const short2* r = d + (size_t)y * cols + x0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r[i];
+    } else {                                                 // the derivative's border: BORDER_CONSTANT 0
+        const bool yin = y >= 0 && y < rows;
+        const short2* r = d + (size_t)(yin ? y : 0) * cols;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int x = x0 + i;
+            v[i] = (yin && x >= 0 && x < cols) ? r[x] : make_short2(0, 0);
+        }
+    }
+}
+// window of the previous image: I and its derivatives for one segment, and the segment's part of the 2 x 2 system
+template <bool INTERIOR, int BASE>
+__device__ __forceinline__ void lk_patch_seg(const uint8_t* __restrict__ I, const short2* __restrict__ dI, int rows, int cols,
+                                             int y, int x0, int w00, int w01, int w10, int w11, short (&Iw)[2 * LK_SEG],
+                                             short (&Ix)[2 * LK_SEG], short (&Iy)[2 * LK_SEG], int& s11, int& s12, int& s22) {
+    int a[8], b[8];
+    short2 da[8], db[8];
+    lk_row8<INTERIOR>(I, rows, cols, y, x0, a);
+    lk_row8<INTERIOR>(I, rows, cols, y + 1, x0, b);
+    lk_drow8<INTERIOR>(dI, rows, cols, y, x0, da);
+    lk_drow8<INTERIOR>(dI, rows, cols, y + 1, x0, db);
+#pragma unroll
+    for (int i = 0; i < LK_SEG; ++i) {
+        const int iv = a[i] * w00 + a[i + 1] * w01 + b[i] * w10 + b[i + 1] * w11;
+        const int ixv = (da[i].x * w00 + da[i + 1].x * w01 + db[i].x * w10 + db[i + 1].x * w11 + (1 << 13)) >> 14;
+        const int iyv = (da[i].y * w00 + da[i + 1].y * w01 + db[i].y * w10 + db[i + 1].y * w11 + (1 << 13)) >> 14;
+        Iw[BASE + i] = (short)((iv + (1 << 8)) >> 9);                         // CV_DESCALE(., W_BITS1 - 5)
+        Ix[BASE + i] = (short)ixv;
+        Iy[BASE + i] = (short)iyv;
+        s11 += ixv * ixv;
+        s12 += ixv * iyv;
+        s22 += iyv * iyv;
+    }
+}
+// window of the next image at the current position against the stored one: the segment's part of the right-hand side
+// (SAD = false) or of the absolute difference (SAD = true, the `err` pass)
+template <bool INTERIOR, int BASE, bool SAD>
+__device__ __forceinline__ void lk_diff_seg(const uint8_t* __restrict__ J, int rows, int cols, int y, int x0, int w00, int w01,
+                                            int w10, int w11, const short (&Iw)[2 * LK_SEG], const short (&Ix)[2 * LK_SEG],
+                                            const short (&Iy)[2 * LK_SEG], int& s1, int& s2) {
+    int a[8], b[8];
+    lk_row8<INTERIOR>(J, rows, cols, y, x0, a);
+    lk_row8<INTERIOR>(J, rows, cols, y + 1, x0, b);
+#pragma unroll
+    for (int i = 0; i < LK_SEG; ++i) {
+        const int jv = a[i] * w00 + a[i + 1] * w01 + b[i] * w10 + b[i + 1] * w11;
+        const int diff = ((jv + (1 << 8)) >> 9) - Iw[BASE + i];
+        if (SAD) {
+            s1 += abs(diff);
+        } else {
+            s1 += diff * Ix[BASE + i];
+            s2 += diff * Iy[BASE + i];
+        }
+    }
+}
+
 // one warp per point: all pyramid levels, all iterations
 #ifndef EPV_LK_MINBLOCKS
 #define EPV_LK_MINBLOCKS 5
@@ -291,7 +370,10 @@ __global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t
     const float FLT_SCALE = 1.f / (1 << 20);
     float nx = 0.f, ny = 0.f;            // nextPts[ptidx]
     bool ok = true;
-    short Iw[LK_PPL], Ix[LK_PPL], Iy[LK_PPL];
+    short Iw[2 * LK_SEG], Ix[2 * LK_SEG], Iy[2 * LK_SEG];
+    const int wyA = lane / 3, wxA = LK_SEG * (lane - 3 * wyA);                     // segment `lane`: window row, first column
+    const bool segB = lane + 32 < LK_NSEG;                                         // segment `lane + 32` (lane 31 has none)
+    const int wyB = (lane + 32) / 3, wxB = LK_SEG * (lane + 32 - 3 * wyB);
     for (int level = g.levels - 1; level >= 0; --level) {
         const int rows = g.rows[level], cols = g.cols[level];
         const uint8_t* I = pyr + (size_t)pair * g.frame_stride + g.off[level];
@@ -310,34 +392,12 @@ __global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
         int s11 = 0, s12 = 0, s22 = 0;                      // per lane: 14 x 4080^2 < 2^31
-#pragma unroll
-        for (int k = 0; k < LK_PPL; ++k) {
-            const int idx = lane + 32 * k;
-            Iw[k] = Ix[k] = Iy[k] = 0;
-            if (idx < LK_AREA) {
-                const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
-                const int y0 = ipy + wy, x0 = ipx + wx;
-                const int ry0 = reflect101(y0, rows), ry1 = reflect101(y0 + 1, rows);
-                const int rx0 = reflect101(x0, cols), rx1 = reflect101(x0 + 1, cols);
-                const int iv = I[(size_t)ry0 * cols + rx0] * w00 + I[(size_t)ry0 * cols + rx1] * w01 +
-                               I[(size_t)ry1 * cols + rx0] * w10 + I[(size_t)ry1 * cols + rx1] * w11;
-                // the derivative image has a zero border (BORDER_CONSTANT), the pyramid a reflected one
-                const bool yin0 = y0 >= 0 && y0 < rows, yin1 = y0 + 1 >= 0 && y0 + 1 < rows;
-                const bool xin0 = x0 >= 0 && x0 < cols, xin1 = x0 + 1 >= 0 && x0 + 1 < cols;
-                const short2 z = make_short2(0, 0);
-                const short2 d00 = (yin0 && xin0) ? dI[(size_t)y0 * cols + x0] : z;
-                const short2 d01 = (yin0 && xin1) ? dI[(size_t)y0 * cols + x0 + 1] : z;
-                const short2 d10 = (yin1 && xin0) ? dI[(size_t)(y0 + 1) * cols + x0] : z;
-                const short2 d11 = (yin1 && xin1) ? dI[(size_t)(y0 + 1) * cols + x0 + 1] : z;
-                const int ixv = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
-                const int iyv = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
-                Iw[k] = (short)((iv + (1 << 8)) >> 9);                        // CV_DESCALE(., W_BITS1 - 5)
-                Ix[k] = (short)ixv;
-                Iy[k] = (short)iyv;
-                s11 += ixv * ixv;
-                s12 += ixv * iyv;
-                s22 += iyv * iyv;
-            }
+        if (ipx >= 0 && ipy >= 0 && ipx + LK_WIN < cols && ipy + LK_WIN < rows) {       // whole footprint inside: warp-uniform
+            lk_patch_seg<true, 0>(I, dI, rows, cols, ipy + wyA, ipx + wxA, w00, w01, w10, w11, Iw, Ix, Iy, s11, s12, s22);
+            if (segB) lk_patch_seg<true, LK_SEG>(I, dI, rows, cols, ipy + wyB, ipx + wxB, w00, w01, w10, w11, Iw, Ix, Iy, s11, s12, s22);
+        } else {
+            lk_patch_seg<false, 0>(I, dI, rows, cols, ipy + wyA, ipx + wxA, w00, w01, w10, w11, Iw, Ix, Iy, s11, s12, s22);
+            if (segB) lk_patch_seg<false, LK_SEG>(I, dI, rows, cols, ipy + wyB, ipx + wxB, w00, w01, w10, w11, Iw, Ix, Iy, s11, s12, s22);
         }
         const float A11 = __fmul_rn(__ll2float_rn(warp_sum_i32(s11)), FLT_SCALE),
                     A12 = __fmul_rn(__ll2float_rn(warp_sum_i32(s12)), FLT_SCALE),
@@ -364,34 +424,11 @@ __global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t
             int s1 = 0, s2 = 0;
             if (inx >= 0 && iny >= 0 && inx + LK_WIN < cols && iny + LK_WIN < rows) {
                 // the whole 22 x 22 footprint lies inside the image (the common case, warp-uniform): no border arithmetic
-                const uint8_t* Jb = J + (size_t)iny * cols + inx;
-#pragma unroll
-                for (int k = 0; k < LK_PPL; ++k) {
-                    const int idx = lane + 32 * k;
-                    if (idx < LK_AREA) {
-                        const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
-                        const uint8_t* q = Jb + wy * cols + wx;
-                        const int jv = q[0] * w00 + q[1] * w01 + q[cols] * w10 + q[cols + 1] * w11;
-                        const int diff = ((jv + (1 << 8)) >> 9) - Iw[k];
-                        s1 += diff * Ix[k];
-                        s2 += diff * Iy[k];
-                    }
-                }
+                lk_diff_seg<true, 0, false>(J, rows, cols, iny + wyA, inx + wxA, w00, w01, w10, w11, Iw, Ix, Iy, s1, s2);
+                if (segB) lk_diff_seg<true, LK_SEG, false>(J, rows, cols, iny + wyB, inx + wxB, w00, w01, w10, w11, Iw, Ix, Iy, s1, s2);
             } else {
-#pragma unroll
-                for (int k = 0; k < LK_PPL; ++k) {
-                    const int idx = lane + 32 * k;
-                    if (idx < LK_AREA) {
-                        const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
-                        const int ry0 = reflect101(iny + wy, rows), ry1 = reflect101(iny + wy + 1, rows);
-                        const int rx0 = reflect101(inx + wx, cols), rx1 = reflect101(inx + wx + 1, cols);
-                        const int jv = J[(size_t)ry0 * cols + rx0] * w00 + J[(size_t)ry0 * cols + rx1] * w01 +
-                                       J[(size_t)ry1 * cols + rx0] * w10 + J[(size_t)ry1 * cols + rx1] * w11;
-                        const int diff = ((jv + (1 << 8)) >> 9) - Iw[k];
-                        s1 += diff * Ix[k];
-                        s2 += diff * Iy[k];
-                    }
-                }
+                lk_diff_seg<false, 0, false>(J, rows, cols, iny + wyA, inx + wxA, w00, w01, w10, w11, Iw, Ix, Iy, s1, s2);
+                if (segB) lk_diff_seg<false, LK_SEG, false>(J, rows, cols, iny + wyB, inx + wxB, w00, w01, w10, w11, Iw, Ix, Iy, s1, s2);
             }
             const long long b1 = warp_sum_i32(s1), b2 = warp_sum_i32(s2);
             const float fb1 = __fmul_rn(__ll2float_rn(b1), FLT_SCALE), fb2 = __fmul_rn(__ll2float_rn(b2), FLT_SCALE);
@@ -420,19 +457,9 @@ __global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t
                 ok = false;
             } else {
                 lk_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
-                int sad = 0;
-#pragma unroll
-                for (int k = 0; k < LK_PPL; ++k) {
-                    const int idx = lane + 32 * k;
-                    if (idx < LK_AREA) {
-                        const int wy = idx / LK_WIN, wx = idx - wy * LK_WIN;
-                        const int ry0 = reflect101(iey + wy, rows), ry1 = reflect101(iey + wy + 1, rows);
-                        const int rx0 = reflect101(iex + wx, cols), rx1 = reflect101(iex + wx + 1, cols);
-                        const int jv = J[(size_t)ry0 * cols + rx0] * w00 + J[(size_t)ry0 * cols + rx1] * w01 +
-                                       J[(size_t)ry1 * cols + rx0] * w10 + J[(size_t)ry1 * cols + rx1] * w11;
-                        sad += abs(((jv + (1 << 8)) >> 9) - Iw[k]);
-                    }
-                }
+                int sad = 0, unused = 0;
+                lk_diff_seg<false, 0, true>(J, rows, cols, iey + wyA, iex + wxA, w00, w01, w10, w11, Iw, Ix, Iy, sad, unused);
+                if (segB) lk_diff_seg<false, LK_SEG, true>(J, rows, cols, iey + wyB, iex + wxB, w00, w01, w10, w11, Iw, Ix, Iy, sad, unused);
                 sad = __reduce_add_sync(0xFFFFFFFFu, sad);          // < 2^24: the float sum OpenCV forms is exact, in any order
                 if (lane == 0) err[(size_t)pair * max_pts + p] = __fdiv_rn((float)sad, (float)(32 * LK_AREA));
             }
