@@ -399,7 +399,7 @@ class PairsRunner:
         self.pipe.close()
 
 
-def front_end_measure(ctx, frames=32):
+def front_end_measure(ctx, frames=128):
     """N4: FastFeatureDetector(40) on every frame and calcOpticalFlowPyrLK into the next one (kitti_E.cpp:70-84) for a
     KITTI-sized synthetic sequence, through the host API (the frames are uploaded inside the timed region)."""
     from epivo_b200 import api
