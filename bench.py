@@ -415,7 +415,7 @@ def front_end_measure(ctx, frames=128):
     best, pipe = None, None
     for _ in range(3):
         t0 = time.perf_counter()
-        det = api.fastDetect(seq[:-1], 40, True, max_keypoints=16384, ctx=ctx)
+        det = api.fastDetect(seq[:-1], 40, True, max_keypoints=8192, ctx=ctx)
         t1 = time.perf_counter()
         nxt, st = api.trackSequenceLK(seq, [d[0] for d in det], ctx=ctx)
         t2 = time.perf_counter()
