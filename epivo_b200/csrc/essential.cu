@@ -574,24 +574,56 @@ __global__ void __launch_bounds__(SB2_THREADS, EPV_SB2_MINBLOCKS) solve_b2_kerne
 #endif
 constexpr int ES_UNROLL = EPV_ES_UNROLL;   // correspondences in flight per lane in the scoring loops
 
+// Inlier counts of two models over the correspondences first, first + step, ... (both models in registers, every
+// correspondence tested against both).
+// bound >= 0 (whole-model calls only: first = lane, step = 32): the caller needs a count only if it EXCEEDS `bound` --
+// RANSAC: the best count before this sub-chunk (a model can only win with strictly more), LMedS: n/2 (the filter asks
+// for more than half of the errors below the best median).  Every ES_CHECK iterations the warp adds up what both models
+// have (undecided points counted as if they were inliers) plus what is still to come; when neither can exceed the bound
+// any more the pass ends -- the returned counts are then partial, which the callers treat exactly like "not more than
+// bound".  On the headline data a wrong model (30 % inliers against a best of 84 %) is out after a quarter of the
+// points; the result of the estimator is unchanged by construction.
+constexpr int ES_CHECK = 2 * ES_UNROLL;
 template <class P>
 __device__ __forceinline__ void count_two(P X1, int stride, int n, int first, int step, const double* M0,
-                                          const double* M1, const SampThr& T, int& c0, int& c1) {
+                                          const double* M1, const SampThr& T, int& c0, int& c1, int bound = -1) {
     double E0[9], E1[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) { E0[c] = M0[c]; E1[c] = M1[c]; }
-    bool undecided = false;
+    int und = 0;                                  // correspondences of this lane the fast test left open (either model)
+    int i = first;
+    if (bound >= 0) {
+        while (i - first < n) {                   // warp-uniform (first = lane, step = 32): every lane reaches the warp sums below
+#pragma unroll
+            for (int u = 0; u < ES_CHECK; ++u, i += step) {
+                if (i < n) {
+                    const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
+                    bool in0, in1;
+                    const bool d0 = sampson_fast(E0, a1, b1, a2, b2, T, T.hdmin, in0);
+                    const bool d1 = sampson_fast(E1, a1, b1, a2, b2, T, T.hdmin, in1);
+                    c0 += (d0 && in0) ? 1 : 0;
+                    c1 += (d1 && in1) ? 1 : 0;
+                    und += (d0 && d1) ? 0 : 1;
+                }
+            }
+            // i - first is the same for all lanes: the warp has seen every index below base = i - lane
+            const int left = max(n - (i - first), 0);                       // >= correspondences still to come
+            const int best_possible = max(warp_sum(c0 + und), warp_sum(c1 + und)) + left;
+            if (best_possible <= bound) return;                             // neither model can exceed the bound
+        }
+    } else {
 #pragma unroll ES_UNROLL
-    for (int i = first; i < n; i += step) {
-        const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
-        bool in0, in1;
-        const bool d0 = sampson_fast(E0, a1, b1, a2, b2, T, T.hdmin, in0);
-        const bool d1 = sampson_fast(E1, a1, b1, a2, b2, T, T.hdmin, in1);
-        c0 += (d0 && in0) ? 1 : 0;
-        c1 += (d1 && in1) ? 1 : 0;
-        undecided |= !(d0 && d1);
+        for (; i < n; i += step) {
+            const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
+            bool in0, in1;
+            const bool d0 = sampson_fast(E0, a1, b1, a2, b2, T, T.hdmin, in0);
+            const bool d1 = sampson_fast(E1, a1, b1, a2, b2, T, T.hdmin, in1);
+            c0 += (d0 && in0) ? 1 : 0;
+            c1 += (d1 && in1) ? 1 : 0;
+            und += (d0 && d1) ? 0 : 1;
+        }
     }
-    if (undecided) {
+    if (und) {
         for (int i = first; i < n; i += step) {
             const double a1 = X1[i], b1 = X1[stride + i], a2 = X1[2 * stride + i], b2 = X1[3 * stride + i];
             bool in0, in1;
@@ -718,6 +750,12 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
             const int M = s_nitems;
             if (n != 5 && M > 0) {
                 if (!lmeds) {
+                    // a model matters only with more inliers than the best before this sub-chunk (and more than 4).  The
+                    // bounded pass pays a warp sum every ES_CHECK iterations, so it is used only where it can end early
+                    // enough: with a best of 11 % of the correspondences (RANSAC at 0.05 px) a hopeless model is known
+                    // to be hopeless only after 90 % of them and the check costs more than it saves.
+                    const int best_now = max((int)s_best_score, 4);
+                    const int ransac_bound = 3 * best_now > n ? best_now : -1;
                     if (M >= ES_WARPS) {
                         // the warps claim items two at a time from a shared counter (models differ in nothing, but
                         // a static split leaves the barrier waiting for the warp with the odd item): both models
@@ -734,8 +772,8 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                             const double* M1 = s_models[code1 >> 4][code1 & 15];
                             int c0 = 0, c1 = 0;
                             if (two) {
-                                if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, M0, M1, thrR, c0, c1);
-                                else count_two(a.xn + so, a.stride, n, lane, 32, M0, M1, thrR, c0, c1);
+                                if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, M0, M1, thrR, c0, c1, ransac_bound);
+                                else count_two(a.xn + so, a.stride, n, lane, 32, M0, M1, thrR, c0, c1, ransac_bound);
                             } else {
                                 c0 = pts_in_smem ? count_one(s_pts, a.stride, n, lane, 32, M0, thrR)
                                                  : count_one(a.xn + so, a.stride, n, lane, 32, M0, thrR);
@@ -809,8 +847,8 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                             c0 = c1 = 0;                                     // best median is 0: nothing can beat it
                         } else if (can_filter) {
                             c0 = c1 = 0;
-                            if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, M0, M1, thrL, c0, c1);
-                            else count_two(a.xn + so, a.stride, n, lane, 32, M0, M1, thrL, c0, c1);
+                            if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, M0, M1, thrL, c0, c1, need - 1);
+                            else count_two(a.xn + so, a.stride, n, lane, 32, M0, M1, thrL, c0, c1, need - 1);
                             c0 = warp_sum(c0);
                             c1 = warp_sum(c1);
                         }
