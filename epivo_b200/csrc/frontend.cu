@@ -12,6 +12,8 @@
 // threshold for which it is still a corner -- is strictly greater than the scores of its 8 neighbours (0 where the
 // neighbour is not a corner); the response is the score, or 0 without suppression.  Keypoints come out row by row,
 // left to right.
+#include <limits.h>
+
 #include "stages.cuh"
 
 namespace {
@@ -266,6 +268,11 @@ __device__ __forceinline__ long long warp_sum_i32(int v) {
     return ((long long)hi << 16) + lo;
 }
 
+// cvFloor as the x86 build OpenCV ships: NaN and values beyond the int range convert to INT_MIN, which the range tests
+// then reject (CUDA's conversion would give 0 for NaN and let the point through)
+__device__ __forceinline__ int lk_floor(float v) {
+    return (v == v && fabsf(v) < 2147483520.f) ? (int)floorf(v) : INT_MIN;
+}
 __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
     const float s = 16384.0f;                                                   // 1 << W_BITS
     w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), s));   // cvRound: half to even
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t
         if (level == g.levels - 1) { nx = ppx; ny = ppy; } else { nx = __fmul_rn(nx, 2.f); ny = __fmul_rn(ny, 2.f); }
         ppx = __fsub_rn(ppx, half);
         ppy = __fsub_rn(ppy, half);
-        const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
+        const int ipx = lk_floor(ppx), ipy = lk_floor(ppy);
         if (ipx < -LK_WIN || ipx >= cols || ipy < -LK_WIN || ipy >= rows) {
             if (level == 0) ok = false;
             continue;
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t
         float tx = __fsub_rn(nx, half), ty = __fsub_rn(ny, half);             // nextPt -= halfWin
         float pdx = 0.f, pdy = 0.f;
         for (int j = 0; j < max_count; ++j) {
-            const int inx = (int)floorf(tx), iny = (int)floorf(ty);
+            const int inx = lk_floor(tx), iny = lk_floor(ty);
             if (inx < -LK_WIN || inx >= cols || iny < -LK_WIN || iny >= rows) {
                 if (level == 0) ok = false;
                 break;
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(128, EPV_LK_MINBLOCKS) lk_kernel(const uint8_t
             // mean absolute window difference at the FINAL position -- which the loop did not range-check after its
             // last update: outside [-win, size) the status is cleared
             const float ex = __fsub_rn(nx, half), ey = __fsub_rn(ny, half);
-            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            const int iex = lk_floor(ex), iey = lk_floor(ey);
             if (iex < -LK_WIN || iex >= cols || iey < -LK_WIN || iey >= rows) {
                 ok = false;
             } else {

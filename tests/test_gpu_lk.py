@@ -47,6 +47,21 @@ def test_gpu_lk_levels_and_criteria(ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_lk_points_outside_the_image(ctx):
+    """Out-of-frame, edge and far-away points: status and the positions OpenCV leaves behind, lost tracks included
+    (the restatement is pinned to live cv2 on the same points in tests/test_oracle_lk.py)."""
+    a, b = GOLD["prev_affine"], GOLD["next_affine"]
+    h, w = a.shape
+    pts = np.array([[-5, -5], [-30, 10], [w + 5, 10], [w + 40, h + 40], [w - 1, h - 1], [0, 0], [1e6, 1e6], [-1e6, 5],
+                    [w - 0.5, h - 0.5], [10.5, -12.25], [w + 9.75, h / 2], [np.inf, 3], [np.nan, np.nan]], np.float32)
+    nxt, st = api.calcOpticalFlowPyrLK(a, b, pts, ctx=ctx)
+    o_nxt, o_st = OF.calc_optical_flow_pyr_lk(a, b, pts[:11])
+    assert np.array_equal(st[:11], o_st)
+    assert np.abs(nxt[:11] - o_nxt).max() <= 1e-3
+    assert st[11] == 0 and st[12] == 0                   # inf and NaN: cvFloor gives INT_MIN, outside every range test
+
+
+@pytest.mark.gpu
 def test_gpu_kitti_front_end_vs_live_cv2(ctx):
     """kitti_E.cpp:66-95 for a five-frame KITTI-sized sequence: FAST(40) on frame i, LK into frame i + 1, keep
     status == 1 -- the GPU chain against the same cv2 calls."""

@@ -45,3 +45,16 @@ def test_oracle_lk_matches_live_cv2():
     ref, st, _ = cv2.calcOpticalFlowPyrLK(src, tgt, pts, None)
     nxt, st2 = OF.calc_optical_flow_pyr_lk(src, tgt, pts)
     check_lk(nxt, st2, ref, st, "live")
+
+
+def test_oracle_lk_points_outside_the_image_live_cv2():
+    """Points outside the frame (lost at level 0), on its edges (tracked through the reflected border) and far away."""
+    cv2 = pytest.importorskip("cv2")
+    a, b = GOLD["prev_affine"], GOLD["next_affine"]
+    h, w = a.shape
+    pts = np.array([[-5, -5], [-30, 10], [w + 5, 10], [w + 40, h + 40], [w - 1, h - 1], [0, 0], [1e6, 1e6], [-1e6, 5],
+                    [w - 0.5, h - 0.5], [10.5, -12.25], [w + 9.75, h / 2]], np.float32)
+    ref, st, _ = cv2.calcOpticalFlowPyrLK(a, b, pts, None)
+    nxt, st2 = OF.calc_optical_flow_pyr_lk(a, b, pts)
+    assert np.array_equal(st.ravel(), st2) and 0 < st2.sum() < len(pts)
+    assert np.abs(ref.reshape(-1, 2) - nxt).max() <= 1e-3 * max(1.0, np.abs(nxt).max() * 1e-6)     # lost tracks included
