@@ -754,7 +754,31 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                     // bounded pass pays a warp sum every ES_CHECK iterations, so it is used only where it can end early
                     // enough: with a best of 11 % of the correspondences (RANSAC at 0.05 px) a hopeless model is known
                     // to be hopeless only after 90 % of them and the check costs more than it saves.
-                    const int best_now = max((int)s_best_score, 4);
+                    int best_now = max((int)s_best_score, 4);
+                    int first = 0;                                           // items [0, first) are already counted
+                    if (s_have == 0 && M > 3 * ES_WARPS) {
+                        // No best yet (the pair's first sub-chunk): the first 2 * ES_WARPS models are counted in full,
+                        // one pair of models per warp; the largest of those counts is a lower bound of the best BEFORE
+                        // every later model of the sub-chunk, which bounds their passes (as the LMedS branch does with
+                        // the first medians).  CTA-uniform branch: shared state only.
+                        first = 2 * ES_WARPS;
+                        {
+                            const int code0 = s_item[2 * warp], code1 = s_item[2 * warp + 1];
+                            const double* M0 = s_models[code0 >> 4][code0 & 15];
+                            const double* M1 = s_models[code1 >> 4][code1 & 15];
+                            int c0 = 0, c1 = 0;
+                            if (pts_in_smem) count_two(s_pts, a.stride, n, lane, 32, M0, M1, thrR, c0, c1);
+                            else count_two(a.xn + so, a.stride, n, lane, 32, M0, M1, thrR, c0, c1);
+                            c0 = warp_sum(c0);
+                            c1 = warp_sum(c1);
+                            if (lane == 0) {
+                                s_cnt[code0 >> 4][code0 & 15] = c0;
+                                s_cnt[code1 >> 4][code1 & 15] = c1;
+                            }
+                        }
+                        __syncthreads();
+                        for (int j = 0; j < first; ++j) best_now = max(best_now, s_cnt[s_item[j] >> 4][s_item[j] & 15]);
+                    }
                     const int ransac_bound = 3 * best_now > n ? best_now : -1;
                     if (M >= ES_WARPS) {
                         // the warps claim items two at a time from a shared counter (models differ in nothing, but
@@ -762,7 +786,7 @@ __global__ void __launch_bounds__(ES_THREADS, 2) ess_round_kernel(EssArgs a, int
                         // live in registers and every correspondence (shared memory) is tested against both
                         for (;;) {
                             int j0 = 0;
-                            if (lane == 0) j0 = 2 * atomicAdd(&s_next, 1);
+                            if (lane == 0) j0 = first + 2 * atomicAdd(&s_next, 1);
                             j0 = __shfl_sync(0xFFFFFFFFu, j0, 0);
                             if (j0 >= M) break;
                             const int code0 = s_item[j0];
