@@ -242,6 +242,40 @@ def fastDetect(images, threshold: int = 10, nonmaxSuppression: bool = True, max_
     return out[0] if single else out
 
 
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])          # = cv::KeyPoint = epivo_keypoint
+
+
+def orbDetectAndCompute(images, nfeatures: int = 10000, scaleFactor: float = 1.2, nlevels: int = 8, edgeThreshold: int = 15,
+                        fastThreshold: int = 20, max_keypoints: int | None = None, ctx: Context | None = None):
+    """cv2.ORB_create(nfeatures, scaleFactor, nlevels, edgeThreshold, 0, 2, cv2.ORB_FAST_SCORE, 31, fastThreshold)
+    .detectAndCompute(img, None) for a batch of equally sized 8-bit images (kitti_ba.cpp:128-152 runs it with
+    10000, 1.2f, 8, 15).  images: (rows, cols) or (n, rows, cols) uint8.  Returns per image (keypoints: structured
+    array of KEYPOINT_DTYPE in OpenCV's order, descriptors (k, 32) uint8); identical to OpenCV's.  max_keypoints bounds
+    the per-image output buffer (default: nfeatures plus room for ties; a frame that exceeds it is re-run)."""
+    ctx = ctx or default_context()
+    im = np.ascontiguousarray(images, dtype=np.uint8)
+    single = im.ndim == 2
+    if single:
+        im = im[None]
+    if im.ndim != 3:
+        raise ValueError("images must be (rows, cols) or (n, rows, cols) uint8")
+    n, rows, cols = im.shape
+    cap = int(max_keypoints) if max_keypoints is not None else int(nfeatures) + int(nfeatures) // 8 + 256
+    while True:
+        kps = np.zeros((n, cap), dtype=KEYPOINT_DTYPE)
+        desc = np.zeros((n, cap, 32), dtype=np.uint8)
+        counts = np.zeros(n, dtype=np.int32)
+        ctx.check(ctx.lib.epivo_orb_detect_and_compute(ctx.h, _p(im), n, rows, cols, int(nfeatures), float(scaleFactor),
+                                                       int(nlevels), int(edgeThreshold), int(fastThreshold), cap, _p(kps),
+                                                       _p(desc), _p(counts)))
+        if max_keypoints is not None or n == 0 or counts.max() <= cap:
+            break
+        cap = int(counts.max())
+    out = [(kps[i, :min(counts[i], cap)].copy(), desc[i, :min(counts[i], cap)].copy()) for i in range(n)]
+    return out[0] if single else out
+
+
 def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, maxLevel: int = 3, maxCount: int = 30, epsilon: float = 0.01,
                          minEigThreshold: float = 1e-4, ctx: Context | None = None, returnErr: bool = False):
     """cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, None) with the 21 x 21 window (kitti_E.cpp:79-84):

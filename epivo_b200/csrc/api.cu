@@ -452,6 +452,47 @@ int epivo_remap(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, i
     return EPIVO_OK;
 }
 
+int epivo_orb_detect_and_compute(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, int nfeatures,
+                                 float scale_factor, int nlevels, int edge_threshold, int fast_threshold, int max_kp,
+                                 epivo_keypoint* kps, uint8_t* desc, int32_t* counts) {
+    if (!ctx) return EPIVO_ERR_INVALID;
+    if (n_images < 0 || rows < 0 || cols < 0 || max_kp < 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "negative size");
+    if (fast_threshold < 0 || fast_threshold > 255) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "fast_threshold %d outside [0, 255]", fast_threshold);
+    if (n_images > 0 && (!images || !counts || (max_kp > 0 && (!kps || !desc)))) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null argument");
+    if (n_images == 0) return EPIVO_OK;
+    if (rows == 0 || cols == 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "empty image");
+    EpvOrbPlan plan;
+    int rc = epv_orb_plan(ctx, n_images, rows, cols, nfeatures, scale_factor, nlevels, edge_threshold, max_kp, &plan);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nk = (size_t)n_images * max_kp;
+    rc = epv_ws_reserve(ctx, epv_orb_work_bytes(plan) + nk * (sizeof(epivo_keypoint) + 32) + (size_t)n_images * 4 + 4096);
+    if (rc) return rc;
+    rc = epv_pin_reserve(ctx, (plan.tab_entries + 1) * 4 + 512);
+    if (rc) return rc;
+    uint8_t* d_pyr = epv_ws_take<uint8_t>(ctx, plan.pyr_bytes);
+    epivo_keypoint* d_kps = epv_ws_take<epivo_keypoint>(ctx, nk + 1);
+    uint8_t* d_desc = epv_ws_take<uint8_t>(ctx, nk * 32 + 32);
+    int32_t* d_counts = epv_ws_take<int32_t>(ctx, n_images);
+    uint32_t* h_tab = epv_pin_take<uint32_t>(ctx, plan.tab_entries + 1);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_pyr, images, (size_t)n_images * rows * cols, cudaMemcpyHostToDevice, ctx->stream));
+    rc = epv_orb_launch(ctx, plan, fast_threshold, d_pyr, d_kps, d_desc, d_counts, h_tab);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)n_images * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // only what was found travels back: image i's first min(counts[i], max_kp) keypoints and descriptors
+    for (int i = 0; i < n_images; ++i) {
+        const size_t k = (size_t)std::min(std::max(counts[i], 0), max_kp);
+        if (!k) continue;
+        EPV_CUDA(ctx, cudaMemcpyAsync(kps + (size_t)i * max_kp, d_kps + (size_t)i * max_kp, k * sizeof(epivo_keypoint),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        EPV_CUDA(ctx, cudaMemcpyAsync(desc + (size_t)i * max_kp * 32, d_desc + (size_t)i * max_kp * 32, k * 32,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPIVO_OK;
+}
+
 int epivo_score_sampson(epivo_ctx* ctx, const double* E, int m, const float* p0, const float* p1, int n,
                         const double K[9], double threshold, int32_t* counts, float* medians, int* best,
                         uint8_t* best_mask) {

@@ -84,3 +84,16 @@ int epv_lk_launch(epivo_ctx* ctx, const uint8_t* d_images, int n_frames, int row
                   float* d_next, uint8_t* d_status, float* d_err /* nullable */, void* work);
 int epv_remap_launch(epivo_ctx* ctx, const uint8_t* d_img, int n_images, int rows, int cols, const int16_t* d_map_xy,
                      const uint16_t* d_map_frac, int drows, int dcols, int border, uint8_t* d_out);
+
+// ---- orb.cu (N4: cv::ORB::detectAndCompute, kitti_ba.cpp:128-152) ------------------------------
+struct EpvOrbPlan {
+    alignas(8) char geom[704];          // OrbGeom (orb.cu): level sizes, scales, budgets, buffer offsets
+    size_t pyr_bytes;                   // pyramid bytes for the whole batch (level 0 block first)
+    size_t cand_total;                  // candidate slots over all levels and images
+    size_t tab_entries;                 // words of the resize weight tables
+};
+int epv_orb_plan(epivo_ctx* ctx, int n_images, int rows, int cols, int nfeatures, float scale_factor, int nlevels,
+                 int edge_threshold, int max_kp, EpvOrbPlan* plan);
+size_t epv_orb_work_bytes(const EpvOrbPlan& plan);
+int epv_orb_launch(epivo_ctx* ctx, const EpvOrbPlan& plan, int fast_threshold, uint8_t* d_pyr, void* d_kps,
+                   uint8_t* d_desc, int32_t* d_counts, uint32_t* h_tab);

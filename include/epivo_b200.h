@@ -124,6 +124,23 @@ int epivo_lk_track(epivo_ctx* ctx, const uint8_t* images, int n_frames, int rows
 int epivo_remap(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, const int16_t* map_xy,
                 const uint16_t* map_frac, int drows, int dcols, int border_value, uint8_t* out);
 
+/* N4 front end, descriptor extractor: cv::ORB::detectAndCompute for a batch of n_images 8-bit images of rows x cols --
+ * replaces `ORB::create(10000, 1.2f, 8, 15, 0, 2, ORB::FAST_SCORE)` + `orb->detect(src, kp)` + `orb->compute(src, kp, desc)`
+ * at kitti_ba.cpp:128-152.  Built for that configuration's family: firstLevel 0, WTA_K 2, FAST score, patchSize 31;
+ * nfeatures, scale_factor (1 < s <= 2), nlevels (<= 16), edge_threshold (>= 15) and fast_threshold are free.
+ * kps: n_images x max_kp epivo_keypoint (cv::KeyPoint's layout: x, y in image coordinates, size = 31 * level scale,
+ * angle in degrees, response = FAST score, octave = level, class_id -1) in OpenCV's order (level by level, inside a
+ * level the order KeyPointsFilter::retainBest leaves); desc: n_images x max_kp x 32 bytes; counts[i] = keypoints FOUND
+ * in image i (ties at a level's budget are all kept, as in OpenCV, so it may exceed nfeatures) -- when it exceeds
+ * max_kp only the first max_kp are stored.  Every field and every descriptor bit is identical to OpenCV 4.13's. */
+typedef struct epivo_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} epivo_keypoint;
+int epivo_orb_detect_and_compute(epivo_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, int nfeatures,
+                                 float scale_factor, int nlevels, int edge_threshold, int fast_threshold, int max_kp,
+                                 epivo_keypoint* kps, uint8_t* desc, int32_t* counts);
+
 /* K3 alone: Sampson scoring of a fixed hypothesis set of m models (m x 9) against n
  * correspondences with OpenCV's exact inlier rule.  threshold in pixels (RANSAC rule);
  * counts: m inlier counts; medians: m LMedS medians (float32, may be NULL); best: index of

@@ -16,6 +16,8 @@
 //   detector->detect(src, kp0, Mat());                                                  kitti_E.cpp:73
 //   calcOpticalFlowPyrLK(src, tgt, pt0, pt1_, status, err);                             kitti_E.cpp:79-84
 //   remap(src, src_, map1, map2, INTER_LINEAR);                                         euroc_E.cpp:170
+//   Ptr<ORB> orb = ORB::create(10000, 1.2f, 8, 15, 0, 2, ORB::FAST_SCORE);              kitti_ba.cpp:128
+//   orb->detect(src, kp0, Mat());  orb->compute(src, kp0, desc0);                       kitti_ba.cpp:141,149
 //
 // How the unqualified calls reach these functions.  The drivers say `using namespace cv;` and call
 // `findEssentialMat(...)` unqualified.  The templates below live in the GLOBAL namespace and take the
@@ -24,7 +26,8 @@
 // conversion from every argument: overload resolution picks the exact match, i.e. the template, without
 // any edit.  A class cannot be overloaded that way, so for the matcher the driver writes
 // `epivo::BFMatcher` instead of `BFMatcher` (one token, kitti_ba.cpp:602), and for the detector
-// `epivo::FastFeatureDetector` in the declaration and the create() call (kitti_E.cpp:70).
+// `epivo::FastFeatureDetector` in the declaration and the create() call (kitti_E.cpp:70), and likewise
+// `epivo::ORB` (kitti_ba.cpp:128).
 //
 // Context.  The calls carry no handle, so each host thread gets its own lazily created epivo::Context
 // (`thread_local`; device from $EPIVO_DEVICE, default 0) -- kitti_ba.cpp:1153-1163 calls the path from
@@ -35,6 +38,7 @@
 // such as Eigen::MatrixXd.  Neither OpenCV nor Eigen exists in this image: tests/cpp/dropin_test.cpp
 // compiles the literal call lines above against stand-ins with the same member API.
 #pragma once
+#include <cstring>
 #include <memory>
 #include <type_traits>
 
@@ -159,6 +163,103 @@ class FastFeatureDetector {
     FastFeatureDetector(int t, bool n) : threshold_(t), nonmax_(n) {}
     int threshold_;
     bool nonmax_;
+};
+
+// cv::ORB as kitti_ba.cpp:128 builds it:  `Ptr<epivo::ORB> orb = epivo::ORB::create(10000, 1.2f, 8, 15, 0, 2, epivo::ORB::FAST_SCORE);`
+// then `orb->detect(src, kp0, Mat());` and `orb->compute(src, kp0, desc0);` unchanged (kitti_ba.cpp:141,149).  detect() runs
+// the whole detectAndCompute on the GPU and keeps the descriptors; compute() on the same image and the keypoints detect()
+// returned hands them out (OpenCV's compute() on those keypoints produces exactly these rows).  Keypoints that did not come
+// from this detector are refused: describing foreign keypoints is not part of the reference's path.
+class ORB {
+  public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+    static std::shared_ptr<ORB> create(int nfeatures = 500, float scaleFactor = 1.2f, int nlevels = 8, int edgeThreshold = 31,
+                                       int firstLevel = 0, int WTA_K = 2, int scoreType = HARRIS_SCORE, int patchSize = 31,
+                                       int fastThreshold = 20) {
+        if (firstLevel != 0 || WTA_K != 2 || scoreType != FAST_SCORE || patchSize != 31)
+            throw std::invalid_argument("epivo::ORB: built for firstLevel 0, WTA_K 2, FAST_SCORE, patchSize 31 (kitti_ba.cpp:128)");
+        return std::shared_ptr<ORB>(new ORB(nfeatures, scaleFactor, nlevels, edgeThreshold, fastThreshold));
+    }
+    template <typename MatT, typename KP>
+    void detect(const MatT& image, std::vector<KP>& keypoints, const MatT& mask = MatT()) {
+        typedef mat_traits<MatT> MT;
+        if (!MT::empty(mask)) throw std::invalid_argument("ORB::detect: masks are not supported");
+        run(image);
+        keypoints.resize(kps_.size());
+        for (size_t i = 0; i < kps_.size(); ++i) {
+            KP& k = keypoints[i];
+            k.pt.x = kps_[i].x;
+            k.pt.y = kps_[i].y;
+            k.size = kps_[i].size;
+            k.angle = kps_[i].angle;
+            k.response = kps_[i].response;
+            k.octave = kps_[i].octave;
+            k.class_id = kps_[i].class_id;
+        }
+    }
+    template <typename MatT, typename KP>
+    void compute(const MatT& image, std::vector<KP>& keypoints, MatT& descriptors) {
+        typedef mat_traits<MatT> MT;
+        if (!same_image(image)) run(image);
+        bool same = keypoints.size() == kps_.size();
+        for (size_t i = 0; same && i < kps_.size(); ++i)
+            same = keypoints[i].pt.x == kps_[i].x && keypoints[i].pt.y == kps_[i].y && keypoints[i].octave == kps_[i].octave;
+        if (!same) throw std::invalid_argument("ORB::compute: the keypoints are not the ones detect() returned for this image");
+        descriptors = MT::create_u8((int)kps_.size(), 32);
+        if (!kps_.empty()) memcpy(MT::bytes_mut(descriptors), desc_.data(), kps_.size() * 32);
+    }
+    template <typename MatT, typename KP>
+    void detectAndCompute(const MatT& image, const MatT& mask, std::vector<KP>& keypoints, MatT& descriptors) {
+        detect(image, keypoints, mask);
+        compute(image, keypoints, descriptors);
+    }
+
+  private:
+    ORB(int nf, float sf, int nl, int et, int ft) : nfeatures_(nf), scale_(sf), nlevels_(nl), edge_(et), fast_(ft), rows_(0), cols_(0), sum_(0) {}
+    template <typename MatT>
+    static uint64_t checksum(const MatT& image) {             // FNV-1a over the pixels: which image the cached result belongs to
+        typedef mat_traits<MatT> MT;
+        const unsigned char* p = MT::bytes(image);
+        const size_t n = (size_t)MT::rows(image) * MT::cols(image);
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+        return h;
+    }
+    template <typename MatT>
+    bool same_image(const MatT& image) const {
+        typedef mat_traits<MatT> MT;
+        return MT::rows(image) == rows_ && MT::cols(image) == cols_ && rows_ > 0 && checksum(image) == sum_;
+    }
+    template <typename MatT>
+    void run(const MatT& image) {
+        typedef mat_traits<MatT> MT;
+        kps_.clear();
+        desc_.clear();
+        rows_ = MT::rows(image);
+        cols_ = MT::cols(image);
+        if (MT::empty(image)) return;
+        sum_ = checksum(image);
+        Context& ctx = default_context();
+        int cap = nfeatures_ + nfeatures_ / 8 + 256;
+        int32_t found = 0;
+        for (;;) {                              // ties at a level's budget are all kept: a frame that overflows is run again
+            kps_.assign((size_t)cap, epivo_keypoint());
+            desc_.assign((size_t)cap * 32, 0);
+            ctx.check(epivo_orb_detect_and_compute(ctx.get(), MT::bytes(image), 1, rows_, cols_, nfeatures_, scale_, nlevels_,
+                                                   edge_, fast_, cap, kps_.data(), desc_.data(), &found));
+            if (found <= cap) break;
+            cap = found;
+        }
+        kps_.resize((size_t)found);
+        desc_.resize((size_t)found * 32);
+    }
+    int nfeatures_;
+    float scale_;
+    int nlevels_, edge_, fast_;
+    int rows_, cols_;
+    uint64_t sum_;
+    std::vector<epivo_keypoint> kps_;
+    std::vector<unsigned char> desc_;
 };
 
 }  // namespace epivo

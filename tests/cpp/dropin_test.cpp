@@ -281,6 +281,53 @@ int main() {
         if (kp0.size() < 20 || pt1_.size() != pt0.size() || tracked < (int)kp0.size() * 8 / 10 || close < tracked * 8 / 10) return 11;
         if (kp0[0].size != 7.f || kp0[0].angle != -1.f || kp0[0].response < 40.f) return 12;
     }
+    // kitti_ba.cpp:114-156 (extract_good_kp): ORB keypoints and descriptors of two frames, matched as really_robust_ass does
+    {
+        const int rows = 160, cols = 240;
+        Mat frames[2] = {Mat(rows, cols, CV_8U), Mat(rows, cols, CV_8U)};
+        unsigned lcg = 12345u;
+        std::vector<int> blocks((rows / 8 + 2) * (cols / 8 + 2));
+        for (size_t i = 0; i < blocks.size(); ++i) { lcg = lcg * 1664525u + 1013904223u; blocks[i] = 40 + (lcg >> 24) % 180; }
+        for (int f = 0; f < 2; ++f)
+            for (int y = 0; y < rows; ++y)
+                for (int x = 0; x < cols; ++x)             // a blocky texture (corners everywhere), frame 1 shifted by (3, 1)
+                    frames[f].at<uchar>(y, x) = (uchar)(blocks[((y + f) / 8) * (cols / 8 + 2) + (x + 3 * f) / 8] + ((x * 5 + y * 3) % 7));
+        vector<vector<Point2f> > key_points;
+        vector<Mat> descs;
+        // [verbatim, class name qualified] kitti_ba.cpp:128
+        Ptr<epivo::ORB> orb = epivo::ORB::create(10000, 1.2f, 8, 15, 0, 2, epivo::ORB::FAST_SCORE);
+        for (int i = 0; i < 2; i++) {
+            Mat src = frames[i];
+            // [verbatim] kitti_ba.cpp:140-153
+            vector<KeyPoint> kp0;
+            orb->detect(src, kp0, Mat());
+            //detector.detect(src, kp0);
+
+            vector<Point2f> pt0;
+            cv::KeyPoint::convert(kp0, pt0);
+
+            Mat desc0;
+            //extractor.compute(src, kp0, desc0);
+            orb->compute(src, kp0, desc0);
+
+            key_points.push_back(pt0);
+            descs.push_back(desc0);
+            if (kp0.size() < 50 || desc0.rows != (int)kp0.size() || desc0.cols != 32) return 15;
+            if (kp0[0].octave != 0 || kp0[0].size != 31.f || kp0[0].angle < 0.f || kp0[0].angle >= 360.f || kp0[0].response < 20.f) return 16;
+        }
+        // [verbatim] kitti_ba.cpp:602,641
+        epivo::BFMatcher matcher(NORM_HAMMING2, true);
+        vector<DMatch> matches;
+        matcher.match(descs[0], descs[1], matches);
+        int good = 0;
+        for (size_t m = 0; m < matches.size(); ++m) {
+            const Point2f a = key_points[0][matches[m].queryIdx], b = key_points[1][matches[m].trainIdx];
+            good += fabs(a.x - b.x - 3.0) < 2.5 && fabs(a.y - b.y - 1.0) < 2.5;
+        }
+        printf("ORB: %zu / %zu keypoints, %zu mutual matches, %d on the true shift\n", key_points[0].size(), key_points[1].size(),
+               matches.size(), good);
+        if (matches.size() < 30 || good < (int)matches.size() / 2) return 17;
+    }
     printf("dropin ok\n");
     return 0;
 }

@@ -1,0 +1,88 @@
+"""ORB's keypoint selection (KeyPointsFilter::retainBest): the kernel's code (epivo_b200/csrc/orb_select.cuh, compiled for
+the host), the numpy oracle (oracle/orb.py) and the real libstdc++ algorithms OpenCV calls agree on the kept set AND its
+order."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import orb as OO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "tests", "cpp", "orb_select_host.bin")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    src = os.path.join(ROOT, "tests", "cpp", "orb_select_host.cpp")
+    p = subprocess.run(["g++", "-O1", "-std=c++14", "-shared", "-fPIC", src, "-o", LIB], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    return C.CDLL(LIB)
+
+
+def _call(fn, resp, *args):
+    out = np.full(len(resp) + 1, -1, dtype=np.int32)
+    r = np.ascontiguousarray(resp, dtype=np.uint8)
+    k = fn(r.ctypes.data_as(C.c_void_p), len(r), *args, out.ctypes.data_as(C.c_void_p))
+    return out[:k] if k is not None else out[:len(resp)]
+
+
+def _cases():
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 4, 5, 9, 33, 257, 1000, 4097, 20000):
+        for kind in ("wide", "ties", "flat", "sorted", "reversed", "organ"):
+            if kind == "wide":
+                r = rng.integers(20, 256, n)
+            elif kind == "ties":
+                r = rng.integers(20, 26, n)
+            elif kind == "flat":
+                r = np.full(n, 37)
+            elif kind == "sorted":
+                r = np.sort(rng.integers(20, 256, n))
+            elif kind == "reversed":
+                r = np.sort(rng.integers(20, 256, n))[::-1]
+            else:
+                r = np.concatenate([np.arange(n // 2), np.arange(n - n // 2)[::-1]]) % 256
+            yield r.astype(np.uint8)
+
+
+def test_retain_best_matches_libstdcxx(lib):
+    lib.ref_retain_best.restype = C.c_int
+    lib.epv_retain_best_host.restype = C.c_int
+    checked = 0
+    for r in _cases():
+        n = len(r)
+        for n_points in sorted({0, 1, 2, 3, n // 7, n // 2, n - 2, n - 1, n, n + 5}):
+            if n_points < 0:
+                continue
+            ref = _call(lib.ref_retain_best, r, n_points)
+            mine = _call(lib.epv_retain_best_host, r, n_points)
+            assert np.array_equal(ref, mine), (n, n_points)
+            if n <= 4097:
+                assert np.array_equal(ref, OO.retain_best(r.astype(np.float32), n_points)), (n, n_points)
+            # what OpenCV documents: everything at least as good as the n_points-th best survives
+            if 0 < n_points < n:
+                thr = np.sort(r)[::-1][n_points - 1]
+                assert sorted(ref.tolist()) == np.nonzero(r >= thr)[0].tolist()
+            checked += 1
+    assert checked > 300
+
+
+def test_heap_select_fallback_matches_libstdcxx(lib):
+    """std::nth_element's depth-limit branch (__heap_select + swap) is unreachable with random data; its restatements
+    are checked against libstdc++'s own __heap_select directly."""
+    lib.ref_heap_select.restype = None
+    lib.epv_heap_select_host.restype = None
+    for r in _cases():
+        n = len(r)
+        if n < 4 or n > 4097:
+            continue
+        for first, middle in ((0, 1), (0, n // 2), (n // 3, n // 3 + 2), (1, n - 1), (0, n)):
+            ref = _call(lib.ref_heap_select, r, first, middle)
+            mine = _call(lib.epv_heap_select_host, r, first, middle)
+            assert np.array_equal(ref, mine), (n, first, middle)
+            idx = list(range(n))
+            OO._heap_select([float(v) for v in r], idx, first, middle, n)
+            assert np.array_equal(ref, idx), (n, first, middle)
