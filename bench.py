@@ -440,6 +440,50 @@ def front_end_measure(ctx, frames=128):
                         "status filtering, wall clock"}
 
 
+def orb_front_end_measure(ctx, frames=32, batch=8):
+    """N4: kitti_ba's front end (extract_good_kp, kitti_ba.cpp:114-156, then really_robust_ass's matcher, :602,641) from
+    KITTI-sized synthetic frames through the host API: ORB(10000, 1.2, 8, 15, 0, 2, FAST_SCORE) detect + compute on every
+    frame, then BFMatcher(HAMMING2, crossCheck) at ~10000 x 10000 + findEssentialMat(RANSAC, .99, .05) + recoverPose + LM
+    on consecutive frames."""
+    from epivo_b200 import api, synth
+    big = synth.corner_scene(376 + 40, 1241 + 3 * frames + 8, 31)
+    seq = np.stack([big[(k % 5):(k % 5) + 376, 3 * k:3 * k + 1241] for k in range(frames)])
+    K = synth.KITTI_K.astype(np.float32)
+    prm = api.default_params(K, method=api.RANSAC, prob=0.99, threshold=0.05)          # kitti_ba.cpp:308
+    cap = 12288
+    best, pipe = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        feats = []
+        for i in range(0, frames, batch):
+            feats += api.orbDetectAndCompute(seq[i:i + batch], 10000, max_keypoints=cap, ctx=ctx)
+        t1 = time.perf_counter()
+        counts = np.array([len(k) for k, _ in feats], dtype=np.int32)
+        kps = np.zeros((frames, cap, 2), dtype=np.float32)
+        descs = np.zeros((frames, cap, 32), dtype=np.uint8)
+        for i, (k, d) in enumerate(feats):                                             # KeyPoint::convert, kitti_ba.cpp:145
+            kps[i, :counts[i], 0], kps[i, :counts[i], 1] = k["x"], k["y"]
+            descs[i, :counts[i]] = d
+        if pipe is None:
+            pipe = api.SequencePipeline(frames, cap, ctx=ctx)
+        pipe.upload(kps, descs)
+        pipe.set_counts(counts)
+        pipe.run(prm, 0, frames - 1)
+        res = pipe.download(0, frames - 1)
+        t2 = time.perf_counter()
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1)
+    pipe.close()
+    return {"workload": "kitti_ba.cpp:114-156 + :602,641 from %d synthetic 1241x376 frames: ORB::create(10000, 1.2f, 8, 15, 0, 2, "
+                        "FAST_SCORE) detect + compute (batches of %d frames), BFMatcher(NORM_HAMMING2, crossCheck) on consecutive "
+                        "frames, findEssentialMat(RANSAC, .99, .05) + recoverPose + 48-pt LM" % (frames, batch),
+            "value": frames / best[0], "unit": "frames/s", "orb_ms_per_frame": best[1] * 1e3 / frames,
+            "match_geometry_ms_per_pair": best[2] * 1e3 / (frames - 1), "mean_keypoints": float(counts.mean()),
+            "mean_matches": float(res["n_matches"].mean()), "mean_inlier_frac": float(np.mean(res["n_inliers"] / np.maximum(res["n_matches"], 1))),
+            "includes": "host->device upload of the frames, device->host of keypoints and descriptors, host-side packing into "
+                        "frame slots, upload of the slots, device->host of the results, wall clock"}
+
+
 def rot_angle(a, b):
     return float(np.arccos(np.clip((np.trace(a.T @ b) - 1) / 2, -1, 1)))
 
@@ -671,6 +715,7 @@ def main():
                                     "e2e": m["windows"] / (m["wall_ms"] * 1e-3), "e2e_ms_per_step": m["wall_ms"],
                                     "mean_iters": m["mean_iters"], "windows_on_rank0": m["B"]}
         cfgs["kitti_E from frames: FAST(40) + LK + LMedS geometry"] = front_end_measure(ctx)
+        cfgs["kitti_ba from frames: ORB(10000) + matcher + RANSAC(.99,.05) geometry"] = orb_front_end_measure(ctx)
         line["configs"] = cfgs
 
     # ---------------- N > 1: config 3 as written (one sequence sharded, gathered, chained) ---------------

@@ -324,3 +324,22 @@ def make_reprojs(seed: int, num_frames: int, window, K: np.ndarray = KITTI_K, n_
         w = 0.0 if (stereo and i0 % 2 == 0 and i1 == i0 + 1) else 1.0
         out[(i0, i1)] = Reproj(p0.astype(np.float32), p1.astype(np.float32), R, t, w)
     return out
+
+
+def corner_scene(rows: int, cols: int, seed: int) -> np.ndarray:
+    """An 8-bit test image with corners at every scale for the detector / descriptor front end (FAST, ORB): smooth random
+    background, filled rectangles of random grey, a little noise (no OpenCV needed)."""
+    rng = np.random.default_rng(seed)
+    coarse = rng.integers(60, 200, (rows // 8 + 3, cols // 8 + 3)).astype(np.float64)
+    yy = np.arange(rows) / 8.0
+    xx = np.arange(cols) / 8.0
+    y0, x0 = yy.astype(int), xx.astype(int)
+    fy, fx = (yy - y0)[:, None], (xx - x0)[None, :]
+    img = (coarse[y0][:, x0] * (1 - fy) * (1 - fx) + coarse[y0 + 1][:, x0] * fy * (1 - fx) +
+           coarse[y0][:, x0 + 1] * (1 - fy) * fx + coarse[y0 + 1][:, x0 + 1] * fy * fx)
+    for _ in range(max(8, rows * cols // 600)):
+        x, y = int(rng.integers(0, cols)), int(rng.integers(0, rows))
+        w, h = (int(v) for v in rng.integers(4, 40, 2))
+        img[y:y + h, x:x + w] = float(rng.integers(0, 256))
+    img += rng.normal(0, 3, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
