@@ -99,17 +99,23 @@ __device__ __forceinline__ bool fast_keep(const uint16_t* __restrict__ s, int ro
            sc > (r1[1] & 0xFF) && sc > (r2[-1] & 0xFF) && sc > (r2[0] & 0xFF) && sc > (r2[1] & 0xFF);
 }
 
-// one warp per (row, image): number of kept corners in the row
-__global__ void __launch_bounds__(128) fast_count_kernel(const uint16_t* __restrict__ S, int rows, int cols, int nonmax,
-                                                         int32_t* __restrict__ rowcount) {
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= rows) return;
+// A row is cut into segments of FT_SEG pixels so that a single frame still fills the GPU with warps (one warp per
+// segment: 8 steps of 32 pixels instead of a whole 1241-pixel row); counts / offsets are per (row, segment), in row-major
+// order, which is OpenCV's keypoint order.
+constexpr int FT_SEG = 256;
+
+// one warp per (row segment, image): number of kept corners in the segment
+__global__ void __launch_bounds__(128) fast_count_kernel(const uint16_t* __restrict__ S, int rows, int cols, int nseg, int nonmax,
+                                                         int32_t* __restrict__ segcount) {
+    const int item = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= rows * nseg) return;
+    const int row = item / nseg, x_lo = (item % nseg) * FT_SEG, x_hi = min(x_lo + FT_SEG, cols);
     const uint16_t* s = S + (size_t)blockIdx.y * rows * cols;
     int n = 0;
     if (row >= 3 && row < rows - 3)
-        for (int x = lane; x < cols; x += 32) n += fast_keep(s, rows, cols, x, row, nonmax) ? 1 : 0;
+        for (int x = x_lo + lane; x < x_hi; x += 32) n += fast_keep(s, rows, cols, x, row, nonmax) ? 1 : 0;
     n = __reduce_add_sync(0xFFFFFFFFu, n);
-    if (lane == 0) rowcount[(size_t)blockIdx.y * rows + row] = n;
+    if (lane == 0) segcount[(size_t)blockIdx.y * rows * nseg + item] = n;
 }
 
 // one CTA per image: exclusive scan of the row counts in place, total to counts[img]
@@ -141,19 +147,21 @@ __global__ void __launch_bounds__(256) fast_scan_kernel(int32_t* __restrict__ ro
     if (tid == 0) counts[blockIdx.x] = s_carry;
 }
 
-// one warp per (row, image): write the kept corners of the row, left to right, at the row's offset
-__global__ void __launch_bounds__(128) fast_write_kernel(const uint16_t* __restrict__ S, int rows, int cols, int nonmax,
-                                                         const int32_t* __restrict__ rowoff, int max_kp,
+// one warp per (row segment, image): write the kept corners of the segment, left to right, at the segment's offset
+__global__ void __launch_bounds__(128) fast_write_kernel(const uint16_t* __restrict__ S, int rows, int cols, int nseg, int nonmax,
+                                                         const int32_t* __restrict__ segoff, int max_kp,
                                                          float* __restrict__ kps, float* __restrict__ resp) {
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= rows * nseg) return;
+    const int row = item / nseg, x_lo = (item % nseg) * FT_SEG, x_hi = min(x_lo + FT_SEG, cols);
     if (row < 3 || row >= rows - 3) return;
     const uint16_t* s = S + (size_t)blockIdx.y * rows * cols;
-    int pos = rowoff[(size_t)blockIdx.y * rows + row];
+    int pos = segoff[(size_t)blockIdx.y * rows * nseg + item];
     float* kp = kps + (size_t)blockIdx.y * max_kp * 2;
     float* rs = resp ? resp + (size_t)blockIdx.y * max_kp : nullptr;
-    for (int x0 = 0; x0 < cols; x0 += 32) {
+    for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
         const int x = x0 + lane;
-        const bool keep = x < cols && fast_keep(s, rows, cols, x, row, nonmax);
+        const bool keep = x < x_hi && fast_keep(s, rows, cols, x, row, nonmax);
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
         if (keep) {
             const int k = pos + __popc(bal & ((1u << lane) - 1));
@@ -169,8 +177,10 @@ __global__ void __launch_bounds__(128) fast_write_kernel(const uint16_t* __restr
 
 }  // namespace
 
+static inline int fast_nseg(int cols) { return (cols + FT_SEG - 1) / FT_SEG; }
+
 size_t epv_fast_work_bytes(int n_images, int rows, int cols) {
-    return (size_t)n_images * rows * cols * 2 + (size_t)n_images * rows * 4 + 256;
+    return (size_t)n_images * rows * cols * 2 + (size_t)n_images * rows * fast_nseg(cols) * 4 + 256;
 }
 
 // d_img: [n_images][rows][cols] bytes; d_kps: [n_images][max_kp][2]; d_resp: optional [n_images][max_kp];
@@ -179,17 +189,18 @@ int epv_fast_launch(epivo_ctx* ctx, const uint8_t* d_img, int n_images, int rows
                     int max_kp, float* d_kps, float* d_resp, int32_t* d_counts, void* work) {
     if (n_images <= 0) return EPIVO_OK;
     uint16_t* S = (uint16_t*)work;
-    int32_t* rowcount = (int32_t*)((uint8_t*)work + (((size_t)n_images * rows * cols * 2 + 127) & ~(size_t)127));
+    int32_t* segcount = (int32_t*)((uint8_t*)work + (((size_t)n_images * rows * cols * 2 + 127) & ~(size_t)127));
     if (n_images > 65535) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "more than 65535 images per call");
+    const int nseg = fast_nseg(cols), items = rows * nseg;
     const dim3 g((cols + FT_BX - 1) / FT_BX, (rows + FT_BY - 1) / FT_BY, n_images);
     fast_score_kernel<<<g, dim3(FT_BX, FT_BY), 0, ctx->stream>>>(d_img, rows, cols, threshold, nonmax, S);
     EPV_LAUNCHED(ctx);
-    const dim3 gr((rows + 3) / 4, n_images);
-    fast_count_kernel<<<gr, 128, 0, ctx->stream>>>(S, rows, cols, nonmax, rowcount);
+    const dim3 gr((items + 3) / 4, n_images);
+    fast_count_kernel<<<gr, 128, 0, ctx->stream>>>(S, rows, cols, nseg, nonmax, segcount);
     EPV_LAUNCHED(ctx);
-    fast_scan_kernel<<<n_images, 256, 0, ctx->stream>>>(rowcount, rows, d_counts);
+    fast_scan_kernel<<<n_images, 256, 0, ctx->stream>>>(segcount, items, d_counts);
     EPV_LAUNCHED(ctx);
-    fast_write_kernel<<<gr, 128, 0, ctx->stream>>>(S, rows, cols, nonmax, rowcount, max_kp, d_kps, d_resp);
+    fast_write_kernel<<<gr, 128, 0, ctx->stream>>>(S, rows, cols, nseg, nonmax, segcount, max_kp, d_kps, d_resp);
     EPV_LAUNCHED(ctx);
     return EPIVO_OK;
 }

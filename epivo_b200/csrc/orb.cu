@@ -9,7 +9,8 @@
 //   detection    FAST-9/16 (fastThreshold, non-max suppression) per level                                     frontend.cu
 //   selection    border filter (edgeThreshold) + KeyPointsFilter::retainBest(nfeaturesPerLevel): keeps every
 //                corner whose score is >= the n-th best one, in the order libstdc++'s std::nth_element +
-//                std::partition leave them in -- reproduced by running those two algorithms                   orb_select_kernel
+//                std::partition leave them in -- reproduced by running those two algorithms, each partition
+//                pass as two ordered compactions + independent swaps on a block of threads                    orb_select_kernel
 //   orientation  intensity centroid of the radius-15 disc, fastAtan2's polynomial                             orb_describe_kernel
 //   blur         GaussianBlur(7 x 7, sigma 2) as OpenCV runs it on a ROI: sepFilter2D in float32              orb_blur_kernel
 //   descriptor   256 steered BRIEF tests (WTA_K 2) on the blurred level; samples that leave the level read
@@ -103,64 +104,103 @@ __global__ void __launch_bounds__(BL_X * BL_Y) orb_blur_kernel(const uint8_t* __
 }
 
 // ---- selection ------------------------------------------------------------------------------------------------------------
-// orb_retain_best (orb_select.cuh): libstdc++'s std::nth_element + std::partition on packed keys, one thread
+// orb_retain_best_block (orb_select.cuh): libstdc++'s std::nth_element + std::partition on packed keys
+constexpr int SEL_T = 512;                                    // threads of the selection CTA
+
+// the block of threads orb_retain_best_block runs on (orb_select.cuh)
+struct OrbSelectBlockExec {
+    int* s_cnt;                                               // 2 x 16 warp counts + 2 running offsets, shared memory
+    __device__ int tid() const { return threadIdx.x; }
+    __device__ int nthreads() const { return SEL_T; }
+    __device__ void sync() const { __syncthreads(); }
+    __device__ void imin(int* p, int v) const { atomicMin(p, v); }
+    // A gets every c in [0, m) with fa(c) in ascending order, B likewise with fb
+    template <class FA, class FB>
+    __device__ void compact2(int m, FA fa, FB fb, uint32_t* A, uint32_t* B, int* nA, int* nB) const {
+        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+        int* wa = s_cnt;
+        int* wb = s_cnt + SEL_T / 32;
+        int* off = s_cnt + 2 * (SEL_T / 32);
+        if (t == 0) off[0] = off[1] = 0;
+        __syncthreads();
+        for (int base = 0; base < m; base += SEL_T) {
+            const int c = base + t;
+            const bool a = c < m && fa(c), b = c < m && fb(c);
+            const unsigned ba = __ballot_sync(0xFFFFFFFFu, a), bb = __ballot_sync(0xFFFFFFFFu, b);
+            if (lane == 0) {
+                wa[warp] = __popc(ba);
+                wb[warp] = __popc(bb);
+            }
+            __syncthreads();
+            int oa = off[0], ob = off[1];
+            for (int w = 0; w < warp; ++w) {
+                oa += wa[w];
+                ob += wb[w];
+            }
+            const unsigned lt = (1u << lane) - 1;
+            if (a) A[oa + __popc(ba & lt)] = (uint32_t)c;
+            if (b) B[ob + __popc(bb & lt)] = (uint32_t)c;
+            __syncthreads();
+            if (t == SEL_T - 1) {
+                off[0] = oa + __popc(ba);
+                off[1] = ob + __popc(bb);
+            }
+            __syncthreads();
+        }
+        if (t == 0) {
+            *nA = off[0];
+            *nB = off[1];
+        }
+        __syncthreads();
+    }
+};
+
 // one CTA per (image, level): border filter in FAST's order, then retainBest.  sel[level block][image][k] = candidate
-// index of the k-th kept keypoint; sel_cnt[image][level] = how many.
-__global__ void __launch_bounds__(256) orb_select_kernel(OrbGeom g, const float* __restrict__ cand_kps,
-                                                         const float* __restrict__ cand_resp,
-                                                         const int32_t* __restrict__ cand_cnt, uint32_t* __restrict__ sel,
-                                                         int32_t* __restrict__ sel_cnt, int smem_keys) {
+// index of the k-th kept keypoint; sel_cnt[image][level] = how many.  Keys and the two stop lists of a partition pass
+// live in shared memory when the level's candidates fit (smem_keys each), else in HBM (the sel slot and scratch).
+__global__ void __launch_bounds__(SEL_T) orb_select_kernel(OrbGeom g, const float* __restrict__ cand_kps,
+                                                           const float* __restrict__ cand_resp,
+                                                           const int32_t* __restrict__ cand_cnt, uint32_t* __restrict__ sel,
+                                                           uint32_t* __restrict__ scratch, int32_t* __restrict__ sel_cnt,
+                                                           int smem_keys) {
     extern __shared__ uint32_t s_keys[];
-    __shared__ int s_warp[8];
-    __shared__ int s_base, s_kept;
+    __shared__ int s_cnt[2 * (SEL_T / 32) + 2];
+    __shared__ OrbSelectShared s_sh;
     const int img = blockIdx.x, lv = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int cap = g.cap[lv], rows = g.rows[lv], cols = g.cols[lv], edge = g.edge;
     const int n = min(cand_cnt[lv * g.n_images + img], cap);
     const float* kp = cand_kps + (g.cand_off[lv] + (int64_t)img * cap) * 2;
     const float* rs = cand_resp + g.cand_off[lv] + (int64_t)img * cap;
     uint32_t* out = sel + g.cand_off[lv] + (int64_t)img * cap;
+    uint32_t* scr = scratch + (g.cand_off[lv] + (int64_t)img * cap) * 2;
     const bool room = rows > 2 * edge && cols > 2 * edge;
-    // pass 1: how many survive the border filter (decides where the keys live)
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    uint32_t* keys = out;
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int base = 0; base < n; base += 256) {
-            const int j = base + tid;
-            bool in = false;
-            if (j < n && room) {
-                const float x = kp[2 * j], y = kp[2 * j + 1];
-                in = x >= edge && x < cols - edge && y >= edge && y < rows - edge;       // Rect::contains
-            }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
-            if (lane == 0) s_warp[warp] = __popc(bal);
-            __syncthreads();
-            int off = s_base;
-            for (int w = 0; w < warp; ++w) off += s_warp[w];
-            if (pass == 1 && in) keys[off + __popc(bal & ((1u << lane) - 1))] = ((uint32_t)rs[j] << 24) | (uint32_t)j;
-            __syncthreads();
-            if (tid == 255) s_base = off + __popc(bal);
-            __syncthreads();
-        }
-        if (pass == 0) {
-            keys = s_base <= smem_keys ? s_keys : out;
-            __syncthreads();
-            if (tid == 0) s_base = 0;
-            __syncthreads();
-        }
+    OrbSelectBlockExec ex{s_cnt};
+    // survivors of the border filter, in FAST's order (A; B is not needed here)
+    uint32_t* A = scr;
+    uint32_t* B = scr + cap;
+    ex.compact2(n, [&](int j) {
+        const float x = kp[2 * j], y = kp[2 * j + 1];
+        return room && x >= edge && x < cols - edge && y >= edge && y < rows - edge;              // Rect::contains
+    }, [](int) { return false; }, A, B, &s_sh.nA, &s_sh.nB);
+    const int nf = s_sh.nA;
+    const bool in_smem = nf <= smem_keys;
+    uint32_t* keys = in_smem ? s_keys : out;
+    for (int i = tid; i < nf; i += SEL_T) {
+        const uint32_t j = A[i];
+        keys[i] = ((uint32_t)rs[j] << 24) | j;
     }
-    const int nf = s_base;
+    __syncthreads();
+    if (in_smem) {
+        A = s_keys + smem_keys;
+        B = s_keys + 2 * smem_keys;
+    }
     const int n_points = g.nfeat[lv];
-    if (tid == 0) {
-        int kept = nf;
-        if (nf > n_points) kept = n_points == 0 ? 0 : orb_retain_best(keys, nf, n_points);
-        s_kept = kept;
-        sel_cnt[img * g.nlevels + lv] = kept;
-    }
+    int kept = nf;
+    if (nf > n_points) kept = n_points == 0 ? 0 : orb_retain_best_block(ex, keys, nf, n_points, A, B, &s_sh);
     __syncthreads();
-    const int kept = s_kept;
-    for (int i = tid; i < kept; i += 256) out[i] = keys[i] & 0xFFFFFFu;
+    if (tid == 0) sel_cnt[img * g.nlevels + lv] = kept;
+    for (int i = tid; i < kept; i += SEL_T) out[i] = keys[i] & 0xFFFFFFu;
 }
 
 // one thread per image: where each level's keypoints start in the image's output, and the total
@@ -364,7 +404,7 @@ int epv_orb_plan(epivo_ctx* ctx, int n_images, int rows, int cols, int nfeatures
 
 size_t epv_orb_work_bytes(const EpvOrbPlan& plan) {
     const OrbGeom& g = *reinterpret_cast<const OrbGeom*>(plan.geom);
-    return 2 * plan.pyr_bytes + epv_fast_work_bytes(g.n_images, g.rows[0], g.cols[0]) + plan.cand_total * 16 +
+    return 2 * plan.pyr_bytes + epv_fast_work_bytes(g.n_images, g.rows[0], g.cols[0]) + plan.cand_total * 24 +
            (size_t)plan.tab_entries * 4 + (size_t)g.n_images * (ORB_MAX_LEVELS * 3 + 2) * 4 + 16 * 4096;
 }
 
@@ -383,6 +423,7 @@ int epv_orb_launch(epivo_ctx* ctx, const EpvOrbPlan& plan, int fast_threshold, u
     float* cand_kps = epv_ws_take<float>(ctx, plan.cand_total * 2);
     float* cand_resp = epv_ws_take<float>(ctx, plan.cand_total);
     uint32_t* sel = epv_ws_take<uint32_t>(ctx, plan.cand_total);
+    uint32_t* scratch = epv_ws_take<uint32_t>(ctx, plan.cand_total * 2);
     uint32_t* d_tab = epv_ws_take<uint32_t>(ctx, plan.tab_entries + 1);
     int32_t* cand_cnt = epv_ws_take<int32_t>(ctx, (size_t)n_images * ORB_MAX_LEVELS);
     int32_t* sel_cnt = epv_ws_take<int32_t>(ctx, (size_t)n_images * ORB_MAX_LEVELS);
@@ -427,10 +468,10 @@ int epv_orb_launch(epivo_ctx* ctx, const EpvOrbPlan& plan, int fast_threshold, u
         EpvRange r(ctx, "orb_select_describe");
         int max_cap = 0;
         for (int l = 0; l < g.nlevels; ++l) max_cap = std::max(max_cap, g.cap[l]);
-        const int smem_keys = std::min(max_cap, 48 * 1024);                // 192 KB of keys at most; larger sets select in HBM
-        EPV_CUDA(ctx, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_keys * 4));
-        orb_select_kernel<<<dim3(n_images, g.nlevels), 256, (size_t)smem_keys * 4, st>>>(g, cand_kps, cand_resp, cand_cnt, sel,
-                                                                                         sel_cnt, smem_keys);
+        const int smem_keys = std::min(max_cap, 16 * 1024);                // keys + two stop lists: 192 KB at most; larger sets select in HBM
+        EPV_CUDA(ctx, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_keys * 12));
+        orb_select_kernel<<<dim3(n_images, g.nlevels), SEL_T, (size_t)smem_keys * 12, st>>>(g, cand_kps, cand_resp, cand_cnt, sel,
+                                                                                            scratch, sel_cnt, smem_keys);
         EPV_LAUNCHED(ctx);
         orb_offsets_kernel<<<(n_images + 127) / 128, 128, 0, st>>>(g, sel_cnt, base, d_counts);
         EPV_LAUNCHED(ctx);

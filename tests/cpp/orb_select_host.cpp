@@ -49,6 +49,19 @@ int epv_retain_best_host(const uint8_t* resp, int n, int n_points, int* out_idx)
     return kept;
 }
 
+// the block-parallel form of the same selection (what orb_select_kernel runs), executed by one host "thread"; depth < 0
+// keeps libstdc++'s 2 lg n, depth >= 0 forces the heap-select fallback after that many partition passes
+int epv_retain_best_block_host(const uint8_t* resp, int n, int n_points, int* out_idx) {
+    std::vector<uint32_t> k(n), A(n + 1), B(n + 1);
+    for (int i = 0; i < n; ++i) k[i] = ((uint32_t)resp[i] << 24) | (uint32_t)i;
+    int kept = n;
+    OrbSelectHostExec ex;
+    OrbSelectShared sh;
+    if (n > n_points) kept = n_points == 0 ? 0 : orb_retain_best_block(ex, k.data(), n, n_points, A.data(), B.data(), &sh);
+    for (int i = 0; i < kept; ++i) out_idx[i] = (int)(k[i] & 0xFFFFFFu);
+    return kept;
+}
+
 // the depth-limit fallback of std::nth_element, which random inputs never reach: both forms permute all n entries
 void ref_heap_select(const uint8_t* resp, int n, int first, int middle, int* out_idx) {
     std::vector<Kp> k(n);

@@ -51,6 +51,7 @@ def _cases():
 def test_retain_best_matches_libstdcxx(lib):
     lib.ref_retain_best.restype = C.c_int
     lib.epv_retain_best_host.restype = C.c_int
+    lib.epv_retain_best_block_host.restype = C.c_int
     checked = 0
     for r in _cases():
         n = len(r)
@@ -60,6 +61,7 @@ def test_retain_best_matches_libstdcxx(lib):
             ref = _call(lib.ref_retain_best, r, n_points)
             mine = _call(lib.epv_retain_best_host, r, n_points)
             assert np.array_equal(ref, mine), (n, n_points)
+            assert np.array_equal(ref, _call(lib.epv_retain_best_block_host, r, n_points)), ("block form", n, n_points)
             if n <= 4097:
                 assert np.array_equal(ref, OO.retain_best(r.astype(np.float32), n_points)), (n, n_points)
             # what OpenCV documents: everything at least as good as the n_points-th best survives
@@ -86,3 +88,19 @@ def test_heap_select_fallback_matches_libstdcxx(lib):
             idx = list(range(n))
             OO._heap_select([float(v) for v in r], idx, first, middle, n)
             assert np.array_equal(ref, idx), (n, first, middle)
+
+
+def test_retain_best_fuzz(lib):
+    """Many small random cases (where an off-by-one in the pairing of the two scans would show): all three forms."""
+    lib.ref_retain_best.restype = C.c_int
+    lib.epv_retain_best_host.restype = C.c_int
+    lib.epv_retain_best_block_host.restype = C.c_int
+    rng = np.random.default_rng(3)
+    for it in range(4000):
+        n = int(rng.integers(1, 400 if it % 8 else 6000))
+        lo = int(rng.integers(0, 250))
+        r = rng.integers(lo, lo + int(rng.integers(1, 256 - lo)) + 1, n).clip(0, 255).astype(np.uint8)
+        n_points = int(rng.integers(0, n + 2))
+        ref = _call(lib.ref_retain_best, r, n_points)
+        assert np.array_equal(ref, _call(lib.epv_retain_best_host, r, n_points)), (it, n, n_points)
+        assert np.array_equal(ref, _call(lib.epv_retain_best_block_host, r, n_points)), (it, n, n_points)
