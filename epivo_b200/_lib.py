@@ -73,6 +73,7 @@ SIGNATURES = {
     "epivo_seq_upload": (_i, [_vp, _i, _i, _vp, _vp]),
     "epivo_last_kernel_ms": (_i, [_vp, _vp]),
     "epivo_seq_set_counts": (_i, [_vp, _i, _i, _vp]),
+    "epivo_seq_extract_orb": (_i, [_vp, _i, _i, _vp, _i, _i, _i, C.c_float, _i, _i, _i, _vp]),
     "epivo_seq_create_pairs": (_i, [_vp, C.POINTER(_vp), _i, _i, _i]),
     "epivo_seq_set_pairs": (_i, [_vp, _i, _vp, _vp]),
     "epivo_seq_run": (_i, [_vp, C.POINTER(PipelineParams), _i, _i]),

@@ -484,6 +484,21 @@ class SequencePipeline:
         c = np.ascontiguousarray(counts, dtype=np.int32)
         self.ctx.check(self.ctx.lib.epivo_seq_set_counts(self.h, int(first_frame), int(c.shape[0]), _p(c)))
 
+    def extract_orb(self, images, first_frame: int = 0, nfeatures: int = 10000, scaleFactor: float = 1.2, nlevels: int = 8,
+                    edgeThreshold: int = 15, fastThreshold: int = 20):
+        """kitti_ba.cpp:114-156 into the sequence: ORB on images (n, rows, cols) uint8; positions, descriptors and counts of
+        frame slots first_frame.. are filled on the device (no download / re-upload).  Returns the keypoints found per frame
+        (a frame with more than kp_per_frame keeps the first kp_per_frame)."""
+        im = np.ascontiguousarray(images, dtype=np.uint8)
+        if im.ndim == 2:
+            im = im[None]
+        n, rows, cols = im.shape
+        counts = np.zeros(n, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.epivo_seq_extract_orb(self.h, int(first_frame), n, _p(im), rows, cols, int(nfeatures),
+                                                          float(scaleFactor), int(nlevels), int(edgeThreshold),
+                                                          int(fastThreshold), _p(counts)))
+        return counts
+
     def set_pairs(self, fq=None, ft=None):
         """Explicit pair list: pair p matches frame fq[p] (query) against ft[p] (train), as the window walk of
         kitti_ba.cpp:603-607 does; None restores the consecutive pairs (p, p + 1)."""

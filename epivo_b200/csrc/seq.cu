@@ -401,6 +401,61 @@ int epivo_seq_set_counts(epivo_seq* s, int first_frame, int n_frames, const int3
     return EPIVO_OK;
 }
 
+// keypoints (epivo_keypoint) and descriptors of a batch of frames -> the frame slots of the sequence; one thread per
+// (frame, keypoint) word: 2 position floats + 8 descriptor words
+__global__ void __launch_bounds__(256) seq_orb_to_slots_kernel(const epivo_keypoint* __restrict__ kps, const uint32_t* __restrict__ desc,
+                                                               const int32_t* __restrict__ found, int n_frames, int kp,
+                                                               float* __restrict__ slot_kps, uint32_t* __restrict__ slot_desc,
+                                                               int32_t* __restrict__ slot_counts) {
+    const int f = blockIdx.y;
+    const int n = min(found[f], kp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) slot_counts[f] = n;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n * 8; i += gridDim.x * 256) {
+        const int k = i >> 3, w = i & 7;
+        slot_desc[((size_t)f * kp + k) * 8 + w] = desc[((size_t)f * kp + k) * 8 + w];
+        if (w < 2) slot_kps[((size_t)f * kp + k) * 2 + w] = w == 0 ? kps[(size_t)f * kp + k].x : kps[(size_t)f * kp + k].y;
+    }
+}
+
+int epivo_seq_extract_orb(epivo_seq* s, int first_frame, int n_frames, const uint8_t* images, int rows, int cols,
+                          int nfeatures, float scale_factor, int nlevels, int edge_threshold, int fast_threshold,
+                          int32_t* counts_out) {
+    if (!s) return EPIVO_ERR_INVALID;
+    epivo_ctx* ctx = s->ctx;
+    if (first_frame < 0 || n_frames < 0 || first_frame + n_frames > s->max_frames)
+        EPV_FAIL(ctx, EPIVO_ERR_INVALID, "frame range [%d,+%d) outside [0,%d)", first_frame, n_frames, s->max_frames);
+    if (n_frames == 0) return EPIVO_OK;
+    if (!images || rows <= 0 || cols <= 0) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "null or empty images");
+    if (fast_threshold < 0 || fast_threshold > 255) EPV_FAIL(ctx, EPIVO_ERR_INVALID, "fast_threshold %d outside [0, 255]", fast_threshold);
+    const int kp = s->kp;
+    EpvOrbPlan plan;
+    int rc = epv_orb_plan(ctx, n_frames, rows, cols, nfeatures, scale_factor, nlevels, edge_threshold, kp, &plan);
+    if (rc) return rc;
+    EPV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nk = (size_t)n_frames * kp;
+    rc = epv_ws_reserve(ctx, epv_orb_work_bytes(plan) + nk * (sizeof(epivo_keypoint) + 32) + (size_t)n_frames * 4 + 4096);
+    if (rc) return rc;
+    rc = epv_pin_reserve(ctx, (plan.tab_entries + 1) * 4 + 512);
+    if (rc) return rc;
+    uint8_t* d_pyr = epv_ws_take<uint8_t>(ctx, plan.pyr_bytes);
+    epivo_keypoint* d_kps = epv_ws_take<epivo_keypoint>(ctx, nk + 1);
+    uint8_t* d_desc = epv_ws_take<uint8_t>(ctx, nk * 32 + 32);
+    int32_t* d_found = epv_ws_take<int32_t>(ctx, n_frames);
+    uint32_t* h_tab = epv_pin_take<uint32_t>(ctx, plan.tab_entries + 1);
+    EPV_CUDA(ctx, cudaMemcpyAsync(d_pyr, images, (size_t)n_frames * rows * cols, cudaMemcpyHostToDevice, ctx->stream));
+    rc = epv_orb_launch(ctx, plan, fast_threshold, d_pyr, d_kps, d_desc, d_found, h_tab);
+    if (rc) return rc;
+    seq_orb_to_slots_kernel<<<dim3(std::max(1, std::min((kp * 8 + 255) / 256, 64)), n_frames), 256, 0, ctx->stream>>>(
+        d_kps, (const uint32_t*)d_desc, d_found, n_frames, kp, s->d_kps + (size_t)first_frame * kp * 2,
+        s->d_desc + (size_t)first_frame * kp * 8, s->d_counts + first_frame);
+    EPV_LAUNCHED(ctx);
+    if (counts_out) EPV_CUDA(ctx, cudaMemcpyAsync(counts_out, d_found, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EPV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // the workspace and the resize tables are free for the next call
+    s->counts_set = true;
+    s->frames_hi = std::max(s->frames_hi, first_frame + n_frames);
+    return EPIVO_OK;
+}
+
 int epivo_seq_set_overlap(epivo_seq* s, int overlap) {
     if (!s) return EPIVO_ERR_INVALID;
     s->overlap = overlap == 1 ? 1 : 0;

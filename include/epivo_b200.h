@@ -217,6 +217,14 @@ void epivo_seq_destroy(epivo_seq* seq);
 /* host -> device copy of n_frames frames starting at frame slot first_frame (async on the
  * context stream; kps n_frames x kp x 2 f32, descs n_frames x kp x 32 u8) */
 int epivo_seq_upload(epivo_seq* seq, int first_frame, int n_frames, const float* kps, const uint8_t* descs);
+/* kitti_ba.cpp:114-156 (extract_good_kp) straight into the sequence: ORB (epivo_orb_detect_and_compute's configuration
+ * arguments) on n_frames 8-bit images of rows x cols; keypoint positions, descriptors and the per-frame counts go into
+ * frame slots first_frame .. first_frame + n_frames - 1 without leaving the device -- the same bytes as
+ * epivo_orb_detect_and_compute + KeyPoint::convert + epivo_seq_upload + epivo_seq_set_counts.  A frame with more than
+ * kp_per_frame keypoints keeps the first kp_per_frame (OpenCV's order).  counts_out (nullable): keypoints FOUND per frame. */
+int epivo_seq_extract_orb(epivo_seq* seq, int first_frame, int n_frames, const uint8_t* images, int rows, int cols,
+                          int nfeatures, float scale_factor, int nlevels, int edge_threshold, int fast_threshold,
+                          int32_t* counts_out);
 /* Real detectors return a different number of keypoints per frame: counts[i] (<= kp_per_frame) keypoints of
  * frame slot first_frame + i are valid (the rest of the slot is ignored).  Default: every slot is full. */
 int epivo_seq_set_counts(epivo_seq* seq, int first_frame, int n_frames, const int32_t* counts);

@@ -95,3 +95,42 @@ def test_gpu_orb_feeds_the_matcher(ctx):
     dy = k1["y"][ti] - k0["y"][qi]
     on = (np.abs(dx - 5) < 2.5) & (np.abs(dy - 2) < 2.5)
     assert len(qi) > 300 and on.mean() > 0.8, (len(qi), on.mean())
+
+
+@pytest.mark.gpu
+def test_gpu_orb_into_the_sequence_on_device(ctx):
+    """epivo_seq_extract_orb (frames -> ORB -> frame slots without leaving the device) gives the same bytes as
+    orbDetectAndCompute + KeyPoint::convert + upload + set_counts: matches, masks and poses of every pair identical; a
+    slot smaller than the result keeps the first kp_per_frame keypoints."""
+    from epivo_b200 import synth
+    big = scene(260, 420, 91)
+    frames = np.stack([big[2 * k:2 * k + 200, 3 * k:3 * k + 360] for k in range(4)])
+    prm = api.default_params(synth.KITTI_K.astype(np.float32), method=api.RANSAC, prob=0.99, threshold=0.3)
+    for cap, nf in [(4096, 10000), (600, 10000), (4096, 300)]:
+        feats = api.orbDetectAndCompute(frames, nf, ctx=ctx)
+        counts = np.array([min(len(k), cap) for k, _ in feats], dtype=np.int32)
+        kps = np.zeros((4, cap, 2), np.float32)
+        descs = np.zeros((4, cap, 32), np.uint8)
+        for i, (k, d) in enumerate(feats):
+            kps[i, :counts[i], 0], kps[i, :counts[i], 1] = k["x"][:counts[i]], k["y"][:counts[i]]
+            descs[i, :counts[i]] = d[:counts[i]]
+        a = api.SequencePipeline(4, cap, ctx=ctx)
+        a.upload(kps, descs)
+        a.set_counts(counts)
+        a.run(prm, 0, 3)
+        ra = a.download(0, 3)
+        b = api.SequencePipeline(4, cap, ctx=ctx)
+        found = b.extract_orb(frames[:3], 0, nf)                         # two calls: slots 0-2, then slot 3
+        found = np.concatenate([found, b.extract_orb(frames[3:], 3, nf)])
+        assert np.array_equal(found, [len(k) for k, _ in feats])
+        b.run(prm, 0, 3)
+        rb = b.download(0, 3)
+        assert ra.tobytes() == rb.tobytes(), (cap, nf)
+        assert ra["n_matches"].min() > 50
+        for i in range(3):
+            for x, y in zip(a.matches(i), b.matches(i)):
+                assert np.array_equal(x, y)
+            for x, y in zip(a.masks(i), b.masks(i)):
+                assert np.array_equal(x, y)
+        a.close()
+        b.close()
