@@ -217,12 +217,19 @@ class ORB {
   private:
     ORB(int nf, float sf, int nl, int et, int ft) : nfeatures_(nf), scale_(sf), nlevels_(nl), edge_(et), fast_(ft), rows_(0), cols_(0), sum_(0) {}
     template <typename MatT>
-    static uint64_t checksum(const MatT& image) {             // FNV-1a over the pixels: which image the cached result belongs to
-        typedef mat_traits<MatT> MT;
+    static uint64_t checksum(const MatT& image) {             // which image the cached result belongs to: a 64-bit
+        typedef mat_traits<MatT> MT;                          // multiplicative hash over the pixels, 8 bytes per step
         const unsigned char* p = MT::bytes(image);
         const size_t n = (size_t)MT::rows(image) * MT::cols(image);
-        uint64_t h = 1469598103934665603ull;
-        for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+        uint64_t h = 1469598103934665603ull ^ n;
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            uint64_t w;
+            memcpy(&w, p + i, 8);
+            h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29;
+        }
+        for (; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
         return h;
     }
     template <typename MatT>
