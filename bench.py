@@ -452,7 +452,7 @@ def orb_front_end_measure(ctx, frames=32, batch=8):
     prm = api.default_params(K, method=api.RANSAC, prob=0.99, threshold=0.05)          # kitti_ba.cpp:308
     cap = 12288
     pipe = api.SequencePipeline(frames, cap, ctx=ctx)
-    best, host = None, None
+    best, host, same = None, None, True
     for _ in range(3):
         # (a) ORB through its own host-buffer call (what the drop-in epivo::ORB does), packed and uploaded by the host
         t0 = time.perf_counter()
@@ -481,7 +481,7 @@ def orb_front_end_measure(ctx, frames=32, batch=8):
         pipe.run(prm, 0, frames - 1)
         res = pipe.download(0, frames - 1)
         t2 = time.perf_counter()
-        assert res.tobytes() == res_host.tobytes()                                     # the two routes agree byte for byte
+        same = same and res.tobytes() == res_host.tobytes()                            # the two routes agree byte for byte
         if best is None or t2 - t0 < best[0]:
             best = (t2 - t0, t1 - t0, t2 - t1)
     pipe.close()
@@ -492,7 +492,7 @@ def orb_front_end_measure(ctx, frames=32, batch=8):
             "match_geometry_ms_per_pair": best[2] * 1e3 / (frames - 1), "mean_keypoints": float(counts.mean()),
             "via_host_buffers": {"value": frames / host[0], "unit": "frames/s", "orb_ms_per_frame": host[1] * 1e3 / frames,
                                  "pack_upload_match_geometry_ms_per_pair": host[2] * 1e3 / (frames - 1),
-                                 "note": "epivo_orb_detect_and_compute -> host -> epivo_seq_upload: identical results"},
+                                 "note": "epivo_orb_detect_and_compute -> host -> epivo_seq_upload", "results_identical": bool(same)},
             "mean_matches": float(res["n_matches"].mean()), "mean_inlier_frac": float(np.mean(res["n_inliers"] / np.maximum(res["n_matches"], 1))),
             "includes": "host->device upload of the frames, ORB into the frame slots on the device (epivo_seq_extract_orb), "
                         "matcher + geometry, device->host of the results, wall clock"}
@@ -728,8 +728,12 @@ def main():
                                     "value": m["windows"] / (m["k_ms"] * 1e-3), "unit": "windows/s", "ms_per_step": m["k_ms"],
                                     "e2e": m["windows"] / (m["wall_ms"] * 1e-3), "e2e_ms_per_step": m["wall_ms"],
                                     "mean_iters": m["mean_iters"], "windows_on_rank0": m["B"]}
-        cfgs["kitti_E from frames: FAST(40) + LK + LMedS geometry"] = front_end_measure(ctx)
-        cfgs["kitti_ba from frames: ORB(10000) + matcher + RANSAC(.99,.05) geometry"] = orb_front_end_measure(ctx)
+        for name, fn in (("kitti_E from frames: FAST(40) + LK + LMedS geometry", front_end_measure),
+                         ("kitti_ba from frames: ORB(10000) + matcher + RANSAC(.99,.05) geometry", orb_front_end_measure)):
+            try:                                     # side measurements: a failure here is reported, it does not take the line down
+                cfgs[name] = fn(ctx)
+            except Exception as e:                   # noqa: BLE001
+                cfgs[name] = {"error": "%s: %s" % (type(e).__name__, e)}
         line["configs"] = cfgs
 
     # ---------------- N > 1: config 3 as written (one sequence sharded, gathered, chained) ---------------

@@ -9,7 +9,8 @@ import cv2
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(HERE))                       # tests/ (orb_util)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))      # the repository root (epivo_b200.synth)
 from orb_util import cv2_orb, scene  # noqa: E402
 
 CASES = {   # name: (rows, cols, seed, nfeatures, scale, nlevels, edge, fast_thr)
