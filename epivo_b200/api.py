@@ -263,8 +263,8 @@ def orbDetectAndCompute(images, nfeatures: int = 10000, scaleFactor: float = 1.2
     n, rows, cols = im.shape
     cap = int(max_keypoints) if max_keypoints is not None else int(nfeatures) + int(nfeatures) // 8 + 256
     while True:
-        kps = np.zeros((n, cap), dtype=KEYPOINT_DTYPE)
-        desc = np.zeros((n, cap, 32), dtype=np.uint8)
+        kps = np.empty((n, cap), dtype=KEYPOINT_DTYPE)            # only the first counts[i] entries of a frame are written and read
+        desc = np.empty((n, cap, 32), dtype=np.uint8)
         counts = np.zeros(n, dtype=np.int32)
         ctx.check(ctx.lib.epivo_orb_detect_and_compute(ctx.h, _p(im), n, rows, cols, int(nfeatures), float(scaleFactor),
                                                        int(nlevels), int(edgeThreshold), int(fastThreshold), cap, _p(kps),
