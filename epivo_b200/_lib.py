@@ -89,6 +89,7 @@ SIGNATURES = {
     "epivo_fast_detect": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "epivo_lk_track": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp]),
     "epivo_orb_detect_and_compute": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_float, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "epivo_orb_level_geometry": (_i, [_i, _i, _i, C.c_float, _i, _vp, _vp, _vp]),
     "epivo_remap": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "epivo_seq_process_points": (_i, [_vp, C.POINTER(PipelineParams), _i, _vp, _vp, _vp, _i, _vp]),
     "epivo_microbench": (_i, [_vp, _i, C.POINTER(_d)]),

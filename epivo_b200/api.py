@@ -276,6 +276,20 @@ def orbDetectAndCompute(images, nfeatures: int = 10000, scaleFactor: float = 1.2
     return out[0] if single else out
 
 
+def orbLevelGeometry(rows: int, cols: int, nfeatures: int = 10000, scaleFactor: float = 1.2, nlevels: int = 8):
+    """The pyramid orbDetectAndCompute builds: (level rows, level cols, retainBest budget per level) as int32 arrays.
+    Host arithmetic only -- needs the library but no GPU and no context."""
+    from . import _lib
+    lib = _lib.load()
+    r = np.zeros(max(int(nlevels), 1), dtype=np.int32)
+    c = np.zeros_like(r)
+    f = np.zeros_like(r)
+    rc = lib.epivo_orb_level_geometry(int(rows), int(cols), int(nfeatures), float(scaleFactor), int(nlevels), _p(r), _p(c), _p(f))
+    if rc:
+        raise EpivoError(rc, "epivo_orb_level_geometry(%d x %d, scale %g, %d levels) refused" % (rows, cols, scaleFactor, nlevels))
+    return r, c, f
+
+
 def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, maxLevel: int = 3, maxCount: int = 30, epsilon: float = 0.01,
                          minEigThreshold: float = 1e-4, ctx: Context | None = None, returnErr: bool = False):
     """cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, None) with the 21 x 21 window (kitti_E.cpp:79-84):

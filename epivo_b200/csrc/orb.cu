@@ -376,8 +376,9 @@ int epv_orb_plan(epivo_ctx* ctx, int n_images, int rows, int cols, int nfeatures
     for (int l = 0; l < nlevels; ++l) {
         const float s = (float)pow((double)scale_factor, (double)l);      // getScale(level, firstLevel = 0, scaleFactor)
         g.scale[l] = s;
-        g.cols[l] = (int)lrintf((float)cols / s);                          // Size sz(cvRound(cols/scale), cvRound(rows/scale))
-        g.rows[l] = (int)lrintf((float)rows / s);
+        const float inv = 1.f / s;                                         // float inv_scale = 1.f / scale;
+        g.cols[l] = (int)lrintf((float)cols * inv);                        // Size sz(cvRound(cols*inv_scale), cvRound(rows*inv_scale)):
+        g.rows[l] = (int)lrintf((float)rows * inv);                        // 285 columns at 1.2f are 238 this way, 237 by division
         if (g.rows[l] < 1 || g.cols[l] < 1) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "level %d of a %d x %d image is empty", l, rows, cols);
         g.cap[l] = ((g.rows[l] + 1) / 2) * ((g.cols[l] + 1) / 2) + 1;      // suppressed corners are never 8-neighbours
         if (g.cap[l] >= (1 << 24)) EPV_FAIL(ctx, EPIVO_ERR_UNSUPPORTED, "image too large");
@@ -399,6 +400,22 @@ int epv_orb_plan(epivo_ctx* ctx, int n_images, int rows, int cols, int nfeatures
         nd *= factor;
     }
     g.nfeat[nlevels - 1] = std::max(nfeatures - sum, 0);
+    return EPIVO_OK;
+}
+
+int epivo_orb_level_geometry(int rows, int cols, int nfeatures, float scale_factor, int nlevels, int32_t* level_rows,
+                             int32_t* level_cols, int32_t* level_features) {
+    if (rows <= 0 || cols <= 0 || !level_rows || !level_cols || !level_features) return EPIVO_ERR_INVALID;
+    epivo_ctx scratch;                         // host-only: carries the error text of epv_orb_plan, no CUDA call is made
+    EpvOrbPlan plan;
+    const int rc = epv_orb_plan(&scratch, 1, rows, cols, nfeatures, scale_factor, nlevels, ORB_HALF_PATCH, 0, &plan);
+    if (rc) return rc;
+    const OrbGeom& g = *reinterpret_cast<const OrbGeom*>(plan.geom);
+    for (int l = 0; l < nlevels; ++l) {
+        level_rows[l] = g.rows[l];
+        level_cols[l] = g.cols[l];
+        level_features[l] = g.nfeat[l];
+    }
     return EPIVO_OK;
 }
 

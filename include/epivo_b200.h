@@ -141,6 +141,13 @@ int epivo_orb_detect_and_compute(epivo_ctx* ctx, const uint8_t* images, int n_im
                                  float scale_factor, int nlevels, int edge_threshold, int fast_threshold, int max_kp,
                                  epivo_keypoint* kps, uint8_t* desc, int32_t* counts);
 
+/* The pyramid epivo_orb_detect_and_compute builds for these arguments, without touching a GPU (no context needed):
+ * level_rows / level_cols / level_features: nlevels entries each -- size of every level and its retainBest budget, as
+ * OpenCV's ORB computes them.  Returns EPIVO_ERR_UNSUPPORTED for the configurations the extractor refuses (a level that
+ * rounds to an empty image -- OpenCV asserts there --, nlevels outside [1, 16], scale_factor outside (1, 2]). */
+int epivo_orb_level_geometry(int rows, int cols, int nfeatures, float scale_factor, int nlevels, int32_t* level_rows,
+                             int32_t* level_cols, int32_t* level_features);
+
 /* K3 alone: Sampson scoring of a fixed hypothesis set of m models (m x 9) against n
  * correspondences with OpenCV's exact inlier rule.  threshold in pixels (RANSAC rule);
  * counts: m inlier counts; medians: m LMedS medians (float32, may be NULL); best: index of

@@ -36,8 +36,14 @@ def layer_scales(nlevels: int, scale_factor: float, first_level: int = 0) -> np.
 
 
 def layer_sizes(rows: int, cols: int, scales: np.ndarray):
-    """Size sz(cvRound(image.cols/scale), cvRound(image.rows/scale)) with float division (orb.cpp detectAndCompute)."""
-    return [(_cv_round(np.float32(rows) / s), _cv_round(np.float32(cols) / s)) for s in scales]
+    """orb.cpp detectAndCompute:  float inv_scale = 1.f / scale;  Size sz(cvRound(cols * inv_scale), cvRound(rows * inv_scale))
+    -- the product with the float reciprocal, not a division: 285 columns at scale 1.2f give 237.5 -> 238 this way and
+    237.49998 -> 237 by division (cv2 4.13.0 returns the 238-column level; tests/orb_census.py found the case)."""
+    out = []
+    for s in scales:
+        inv = np.float32(np.float32(1.0) / np.float32(s))
+        out.append((_cv_round(np.float32(np.float32(rows) * inv)), _cv_round(np.float32(np.float32(cols) * inv))))
+    return out
 
 
 def features_per_level(nfeatures: int, nlevels: int, scale_factor: float) -> list[int]:

@@ -45,7 +45,8 @@ def test_gpu_orb_matches_cv2_golden(ctx, name):
 @pytest.mark.gpu
 def test_gpu_orb_batch_vs_oracle(ctx):
     """A batch of frames in one call, odd sizes, a flat frame (no corners) inside the batch."""
-    for rows, cols, nf in [(97, 131, 10000), (64, 200, 120), (33, 33, 500), (8, 9, 500), (3, 3, 500)]:
+    # 174 x 285: level 1 is 238 columns wide (cols * (1.f / 1.2f) = 237.5), 237 by division -- OpenCV multiplies
+    for rows, cols, nf in [(97, 131, 10000), (64, 200, 120), (174, 285, 10000), (33, 33, 500), (8, 9, 500), (3, 3, 500)]:
         ims = np.stack([scene(rows, cols, 40 + i) for i in range(4)])
         ims[2] = 90
         out = api.orbDetectAndCompute(ims, nf, ctx=ctx)

@@ -62,3 +62,32 @@ def test_oracle_orb_vs_live_cv2():
         kps, desc = OO.detect_and_compute(img, BIT_PATTERN_31, nf)
         assert np.array_equal(kps_array(kps), ref_k), (rows, cols, nf)
         assert np.array_equal(desc, ref_d), (rows, cols, nf)
+
+
+def test_level_geometry_of_the_library_matches_the_oracle():
+    """The host-side set-up of epivo_orb_detect_and_compute (level sizes by the float reciprocal, feature budgets in
+    float) is the oracle's for random configurations -- incl. 285 columns at scale 1.2f, which are 238 (not 237) wide on
+    level 1 -- and refuses what OpenCV asserts on (a level that rounds to an empty image)."""
+    from epivo_b200 import api
+    r, c, f = api.orbLevelGeometry(174, 285, 10000, 1.2, 3)
+    assert r.tolist() == [174, 145, 121] and c.tolist() == [285, 238, 198] and f.tolist() == [3956, 3297, 2747]
+    rng = np.random.default_rng(8)
+    refused = 0
+    for _ in range(4000):
+        rows, cols = int(rng.integers(1, 2200)), int(rng.integers(1, 2200))
+        nf = int(rng.integers(0, 20001))
+        sc = float(np.float32(rng.choice([1.05, 1.1, 1.2, 1.25, 1.3, 1.41, 1.5, 1.7, 2.0])))
+        nl = int(rng.integers(1, 17))
+        sizes = OO.layer_sizes(rows, cols, OO.layer_scales(nl, sc))
+        if min(min(a, b) for a, b in sizes) < 1:
+            with pytest.raises(Exception):
+                api.orbLevelGeometry(rows, cols, nf, sc, nl)
+            refused += 1
+            continue
+        r, c, f = api.orbLevelGeometry(rows, cols, nf, sc, nl)
+        assert [tuple(x) for x in zip(r.tolist(), c.tolist())] == sizes, (rows, cols, sc, nl)
+        assert f.tolist() == OO.features_per_level(nf, nl, sc), (nf, sc, nl)
+    assert refused > 0
+    for bad in [(100, 100, 500, 1.0, 8), (100, 100, 500, 2.5, 8), (100, 100, 500, 1.2, 0), (100, 100, 500, 1.2, 17)]:
+        with pytest.raises(Exception):
+            api.orbLevelGeometry(*bad)
