@@ -1,8 +1,10 @@
 // KeyPointsFilter::retainBest (OpenCV features2d/src/keypoint.cpp) on packed keys, restating the two libstdc++ algorithms it
 // calls -- std::nth_element (bits/stl_algo.h __introselect: median-of-three Hoare partition, heap-select after 2 lg n
 // rounds, insertion sort of the last <= 3) and std::partition (bidirectional form) -- so that the kept keypoints come
-// out in exactly OpenCV's order.  Compiles for the device (orb.cu runs it on one thread per image and level) and for the
-// host (tests/cpp/orb_select_host.cpp checks it against the real std:: algorithms).
+// out in exactly OpenCV's order.  Two forms: the algorithms as libstdc++ writes them, for one thread (orb_retain_best: the
+// readable statement, and the host tests' second opinion), and the same result computed by a block of threads
+// (orb_retain_best_block, below: what orb.cu's orb_select_kernel runs, one block per image and level).  Both compile
+// for the device and for the host (tests/cpp/orb_select_host.cpp checks them against the real std:: algorithms).
 #pragma once
 #include <stdint.h>
 
