@@ -440,7 +440,7 @@ def front_end_measure(ctx, frames=128):
                         "status filtering, wall clock"}
 
 
-def orb_front_end_measure(ctx, frames=32, batch=8):
+def orb_front_end_measure(ctx, frames=32, batch=8, cpu=True):
     """N4: kitti_ba's front end (extract_good_kp, kitti_ba.cpp:114-156, then really_robust_ass's matcher, :602,641) from
     KITTI-sized synthetic frames through the host API: ORB(10000, 1.2, 8, 15, 0, 2, FAST_SCORE) detect + compute on every
     frame, then BFMatcher(HAMMING2, crossCheck) at ~10000 x 10000 + findEssentialMat(RANSAC, .99, .05) + recoverPose + LM
@@ -485,6 +485,21 @@ def orb_front_end_measure(ctx, frames=32, batch=8):
         if best is None or t2 - t0 < best[0]:
             best = (t2 - t0, t1 - t0, t2 - t1)
     pipe.close()
+    cpu_ref = None
+    if cpu:                                # the same OpenCV calls on the host cores, a few frames (not oracle code: cv2 itself)
+        try:
+            import cv2
+            orb = cv2.ORB_create(10000, 1.2, 8, 15, 0, 2, cv2.ORB_FAST_SCORE)
+            m = min(frames, 6)
+            t0 = time.perf_counter()
+            for i in range(m):
+                kp = orb.detect(seq[i], None)
+                kp, d = orb.compute(seq[i], kp)
+            cpu_ref = {"value": (time.perf_counter() - t0) * 1e3 / m, "unit": "ms per frame", "what": "cv2 %s ORB detect + compute, "
+                       "OpenCV's own threading (%d host cores)" % (cv2.__version__, os.cpu_count() or 1),
+                       "identical_to_gpu_last_frame": bool(len(kp) == len(feats[m - 1][0]) and np.array_equal(d, feats[m - 1][1]))}
+        except Exception as e:             # noqa: BLE001 -- cv2 missing or failing must not cost the GPU numbers
+            cpu_ref = {"error": "%s: %s" % (type(e).__name__, e)}
     return {"workload": "kitti_ba.cpp:114-156 + :602,641 from %d synthetic 1241x376 frames: ORB::create(10000, 1.2f, 8, 15, 0, 2, "
                         "FAST_SCORE) detect + compute (batches of %d frames), BFMatcher(NORM_HAMMING2, crossCheck) on consecutive "
                         "frames, findEssentialMat(RANSAC, .99, .05) + recoverPose + 48-pt LM" % (frames, batch),
@@ -494,6 +509,7 @@ def orb_front_end_measure(ctx, frames=32, batch=8):
                                  "pack_upload_match_geometry_ms_per_pair": host[2] * 1e3 / (frames - 1),
                                  "note": "epivo_orb_detect_and_compute -> host -> epivo_seq_upload", "results_identical": bool(same)},
             "mean_matches": float(res["n_matches"].mean()), "mean_inlier_frac": float(np.mean(res["n_inliers"] / np.maximum(res["n_matches"], 1))),
+            "cv2_orb": cpu_ref,
             "includes": "host->device upload of the frames, ORB into the frame slots on the device (epivo_seq_extract_orb), "
                         "matcher + geometry, device->host of the results, wall clock"}
 
@@ -729,7 +745,8 @@ def main():
                                     "e2e": m["windows"] / (m["wall_ms"] * 1e-3), "e2e_ms_per_step": m["wall_ms"],
                                     "mean_iters": m["mean_iters"], "windows_on_rank0": m["B"]}
         for name, fn in (("kitti_E from frames: FAST(40) + LK + LMedS geometry", front_end_measure),
-                         ("kitti_ba from frames: ORB(10000) + matcher + RANSAC(.99,.05) geometry", orb_front_end_measure)):
+                         ("kitti_ba from frames: ORB(10000) + matcher + RANSAC(.99,.05) geometry",
+                          lambda c: orb_front_end_measure(c, cpu=(world == 1)))):
             try:                                     # side measurements: a failure here is reported, it does not take the line down
                 cfgs[name] = fn(ctx)
             except Exception as e:                   # noqa: BLE001
